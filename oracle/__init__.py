@@ -1,0 +1,15 @@
+"""CPU oracle for the SuperPoint extract + match hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is part of the product:
+only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs may import it, and there only as
+the checker or the timed CPU baseline -- never as a fallback for the CUDA path.
+
+Parity status: **parity unpinned by the reference** -- the reference ships no
+tests, golden vectors or fixtures for this path.  The
+oracle is instead pinned against (i) the reference's own ``SPFrontend`` C++
+compiled against libtorch in this container (``oracle/ref_build.sh`` ->
+``oracle/_ref/``) and (ii) OpenCV (``cv2.BFMatcher``, ``cv2.sortIdx``,
+``cv2.minMaxLoc``) for the third-party arithmetic the reference calls; the
+resulting vectors are committed under ``tests/golden/``.
+"""

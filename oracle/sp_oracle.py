@@ -1,0 +1,212 @@
+"""CPU oracle for SPExtractor / SPMatcher -- TEST INFRASTRUCTURE ONLY.
+
+fp32 restatement of the reference path, function by function:
+
+  frontend_forward   <- orb_slam2/src/cv/sp_extractor.cpp:79-159  (SPFrontend::forward)
+  extract            <- orb_slam2/src/cv/sp_extractor.cpp:361-514 (SPExtractor::operator())
+  match_mutual_nn    <- orb_slam2/src/cv/sp_matcher.cpp:1642-1674 (SearchByBruteForce core)
+
+The network half runs on torch CPU (the reference runs the same ATen ops
+through libtorch); the post-processing half is the C restatement in
+``oracle/sp_post.c`` (built by ``oracle/build.py`` with gcc).  Parity status:
+unpinned by the reference (no tests / goldens exist upstream); see
+``oracle/__init__.py`` for what this oracle is pinned against instead.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+SCORE_THRESH = 0.007   # sp_extractor.cpp:122 (hard-coded)
+NMS_RADIUS = 4         # sp_extractor.cpp:502
+BORDER = 8             # sp_extractor.cpp:502
+CELL = 8               # sp_extractor.cpp:354
+HEAT_CLAMP = 0.001     # sp_extractor.cpp:129
+
+
+def build_post(force: bool = False) -> str:
+    """Compile oracle/sp_post.c -> oracle/_build/libsporacle.so (gcc, no deps)."""
+    out_dir = os.path.join(_HERE, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libsporacle.so")
+    src = os.path.join(_HERE, "sp_post.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src, "-lm"])
+    return so
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build_post())
+        _LIB.orc_nms.restype = C.c_int
+        _LIB.orc_l2.restype = C.c_float
+    return _LIB
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+# ----------------------------------------------------------------------------
+# network half (torch CPU fp32)
+# ----------------------------------------------------------------------------
+def frontend_forward(weights: dict, img_u8: np.ndarray, keep_layers: bool = False) -> dict:
+    """SPFrontend::forward on one H x W u8 frame (H, W multiples of 8)."""
+    import torch
+    import torch.nn.functional as F
+
+    H, W = img_u8.shape
+    hc, wc = H // CELL, W // CELL
+    w = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in weights.items()}
+    layers = {}
+
+    def conv(x, name, pad):
+        return F.conv2d(x, w[name + ".weight"], w[name + ".bias"], stride=1, padding=pad)
+
+    with torch.no_grad():
+        # sp_extractor.cpp:386-390: convertTo(CV_32FC1, 1/255) then [1,1,H,W]
+        x = (torch.from_numpy(img_u8.astype(np.float32)) * np.float32(1.0 / 255.0)).view(1, 1, H, W)
+        for blk, pool in (("1", True), ("2", True), ("3", True), ("4", False)):   # :81-94
+            x = torch.relu(conv(x, f"conv{blk}a", 1))
+            if keep_layers:
+                layers[f"conv{blk}a"] = x[0].numpy().copy()
+            x = torch.relu(conv(x, f"conv{blk}b", 1))
+            if pool:
+                x = F.max_pool2d(x, 2, 2)
+            if keep_layers:
+                layers[f"conv{blk}b"] = x[0].numpy().copy()
+        cPa = torch.relu(conv(x, "convPa", 1))                                     # :96
+        semi = conv(cPa, "convPb", 0).squeeze()                                    # :97  [65,hc,wc]
+        cDa = torch.relu(conv(x, "convDa", 1))                                     # :99
+        coarse = conv(cDa, "convDb", 0)                                            # :100 [1,256,hc,wc]
+        dn = torch.norm(coarse, 2, 1)                                              # :102
+        coarse = coarse.div(torch.unsqueeze(dn, 1))                                # :103
+        dense = torch.softmax(semi, 0)                                             # :105
+        semi_dust, dense_dust, nodust = semi[-1], dense[-1], dense[:-1]            # :106-108
+        score_map, indices = nodust.max(0)                                         # :112-114
+        # :64-73,117-119: candidate pixel of cell (cy,cx) with channel i -> (cx*8 + i%8, cy*8 + i//8)
+        cy, cx = torch.meshgrid(torch.arange(hc), torch.arange(wc), indexing="ij")
+        px = (cx * CELL + indices % CELL)
+        py = (cy * CELL + indices // CELL)
+        mask = score_map >= SCORE_THRESH                                           # :122
+        pixels_in = torch.stack([px[mask], py[mask]]).to(torch.float32)            # :123-125 [2,n]
+        score = score_map[mask]                                                    # :126
+        heat_log = F.pixel_shuffle(torch.log(torch.clamp(nodust, min=HEAT_CLAMP)).unsqueeze(0), CELL)  # :129-131
+        x_s = pixels_in[0].div(W / 2.0) - 1.0                                      # :137
+        y_s = pixels_in[1].div(H / 2.0) - 1.0                                      # :138
+        samp = torch.stack([x_s, y_s], -1).view(1, 1, -1, 2)                       # :142-143
+        if samp.shape[2] > 0:
+            desc = F.grid_sample(coarse, samp, mode="bilinear", padding_mode="zeros",
+                                 align_corners=True).squeeze(2).squeeze(0)         # :145-146 [256,n]
+            desc = desc.div(torch.norm(desc, 2, 0, True))                          # :148
+        else:
+            desc = torch.zeros(256, 0)
+    out = dict(semi_dust=semi_dust.numpy().copy(), dense_dust=dense_dust.numpy().copy(),
+               pixels_in=pixels_in.numpy().copy(), score=score.numpy().copy(),
+               desc_sampled=desc.numpy().copy(), heat_log=heat_log[0, 0].numpy().copy(),
+               # extra taps for kernel bring-up / parity margins (not reference outputs)
+               semi=semi.numpy().copy(), coarse=coarse[0].numpy().copy(),
+               score_map=score_map.numpy().copy(), argmax=indices.numpy().astype(np.int32),
+               nodust=nodust.numpy().copy())
+    if keep_layers:
+        layers["convPa"] = cPa[0].numpy().copy()
+        layers["convDa"] = cDa[0].numpy().copy()
+        out["layers"] = layers
+    return out
+
+
+# ----------------------------------------------------------------------------
+# post-processing half (C restatement)
+# ----------------------------------------------------------------------------
+def to_heat(heat_log: np.ndarray):
+    h = np.ascontiguousarray(heat_log, np.float32)
+    heat, heat_inv = np.empty_like(h), np.empty_like(h)
+    mn, mx = C.c_double(), C.c_double()
+    _lib().orc_to_heat(_p(h, C.c_float), h.size, _p(heat, C.c_float), _p(heat_inv, C.c_float),
+                       C.byref(mn), C.byref(mx))
+    return heat, heat_inv, mn.value, mx.value
+
+
+def sort_desc(score: np.ndarray) -> np.ndarray:
+    s = np.ascontiguousarray(score, np.float32)
+    order = np.empty(s.size, np.int32)
+    _lib().orc_sort_desc(_p(s, C.c_float), s.size, _p(order, C.c_int32))
+    return order
+
+
+def nms(pts_sorted: np.ndarray, num_features: int, W: int, H: int, border: int = BORDER, r: int = NMS_RADIUS):
+    """pts_sorted: n x 2 float32 (x, y) in descending score order -> (sel indices, occ_grid)."""
+    pts = np.ascontiguousarray(pts_sorted, np.float32).reshape(-1, 2)
+    sel = np.empty(max(len(pts), 1), np.int32)
+    occ = np.empty((H // CELL, W // CELL), np.int16)
+    n = _lib().orc_nms(_p(pts, C.c_float), len(pts), num_features, border, r, W, H,
+                       _p(sel, C.c_int32), _p(occ, C.c_int16))
+    return sel[:n].copy(), occ
+
+
+def covariance(heat_inv: np.ndarray, kps_xy: np.ndarray):
+    h = np.ascontiguousarray(heat_inv, np.float32)
+    k = np.ascontiguousarray(kps_xy, np.float32).reshape(-1, 2)
+    n = len(k)
+    resp = np.empty(n, np.float32)
+    cov2 = np.empty((n, 2), np.float32)
+    cov2_inv = np.empty((n, 2), np.float32)
+    _lib().orc_covariance(_p(h, C.c_float), h.shape[0], h.shape[1], _p(k, C.c_float), n,
+                          _p(resp, C.c_float), _p(cov2, C.c_float), _p(cov2_inv, C.c_float))
+    return resp, cov2, cov2_inv
+
+
+def postprocess(fwd: dict, H: int, W: int, num_features: int) -> dict:
+    """Everything SPExtractor::operator() does after the forward (:426-513)."""
+    heat, heat_inv, mn, mx = to_heat(fwd["heat_log"])
+    pts = np.ascontiguousarray(fwd["pixels_in"].T)            # n x 2
+    desc = np.ascontiguousarray(fwd["desc_sampled"].T)        # n x 256
+    order = sort_desc(fwd["score"])
+    sel, occ = nms(pts[order], num_features, W, H)
+    src = order[sel]                                          # index into the unsorted candidate list
+    kps = pts[src].copy()
+    resp, cov2, cov2_inv = covariance(heat_inv, kps)
+    return dict(n=len(src), kp_xy=kps, kp_response=resp, desc=desc[src].copy(), occ_grid=occ,
+                score=fwd["score"][src].copy(), cov2=cov2, cov2_inv=cov2_inv,
+                heat=heat, heat_inv=heat_inv, heat_min=mn, heat_max=mx,
+                dense_dust=fwd["dense_dust"], semi_dust=fwd["semi_dust"])
+
+
+def extract(weights: dict, img_u8: np.ndarray, num_features: int = 800, keep_forward: bool = False) -> dict:
+    if img_u8 is None or img_u8.size == 0:
+        raise RuntimeError("input image is empty")            # sp_extractor.cpp:364-365
+    assert img_u8.dtype == np.uint8 and img_u8.ndim == 2      # :368
+    H, W = img_u8.shape
+    fwd = frontend_forward(weights, img_u8)
+    out = postprocess(fwd, H, W, num_features)
+    if keep_forward:
+        out["forward"] = fwd
+    return out
+
+
+# ----------------------------------------------------------------------------
+# matcher
+# ----------------------------------------------------------------------------
+def l2(a: np.ndarray, b: np.ndarray) -> float:
+    a = np.ascontiguousarray(a, np.float32).ravel()
+    b = np.ascontiguousarray(b, np.float32).ravel()
+    return float(_lib().orc_l2(_p(a, C.c_float), _p(b, C.c_float), a.size))
+
+
+def match_mutual_nn(q: np.ndarray, t: np.ndarray):
+    """-> (q2t int32[nq] with -1 = unmatched, dist float32[nq], second-best dist float32[nq])."""
+    q = np.ascontiguousarray(q, np.float32).reshape(-1, 256) if q.size else np.zeros((0, 256), np.float32)
+    t = np.ascontiguousarray(t, np.float32).reshape(-1, 256) if t.size else np.zeros((0, 256), np.float32)
+    q2t = np.empty(len(q), np.int32)
+    dist = np.empty(len(q), np.float32)
+    sec = np.empty(len(q), np.float32)
+    _lib().orc_match_mutual(_p(q, C.c_float), len(q), _p(t, C.c_float), len(t), 256,
+                            _p(q2t, C.c_int32), _p(dist, C.c_float), _p(sec, C.c_float))
+    return q2t, dist, sec

@@ -1,0 +1,187 @@
+/*
+ * CPU oracle, post-processing half -- TEST INFRASTRUCTURE ONLY (see
+ * oracle/__init__.py).  Plain-C restatement of the reference's host-side
+ * algorithms with cv::Mat / Eigen replaced by flat arrays.  Parity status:
+ * unpinned by the reference (it ships no tests); pinned here against OpenCV
+ * (cv2.BFMatcher / sortIdx) in tests/test_oracle.py.
+ *
+ *   orc_to_heat       <- orb_slam2/src/cv/sp_extractor.cpp:461-474 (to_heat lambda)
+ *   orc_sort_desc     <- :489-498 (cv::sortIdx, SORT_DESCENDING; ties: lower index first)
+ *   orc_nms           <- :161-250 (nms)
+ *   orc_covariance    <- :252-340 (computeCovariance)
+ *   orc_l2            <- orb_slam2/src/cv/sp_matcher.cpp:1636-1640 (DescriptorDistance)
+ *   orc_match_mutual  <- :1666-1669 and sp_matcher_loop.cpp:365-368
+ *                        (cv::BFMatcher(NORM_L2, crossCheck=true)::match)
+ */
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* heat = (-x - min)/(max - min), heat_inv = (max - (-x))/(max - min), evaluated the
+ * way OpenCV's MatExpr folds them: one convertTo(alpha, beta) per output with
+ * alpha/beta computed in double, narrowed to float, applied as x*alpha + beta. */
+void orc_to_heat(const float *heat_log, int n, float *heat, float *heat_inv,
+                 double *min_out, double *max_out) {
+  double mn = DBL_MAX, mx = -DBL_MAX;
+  for (int i = 0; i < n; i++) {
+    double v = (double)(heat_log[i] * -1.0f);
+    if (v < mn) mn = v;
+    if (v > mx) mx = v;
+  }
+  const double inv = 1.0 / (mx - mn);
+  const float a0 = (float)(-1.0 * inv), b0 = (float)((-mn) * inv);
+  const float a1 = (float)(1.0 * inv), b1 = (float)(mx * inv);
+  for (int i = 0; i < n; i++) {
+    volatile float p0 = heat_log[i] * a0; /* volatile: forbid fma contraction */
+    volatile float p1 = heat_log[i] * a1;
+    heat[i] = p0 + b0;
+    heat_inv[i] = p1 + b1;
+  }
+  if (min_out) *min_out = mn;
+  if (max_out) *max_out = mx;
+}
+
+typedef struct { float s; int i; } si_t;
+static int cmp_desc(const void *a, const void *b) {
+  const si_t *x = (const si_t *)a, *y = (const si_t *)b;
+  if (x->s > y->s) return -1;
+  if (x->s < y->s) return 1;
+  return (x->i > y->i) - (x->i < y->i);
+}
+void orc_sort_desc(const float *score, int n, int32_t *order) {
+  si_t *v = (si_t *)malloc(sizeof(si_t) * (n > 0 ? n : 1));
+  for (int i = 0; i < n; i++) { v[i].s = score[i]; v[i].i = i; }
+  qsort(v, n, sizeof(si_t), cmp_desc);
+  for (int i = 0; i < n; i++) order[i] = v[i].i;
+  free(v);
+}
+
+/* Greedy radius-`r` suppression over candidates given in descending score
+ * order (pts = n x 2 floats, x then y).  Returns the number of survivors N;
+ * sel[N] = indices into the sorted candidate list in raster (v outer, u inner)
+ * order; occ[hc*wc] = survivor index per 8x8 cell or -1. */
+int orc_nms(const float *pts, int n, int num_features, int border, int r,
+            int W, int H, int32_t *sel, int16_t *occ) {
+  const int PW = W + 2 * r, PH = H + 2 * r;
+  uint8_t *grid = (uint8_t *)calloc((size_t)PW * PH, 1);
+  uint16_t *inds = (uint16_t *)calloc((size_t)W * H, sizeof(uint16_t));
+  for (int i = 0; i < (W / 8) * (H / 8); i++) occ[i] = -1;
+  for (int i = 0; i < n; i++) {
+    int u = (int)pts[2 * i], v = (int)pts[2 * i + 1];
+    grid[(size_t)(v + r) * PW + (u + r)] = 1;
+    inds[(size_t)v * W + u] = (uint16_t)i;
+  }
+  int kept = 0;
+  for (int i = 0; i < n; i++) {
+    int u = (int)pts[2 * i] + r, v = (int)pts[2 * i + 1] + r;
+    if (grid[(size_t)v * PW + u] != 1) continue;
+    for (int k = -r; k <= r; k++)
+      for (int j = -r; j <= r; j++)
+        if (j || k) grid[(size_t)(v + k) * PW + (u + j)] = 0;
+    grid[(size_t)v * PW + u] = 2;
+    if (++kept > num_features) break;
+  }
+  int N = 0;
+  for (int v = border; v < H - border; v++)
+    for (int u = border; u < W - border; u++)
+      if (grid[(size_t)(v + r) * PW + (u + r)] == 2) {
+        occ[(v / 8) * (W / 8) + (u / 8)] = (int16_t)N;
+        sel[N++] = inds[(size_t)v * W + u];
+      }
+  free(grid);
+  free(inds);
+  return N;
+}
+
+/* Flood-fill second moments around each keypoint on heat_inv (h x w).
+ * kps = N x 2 floats (x, y) in output order; the visited map is shared by all
+ * keypoints and a pixel is marked when popped, exactly as in the reference. */
+void orc_covariance(const float *heat, int h, int w, const float *kps, int N,
+                    float *response, float *cov2, float *cov2_inv) {
+  uint8_t *fresh = (uint8_t *)malloc((size_t)h * w);
+  memset(fresh, 1, (size_t)h * w);
+  size_t cap = 1 << 16, head, tail;
+  int32_t *q = (int32_t *)malloc(cap * sizeof(int32_t));
+  size_t pcap = 1 << 16, np_;
+  float *du = (float *)malloc(pcap * sizeof(float));
+  float *dv = (float *)malloc(pcap * sizeof(float));
+  float *sc = (float *)malloc(pcap * sizeof(float));
+  for (int k = 0; k < N; k++) {
+    const int uu = (int)kps[2 * k], vv = (int)kps[2 * k + 1];
+    response[k] = heat[(size_t)vv * w + uu];
+    head = tail = 0; np_ = 0;
+    q[tail++] = vv * w + uu;
+    while (head < tail) {
+      const int p = q[head++];
+      const int u = p % w, v = p / w;
+      fresh[p] = 0;
+      if (np_ == pcap) {
+        pcap *= 2;
+        du = (float *)realloc(du, pcap * sizeof(float));
+        dv = (float *)realloc(dv, pcap * sizeof(float));
+        sc = (float *)realloc(sc, pcap * sizeof(float));
+      }
+      const float fu = (float)u - (float)uu, fv = (float)v - (float)vv;
+      du[np_] = fu * fu; dv[np_] = fv * fv; sc[np_] = heat[p]; np_++;
+      const float centroid = heat[p];
+      int nb[4], m = 0;
+      if (u - 1 > 0) nb[m++] = p - 1;      /* left  */
+      if (v - 1 > 0) nb[m++] = p - w;      /* up    */
+      if (u + 1 < w) nb[m++] = p + 1;      /* right */
+      if (v + 1 < h) nb[m++] = p + w;      /* down  */
+      for (int t = 0; t < m; t++) {
+        const float hv = heat[nb[t]];
+        if (fresh[nb[t]] && hv > 0.0f && hv < centroid) {
+          if (tail == cap) { cap *= 2; q = (int32_t *)realloc(q, cap * sizeof(int32_t)); }
+          q[tail++] = nb[t];
+        }
+      }
+    }
+    float sum = 0.0f;
+    for (size_t i = 0; i < np_; i++) sum += sc[i];
+    float cx = 0.0f, cy = 0.0f;
+    for (size_t i = 0; i < np_; i++) {
+      const float wgt = sc[i] / sum;
+      cx += wgt * du[i];
+      cy += wgt * dv[i];
+    }
+    if (cx < 1.0f) cx = 1.0f;
+    if (cy < 1.0f) cy = 1.0f;
+    cov2[2 * k] = cx; cov2[2 * k + 1] = cy;
+    cov2_inv[2 * k] = 1.0f / cx; cov2_inv[2 * k + 1] = 1.0f / cy;
+  }
+  free(fresh); free(q); free(du); free(dv); free(sc);
+}
+
+float orc_l2(const float *a, const float *b, int d) {
+  float s = 0.0f;
+  for (int i = 0; i < d; i++) { const float t = a[i] - b[i]; s += t * t; }
+  return sqrtf(s);
+}
+
+/* BFMatcher(NORM_L2, crossCheck=true).match(query) against one train set:
+ * q2t[i] = first-index arg-min train row of query i if that train row's
+ * first-index arg-min query row is i, else -1.  dist[i] = that L2 distance.
+ * second[i] (optional) = 2nd-smallest distance of query i (parity margins). */
+void orc_match_mutual(const float *q, int nq, const float *t, int nt, int d,
+                      int32_t *q2t, float *dist, float *second) {
+  int32_t *t2q = (int32_t *)malloc(sizeof(int32_t) * (nt > 0 ? nt : 1));
+  float *tbest = (float *)malloc(sizeof(float) * (nt > 0 ? nt : 1));
+  for (int j = 0; j < nt; j++) { t2q[j] = -1; tbest[j] = FLT_MAX; }
+  for (int i = 0; i < nq; i++) {
+    float best = FLT_MAX, sec = FLT_MAX; int bj = -1;
+    for (int j = 0; j < nt; j++) {
+      const float dd = orc_l2(q + (size_t)i * d, t + (size_t)j * d, d);
+      if (dd < best) { sec = best; best = dd; bj = j; }
+      else if (dd < sec) sec = dd;
+      if (dd < tbest[j]) { tbest[j] = dd; t2q[j] = i; }
+    }
+    q2t[i] = bj; dist[i] = best;
+    if (second) second[i] = sec;
+  }
+  for (int i = 0; i < nq; i++)
+    if (q2t[i] < 0 || t2q[q2t[i]] != i) q2t[i] = -1;
+  free(t2q); free(tbest);
+}
