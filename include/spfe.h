@@ -1,0 +1,150 @@
+/*
+ * spfe.h -- C ABI of the B200-native SuperPoint front-end (extract + match).
+ *
+ * This is the drop-in boundary for the hot path of HyHuang1995/sp_orb_slam.
+ * The only intended caller is the C++ shim in sp_orb_slam_b200/cpp/ that
+ * re-creates the reference classes `orbslam::SPExtractor` and
+ * `orbslam::SPMatcher` with their exact signatures.
+ * Plain pointers and sizes only: no libtorch, no OpenCV, no CUDA types.
+ *
+ * Reference interfaces replaced (paths relative to the reference repo):
+ *   spfe_create            <- SPExtractor::SPExtractor(int)          orb_slam2/src/cv/sp_extractor.cpp:342-359
+ *                             (+ SPFrontend ctor :23-76, torch::load of common::model_path :355)
+ *   spfe_extract           <- SPExtractor::operator()                orb_slam2/src/cv/sp_extractor.cpp:361-514
+ *                             = SPFrontend::forward :79-159, to_heat :461-474, sortIdx :489-498,
+ *                               nms :161-250, computeCovariance :252-340
+ *   spfe_frame_out fields  <- public members read by Frame::ExtractORB   orb_slam2/src/type/frame.cpp:296-314
+ *                             (sp_extractor.h:61-77: semi_dust_, dense_dust_, heat_, heat_inv_, occ_grid_,
+ *                              getCov(), getCov2Inv())
+ *   spfe_match_mutual_nn   <- cv::BFMatcher(NORM_L2, crossCheck=true)::match as used by
+ *                             SPMatcher::SearchByBruteForce             orb_slam2/src/cv/sp_matcher.cpp:1642-1674
+ *                                                                       orb_slam2/src/cv/sp_matcher_loop.cpp:334-376
+ *   spfe_l2                <- SPMatcher::DescriptorDistance             orb_slam2/src/cv/sp_matcher.cpp:1636-1640
+ *
+ * The reference is one-frame-blocking with batch size 1 (sp_extractor.cpp:70
+ * "TODO: batch-size").  spfe_extract keeps that contract; spfe_submit /
+ * spfe_wait add the batched, pipelined entry the B200 needs to be fed.
+ *
+ * Error convention: every function returns SPFE_OK (0) or a negative code and
+ * never throws across the ABI; spfe_last_error() returns the message.  There
+ * is NO CPU fallback: if no sm_100 device is present spfe_create fails.
+ */
+#ifndef SPFE_H_
+#define SPFE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPFE_VERSION 1
+#define SPFE_DESC_DIM 256
+
+enum {
+  SPFE_OK = 0,
+  SPFE_ERR_INVALID = -1,   /* bad argument (NULL, size mismatch, H/W not multiple of 8, batch too large) */
+  SPFE_ERR_EMPTY = -2,     /* empty image: the shim turns this into std::runtime_error("input image is empty") */
+  SPFE_ERR_WEIGHTS = -3,   /* weight file missing / malformed */
+  SPFE_ERR_NO_DEVICE = -4, /* no CUDA device with compute capability 10.x */
+  SPFE_ERR_CUDA = -5,      /* CUDA runtime / driver error (message has details) */
+  SPFE_ERR_STATE = -6      /* wait without submit, slot busy, ... */
+};
+
+enum {
+  SPFE_EMIT_HEAT = 1u << 0, /* produce heat / heat_inv (H x W f32 each) and copy them to the host  */
+  SPFE_EMIT_COV = 1u << 1   /* run computeCovariance (implies SPFE_EMIT_HEAT); fills kp_response from heat_inv */
+};
+
+typedef struct spfe_ctx spfe_ctx;
+
+typedef struct spfe_config {
+  int32_t struct_size;   /* = sizeof(spfe_config) */
+  int32_t height;        /* camera::height, multiple of 8   (sp_extractor.cpp:354) */
+  int32_t width;         /* camera::width,  multiple of 8 */
+  int32_t max_keypoints; /* tracking::num_features; up to max_keypoints+1 survive (sp_extractor.cpp:211) */
+  float score_thresh;    /* 0.007f  (sp_extractor.cpp:122) */
+  int32_t nms_radius;    /* 4       (sp_extractor.cpp:502); must be <= 8 */
+  int32_t border;        /* 8       (sp_extractor.cpp:502) */
+  int32_t device_id;     /* CUDA ordinal */
+  int32_t max_batch;     /* frames per submit (>= 1) */
+  int32_t num_slots;     /* independent in-flight batches (>= 1), each with its own stream + buffers */
+  uint32_t flags;        /* SPFE_EMIT_* */
+  const char *weights_path; /* legacy superpoint.pt (PyTorch-1.0 archive) or .spw */
+} spfe_config;
+
+/* Fills *cfg with the reference's hard-coded values for the given geometry. */
+void spfe_default_config(spfe_config *cfg, int32_t height, int32_t width, int32_t max_keypoints);
+
+/* Host-visible result of one frame.  All pointers are owned by the context
+ * (pinned host memory), valid until the slot is submitted again / destroyed. */
+typedef struct spfe_frame_out {
+  int32_t n;               /* keypoints, raster order (v outer, u inner) */
+  const float *kp_xy;      /* [n][2] (x, y), integer-valued          -> cv::KeyPoint(x, y, size=1) */
+  const float *kp_score;   /* [n] softmax score of the keypoint's cell */
+  const float *kp_response;/* [n] heat_inv(y, x) (kp.response, sp_extractor.cpp:271); NULL without EMIT_COV */
+  const float *desc;       /* [n][256] L2-normalised                  -> CV_32FC1 n x 256 */
+  const int16_t *occ_grid; /* [H/8][W/8] keypoint index or -1         -> occ_grid_  (CV_16SC1) */
+  const float *dense_dust; /* [H/8][W/8] softmax dustbin probability  -> dense_dust_ */
+  const float *semi_dust;  /* [H/8][W/8] raw dustbin logit            -> semi_dust_ */
+  const float *heat;       /* [H][W] or NULL                          -> heat_ */
+  const float *heat_inv;   /* [H][W] or NULL                          -> heat_inv_ */
+  const float *cov2;       /* [n][2] or NULL                          -> getCov() */
+  const float *cov2_inv;   /* [n][2] or NULL                          -> getCov2Inv() */
+} spfe_frame_out;
+
+int spfe_create(const spfe_config *cfg, spfe_ctx **out);
+void spfe_destroy(spfe_ctx *ctx);
+/* Message of the last failure on this context (ctx == NULL: last spfe_create failure). */
+const char *spfe_last_error(const spfe_ctx *ctx);
+
+/* Blocking single-frame extraction == SPExtractor::operator().  gray: H rows of
+ * W bytes (CV_8UC1), row_stride in bytes.  Uses slot 0. */
+int spfe_extract(spfe_ctx *ctx, const uint8_t *gray, size_t row_stride, spfe_frame_out *out);
+
+/* Throughput mode: enqueue `batch` frames (host pointers) on `slot` and return
+ * immediately; spfe_wait blocks until that slot's results are on the host and
+ * fills outs[0..batch).  Different slots overlap copies and kernels. */
+int spfe_submit(spfe_ctx *ctx, int32_t slot, const uint8_t *const *grays, int32_t batch, size_t row_stride);
+int spfe_wait(spfe_ctx *ctx, int32_t slot, spfe_frame_out *outs);
+
+/* Same pipeline on frames that already live in device memory ([batch][H][W] u8,
+ * dense).  Results stay on the device; no host copies.  Asynchronous on the
+ * slot's stream; spfe_slot_sync waits for it. */
+int spfe_submit_device(spfe_ctx *ctx, int32_t slot, const void *d_gray, int32_t batch);
+int spfe_slot_sync(spfe_ctx *ctx, int32_t slot);
+
+/* Mutual nearest neighbour under L2 over 256-d float rows (host pointers):
+ * q2t[i] = first-index arg-min train row of query i if that row's first-index
+ * arg-min query is i, else -1; dist[i] = L2 distance to the arg-min (may be NULL).
+ * Thread-safe (per-call scratch), as SearchByBruteForce runs on two threads. */
+int spfe_match_mutual_nn(spfe_ctx *ctx, const float *q, int32_t nq, const float *t, int32_t nt,
+                         int32_t *q2t, float *dist);
+/* Device-resident variant used by the extract+match stream path: matches the
+ * descriptors of frame `fq` against those of frame `ft` of the same slot
+ * (both already extracted); results in device memory, fetched by spfe_match_fetch. */
+int spfe_match_frames_device(spfe_ctx *ctx, int32_t slot, int32_t fq, int32_t ft);
+int spfe_match_fetch(spfe_ctx *ctx, int32_t slot, int32_t fq, int32_t *q2t, float *dist, int32_t *nq);
+
+/* L2 distance between two 256-d descriptors (host, scalar). */
+float spfe_l2(const float *a, const float *b);
+
+/* ---- introspection used by tests / bench (not needed by the shim) ---- */
+/* Copies a named intermediate device tensor of `slot` to dst (host).  Names:
+ * "conv1a".."conv4b", "heads", "coarse" (fp16 NHWC), "score", "semi_dust",
+ * "dense_dust", "heat_log" (f32), "argmax" (u8), "count" (i32 per frame).
+ * Returns bytes copied or a negative error. */
+int64_t spfe_debug_read(spfe_ctx *ctx, int32_t slot, const char *name, void *dst, size_t dst_bytes);
+/* Number of kernels this library has launched on the context so far. */
+int64_t spfe_launch_count(const spfe_ctx *ctx);
+/* Runs one device-resident batch with CUDA events around every stage; writes
+ * up to `cap` (name, ms) pairs.  Returns the number of stages. */
+typedef struct spfe_stage_time { char name[24]; float ms; double flop; double bytes; } spfe_stage_time;
+int spfe_profile_device(spfe_ctx *ctx, int32_t slot, const void *d_gray, int32_t batch,
+                        spfe_stage_time *stages, int32_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPFE_H_ */

@@ -1,0 +1,79 @@
+"""ctypes binding of include/spfe.h.  There is no fallback: if libspfe.so is
+missing or no B200 is present the calls raise."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+DESC_DIM = 256
+EMIT_HEAT, EMIT_COV = 1, 2
+OK, ERR_INVALID, ERR_EMPTY, ERR_WEIGHTS, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
+
+EXPORTS = ["spfe_default_config", "spfe_create", "spfe_destroy", "spfe_last_error", "spfe_extract", "spfe_submit",
+           "spfe_wait", "spfe_submit_device", "spfe_slot_sync", "spfe_match_mutual_nn", "spfe_match_frames_device",
+           "spfe_match_fetch", "spfe_l2", "spfe_debug_read", "spfe_launch_count", "spfe_profile_device"]
+
+
+class Config(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("max_keypoints", C.c_int32),
+                ("score_thresh", C.c_float), ("nms_radius", C.c_int32), ("border", C.c_int32), ("device_id", C.c_int32),
+                ("max_batch", C.c_int32), ("num_slots", C.c_int32), ("flags", C.c_uint32), ("weights_path", C.c_char_p)]
+
+
+_FP = C.POINTER(C.c_float)
+
+
+class FrameOut(C.Structure):
+    _fields_ = [("n", C.c_int32), ("kp_xy", _FP), ("kp_score", _FP), ("kp_response", _FP), ("desc", _FP),
+                ("occ_grid", C.POINTER(C.c_int16)), ("dense_dust", _FP), ("semi_dust", _FP), ("heat", _FP),
+                ("heat_inv", _FP), ("cov2", _FP), ("cov2_inv", _FP)]
+
+
+class StageTime(C.Structure):
+    _fields_ = [("name", C.c_char * 24), ("ms", C.c_float), ("flop", C.c_double), ("bytes", C.c_double)]
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    """Load libspfe.so (building it in-tree first if the sources are newer)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing and _build.needs_build():
+        _build.build_lib()
+    if not os.path.exists(_build.LIB):
+        raise RuntimeError(f"{_build.LIB} is missing: run `python -m sp_orb_slam_b200.build` (no CPU fallback exists)")
+    L = C.CDLL(_build.LIB)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.spfe_default_config.argtypes = [C.POINTER(Config), i32, i32, i32]
+    L.spfe_default_config.restype = None
+    L.spfe_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.spfe_destroy.argtypes = [vp]
+    L.spfe_destroy.restype = None
+    L.spfe_last_error.argtypes = [vp]
+    L.spfe_last_error.restype = C.c_char_p
+    L.spfe_extract.argtypes = [vp, vp, C.c_size_t, C.POINTER(FrameOut)]
+    L.spfe_submit.argtypes = [vp, i32, C.POINTER(vp), i32, C.c_size_t]
+    L.spfe_wait.argtypes = [vp, i32, C.POINTER(FrameOut)]
+    L.spfe_submit_device.argtypes = [vp, i32, vp, i32]
+    L.spfe_slot_sync.argtypes = [vp, i32]
+    L.spfe_match_mutual_nn.argtypes = [vp, vp, i32, vp, i32, vp, vp]
+    L.spfe_match_frames_device.argtypes = [vp, i32, i32, i32]
+    L.spfe_match_fetch.argtypes = [vp, i32, i32, vp, vp, C.POINTER(i32)]
+    L.spfe_l2.argtypes = [vp, vp]
+    L.spfe_l2.restype = C.c_float
+    L.spfe_debug_read.argtypes = [vp, i32, C.c_char_p, vp, C.c_size_t]
+    L.spfe_debug_read.restype = i64
+    L.spfe_launch_count.argtypes = [vp]
+    L.spfe_launch_count.restype = i64
+    L.spfe_profile_device.argtypes = [vp, i32, vp, i32, C.POINTER(StageTime), i32]
+    _lib = L
+    return L

@@ -1,0 +1,426 @@
+// tcgen05 implicit-GEMM convolution for the SuperPoint encoder and heads.
+//
+// Replaces the cuDNN calls behind SPFrontend::forward (reference
+// orb_slam2/src/cv/sp_extractor.cpp:82-100): conv1b..conv4b, convPa||convDa
+// (3x3, pad 1) and convPb / convDb (1x1), each with its elementwise tail
+// (ReLU, 2x2 max-pool, channel L2 norm, or the whole detector head :105-131)
+// fused into the TMEM epilogue.
+//
+// GEMM view per CTA tile:  D[128 pixels, N couts] = sum over (tap, 64-channel
+// block) of A[128, 64] * W[N, 64]^T, fp16 operands, fp32 accumulation in TMEM.
+//   * activations are NHWC fp16; an output tile is 8 (x) by 16 (y) pixels, so
+//     one image row of the tile (8 pixels x 64 ch x 2 B = 1024 B) is exactly
+//     one 128B-swizzle atom.
+//   * im2col is done by TMA: for each 64-channel block and each horizontal tap
+//     offset dx a "slab" of 18 rows x 8 pixels x 64 ch is loaded by ONE
+//     cp.async.bulk.tensor.4d with out-of-bounds zero fill (= the conv's zero
+//     padding).  The three vertical taps dy are the same slab read at
+//     +dy*1024 B, so every slab byte feeds 3 taps x 4 UMMA k-steps and L2 is
+//     read 3.4x per input element instead of 9x.
+//   * weights are packed [tap][cblock][cout][64] fp16; small layers keep all
+//     of them resident in shared memory for the CTA's lifetime, large layers
+//     stream [N x 64] blocks through a second ring.
+//   * persistent CTAs (1 per SM), warp-specialised: warp 0 = slab TMA
+//     producer, warp 3 = weight TMA producer, warp 1 = MMA issuer (one lane),
+//     warp 2 = TMEM allocator, warps 4-7 = epilogue.  Two TMEM accumulators so
+//     the epilogue of tile i overlaps the MMAs of tile i+1.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "ptx.cuh"
+
+namespace spfe {
+
+enum { EPI_RELU = 0, EPI_RELU_POOL = 1, EPI_L2NORM = 2, EPI_DETECT = 3 };
+
+struct ConvArgs {
+  int B, H, W;            // conv spatial size (input == output, before pooling)
+  int tiles_x, tiles_y;   // ceil(W/8), ceil(H/16)
+  int NB;                 // cout blocks of N channels each (work items per pixel tile)
+  int n_items;            // B * tiles_y * tiles_x * NB
+  int cin_off;            // first input channel inside the input tensor
+  int cout_stride;        // channels per pixel of the output tensor
+  const float *bias;      // [NB*N]
+  __half *out;            // RELU / RELU_POOL / L2NORM: NHWC fp16
+  // EPI_DETECT outputs (one value per 8x8 cell unless noted)
+  float *score;           // max softmax prob over the 64 position channels
+  uint8_t *argmax;        // its channel index
+  float *semi_dust;       // raw dustbin logit
+  float *dense_dust;      // dustbin softmax prob
+  float *heat_log;        // [B][8H][8W] log(clamp(p, 1e-3)) depth-to-space, or nullptr
+  unsigned *heat_minmax;  // [B][2] ordered-uint min / max of heat_log, or nullptr
+};
+
+template <int TAPS_, int CB_, int N_, int EPI_, bool WRES_, int SA_, int SB_>
+struct ConvCfg {
+  static constexpr int TAPS = TAPS_, CB = CB_, N = N_, EPI = EPI_, SA = SA_, SB = SB_;
+  static constexpr bool WRES = WRES_;
+  static constexpr int NDX = TAPS == 9 ? 3 : 1;
+  static constexpr int NDY = NDX;
+  static constexpr int SLAB_ROWS = 16 + NDY - 1;
+  static constexpr int SLAB_BYTES = SLAB_ROWS * 1024;
+  static constexpr int BBLK_BYTES = N * 128;
+  static constexpr int NWB = TAPS * CB;
+  static constexpr int B_BYTES = (WRES ? NWB : SB) * BBLK_BYTES;
+  static constexpr int ACC_STRIDE = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int NBAR = 2 * SA + 2 * SB + 5;
+  // dynamic shared memory: [1024 align slack][A ring][B ring / resident W][barriers][tmem slot][bias NB*N f32]
+  static constexpr int SMEM_FIXED = 1024 + SA * SLAB_BYTES + B_BYTES + NBAR * 8 + 16;
+  static constexpr int smem_bytes(int nb) { return SMEM_FIXED + nb * N * 4; }
+  static_assert(N % 16 == 0 && N <= 256, "UMMA M=128 needs N % 16 == 0, N <= 256");
+  static_assert(SMEM_FIXED + N * 4 <= 232448, "shared memory budget");
+};
+
+__device__ __forceinline__ unsigned f32_ordered(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ inline float f32_from_ordered(unsigned u) {
+  u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(256, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const ConvArgs p) {
+  constexpr int N = Cfg::N, CB = Cfg::CB, SA = Cfg::SA, SB = Cfg::SB;
+  const int NB = p.NB;  // resident weights (WRES) require NB == 1 (checked on the host)
+  constexpr int NDX = Cfg::NDX, NDY = Cfg::NDY, EPI = Cfg::EPI;
+  constexpr bool WRES = Cfg::WRES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *sA = smem;
+  uint8_t *sB = sA + SA * Cfg::SLAB_BYTES;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sB + Cfg::B_BYTES);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + Cfg::NBAR);
+  float *sBias = reinterpret_cast<float *>(tmem_slot + 4);
+
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (SA + s); };
+  auto b_full = [&](int s) { return bar0 + 8u * (2 * SA + s); };
+  auto b_empty = [&](int s) { return bar0 + 8u * (2 * SA + SB + s); };
+  auto t_full = [&](int s) { return bar0 + 8u * (2 * SA + 2 * SB + s); };
+  auto t_empty = [&](int s) { return bar0 + 8u * (2 * SA + 2 * SB + 2 + s); };
+  const uint32_t w_full = bar0 + 8u * (2 * SA + 2 * SB + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; s++) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < SB; s++) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(t_full(s), 1); mbar_init(t_empty(s), 128); }
+    mbar_init(w_full, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < NB * N; i += blockDim.x) sBias[i] = p.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int item, int &nb, int &x0, int &y0, int &b) {
+    nb = item % NB;
+    int t = item / NB;
+    x0 = (t % p.tiles_x) * 8;
+    t /= p.tiles_x;
+    y0 = (t % p.tiles_y) * 16;
+    b = t / p.tiles_y;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------ activation slab producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        int nb, x0, y0, b;
+        decode(item, nb, x0, y0, b);
+        for (int cb = 0; cb < CB; cb++)
+          for (int dx = 0; dx < NDX; dx++, it++) {
+            const int s = it % SA;
+            mbar_wait(a_empty(s), ((it / SA) & 1) ^ 1);
+            mbar_expect_tx(a_full(s), Cfg::SLAB_BYTES);
+            tma_load_4d(smem_u32(sA + s * Cfg::SLAB_BYTES), &tmA, a_full(s), p.cin_off + cb * 64,
+                        x0 + dx - (NDX == 3 ? 1 : 0), y0 - (NDY == 3 ? 1 : 0), b);
+          }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------ weight producer
+    if (lane == 0) {
+      if (WRES) {
+        mbar_expect_tx(w_full, Cfg::NWB * Cfg::BBLK_BYTES);
+        for (int wb = 0; wb < Cfg::NWB; wb++)
+          tma_load_2d(smem_u32(sB + wb * Cfg::BBLK_BYTES), &tmW, w_full, 0, wb * N);
+      } else {
+        uint32_t jt = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+          const int nb = item % NB;
+          for (int cb = 0; cb < CB; cb++)
+            for (int dx = 0; dx < NDX; dx++)
+              for (int dy = 0; dy < NDY; dy++, jt++) {
+                const int s = jt % SB;
+                mbar_wait(b_empty(s), ((jt / SB) & 1) ^ 1);
+                mbar_expect_tx(b_full(s), Cfg::BBLK_BYTES);
+                const int wb = (dy * NDX + dx) * CB + cb;
+                tma_load_2d(smem_u32(sB + s * Cfg::BBLK_BYTES), &tmW, b_full(s), 0, (wb * NB + nb) * N);
+              }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(N);
+      uint32_t it = 0, jt = 0, tcount = 0;
+      if (WRES) mbar_wait(w_full, 0);
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, tcount++) {
+        const int acc = tcount & 1;
+        mbar_wait(t_empty(acc), ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+        uint32_t accumulate = 0;
+        for (int cb = 0; cb < CB; cb++)
+          for (int dx = 0; dx < NDX; dx++, it++) {
+            const int s = it % SA;
+            mbar_wait(a_full(s), (it / SA) & 1);
+            const uint32_t a_slab = smem_u32(sA + s * Cfg::SLAB_BYTES);
+            for (int dy = 0; dy < NDY; dy++) {
+              uint32_t b_blk;
+              int sb = 0;
+              if (WRES) {
+                b_blk = smem_u32(sB + ((dy * NDX + dx) * CB + cb) * Cfg::BBLK_BYTES);
+              } else {
+                sb = jt % SB;
+                mbar_wait(b_full(sb), (jt / SB) & 1);
+                b_blk = smem_u32(sB + sb * Cfg::BBLK_BYTES);
+              }
+              tc_fence_after();
+              const uint32_t a_tap = a_slab + dy * 1024;
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                umma_f16(d_tmem, umma_desc_sw128(a_tap + k * 32), umma_desc_sw128(b_blk + k * 32), idesc, accumulate);
+                accumulate = 1;
+              }
+              if (!WRES) {
+                umma_commit(b_empty(sb));
+                jt++;
+              }
+            }
+            umma_commit(a_empty(s));
+          }
+        umma_commit(t_full(acc));
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------ epilogue (TMEM -> regs -> global)
+    const int wq = warp & 3;
+    const int hl = wq * 4 + (lane >> 3), wl = lane & 7;
+    uint32_t tcount = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, tcount++) {
+      int nb, x0, y0, b;
+      decode(item, nb, x0, y0, b);
+      const int acc = tcount & 1;
+      mbar_wait(t_full(acc), (tcount >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * Cfg::ACC_STRIDE;
+      const float *bias = sBias + nb * N;
+      const int y = y0 + hl, x = x0 + wl;
+
+      if constexpr (EPI == EPI_RELU) {
+        const bool valid = (y < p.H) && (x < p.W);
+        __half *dst = p.out + ((static_cast<size_t>(b) * p.H + y) * p.W + x) * p.cout_stride + nb * N;
+#pragma unroll 1
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          float v[32];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld16(taddr + c0 + 16, v + 16);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+              uint4 o;
+              uint32_t *ow = reinterpret_cast<uint32_t *>(&o);
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                const int c = g * 8 + j * 2;
+                ow[j] = pack_h2(fmaxf(v[c] + bias[c0 + c], 0.f), fmaxf(v[c + 1] + bias[c0 + c + 1], 0.f));
+              }
+              *reinterpret_cast<uint4 *>(dst + c0 + g * 8) = o;
+            }
+          }
+        }
+      } else if constexpr (EPI == EPI_RELU_POOL) {
+        // 2x2 max-pool inside the warp: partners are lane^1 (x) and lane^8 (y).
+        const int Ho = p.H >> 1, Wo = p.W >> 1;
+        const int yo = (y0 >> 1) + (hl >> 1), xo = (x0 >> 1) + (wl >> 1);
+        const bool valid = (yo < Ho) && (xo < Wo);
+        const int q = (lane & 1) | (((lane >> 3) & 1) << 1);  // which 8-channel slice this lane stores
+        __half *dst = p.out + ((static_cast<size_t>(b) * Ho + yo) * Wo + xo) * p.cout_stride + nb * N + q * 8;
+#pragma unroll 1
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          float v[32];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld16(taddr + c0 + 16, v + 16);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 8));
+          }
+          float w[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const float lo = (q & 1) ? v[8 + j] : v[j];
+            const float hi = (q & 1) ? v[24 + j] : v[16 + j];
+            w[j] = (q & 2) ? hi : lo;
+            w[j] = fmaxf(w[j] + bias[c0 + q * 8 + j], 0.f);
+          }
+          if (valid) {
+            uint4 o;
+            o.x = pack_h2(w[0], w[1]);
+            o.y = pack_h2(w[2], w[3]);
+            o.z = pack_h2(w[4], w[5]);
+            o.w = pack_h2(w[6], w[7]);
+            *reinterpret_cast<uint4 *>(dst + c0) = o;
+          }
+        }
+      } else if constexpr (EPI == EPI_L2NORM) {
+        // convDb + channel-wise L2 normalisation (sp_extractor.cpp:100-103); N == all 256 channels.
+        const bool valid = (y < p.H) && (x < p.W);
+        __half *dst = p.out + ((static_cast<size_t>(b) * p.H + y) * p.W + x) * p.cout_stride + nb * N;
+        float ss = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          float v[32];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld16(taddr + c0 + 16, v + 16);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const float t = v[j] + bias[c0 + j];
+            ss = fmaf(t, t, ss);
+          }
+        }
+        const float inv = 1.0f / sqrtf(ss);
+#pragma unroll 1
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          float v[32];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld16(taddr + c0 + 16, v + 16);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+              uint4 o;
+              uint32_t *ow = reinterpret_cast<uint32_t *>(&o);
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                const int c = g * 8 + j * 2;
+                ow[j] = pack_h2((v[c] + bias[c0 + c]) * inv, (v[c + 1] + bias[c0 + c + 1]) * inv);
+              }
+              *reinterpret_cast<uint4 *>(dst + c0 + g * 8) = o;
+            }
+          }
+        }
+      } else {
+        // EPI_DETECT: convPb logits (65 of the 80 columns) -> detector head, all thread-local:
+        // softmax over 65 (:105), dustbin logit/prob (:106-107), max/argmax over 64 (:112-114),
+        // log(clamp(p, 1e-3)) depth-to-space heat (:129-131).  One thread == one 8x8 cell.
+        static_assert(EPI != EPI_DETECT || N == 80, "detector head expects N = 80 (65 padded)");
+        const bool valid = (y < p.H) && (x < p.W);
+        float l[80];
+#pragma unroll
+        for (int c0 = 0; c0 < 80; c0 += 16) tmem_ld16(taddr + c0, l + c0);
+        tmem_ld_wait();
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 65; j++) {
+          l[j] += bias[j];
+          m = fmaxf(m, l[j]);
+        }
+        const float dust_logit = l[64];
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 65; j++) {
+          l[j] = expf(l[j] - m);
+          sum += l[j];
+        }
+        float best = -1.f;
+        int arg = 0;
+#pragma unroll
+        for (int j = 0; j < 64; j++) {
+          l[j] = l[j] / sum;
+          if (l[j] > best) { best = l[j]; arg = j; }
+        }
+        const float dust_p = l[64] / sum;
+        float hmin = INFINITY, hmax = -INFINITY;
+        if (valid) {
+          const size_t cell = (static_cast<size_t>(b) * p.H + y) * p.W + x;
+          p.score[cell] = best;
+          p.argmax[cell] = static_cast<uint8_t>(arg);
+          p.semi_dust[cell] = dust_logit;
+          p.dense_dust[cell] = dust_p;
+          if (p.heat_log != nullptr) {
+            const int Wf = p.W * 8;
+            float *hrow = p.heat_log + (static_cast<size_t>(b) * p.H * 8 + static_cast<size_t>(y) * 8) * Wf + x * 8;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+              float h[8];
+#pragma unroll
+              for (int c = 0; c < 8; c++) {
+                h[c] = logf(fmaxf(l[r * 8 + c], 0.001f));
+                hmin = fminf(hmin, h[c]);
+                hmax = fmaxf(hmax, h[c]);
+              }
+              float4 *d4 = reinterpret_cast<float4 *>(hrow + static_cast<size_t>(r) * Wf);
+              d4[0] = make_float4(h[0], h[1], h[2], h[3]);
+              d4[1] = make_float4(h[4], h[5], h[6], h[7]);
+            }
+          }
+        }
+        if (p.heat_log != nullptr && p.heat_minmax != nullptr) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            hmin = fminf(hmin, __shfl_xor_sync(0xffffffffu, hmin, o));
+            hmax = fmaxf(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
+          }
+          if (lane == 0 && hmin <= hmax) {
+            atomicMin(p.heat_minmax + 2 * b, f32_ordered(hmin));
+            atomicMax(p.heat_minmax + 2 * b + 1, f32_ordered(hmax));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(t_empty(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace spfe

@@ -1,0 +1,287 @@
+// CUDA-core kernels around the tensor-core convolutions:
+//   conv1a_kernel       u8 -> fp32 3x3 conv (1 -> 64) + ReLU -> fp16 NHWC   (sp_extractor.cpp:81, :386-390)
+//   nms_kernel          threshold + exact greedy NMS + cap + border + raster compaction + occ_grid (:122, :161-250, :489-498)
+//   sample_desc_kernel  bilinear descriptor sampling + L2 normalise at the survivors (:134-148)
+//   heat_norm_kernel    to_heat min/max normalisation (:461-474)
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "conv_tc.cuh"
+
+namespace spfe {
+
+// ---------------------------------------------------------------------------
+// conv1a: K = 9 is not a tensor-core shape and this layer is the precision-
+// critical one (|w| up to 197, SURVEY.md §7 hard part 1): fp32 FFMA on CUDA
+// cores, input scaled exactly like cv::Mat::convertTo(CV_32F, 1/255).
+// One thread = one pixel x 64 output channels; block = 32 x 8 pixels.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv1a_kernel(const uint8_t *__restrict__ in, __half *__restrict__ out,
+                                                     const float *__restrict__ wgt /*[9][64]*/,
+                                                     const float *__restrict__ bias /*[64]*/, int B, int H, int W) {
+  __shared__ float s_in[10][36];
+  __shared__ __align__(16) float s_w[9][64];
+  __shared__ __align__(16) float s_b[64];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8, b = blockIdx.z;
+  const uint8_t *img = in + static_cast<size_t>(b) * H * W;
+  for (int i = threadIdx.x; i < 9 * 64; i += 256) (&s_w[0][0])[i] = wgt[i];
+  if (threadIdx.x < 64) s_b[threadIdx.x] = bias[threadIdx.x];
+  const float scale = 1.0f / 255.0f;
+  for (int i = threadIdx.x; i < 10 * 34; i += 256) {
+    const int r = i / 34, c = i % 34;
+    const int y = y0 + r - 1, x = x0 + c - 1;
+    float v = 0.f;
+    if (y >= 0 && y < H && x >= 0 && x < W) v = static_cast<float>(img[static_cast<size_t>(y) * W + x]) * scale;
+    s_in[r][c] = v;
+  }
+  __syncthreads();
+  const int x = x0 + tx, y = y0 + ty;
+  if (x >= W || y >= H) return;
+  float acc[64];
+#pragma unroll
+  for (int c = 0; c < 64; c++) acc[c] = s_b[c];
+#pragma unroll
+  for (int t = 0; t < 9; t++) {
+    const float xin = s_in[ty + t / 3][tx + t % 3];
+#pragma unroll
+    for (int c4 = 0; c4 < 16; c4++) {
+      const float4 w4 = *reinterpret_cast<const float4 *>(&s_w[t][c4 * 4]);
+      acc[c4 * 4 + 0] = fmaf(w4.x, xin, acc[c4 * 4 + 0]);
+      acc[c4 * 4 + 1] = fmaf(w4.y, xin, acc[c4 * 4 + 1]);
+      acc[c4 * 4 + 2] = fmaf(w4.z, xin, acc[c4 * 4 + 2]);
+      acc[c4 * 4 + 3] = fmaf(w4.w, xin, acc[c4 * 4 + 3]);
+    }
+  }
+  uint4 *dst = reinterpret_cast<uint4 *>(out + ((static_cast<size_t>(b) * H + y) * W + x) * 64);
+#pragma unroll
+  for (int g = 0; g < 8; g++) {
+    uint4 o;
+    o.x = pack_h2(fmaxf(acc[g * 8 + 0], 0.f), fmaxf(acc[g * 8 + 1], 0.f));
+    o.y = pack_h2(fmaxf(acc[g * 8 + 2], 0.f), fmaxf(acc[g * 8 + 3], 0.f));
+    o.z = pack_h2(fmaxf(acc[g * 8 + 4], 0.f), fmaxf(acc[g * 8 + 5], 0.f));
+    o.w = pack_h2(fmaxf(acc[g * 8 + 6], 0.f), fmaxf(acc[g * 8 + 7], 0.f));
+    dst[g] = o;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// NMS.  The reference sorts candidates by score and greedily suppresses a
+// (2r+1)^2 window around each survivor.  There is at most one candidate per
+// 8x8 cell and r <= 8, so a candidate only interacts with the 8 neighbouring
+// cells and the greedy result is the unique fixpoint of
+//   kept(c)  <=>  every higher-priority neighbour within Chebyshev r is suppressed
+// (priority = score desc, ties by raster cell index = stable sort order).
+// The cap "stop once more than nf are kept" keeps the nf+1 best survivors; it
+// is applied BEFORE the border filter, and the output is in raster pixel order
+// with occ_grid[cell] = output index.  One CTA per frame.
+// ---------------------------------------------------------------------------
+struct NmsArgs {
+  const float *score;     // [B][cells]
+  const uint8_t *argmax;  // [B][cells]
+  int hc, wc;             // cells per column / row
+  float thresh;
+  int radius, border, cap;  // cap = max_keypoints + 1
+  int *count;               // [B]
+  float *kp_xy;             // [B][cap][2]
+  float *kp_score;          // [B][cap]
+  int16_t *occ;             // [B][cells]
+  unsigned long long *scratch;  // [B][cells] key list
+};
+
+enum { ST_NONE = 0, ST_UNDEC = 1, ST_KEPT = 2, ST_SUPP = 3 };
+
+__global__ void __launch_bounds__(1024) nms_kernel(const NmsArgs p) {
+  extern __shared__ uint8_t nms_smem[];
+  const int cells = p.hc * p.wc;
+  float *s_sc = reinterpret_cast<float *>(nms_smem);
+  uint8_t *s_pos = reinterpret_cast<uint8_t *>(s_sc + cells);
+  volatile uint8_t *s_st = s_pos + cells;
+  __shared__ int s_cnt, s_cnt2;
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const float *score = p.score + static_cast<size_t>(b) * cells;
+  const uint8_t *amax = p.argmax + static_cast<size_t>(b) * cells;
+  int16_t *occ = p.occ + static_cast<size_t>(b) * cells;
+  unsigned long long *list = p.scratch + static_cast<size_t>(b) * cells;
+  const int W = p.wc * 8, H = p.hc * 8;
+
+  if (tid == 0) { s_cnt = 0; s_cnt2 = 0; }
+  for (int c = tid; c < cells; c += nt) {
+    const float sc = score[c];
+    const bool cand = sc >= p.thresh;
+    s_sc[c] = sc;
+    s_pos[c] = amax[c];
+    s_st[c] = cand ? ST_UNDEC : ST_NONE;
+    occ[c] = -1;
+  }
+  __syncthreads();
+
+  // ---- fixpoint of the greedy suppression
+  for (int round = 0; round < cells + 2; round++) {
+    int undecided = 0;
+    for (int c = tid; c < cells; c += nt) {
+      if (s_st[c] != ST_UNDEC) continue;
+      const int cy = c / p.wc, cx = c - cy * p.wc;
+      const int px = cx * 8 + (s_pos[c] & 7), py = cy * 8 + (s_pos[c] >> 3);
+      const float sc = s_sc[c];
+      bool any_kept = false, all_supp = true;
+      for (int dy = -1; dy <= 1; dy++) {
+        const int ny = cy + dy;
+        if (ny < 0 || ny >= p.hc) continue;
+        for (int dx = -1; dx <= 1; dx++) {
+          const int nx = cx + dx;
+          if ((dx == 0 && dy == 0) || nx < 0 || nx >= p.wc) continue;
+          const int d = ny * p.wc + nx;
+          const int st = s_st[d];
+          if (st == ST_NONE || st == ST_SUPP) continue;
+          const int qx = nx * 8 + (s_pos[d] & 7), qy = ny * 8 + (s_pos[d] >> 3);
+          if (abs(qx - px) > p.radius || abs(qy - py) > p.radius) continue;
+          const float sd = s_sc[d];
+          if (sd > sc || (sd == sc && d < c)) {
+            if (st == ST_KEPT) any_kept = true;
+            else all_supp = false;
+          }
+        }
+      }
+      if (any_kept) s_st[c] = ST_SUPP;
+      else if (all_supp) s_st[c] = ST_KEPT;
+      else undecided = 1;
+    }
+    if (!__syncthreads_or(undecided)) break;
+  }
+
+  // ---- cap: keep the `cap` best survivors (score desc, ties by cell index asc)
+  for (int c = tid; c < cells; c += nt)
+    if (s_st[c] == ST_KEPT) {
+      const int slot = atomicAdd(&s_cnt, 1);
+      list[slot] = (static_cast<unsigned long long>(__float_as_uint(s_sc[c])) << 32) | (0xFFFFFFFFu - static_cast<unsigned>(c));
+    }
+  __syncthreads();
+  const int K = s_cnt;
+  if (K > p.cap) {
+    for (int e = tid; e < K; e += nt) {
+      const unsigned long long key = list[e];
+      int rank = 0;
+      for (int f = 0; f < K; f++) rank += (list[f] > key);
+      if (rank >= p.cap) s_st[0xFFFFFFFFu - static_cast<unsigned>(key & 0xFFFFFFFFu)] = ST_SUPP;
+    }
+  }
+  __syncthreads();
+
+  // ---- border filter + raster (v outer, u inner) ordering
+  for (int c = tid; c < cells; c += nt)
+    if (s_st[c] == ST_KEPT) {
+      const int cy = c / p.wc, cx = c - cy * p.wc;
+      const int px = cx * 8 + (s_pos[c] & 7), py = cy * 8 + (s_pos[c] >> 3);
+      if (px >= p.border && px < W - p.border && py >= p.border && py < H - p.border) {
+        const int slot = atomicAdd(&s_cnt2, 1);
+        list[slot] = (static_cast<unsigned long long>(py * W + px) << 32) | static_cast<unsigned>(c);
+      }
+    }
+  __syncthreads();
+  const int Nk = s_cnt2;
+  float *kp_xy = p.kp_xy + static_cast<size_t>(b) * p.cap * 2;
+  float *kp_sc = p.kp_score + static_cast<size_t>(b) * p.cap;
+  for (int e = tid; e < Nk; e += nt) {
+    const unsigned long long key = list[e];
+    int rank = 0;
+    for (int f = 0; f < Nk; f++) rank += (list[f] < key);
+    const int c = static_cast<int>(key & 0xFFFFFFFFu);
+    const int pix = static_cast<int>(key >> 32);
+    kp_xy[2 * rank] = static_cast<float>(pix % W);
+    kp_xy[2 * rank + 1] = static_cast<float>(pix / W);
+    kp_sc[rank] = s_sc[c];
+    occ[c] = static_cast<int16_t>(rank);
+  }
+  if (tid == 0) p.count[b] = Nk;
+}
+
+// ---------------------------------------------------------------------------
+// Descriptor sampling at the NMS survivors: grid_sampler_2d(coarse, pts,
+// bilinear, zeros, align_corners=true) then per-keypoint L2 normalisation.
+// The reference samples every candidate and discards most of them in nms();
+// sampling only survivors gives the same rows.  One warp per keypoint, each
+// lane owns 8 of the 256 channels (one 16-byte load per corner).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sample_desc_kernel(const __half *__restrict__ coarse /*[B][hc][wc][256]*/,
+                                                          const float *__restrict__ kp_xy, const int *__restrict__ count,
+                                                          float *__restrict__ desc /*[B][cap][256]*/, int hc, int wc,
+                                                          int cap) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= count[b]) return;
+  const float x = kp_xy[(static_cast<size_t>(b) * cap + i) * 2], y = kp_xy[(static_cast<size_t>(b) * cap + i) * 2 + 1];
+  const float W = static_cast<float>(wc * 8), H = static_cast<float>(hc * 8);
+  // sp_extractor.cpp:137-138 then ATen grid_sampler_unnormalize(align_corners=true)
+  const float xs = __fsub_rn(__fdiv_rn(x, W * 0.5f), 1.0f), ys = __fsub_rn(__fdiv_rn(y, H * 0.5f), 1.0f);
+  const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(xs, 1.0f), 2.0f), static_cast<float>(wc - 1));
+  const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(ys, 1.0f), 2.0f), static_cast<float>(hc - 1));
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
+  const float wx1 = ix - fx, wx0 = (fx + 1.0f) - ix, wy1 = iy - fy, wy0 = (fy + 1.0f) - iy;
+  const float wgt[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const __half *base = coarse + static_cast<size_t>(b) * hc * wc * 256 + lane * 8;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int xx = x0 + (k & 1), yy = y0 + (k >> 1);
+    if (xx < 0 || xx >= wc || yy < 0 || yy >= hc) continue;
+    const uint4 raw = *reinterpret_cast<const uint4 *>(base + (static_cast<size_t>(yy) * wc + xx) * 256);
+    const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float2 f = __half22float2(h2[j]);
+      acc[2 * j] = fmaf(wgt[k], f.x, acc[2 * j]);
+      acc[2 * j + 1] = fmaf(wgt[k], f.y, acc[2 * j + 1]);
+    }
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; j++) ss = fmaf(acc[j], acc[j], ss);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float nrm = sqrtf(ss);
+  float4 *dst = reinterpret_cast<float4 *>(desc + (static_cast<size_t>(b) * cap + i) * 256 + lane * 8);
+  dst[0] = make_float4(acc[0] / nrm, acc[1] / nrm, acc[2] / nrm, acc[3] / nrm);
+  dst[1] = make_float4(acc[4] / nrm, acc[5] / nrm, acc[6] / nrm, acc[7] / nrm);
+}
+
+// ---------------------------------------------------------------------------
+// to_heat: heat = (-x - min)/(max - min), heat_inv = (max + x)/(max - min)
+// with min/max of -x, folded the way OpenCV's MatExpr evaluates it (one
+// scale+shift per output, coefficients formed in double then narrowed).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) heat_norm_kernel(const float *__restrict__ heat_log, const unsigned *__restrict__ minmax,
+                                                        float *__restrict__ heat, float *__restrict__ heat_inv,
+                                                        float *__restrict__ minmax_out, int n_per_frame) {
+  __shared__ float s_c[4];
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) {
+    const float lo = f32_from_ordered(minmax[2 * b]), hi = f32_from_ordered(minmax[2 * b + 1]);
+    const double mn = static_cast<double>(-hi), mx = static_cast<double>(-lo);  // of img = -heat_log
+    const double inv = 1.0 / (mx - mn);
+    s_c[0] = static_cast<float>(-1.0 * inv);
+    s_c[1] = static_cast<float>((-mn) * inv);
+    s_c[2] = static_cast<float>(1.0 * inv);
+    s_c[3] = static_cast<float>(mx * inv);
+    if (blockIdx.x == 0 && minmax_out != nullptr) {
+      minmax_out[2 * b] = static_cast<float>(mn);
+      minmax_out[2 * b + 1] = static_cast<float>(mx);
+    }
+  }
+  __syncthreads();
+  const float a0 = s_c[0], b0 = s_c[1], a1 = s_c[2], b1 = s_c[3];
+  const size_t off = static_cast<size_t>(b) * n_per_frame;
+  const float4 *src = reinterpret_cast<const float4 *>(heat_log + off);
+  float4 *d0 = reinterpret_cast<float4 *>(heat + off), *d1 = reinterpret_cast<float4 *>(heat_inv + off);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_per_frame / 4; i += gridDim.x * blockDim.x) {
+    const float4 v = src[i];
+    d0[i] = make_float4(__fadd_rn(__fmul_rn(v.x, a0), b0), __fadd_rn(__fmul_rn(v.y, a0), b0),
+                        __fadd_rn(__fmul_rn(v.z, a0), b0), __fadd_rn(__fmul_rn(v.w, a0), b0));
+    d1[i] = make_float4(__fadd_rn(__fmul_rn(v.x, a1), b1), __fadd_rn(__fmul_rn(v.y, a1), b1),
+                        __fadd_rn(__fmul_rn(v.z, a1), b1), __fadd_rn(__fmul_rn(v.w, a1), b1));
+  }
+}
+
+}  // namespace spfe

@@ -1,0 +1,146 @@
+// Brute-force mutual nearest-neighbour matcher over 256-d float descriptors.
+//
+// Replaces cv::BFMatcher(NORM_L2, crossCheck=true)::match as called by
+// SPMatcher::SearchByBruteForce (reference orb_slam2/src/cv/sp_matcher.cpp:1666-1669,
+// orb_slam2/src/cv/sp_matcher_loop.cpp:365-368):
+//   q2t[i] = j*  where j* = first-index argmin_j ||q_i - t_j||  and  first-index argmin_i ||q_i - t_j*|| == i
+// Squared distances are accumulated in fp32 exactly as sum_k (q_ik - t_jk)^2;
+// each 64x64 tile of the distance matrix is reduced to per-row / per-column
+// minima which are merged across tiles with 64-bit atomicMin on
+// (float_bits(d2) << 32 | index) -- smaller distance wins, ties go to the lower
+// index, which is BFMatcher's first-index rule.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace spfe {
+
+struct MatchScratch {
+  unsigned long long *rowbest = nullptr, *colbest = nullptr;  // [cap]
+  int *q2t = nullptr;                                          // [cap]
+  float *dist = nullptr;                                       // [cap]
+  float *dq = nullptr, *dt = nullptr;                          // [cap][256] staging for host-pointer calls
+  int *dn = nullptr;                                           // [2] nq, nt
+  int cap = 0;
+};
+
+__global__ void init_minmax_kernel(unsigned *mm, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    mm[2 * b] = 0xFFFFFFFFu;
+    mm[2 * b + 1] = 0u;
+  }
+}
+
+__global__ void match_init_kernel(unsigned long long *rowbest, unsigned long long *colbest, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    rowbest[i] = ~0ull;
+    colbest[i] = ~0ull;
+  }
+}
+
+// grid (ceil(cap/64) train tiles, ceil(cap/64) query tiles), 256 threads, 4x4 outputs per thread.
+__global__ void __launch_bounds__(256) match_dist_kernel(const float *__restrict__ q, const float *__restrict__ t,
+                                                         const int *__restrict__ nq_p, const int *__restrict__ nt_p,
+                                                         unsigned long long *rowbest, unsigned long long *colbest) {
+  const int nq = *nq_p, nt = *nt_p;
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  if (i0 >= nq || j0 >= nt) return;
+  __shared__ float sq[16][68], st[16][68];
+  __shared__ unsigned long long s_col[16][64];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) acc[a][b] = 0.f;
+  const int lr = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 4;  // loader: row 0..63, k offset 0,4,8,12
+  for (int k0 = 0; k0 < 256; k0 += 16) {
+    float4 vq = make_float4(0, 0, 0, 0), vt = make_float4(0, 0, 0, 0);
+    if (i0 + lr < nq) vq = *reinterpret_cast<const float4 *>(q + static_cast<size_t>(i0 + lr) * 256 + k0 + lk);
+    if (j0 + lr < nt) vt = *reinterpret_cast<const float4 *>(t + static_cast<size_t>(j0 + lr) * 256 + k0 + lk);
+    __syncthreads();
+    sq[lk + 0][lr] = vq.x; sq[lk + 1][lr] = vq.y; sq[lk + 2][lr] = vq.z; sq[lk + 3][lr] = vq.w;
+    st[lk + 0][lr] = vt.x; st[lk + 1][lr] = vt.y; st[lk + 2][lr] = vt.z; st[lk + 3][lr] = vt.w;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      float a[4], b[4];
+#pragma unroll
+      for (int r = 0; r < 4; r++) { a[r] = sq[k][ty * 4 + r]; b[r] = st[k][tx * 4 + r]; }
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int cidx = 0; cidx < 4; cidx++) {
+          const float d = a[r] - b[cidx];
+          acc[r][cidx] = fmaf(d, d, acc[r][cidx]);
+        }
+    }
+  }
+  // row minima: reduce this thread's 4 columns, then across the 16 tx lanes (same half-warp)
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    unsigned long long best = ~0ull;
+#pragma unroll
+    for (int cidx = 0; cidx < 4; cidx++) {
+      const int j = j0 + tx * 4 + cidx;
+      if (j < nt) {
+        const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(acc[r][cidx])) << 32) | static_cast<unsigned>(j);
+        best = key < best ? key : best;
+      }
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other < best ? other : best;
+    }
+    const int i = i0 + ty * 4 + r;
+    if (tx == 0 && i < nq) atomicMin(rowbest + i, best);
+  }
+  // column minima: per-thread over its 4 rows, then across the 16 ty groups through shared memory
+#pragma unroll
+  for (int cidx = 0; cidx < 4; cidx++) {
+    unsigned long long best = ~0ull;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int i = i0 + ty * 4 + r;
+      if (i < nq) {
+        const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(acc[r][cidx])) << 32) | static_cast<unsigned>(i);
+        best = key < best ? key : best;
+      }
+    }
+    s_col[ty][tx * 4 + cidx] = best;
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    unsigned long long best = ~0ull;
+#pragma unroll
+    for (int g = 0; g < 16; g++) {
+      const unsigned long long v = s_col[g][threadIdx.x];
+      best = v < best ? v : best;
+    }
+    const int j = j0 + threadIdx.x;
+    if (j < nt) atomicMin(colbest + j, best);
+  }
+}
+
+__global__ void match_final_kernel(const unsigned long long *__restrict__ rowbest, const unsigned long long *__restrict__ colbest,
+                                   const int *__restrict__ nq_p, int *__restrict__ q2t, float *__restrict__ dist, int cap) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap) return;
+  int out = -1;
+  float d = 0.f;
+  if (i < *nq_p) {
+    const unsigned long long rb = rowbest[i];
+    if (rb != ~0ull) {
+      const int j = static_cast<int>(rb & 0xFFFFFFFFu);
+      d = sqrtf(__uint_as_float(static_cast<unsigned>(rb >> 32)));
+      if (static_cast<int>(colbest[j] & 0xFFFFFFFFu) == i) out = j;
+    }
+  }
+  q2t[i] = out;
+  dist[i] = d;
+}
+
+}  // namespace spfe

@@ -1,0 +1,843 @@
+// libspfe: context, buffers, launch plan and C ABI of the B200 SuperPoint
+// front-end.  See include/spfe.h for the boundary and DESIGN.md for the plan.
+#include "../../include/spfe.h"
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "conv_tc.cuh"
+#include "kernels_misc.cuh"
+#include "match.cuh"
+#include "weights.h"
+
+using namespace spfe;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+std::string fmt(const char *f, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, f);
+  vsnprintf(buf, sizeof buf, f, ap);
+  va_end(ap);
+  return buf;
+}
+
+// ----------------------------------------------------------------------------
+// kernel configurations (see conv_tc.cuh)
+//                         TAPS CB  N   epilogue        resident-W  A-ring B-ring
+using CfgC64 = ConvCfg<9, 1, 64, EPI_RELU, true, 6, 1>;         // conv2a
+using CfgC64P = ConvCfg<9, 1, 64, EPI_RELU_POOL, true, 6, 1>;   // conv1b, conv2b
+using CfgC3a = ConvCfg<9, 1, 128, EPI_RELU, true, 4, 1>;        // conv3a
+using CfgC128 = ConvCfg<9, 2, 128, EPI_RELU, false, 4, 8>;      // conv4a, conv4b
+using CfgC128P = ConvCfg<9, 2, 128, EPI_RELU_POOL, false, 4, 8>;  // conv3b
+using CfgHeads = ConvCfg<9, 2, 256, EPI_RELU, false, 4, 4>;     // convPa || convDa (NB = 2)
+using CfgPb = ConvCfg<1, 4, 80, EPI_DETECT, true, 4, 1>;        // convPb + detector head
+using CfgDb = ConvCfg<1, 4, 256, EPI_L2NORM, true, 4, 1>;       // convDb + L2 norm
+
+enum { L1B = 0, L2A, L2B, L3A, L3B, L4A, L4B, LHEADS, LPB, LDB, NLAYERS };
+const char *kLayerNames[NLAYERS] = {"conv1b", "conv2a", "conv2b", "conv3a", "conv3b",
+                                    "conv4a", "conv4b", "heads",  "convPb", "convDb"};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct Layer {
+  __half *w = nullptr;  // packed [tap][cblock][cout_total][64]
+  float *bias = nullptr;
+  CUtensorMap tm;
+  int taps = 0, cb = 0, cout_total = 0, n_tile = 0;
+  double flop_per_px = 0;  // 2 * taps * cin * cout (real couts)
+};
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  int batch = 0;
+  bool pending = false, on_host = false;
+  // device activations (NHWC fp16)
+  uint8_t *d_gray = nullptr;
+  __half *a1a = nullptr, *a1b = nullptr, *a2a = nullptr, *a2b = nullptr, *a3a = nullptr, *a3b = nullptr, *a4a = nullptr,
+         *a4b = nullptr, *heads = nullptr, *coarse = nullptr;
+  float *score = nullptr, *semi_dust = nullptr, *dense_dust = nullptr, *heat_log = nullptr, *heat = nullptr,
+        *heat_inv = nullptr, *heat_mm_f = nullptr;
+  unsigned *heat_mm = nullptr;
+  uint8_t *argmax = nullptr;
+  int *count = nullptr;
+  float *kp_xy = nullptr, *kp_score = nullptr, *desc = nullptr;
+  int16_t *occ = nullptr;
+  unsigned long long *scratch = nullptr;
+  CUtensorMap tmA[NLAYERS];
+  MatchScratch match;
+  // pinned host mirrors
+  uint8_t *h_gray = nullptr;
+  int *h_count = nullptr;
+  float *h_kp_xy = nullptr, *h_kp_score = nullptr, *h_desc = nullptr, *h_dense = nullptr, *h_semi = nullptr,
+        *h_heat = nullptr, *h_heat_inv = nullptr;
+  int16_t *h_occ = nullptr;
+  std::vector<float> cov2, cov2_inv, resp;
+};
+
+}  // namespace
+
+struct spfe_ctx {
+  spfe_config cfg;
+  std::string weights_path;
+  int H = 0, W = 0, hc = 0, wc = 0, cells = 0, cap = 0, num_sms = 0;
+  bool heat = false, cov = false;
+  EncodeTiledFn encode = nullptr;
+  float *w1a = nullptr, *b1a = nullptr;  // conv1a fp32 [9][64], [64]
+  Layer layers[NLAYERS];
+  std::vector<Slot> slots;
+  std::vector<void *> dev_allocs, host_allocs;
+  std::atomic<long long> launches{0};
+  std::string error;
+  std::mutex match_mu;
+  cudaStream_t match_stream = nullptr;
+  MatchScratch match;  // for spfe_match_mutual_nn (host pointers)
+  float *h_match_q = nullptr, *h_match_t = nullptr;
+  int *h_match_idx = nullptr;
+  float *h_match_dist = nullptr;
+  int match_cap = 0;
+
+  int fail(int code, const std::string &msg) {
+    error = msg;
+    return code;
+  }
+};
+
+namespace {
+
+#define CU_OK(ctx, call)                                                                         \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess)                                                                       \
+      return (ctx)->fail(SPFE_ERR_CUDA, fmt("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); \
+  } while (0)
+
+template <class T>
+int dev_alloc(spfe_ctx *c, T **p, size_t n) {
+  void *q = nullptr;
+  CU_OK(c, cudaMalloc(&q, n * sizeof(T) + 256));
+  c->dev_allocs.push_back(q);
+  *p = static_cast<T *>(q);
+  return SPFE_OK;
+}
+template <class T>
+int host_alloc(spfe_ctx *c, T **p, size_t n) {
+  void *q = nullptr;
+  CU_OK(c, cudaMallocHost(&q, n * sizeof(T) + 64));
+  c->host_allocs.push_back(q);
+  *p = static_cast<T *>(q);
+  return SPFE_OK;
+}
+
+// 4-D NHWC fp16 activation tensor -> TMA map with box {64 ch, 8 px, box_rows, 1 frame}, 128-B swizzle.
+int make_act_map(spfe_ctx *c, CUtensorMap *tm, const void *ptr, int C, int W, int H, int B, int box_rows) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, 8, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = c->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return c->fail(SPFE_ERR_CUDA, fmt("cuTensorMapEncodeTiled(act C=%d W=%d H=%d B=%d) -> %d", C, W, H, B, (int)r));
+  return SPFE_OK;
+}
+// 2-D [rows][cols] fp16 matrix -> TMA map with box {64, box_rows}, 128-B swizzle.
+int make_mat_map(spfe_ctx *c, CUtensorMap *tm, const void *ptr, int cols, int rows, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = c->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return c->fail(SPFE_ERR_CUDA, fmt("cuTensorMapEncodeTiled(mat %dx%d) -> %d", rows, cols, (int)r));
+  return SPFE_OK;
+}
+
+// Pack OIHW fp32 conv weights of one or two layers (concatenated along cout)
+// into [tap][cblock][cout_total][64] fp16; couts beyond the real ones are zero.
+int upload_layer(spfe_ctx *c, Layer &L, const std::vector<const HostTensor *> &ws, const std::vector<const HostTensor *> &bs,
+                 int n_tile, int cout_total) {
+  const int ci = ws[0]->dims[1], k = ws[0]->dims[2];
+  L.taps = k * k;
+  L.cb = ci / 64;
+  L.cout_total = cout_total;
+  L.n_tile = n_tile;
+  std::vector<__half> packed(static_cast<size_t>(L.taps) * L.cb * cout_total * 64, __float2half(0.f));
+  std::vector<float> bias(cout_total, 0.f);
+  int o0 = 0;
+  double real_couts = 0;
+  for (size_t li = 0; li < ws.size(); li++) {
+    const HostTensor &w = *ws[li];
+    const int co = w.dims[0];
+    real_couts += co;
+    for (int o = 0; o < co; o++) {
+      bias[o0 + o] = bs[li]->data[o];
+      for (int ch = 0; ch < ci; ch++)
+        for (int t = 0; t < L.taps; t++) {
+          const float v = w.data[(static_cast<size_t>(o) * ci + ch) * L.taps + t];
+          const size_t wb = static_cast<size_t>(t) * L.cb + ch / 64;
+          packed[(wb * cout_total + o0 + o) * 64 + (ch % 64)] = __float2half_rn(v);
+        }
+    }
+    o0 += co;
+  }
+  L.flop_per_px = 2.0 * L.taps * ci * real_couts;
+  int rc;
+  if ((rc = dev_alloc(c, &L.w, packed.size()))) return rc;
+  if ((rc = dev_alloc(c, &L.bias, bias.size()))) return rc;
+  CU_OK(c, cudaMemcpy(L.w, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  CU_OK(c, cudaMemcpy(L.bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return make_mat_map(c, &L.tm, L.w, 64, L.taps * L.cb * cout_total, n_tile);
+}
+
+template <class Cfg>
+int launch_conv(spfe_ctx *c, cudaStream_t st, const CUtensorMap &tmA, const Layer &L, ConvArgs a) {
+  static_assert(Cfg::TAPS == 9 || Cfg::TAPS == 1, "taps");
+  if (L.taps != Cfg::TAPS || L.cb != Cfg::CB || L.n_tile != Cfg::N || (Cfg::WRES && a.NB != 1))
+    return c->fail(SPFE_ERR_INVALID, "conv launch: layer / kernel configuration mismatch");
+  const int smem = Cfg::smem_bytes(a.NB);
+  static std::atomic<int> configured{0};
+  if (configured.load() < smem) {
+    CU_OK(c, cudaFuncSetAttribute(conv_tc_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured.store(smem);
+  }
+  a.bias = L.bias;
+  a.tiles_x = (a.W + 7) / 8;
+  a.tiles_y = (a.H + 15) / 16;
+  a.n_items = a.B * a.tiles_x * a.tiles_y * a.NB;
+  const int grid = a.n_items < c->num_sms ? a.n_items : c->num_sms;
+  conv_tc_kernel<Cfg><<<grid, 256, smem, st>>>(tmA, L.tm, a);
+  c->launches++;
+  CU_OK(c, cudaGetLastError());
+  return SPFE_OK;
+}
+
+struct StageTimer {
+  std::vector<cudaEvent_t> ev;
+  std::vector<std::string> names;
+  std::vector<double> flop, bytes;
+  cudaStream_t st;
+  bool on;
+  void mark(const char *name, double f = 0, double b = 0) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.push_back(e);
+    names.push_back(name);
+    flop.push_back(f);
+    bytes.push_back(b);
+  }
+};
+
+// Enqueue the whole per-batch launch plan on the slot's stream.
+int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
+  const int H = c->H, W = c->W, hc = c->hc, wc = c->wc;
+  cudaStream_t st = s.stream;
+  auto mark = [&](const char *n, double f = 0, double b = 0) { if (tm) tm->mark(n, f, b); };
+  mark("start");
+  if (c->heat) {
+    init_minmax_kernel<<<(B + 127) / 128, 128, 0, st>>>(s.heat_mm, B);
+    c->launches++;
+  }
+  {  // conv1a: u8 -> fp16 NHWC64
+    dim3 grid((W + 31) / 32, (H + 7) / 8, B);
+    conv1a_kernel<<<grid, 256, 0, st>>>(s.d_gray, s.a1a, c->w1a, c->b1a, B, H, W);
+    c->launches++;
+    CU_OK(c, cudaGetLastError());
+    mark("conv1a", 2.0 * 9 * 64 * H * W * B, (1.0 + 128.0) * H * W * B);
+  }
+  int rc;
+  auto conv_args = [&](int h, int w, int nb, int cout_stride, __half *out) {
+    ConvArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = B; a.H = h; a.W = w; a.NB = nb; a.cin_off = 0; a.cout_stride = cout_stride; a.out = out;
+    return a;
+  };
+  auto stage_flop = [&](int l, int h, int w) { return c->layers[l].flop_per_px * h * w * B; };
+  if ((rc = launch_conv<CfgC64P>(c, st, s.tmA[L1B], c->layers[L1B], conv_args(H, W, 1, 64, s.a1b)))) return rc;
+  mark("conv1b", stage_flop(L1B, H, W), (128.0 + 32.0) * H * W * B);
+  if ((rc = launch_conv<CfgC64>(c, st, s.tmA[L2A], c->layers[L2A], conv_args(H / 2, W / 2, 1, 64, s.a2a)))) return rc;
+  mark("conv2a", stage_flop(L2A, H / 2, W / 2), 256.0 * (H / 2) * (W / 2) * B);
+  if ((rc = launch_conv<CfgC64P>(c, st, s.tmA[L2B], c->layers[L2B], conv_args(H / 2, W / 2, 1, 64, s.a2b)))) return rc;
+  mark("conv2b", stage_flop(L2B, H / 2, W / 2), 160.0 * (H / 2) * (W / 2) * B);
+  if ((rc = launch_conv<CfgC3a>(c, st, s.tmA[L3A], c->layers[L3A], conv_args(H / 4, W / 4, 1, 128, s.a3a)))) return rc;
+  mark("conv3a", stage_flop(L3A, H / 4, W / 4), 384.0 * (H / 4) * (W / 4) * B);
+  if ((rc = launch_conv<CfgC128P>(c, st, s.tmA[L3B], c->layers[L3B], conv_args(H / 4, W / 4, 1, 128, s.a3b)))) return rc;
+  mark("conv3b", stage_flop(L3B, H / 4, W / 4), 320.0 * (H / 4) * (W / 4) * B);
+  if ((rc = launch_conv<CfgC128>(c, st, s.tmA[L4A], c->layers[L4A], conv_args(hc, wc, 1, 128, s.a4a)))) return rc;
+  mark("conv4a", stage_flop(L4A, hc, wc), 512.0 * hc * wc * B);
+  if ((rc = launch_conv<CfgC128>(c, st, s.tmA[L4B], c->layers[L4B], conv_args(hc, wc, 1, 128, s.a4b)))) return rc;
+  mark("conv4b", stage_flop(L4B, hc, wc), 512.0 * hc * wc * B);
+  if ((rc = launch_conv<CfgHeads>(c, st, s.tmA[LHEADS], c->layers[LHEADS], conv_args(hc, wc, 2, 512, s.heads)))) return rc;
+  mark("convPa|Da", stage_flop(LHEADS, hc, wc), (256.0 + 1024.0) * hc * wc * B);
+  {
+    ConvArgs a = conv_args(hc, wc, 1, 0, nullptr);
+    a.cin_off = 0;
+    a.score = s.score; a.argmax = s.argmax; a.semi_dust = s.semi_dust; a.dense_dust = s.dense_dust;
+    a.heat_log = c->heat ? s.heat_log : nullptr;
+    a.heat_minmax = c->heat ? s.heat_mm : nullptr;
+    if ((rc = launch_conv<CfgPb>(c, st, s.tmA[LPB], c->layers[LPB], a))) return rc;
+    mark("convPb+det", stage_flop(LPB, hc, wc), (512.0 + 13.0 + (c->heat ? 256.0 : 0.0)) * hc * wc * B);
+  }
+  {
+    ConvArgs a = conv_args(hc, wc, 1, 256, s.coarse);
+    a.cin_off = 256;
+    if ((rc = launch_conv<CfgDb>(c, st, s.tmA[LDB], c->layers[LDB], a))) return rc;
+    mark("convDb+norm", stage_flop(LDB, hc, wc), (512.0 + 512.0) * hc * wc * B);
+  }
+  {
+    NmsArgs n;
+    n.score = s.score; n.argmax = s.argmax; n.hc = hc; n.wc = wc; n.thresh = c->cfg.score_thresh;
+    n.radius = c->cfg.nms_radius; n.border = c->cfg.border; n.cap = c->cap;
+    n.count = s.count; n.kp_xy = s.kp_xy; n.kp_score = s.kp_score; n.occ = s.occ; n.scratch = s.scratch;
+    nms_kernel<<<B, 1024, c->cells * 6, st>>>(n);
+    c->launches++;
+    CU_OK(c, cudaGetLastError());
+    mark("nms", 0, 7.0 * c->cells * B);
+  }
+  {
+    dim3 grid((c->cap + 7) / 8, B);
+    sample_desc_kernel<<<grid, 256, 0, st>>>(s.coarse, s.kp_xy, s.count, s.desc, hc, wc, c->cap);
+    c->launches++;
+    CU_OK(c, cudaGetLastError());
+    mark("sample_desc", 0, 3072.0 * c->cap * B);
+  }
+  if (c->heat) {
+    dim3 grid(64, B);
+    heat_norm_kernel<<<grid, 256, 0, st>>>(s.heat_log, s.heat_mm, s.heat, s.heat_inv, s.heat_mm_f, H * W);
+    c->launches++;
+    CU_OK(c, cudaGetLastError());
+    mark("heat_norm", 0, 12.0 * H * W * B);
+  }
+  s.batch = B;
+  return SPFE_OK;
+}
+
+// computeCovariance (sp_extractor.cpp:252-340) on the host, from the device's
+// heat_inv: breadth-first descent from each keypoint over 4-neighbours whose
+// value is positive and strictly below the popped pixel's, sharing one
+// "unvisited" mask across all keypoints of the frame (marked on pop).
+void covariance_host(const float *heat_inv, int H, int W, const float *kp_xy, int n, float *resp, float *cov2,
+                     float *cov2_inv) {
+  std::vector<uint8_t> unvisited(static_cast<size_t>(H) * W, 1);
+  std::vector<int> fifo;
+  for (int k = 0; k < n; k++) {
+    const int cu = static_cast<int>(kp_xy[2 * k]), cv = static_cast<int>(kp_xy[2 * k + 1]);
+    resp[k] = heat_inv[static_cast<size_t>(cv) * W + cu];
+    fifo.clear();
+    fifo.push_back(cv * W + cu);
+    // gather the basin in pop order (duplicates included, as in the reference), then weight by value / sum
+    size_t head = 0;
+    while (head < fifo.size()) {
+      const int pix = fifo[head++];
+      unvisited[pix] = 0;
+      const int u = pix % W, v = pix / W;
+      const float here = heat_inv[pix];
+      const int cand[4] = {u - 1 > 0 ? pix - 1 : -1, v - 1 > 0 ? pix - W : -1, u + 1 < W ? pix + 1 : -1,
+                           v + 1 < H ? pix + W : -1};
+      for (int t = 0; t < 4; t++) {
+        if (cand[t] < 0) continue;
+        const float hv = heat_inv[cand[t]];
+        if (unvisited[cand[t]] && hv > 0.0f && hv < here) fifo.push_back(cand[t]);
+      }
+    }
+    float total = 0.0f;
+    for (int pix : fifo) total += heat_inv[pix];
+    float sx = 0.0f, sy = 0.0f;
+    for (int pix : fifo) {
+      const float du = static_cast<float>(pix % W) - static_cast<float>(cu);
+      const float dv = static_cast<float>(pix / W) - static_cast<float>(cv);
+      const float wgt = heat_inv[pix] / total;
+      sx += wgt * (du * du);
+      sy += wgt * (dv * dv);
+    }
+    if (sx < 1.0f) sx = 1.0f;
+    if (sy < 1.0f) sy = 1.0f;
+    cov2[2 * k] = sx;
+    cov2[2 * k + 1] = sy;
+    cov2_inv[2 * k] = 1.0f / sx;
+    cov2_inv[2 * k + 1] = 1.0f / sy;
+  }
+}
+
+}  // namespace
+
+// ============================================================================
+// C ABI
+// ============================================================================
+extern "C" {
+
+void spfe_default_config(spfe_config *cfg, int32_t height, int32_t width, int32_t max_keypoints) {
+  if (!cfg) return;
+  memset(cfg, 0, sizeof *cfg);
+  cfg->struct_size = sizeof *cfg;
+  cfg->height = height;
+  cfg->width = width;
+  cfg->max_keypoints = max_keypoints;
+  cfg->score_thresh = 0.007f;  // sp_extractor.cpp:122
+  cfg->nms_radius = 4;         // sp_extractor.cpp:502
+  cfg->border = 8;             // sp_extractor.cpp:502
+  cfg->device_id = 0;
+  cfg->max_batch = 1;
+  cfg->num_slots = 1;
+  cfg->flags = SPFE_EMIT_HEAT | SPFE_EMIT_COV;  // what SPExtractor::operator() always produces
+  cfg->weights_path = nullptr;
+}
+
+const char *spfe_last_error(const spfe_ctx *ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+static int create_impl(spfe_ctx *c) {
+  const spfe_config &cfg = c->cfg;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return c->fail(SPFE_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU fallback)");
+  if (cfg.device_id < 0 || cfg.device_id >= ndev) return c->fail(SPFE_ERR_INVALID, "device_id out of range");
+  CU_OK(c, cudaSetDevice(cfg.device_id));
+  cudaDeviceProp prop;
+  CU_OK(c, cudaGetDeviceProperties(&prop, cfg.device_id));
+  if (prop.major != 10)
+    return c->fail(SPFE_ERR_NO_DEVICE, fmt("device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg.device_id, prop.major, prop.minor));
+  c->num_sms = prop.multiProcessorCount;
+  {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU_OK(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return c->fail(SPFE_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    c->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const int H = c->H, W = c->W, hc = c->hc, wc = c->wc, Bm = cfg.max_batch;
+  int rc;
+
+  // ---- weights
+  WeightMap wm;
+  std::string err;
+  if (!load_weights(c->weights_path, wm, err)) return c->fail(SPFE_ERR_WEIGHTS, err);
+  {
+    const HostTensor &w = wm["conv1a.weight"], &b = wm["conv1a.bias"];
+    std::vector<float> w9(9 * 64);
+    for (int o = 0; o < 64; o++)
+      for (int t = 0; t < 9; t++) w9[t * 64 + o] = w.data[o * 9 + t];
+    if ((rc = dev_alloc(c, &c->w1a, w9.size()))) return rc;
+    if ((rc = dev_alloc(c, &c->b1a, 64))) return rc;
+    CU_OK(c, cudaMemcpy(c->w1a, w9.data(), w9.size() * 4, cudaMemcpyHostToDevice));
+    CU_OK(c, cudaMemcpy(c->b1a, b.data.data(), 64 * 4, cudaMemcpyHostToDevice));
+  }
+  auto up = [&](int l, std::vector<const char *> names, int n_tile, int cout_total) {
+    std::vector<const HostTensor *> ws, bs;
+    for (const char *n : names) {
+      ws.push_back(&wm[std::string(n) + ".weight"]);
+      bs.push_back(&wm[std::string(n) + ".bias"]);
+    }
+    return upload_layer(c, c->layers[l], ws, bs, n_tile, cout_total);
+  };
+  if ((rc = up(L1B, {"conv1b"}, 64, 64))) return rc;
+  if ((rc = up(L2A, {"conv2a"}, 64, 64))) return rc;
+  if ((rc = up(L2B, {"conv2b"}, 64, 64))) return rc;
+  if ((rc = up(L3A, {"conv3a"}, 128, 128))) return rc;
+  if ((rc = up(L3B, {"conv3b"}, 128, 128))) return rc;
+  if ((rc = up(L4A, {"conv4a"}, 128, 128))) return rc;
+  if ((rc = up(L4B, {"conv4b"}, 128, 128))) return rc;
+  if ((rc = up(LHEADS, {"convPa", "convDa"}, 256, 512))) return rc;
+  if ((rc = up(LPB, {"convPb"}, 80, 80))) return rc;
+  if ((rc = up(LDB, {"convDb"}, 256, 256))) return rc;
+
+  // ---- per-slot buffers
+  c->slots.resize(cfg.num_slots);
+  const size_t px = static_cast<size_t>(H) * W, cells = c->cells, cap = c->cap;
+  for (Slot &s : c->slots) {
+    CU_OK(c, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    if ((rc = dev_alloc(c, &s.d_gray, Bm * px))) return rc;
+    if ((rc = dev_alloc(c, &s.a1a, Bm * px * 64))) return rc;
+    if ((rc = dev_alloc(c, &s.a1b, Bm * px / 4 * 64))) return rc;
+    if ((rc = dev_alloc(c, &s.a2a, Bm * px / 4 * 64))) return rc;
+    if ((rc = dev_alloc(c, &s.a2b, Bm * px / 16 * 64))) return rc;
+    if ((rc = dev_alloc(c, &s.a3a, Bm * px / 16 * 128))) return rc;
+    if ((rc = dev_alloc(c, &s.a3b, Bm * cells * 128))) return rc;
+    if ((rc = dev_alloc(c, &s.a4a, Bm * cells * 128))) return rc;
+    if ((rc = dev_alloc(c, &s.a4b, Bm * cells * 128))) return rc;
+    if ((rc = dev_alloc(c, &s.heads, Bm * cells * 512))) return rc;
+    if ((rc = dev_alloc(c, &s.coarse, Bm * cells * 256))) return rc;
+    if ((rc = dev_alloc(c, &s.score, Bm * cells))) return rc;
+    if ((rc = dev_alloc(c, &s.argmax, Bm * cells))) return rc;
+    if ((rc = dev_alloc(c, &s.semi_dust, Bm * cells))) return rc;
+    if ((rc = dev_alloc(c, &s.dense_dust, Bm * cells))) return rc;
+    if ((rc = dev_alloc(c, &s.count, Bm))) return rc;
+    if ((rc = dev_alloc(c, &s.kp_xy, Bm * cap * 2))) return rc;
+    if ((rc = dev_alloc(c, &s.kp_score, Bm * cap))) return rc;
+    if ((rc = dev_alloc(c, &s.desc, Bm * cap * 256))) return rc;
+    if ((rc = dev_alloc(c, &s.occ, Bm * cells))) return rc;
+    if ((rc = dev_alloc(c, &s.scratch, Bm * cells))) return rc;
+    CU_OK(c, cudaMemset(s.count, 0, Bm * sizeof(int)));
+    CU_OK(c, cudaMemset(s.kp_xy, 0, Bm * cap * 2 * sizeof(float)));
+    CU_OK(c, cudaMemset(s.desc, 0, Bm * cap * 256 * sizeof(float)));
+    if (c->heat) {
+      if ((rc = dev_alloc(c, &s.heat_log, Bm * px))) return rc;
+      if ((rc = dev_alloc(c, &s.heat, Bm * px))) return rc;
+      if ((rc = dev_alloc(c, &s.heat_inv, Bm * px))) return rc;
+      if ((rc = dev_alloc(c, &s.heat_mm, Bm * 2))) return rc;
+      if ((rc = dev_alloc(c, &s.heat_mm_f, Bm * 2))) return rc;
+      if ((rc = host_alloc(c, &s.h_heat, Bm * px))) return rc;
+      if ((rc = host_alloc(c, &s.h_heat_inv, Bm * px))) return rc;
+    }
+    // matcher scratch (device-resident frame-vs-frame matching inside a slot)
+    if ((rc = dev_alloc(c, &s.match.rowbest, Bm * cap))) return rc;
+    if ((rc = dev_alloc(c, &s.match.colbest, Bm * cap))) return rc;
+    if ((rc = dev_alloc(c, &s.match.q2t, Bm * cap))) return rc;
+    if ((rc = dev_alloc(c, &s.match.dist, Bm * cap))) return rc;
+    s.match.cap = static_cast<int>(cap);
+    if ((rc = host_alloc(c, &s.h_gray, Bm * px))) return rc;
+    if ((rc = host_alloc(c, &s.h_count, Bm))) return rc;
+    if ((rc = host_alloc(c, &s.h_kp_xy, Bm * cap * 2))) return rc;
+    if ((rc = host_alloc(c, &s.h_kp_score, Bm * cap))) return rc;
+    if ((rc = host_alloc(c, &s.h_desc, Bm * cap * 256))) return rc;
+    if ((rc = host_alloc(c, &s.h_dense, Bm * cells))) return rc;
+    if ((rc = host_alloc(c, &s.h_semi, Bm * cells))) return rc;
+    if ((rc = host_alloc(c, &s.h_occ, Bm * cells))) return rc;
+    if (c->cov) {
+      s.cov2.resize(Bm * cap * 2);
+      s.cov2_inv.resize(Bm * cap * 2);
+      s.resp.resize(Bm * cap);
+    }
+    // TMA maps of every layer's input tensor
+    if ((rc = make_act_map(c, &s.tmA[L1B], s.a1a, 64, W, H, Bm, 18))) return rc;
+    if ((rc = make_act_map(c, &s.tmA[L2A], s.a1b, 64, W / 2, H / 2, Bm, 18))) return rc;
+    if ((rc = make_act_map(c, &s.tmA[L2B], s.a2a, 64, W / 2, H / 2, Bm, 18))) return rc;
+    if ((rc = make_act_map(c, &s.tmA[L3A], s.a2b, 64, W / 4, H / 4, Bm, 18))) return rc;
+    if ((rc = make_act_map(c, &s.tmA[L3B], s.a3a, 128, W / 4, H / 4, Bm, 18))) return rc;
+    if ((rc = make_act_map(c, &s.tmA[L4A], s.a3b, 128, wc, hc, Bm, 18))) return rc;
+    if ((rc = make_act_map(c, &s.tmA[L4B], s.a4a, 128, wc, hc, Bm, 18))) return rc;
+    if ((rc = make_act_map(c, &s.tmA[LHEADS], s.a4b, 128, wc, hc, Bm, 18))) return rc;
+    if ((rc = make_act_map(c, &s.tmA[LPB], s.heads, 512, wc, hc, Bm, 16))) return rc;
+    if ((rc = make_act_map(c, &s.tmA[LDB], s.heads, 512, wc, hc, Bm, 16))) return rc;
+  }
+  // ---- host-pointer matcher scratch
+  c->match_cap = static_cast<int>(cap) > 4096 ? static_cast<int>(cap) : 4096;
+  CU_OK(c, cudaStreamCreateWithFlags(&c->match_stream, cudaStreamNonBlocking));
+  if ((rc = dev_alloc(c, &c->match.rowbest, c->match_cap))) return rc;
+  if ((rc = dev_alloc(c, &c->match.colbest, c->match_cap))) return rc;
+  if ((rc = dev_alloc(c, &c->match.q2t, c->match_cap))) return rc;
+  if ((rc = dev_alloc(c, &c->match.dist, c->match_cap))) return rc;
+  if ((rc = dev_alloc(c, &c->match.dq, static_cast<size_t>(c->match_cap) * 256))) return rc;
+  if ((rc = dev_alloc(c, &c->match.dt, static_cast<size_t>(c->match_cap) * 256))) return rc;
+  if ((rc = dev_alloc(c, &c->match.dn, 2))) return rc;
+  c->match.cap = c->match_cap;
+  if ((rc = host_alloc(c, &c->h_match_q, static_cast<size_t>(c->match_cap) * 256))) return rc;
+  if ((rc = host_alloc(c, &c->h_match_t, static_cast<size_t>(c->match_cap) * 256))) return rc;
+  if ((rc = host_alloc(c, &c->h_match_idx, c->match_cap + 2))) return rc;
+  if ((rc = host_alloc(c, &c->h_match_dist, c->match_cap))) return rc;
+  CU_OK(c, cudaDeviceSynchronize());
+  return SPFE_OK;
+}
+
+int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
+  if (out) *out = nullptr;
+  if (!cfg || !out || cfg->struct_size != (int32_t)sizeof(spfe_config)) { g_create_error = "spfe_create: bad config pointer / struct_size"; return SPFE_ERR_INVALID; }
+  if (cfg->height <= 0 || cfg->width <= 0 || cfg->height % 8 || cfg->width % 8) { g_create_error = "spfe_create: height/width must be positive multiples of 8 (sp_extractor.cpp:70)"; return SPFE_ERR_INVALID; }
+  if (cfg->max_keypoints < 1 || cfg->max_batch < 1 || cfg->num_slots < 1 || cfg->nms_radius < 0 || cfg->nms_radius > 8 || cfg->border < 0) { g_create_error = "spfe_create: bad max_keypoints / max_batch / num_slots / nms_radius / border"; return SPFE_ERR_INVALID; }
+  if ((size_t)(cfg->height / 8) * (cfg->width / 8) > 37000) { g_create_error = "spfe_create: more than 37000 cells (NMS shared-memory budget)"; return SPFE_ERR_INVALID; }
+  if (!cfg->weights_path) { g_create_error = "spfe_create: weights_path is NULL"; return SPFE_ERR_WEIGHTS; }
+  spfe_ctx *c = new spfe_ctx();
+  c->cfg = *cfg;
+  c->weights_path = cfg->weights_path;
+  c->cfg.weights_path = c->weights_path.c_str();
+  c->H = cfg->height; c->W = cfg->width; c->hc = c->H / 8; c->wc = c->W / 8; c->cells = c->hc * c->wc;
+  c->cap = cfg->max_keypoints + 1;
+  if (c->cap > c->cells) c->cap = c->cells;
+  c->cov = (cfg->flags & SPFE_EMIT_COV) != 0;
+  c->heat = c->cov || (cfg->flags & SPFE_EMIT_HEAT) != 0;
+  int rc = create_impl(c);
+  if (rc == SPFE_OK) rc = [&]() -> int {
+    CU_OK(c, cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->cells * 6));
+    return SPFE_OK;
+  }();
+  if (rc != SPFE_OK) {
+    g_create_error = c->error;
+    spfe_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return SPFE_OK;
+}
+
+void spfe_destroy(spfe_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device_id);
+  cudaDeviceSynchronize();
+  for (Slot &s : c->slots) if (s.stream) cudaStreamDestroy(s.stream);
+  if (c->match_stream) cudaStreamDestroy(c->match_stream);
+  for (void *p : c->dev_allocs) cudaFree(p);
+  for (void *p : c->host_allocs) cudaFreeHost(p);
+  delete c;
+}
+
+static int check_slot(spfe_ctx *c, int32_t slot) {
+  if (!c) return SPFE_ERR_INVALID;
+  if (slot < 0 || slot >= (int)c->slots.size()) return c->fail(SPFE_ERR_INVALID, "slot out of range");
+  return SPFE_OK;
+}
+
+static int enqueue_d2h(spfe_ctx *c, Slot &s, int B) {
+  const size_t px = (size_t)c->H * c->W, cells = c->cells, cap = c->cap;
+  cudaStream_t st = s.stream;
+  CU_OK(c, cudaMemcpyAsync(s.h_count, s.count, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU_OK(c, cudaMemcpyAsync(s.h_kp_xy, s.kp_xy, B * cap * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU_OK(c, cudaMemcpyAsync(s.h_kp_score, s.kp_score, B * cap * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU_OK(c, cudaMemcpyAsync(s.h_desc, s.desc, B * cap * 256 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU_OK(c, cudaMemcpyAsync(s.h_occ, s.occ, B * cells * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+  CU_OK(c, cudaMemcpyAsync(s.h_dense, s.dense_dust, B * cells * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU_OK(c, cudaMemcpyAsync(s.h_semi, s.semi_dust, B * cells * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (c->heat) {
+    CU_OK(c, cudaMemcpyAsync(s.h_heat, s.heat, B * px * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU_OK(c, cudaMemcpyAsync(s.h_heat_inv, s.heat_inv, B * px * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  return SPFE_OK;
+}
+
+int spfe_submit(spfe_ctx *c, int32_t slot, const uint8_t *const *grays, int32_t batch, size_t row_stride) {
+  int rc = check_slot(c, slot);
+  if (rc) return rc;
+  if (!grays || batch < 1 || batch > c->cfg.max_batch) return c->fail(SPFE_ERR_INVALID, "spfe_submit: bad grays / batch");
+  if (row_stride < (size_t)c->W) return c->fail(SPFE_ERR_INVALID, "spfe_submit: row_stride smaller than width");
+  Slot &s = c->slots[slot];
+  if (s.pending) return c->fail(SPFE_ERR_STATE, "spfe_submit: slot still has an un-waited batch");
+  CU_OK(c, cudaSetDevice(c->cfg.device_id));
+  const size_t px = (size_t)c->H * c->W;
+  for (int b = 0; b < batch; b++) {
+    if (!grays[b]) return c->fail(SPFE_ERR_EMPTY, "input image is empty");
+    if (row_stride == (size_t)c->W) memcpy(s.h_gray + b * px, grays[b], px);
+    else for (int y = 0; y < c->H; y++) memcpy(s.h_gray + b * px + (size_t)y * c->W, grays[b] + y * row_stride, c->W);
+  }
+  CU_OK(c, cudaMemcpyAsync(s.d_gray, s.h_gray, batch * px, cudaMemcpyHostToDevice, s.stream));
+  if ((rc = run_pipeline(c, s, batch, nullptr))) return rc;
+  if ((rc = enqueue_d2h(c, s, batch))) return rc;
+  s.pending = true;
+  s.on_host = true;
+  return SPFE_OK;
+}
+
+int spfe_wait(spfe_ctx *c, int32_t slot, spfe_frame_out *outs) {
+  int rc = check_slot(c, slot);
+  if (rc) return rc;
+  Slot &s = c->slots[slot];
+  if (!s.pending || !s.on_host) return c->fail(SPFE_ERR_STATE, "spfe_wait: nothing submitted on this slot");
+  CU_OK(c, cudaStreamSynchronize(s.stream));
+  s.pending = false;
+  if (!outs) return SPFE_OK;
+  const size_t px = (size_t)c->H * c->W, cells = c->cells, cap = c->cap;
+  for (int b = 0; b < s.batch; b++) {
+    spfe_frame_out &o = outs[b];
+    memset(&o, 0, sizeof o);
+    o.n = s.h_count[b];
+    o.kp_xy = s.h_kp_xy + b * cap * 2;
+    o.kp_score = s.h_kp_score + b * cap;
+    o.desc = s.h_desc + b * cap * 256;
+    o.occ_grid = s.h_occ + b * cells;
+    o.dense_dust = s.h_dense + b * cells;
+    o.semi_dust = s.h_semi + b * cells;
+    if (c->heat) {
+      o.heat = s.h_heat + b * px;
+      o.heat_inv = s.h_heat_inv + b * px;
+    }
+    if (c->cov) {
+      float *resp = s.resp.data() + b * cap, *c2 = s.cov2.data() + b * cap * 2, *c2i = s.cov2_inv.data() + b * cap * 2;
+      covariance_host(o.heat_inv, c->H, c->W, o.kp_xy, o.n, resp, c2, c2i);
+      o.kp_response = resp;
+      o.cov2 = c2;
+      o.cov2_inv = c2i;
+    }
+  }
+  return SPFE_OK;
+}
+
+int spfe_extract(spfe_ctx *c, const uint8_t *gray, size_t row_stride, spfe_frame_out *out) {
+  if (!c) return SPFE_ERR_INVALID;
+  if (!gray) return c->fail(SPFE_ERR_EMPTY, "input image is empty");
+  if (!out) return c->fail(SPFE_ERR_INVALID, "spfe_extract: out is NULL");
+  const uint8_t *one[1] = {gray};
+  int rc = spfe_submit(c, 0, one, 1, row_stride);
+  if (rc) return rc;
+  return spfe_wait(c, 0, out);
+}
+
+int spfe_submit_device(spfe_ctx *c, int32_t slot, const void *d_gray, int32_t batch) {
+  int rc = check_slot(c, slot);
+  if (rc) return rc;
+  if (!d_gray || batch < 1 || batch > c->cfg.max_batch) return c->fail(SPFE_ERR_INVALID, "spfe_submit_device: bad pointer / batch");
+  Slot &s = c->slots[slot];
+  CU_OK(c, cudaSetDevice(c->cfg.device_id));
+  uint8_t *saved = s.d_gray;
+  s.d_gray = const_cast<uint8_t *>(static_cast<const uint8_t *>(d_gray));
+  rc = run_pipeline(c, s, batch, nullptr);
+  s.d_gray = saved;
+  s.pending = false;
+  s.on_host = false;
+  return rc;
+}
+
+int spfe_slot_sync(spfe_ctx *c, int32_t slot) {
+  int rc = check_slot(c, slot);
+  if (rc) return rc;
+  CU_OK(c, cudaStreamSynchronize(c->slots[slot].stream));
+  return SPFE_OK;
+}
+
+// ---- matcher -----------------------------------------------------------------
+static int run_match(spfe_ctx *c, cudaStream_t st, const float *dq, const float *dt, const int *dnq, const int *dnt,
+                     MatchScratch &m, int off, int cap_rows) {
+  match_init_kernel<<<(cap_rows + 255) / 256, 256, 0, st>>>(m.rowbest + off, m.colbest + off, cap_rows);
+  dim3 grid((cap_rows + 63) / 64, (cap_rows + 63) / 64);
+  match_dist_kernel<<<grid, 256, 0, st>>>(dq, dt, dnq, dnt, m.rowbest + off, m.colbest + off);
+  match_final_kernel<<<(cap_rows + 255) / 256, 256, 0, st>>>(m.rowbest + off, m.colbest + off, dnq, m.q2t + off, m.dist + off, cap_rows);
+  c->launches += 3;
+  CU_OK(c, cudaGetLastError());
+  return SPFE_OK;
+}
+
+int spfe_match_mutual_nn(spfe_ctx *c, const float *q, int32_t nq, const float *t, int32_t nt, int32_t *q2t, float *dist) {
+  if (!c) return SPFE_ERR_INVALID;
+  if (nq < 0 || nt < 0 || (nq > 0 && !q) || (nt > 0 && !t) || (nq > 0 && !q2t)) return c->fail(SPFE_ERR_INVALID, "spfe_match_mutual_nn: bad arguments");
+  if (nq > c->match_cap || nt > c->match_cap) return c->fail(SPFE_ERR_INVALID, fmt("spfe_match_mutual_nn: more than %d rows", c->match_cap));
+  if (nq == 0) return SPFE_OK;
+  if (nt == 0) {
+    for (int i = 0; i < nq; i++) { q2t[i] = -1; if (dist) dist[i] = 0.f; }
+    return SPFE_OK;
+  }
+  std::lock_guard<std::mutex> lock(c->match_mu);
+  CU_OK(c, cudaSetDevice(c->cfg.device_id));
+  cudaStream_t st = c->match_stream;
+  MatchScratch &m = c->match;
+  memcpy(c->h_match_q, q, (size_t)nq * 256 * sizeof(float));
+  memcpy(c->h_match_t, t, (size_t)nt * 256 * sizeof(float));
+  c->h_match_idx[c->match_cap] = nq;
+  c->h_match_idx[c->match_cap + 1] = nt;
+  CU_OK(c, cudaMemcpyAsync(m.dq, c->h_match_q, (size_t)nq * 256 * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU_OK(c, cudaMemcpyAsync(m.dt, c->h_match_t, (size_t)nt * 256 * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU_OK(c, cudaMemcpyAsync(m.dn, c->h_match_idx + c->match_cap, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
+  const int rows = nq > nt ? nq : nt;
+  int rc = run_match(c, st, m.dq, m.dt, m.dn, m.dn + 1, m, 0, rows);
+  if (rc) return rc;
+  CU_OK(c, cudaMemcpyAsync(c->h_match_idx, m.q2t, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU_OK(c, cudaMemcpyAsync(c->h_match_dist, m.dist, nq * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU_OK(c, cudaStreamSynchronize(st));
+  memcpy(q2t, c->h_match_idx, nq * sizeof(int));
+  if (dist) memcpy(dist, c->h_match_dist, nq * sizeof(float));
+  return SPFE_OK;
+}
+
+int spfe_match_frames_device(spfe_ctx *c, int32_t slot, int32_t fq, int32_t ft) {
+  int rc = check_slot(c, slot);
+  if (rc) return rc;
+  Slot &s = c->slots[slot];
+  if (fq < 0 || ft < 0 || fq >= c->cfg.max_batch || ft >= c->cfg.max_batch) return c->fail(SPFE_ERR_INVALID, "spfe_match_frames_device: frame index out of range");
+  CU_OK(c, cudaSetDevice(c->cfg.device_id));
+  const size_t cap = c->cap;
+  return run_match(c, s.stream, s.desc + fq * cap * 256, s.desc + ft * cap * 256, s.count + fq, s.count + ft, s.match,
+                   (int)(fq * cap), (int)cap);
+}
+
+int spfe_match_fetch(spfe_ctx *c, int32_t slot, int32_t fq, int32_t *q2t, float *dist, int32_t *nq) {
+  int rc = check_slot(c, slot);
+  if (rc) return rc;
+  Slot &s = c->slots[slot];
+  if (fq < 0 || fq >= c->cfg.max_batch || !q2t) return c->fail(SPFE_ERR_INVALID, "spfe_match_fetch: bad arguments");
+  CU_OK(c, cudaSetDevice(c->cfg.device_id));
+  const size_t cap = c->cap;
+  int n = 0;
+  CU_OK(c, cudaStreamSynchronize(s.stream));
+  CU_OK(c, cudaMemcpy(&n, s.count + fq, sizeof(int), cudaMemcpyDeviceToHost));
+  CU_OK(c, cudaMemcpy(q2t, s.match.q2t + fq * cap, n * sizeof(int), cudaMemcpyDeviceToHost));
+  if (dist) CU_OK(c, cudaMemcpy(dist, s.match.dist + fq * cap, n * sizeof(float), cudaMemcpyDeviceToHost));
+  if (nq) *nq = n;
+  return SPFE_OK;
+}
+
+float spfe_l2(const float *a, const float *b) {
+  // cv::norm(a, b, NORM_L2) on 1x256 CV_32F rows (sp_matcher.cpp:1636-1640)
+  float s = 0.0f;
+  for (int i = 0; i < SPFE_DESC_DIM; i++) {
+    const float d = a[i] - b[i];
+    s += d * d;
+  }
+  return std::sqrt(s);
+}
+
+// ---- introspection --------------------------------------------------------------
+int64_t spfe_debug_read(spfe_ctx *c, int32_t slot, const char *name, void *dst, size_t dst_bytes) {
+  int rc = check_slot(c, slot);
+  if (rc) return rc;
+  if (!name || !dst) return c->fail(SPFE_ERR_INVALID, "spfe_debug_read: NULL argument");
+  Slot &s = c->slots[slot];
+  const size_t B = s.batch > 0 ? s.batch : 1, px = (size_t)c->H * c->W, cells = c->cells, cap = c->cap;
+  struct Ent { const char *n; const void *p; size_t bytes; } tab[] = {
+      {"conv1a", s.a1a, B * px * 64 * 2},        {"conv1b", s.a1b, B * px / 4 * 64 * 2},
+      {"conv2a", s.a2a, B * px / 4 * 64 * 2},    {"conv2b", s.a2b, B * px / 16 * 64 * 2},
+      {"conv3a", s.a3a, B * px / 16 * 128 * 2},  {"conv3b", s.a3b, B * cells * 128 * 2},
+      {"conv4a", s.a4a, B * cells * 128 * 2},    {"conv4b", s.a4b, B * cells * 128 * 2},
+      {"heads", s.heads, B * cells * 512 * 2},   {"coarse", s.coarse, B * cells * 256 * 2},
+      {"score", s.score, B * cells * 4},         {"argmax", s.argmax, B * cells},
+      {"semi_dust", s.semi_dust, B * cells * 4}, {"dense_dust", s.dense_dust, B * cells * 4},
+      {"heat_log", s.heat_log, B * px * 4},      {"heat", s.heat, B * px * 4},
+      {"heat_inv", s.heat_inv, B * px * 4},      {"heat_minmax", s.heat_mm_f, B * 2 * 4},
+      {"count", s.count, B * 4},                 {"kp_xy", s.kp_xy, B * cap * 2 * 4},
+      {"kp_score", s.kp_score, B * cap * 4},     {"desc", s.desc, B * cap * 256 * 4},
+      {"occ_grid", s.occ, B * cells * 2}};
+  for (const Ent &e : tab)
+    if (!strcmp(e.n, name)) {
+      if (!e.p) return c->fail(SPFE_ERR_STATE, fmt("spfe_debug_read: '%s' is not produced with the current flags", name));
+      if (dst_bytes < e.bytes) return c->fail(SPFE_ERR_INVALID, fmt("spfe_debug_read: '%s' needs %zu bytes", name, e.bytes));
+      CU_OK(c, cudaSetDevice(c->cfg.device_id));
+      CU_OK(c, cudaStreamSynchronize(s.stream));
+      CU_OK(c, cudaMemcpy(dst, e.p, e.bytes, cudaMemcpyDeviceToHost));
+      return (int64_t)e.bytes;
+    }
+  return c->fail(SPFE_ERR_INVALID, fmt("spfe_debug_read: unknown tensor '%s'", name));
+}
+
+int64_t spfe_launch_count(const spfe_ctx *c) { return c ? (int64_t)c->launches.load() : 0; }
+
+int spfe_profile_device(spfe_ctx *c, int32_t slot, const void *d_gray, int32_t batch, spfe_stage_time *stages, int32_t cap) {
+  int rc = check_slot(c, slot);
+  if (rc) return rc;
+  if (!d_gray || batch < 1 || batch > c->cfg.max_batch || !stages) return c->fail(SPFE_ERR_INVALID, "spfe_profile_device: bad arguments");
+  Slot &s = c->slots[slot];
+  CU_OK(c, cudaSetDevice(c->cfg.device_id));
+  StageTimer tm;
+  tm.st = s.stream;
+  tm.on = true;
+  uint8_t *saved = s.d_gray;
+  s.d_gray = const_cast<uint8_t *>(static_cast<const uint8_t *>(d_gray));
+  rc = run_pipeline(c, s, batch, &tm);
+  s.d_gray = saved;
+  if (rc) return rc;
+  CU_OK(c, cudaStreamSynchronize(s.stream));
+  int n = 0;
+  for (size_t i = 1; i < tm.ev.size() && n < cap; i++, n++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, tm.ev[i - 1], tm.ev[i]);
+    snprintf(stages[n].name, sizeof stages[n].name, "%s", tm.names[i].c_str());
+    stages[n].ms = ms;
+    stages[n].flop = tm.flop[i];
+    stages[n].bytes = tm.bytes[i];
+  }
+  for (cudaEvent_t e : tm.ev) cudaEventDestroy(e);
+  return n;
+}
+
+}  // extern "C"

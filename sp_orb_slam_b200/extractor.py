@@ -1,0 +1,244 @@
+"""Host-side Python mirror of the reference's extractor / matcher interface.
+
+``SPExtractor`` follows ``orbslam::SPExtractor`` (reference
+``orb_slam2/include/orb_slam/cv/sp_extractor.h:49-88``): construct with
+``nfeatures``, call it with a CV_8UC1 image, get ``(keypoints, descriptors)``
+and read the side outputs ``semi_dust_ / dense_dust_ / heat_ / heat_inv_ /
+occ_grid_ / getCov() / getCov2Inv()`` afterwards.  ``SPMatcher`` follows
+``orbslam::SPMatcher`` (``sp_matcher.h:13-103``) for the brute-force path.
+Geometry and model path are constructor arguments here instead of the
+reference's ``camera::`` / ``common::`` globals.
+
+Everything runs through the C ABI in ``include/spfe.h``; nothing here computes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+class SpfeError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"spfe error {code}: {msg}")
+        self.code = code
+
+
+def _as_np(ptr, shape, dtype):
+    n = int(np.prod(shape))
+    if not ptr or n == 0:
+        return np.zeros(shape, dtype)
+    ct = {np.float32: C.c_float, np.int16: C.c_int16}[dtype]
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,)).reshape(shape).copy()
+
+
+class SPExtractor:
+    """Drop-in mirror of ``orbslam::SPExtractor`` (blocking, batch 1) plus the batched entry points."""
+
+    def __init__(self, nfeatures: int, height: int, width: int, model_path: str, *, device_id: int = 0,
+                 max_batch: int = 1, num_slots: int = 1, emit_heat: bool = True, emit_cov: bool = True):
+        self._lib = capi.load()
+        self._ctx = C.c_void_p()
+        cfg = capi.Config()
+        self._lib.spfe_default_config(C.byref(cfg), height, width, nfeatures)
+        cfg.device_id, cfg.max_batch, cfg.num_slots = device_id, max_batch, num_slots
+        cfg.flags = (capi.EMIT_HEAT if emit_heat else 0) | (capi.EMIT_COV if emit_cov else 0)
+        self._path = str(model_path).encode()
+        cfg.weights_path = self._path
+        self.cfg = cfg
+        rc = self._lib.spfe_create(C.byref(cfg), C.byref(self._ctx))
+        if rc != capi.OK:
+            msg = (self._lib.spfe_last_error(None) or b"").decode()
+            self._ctx = C.c_void_p()
+            raise SpfeError(rc, msg)
+        self.height, self.width, self.nfeatures = height, width, nfeatures
+        self.hc, self.wc = height // 8, width // 8
+        self.max_batch, self.num_slots = max_batch, num_slots
+        self.emit_heat, self.emit_cov = emit_heat or emit_cov, emit_cov
+        self.cap = min(nfeatures + 1, self.hc * self.wc)
+        # side outputs of the last operator() call (sp_extractor.h:69-77)
+        self.semi_dust_ = self.dense_dust_ = self.heat_ = self.heat_inv_ = self.occ_grid_ = self.mask_ = None
+        self._cov2 = self._cov2_inv = None
+        self._keep = None
+
+    # -- BaseExtractor scale getters (base_extractor.h:58-72): one level, factor 1.0
+    def GetLevels(self): return 1
+    def GetScaleFactor(self): return 1.0
+    def GetScaleFactors(self): return [1.0]
+    def GetInverseScaleFactors(self): return [1.0]
+    def GetScaleSigmaSquares(self): return [1.0]
+    def GetInverseScaleSigmaSquares(self): return [1.0]
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.spfe_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc < 0:
+            raise SpfeError(rc, (self._lib.spfe_last_error(self._ctx) or b"").decode())
+        return rc
+
+    def _unpack(self, o: capi.FrameOut) -> dict:
+        n, hc, wc, H, W = o.n, self.hc, self.wc, self.height, self.width
+        d = dict(n=n, kp_xy=_as_np(o.kp_xy, (n, 2), np.float32), kp_score=_as_np(o.kp_score, (n,), np.float32),
+                 desc=_as_np(o.desc, (n, 256), np.float32), occ_grid=_as_np(o.occ_grid, (hc, wc), np.int16),
+                 dense_dust=_as_np(o.dense_dust, (hc, wc), np.float32), semi_dust=_as_np(o.semi_dust, (hc, wc), np.float32))
+        if self.emit_heat:
+            d["heat"] = _as_np(o.heat, (H, W), np.float32)
+            d["heat_inv"] = _as_np(o.heat_inv, (H, W), np.float32)
+        if self.emit_cov:
+            d["kp_response"] = _as_np(o.kp_response, (n,), np.float32)
+            d["cov2"] = _as_np(o.cov2, (n, 2), np.float32)
+            d["cov2_inv"] = _as_np(o.cov2_inv, (n, 2), np.float32)
+        return d
+
+    # -- the reference operator(): image -> (keypoints, descriptors)
+    def __call__(self, image: np.ndarray, mask=None):
+        """``operator()(image, mask, keypoints, descriptors)`` -- mask is ignored, like the reference.
+
+        Returns (keypoints [n,3] = x, y, response ; descriptors [n,256] f32)."""
+        out = self.extract(image)
+        self.semi_dust_, self.dense_dust_ = out["semi_dust"], out["dense_dust"]
+        self.heat_, self.heat_inv_ = out.get("heat"), out.get("heat_inv")
+        self.occ_grid_ = out["occ_grid"]
+        self._cov2, self._cov2_inv = out.get("cov2"), out.get("cov2_inv")
+        resp = out.get("kp_response", out["kp_score"])
+        return np.concatenate([out["kp_xy"], resp[:, None]], 1), out["desc"]
+
+    def getCov(self): return self._cov2
+    def getCov2Inv(self): return self._cov2_inv
+    def getHeatMap(self): return self.heat_
+    def getMask(self): return self.mask_
+
+    def extract(self, image: np.ndarray) -> dict:
+        if image is None or image.size == 0:
+            raise RuntimeError("input image is empty")                 # sp_extractor.cpp:364-365
+        assert image.dtype == np.uint8 and image.ndim == 2             # sp_extractor.cpp:368
+        if image.shape != (self.height, self.width):
+            raise SpfeError(capi.ERR_INVALID, f"image is {image.shape}, extractor was built for {(self.height, self.width)}")
+        img = np.ascontiguousarray(image) if image.strides[1] != 1 else image
+        o = capi.FrameOut()
+        self._check(self._lib.spfe_extract(self._ctx, img.ctypes.data_as(C.c_void_p), img.strides[0], C.byref(o)))
+        return self._unpack(o)
+
+    # -- batched / pipelined entry points (no reference equivalent: sp_extractor.cpp:70 "TODO: batch-size")
+    def submit(self, slot: int, frames) -> None:
+        frames = [np.ascontiguousarray(f) for f in frames]
+        for f in frames:
+            assert f.dtype == np.uint8 and f.shape == (self.height, self.width)
+        self._keep = frames
+        ptrs = (C.c_void_p * len(frames))(*[f.ctypes.data for f in frames])
+        self._check(self._lib.spfe_submit(self._ctx, slot, ptrs, len(frames), self.width))
+
+    def wait(self, slot: int, n_frames: int, unpack: bool = True):
+        outs = (capi.FrameOut * n_frames)()
+        self._check(self._lib.spfe_wait(self._ctx, slot, outs))
+        return [self._unpack(o) for o in outs] if unpack else outs
+
+    def extract_batch(self, frames, slot: int = 0):
+        self.submit(slot, frames)
+        return self.wait(slot, len(frames))
+
+    def submit_device(self, slot: int, d_ptr: int, batch: int) -> None:
+        """Frames already in HBM ([batch][H][W] u8 at device address ``d_ptr``); results stay on the device."""
+        self._check(self._lib.spfe_submit_device(self._ctx, slot, C.c_void_p(d_ptr), batch))
+
+    def sync(self, slot: int) -> None:
+        self._check(self._lib.spfe_slot_sync(self._ctx, slot))
+
+    def match_frames_device(self, slot: int, fq: int, ft: int) -> None:
+        self._check(self._lib.spfe_match_frames_device(self._ctx, slot, fq, ft))
+
+    def match_fetch(self, slot: int, fq: int):
+        q2t = np.empty(self.cap, np.int32)
+        dist = np.empty(self.cap, np.float32)
+        n = C.c_int32()
+        self._check(self._lib.spfe_match_fetch(self._ctx, slot, fq, q2t.ctypes.data_as(C.c_void_p),
+                                               dist.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return q2t[:n.value].copy(), dist[:n.value].copy()
+
+    def match(self, q: np.ndarray, t: np.ndarray):
+        q = np.ascontiguousarray(q, np.float32).reshape(-1, 256)
+        t = np.ascontiguousarray(t, np.float32).reshape(-1, 256)
+        q2t = np.empty(max(len(q), 1), np.int32)
+        dist = np.empty(max(len(q), 1), np.float32)
+        self._check(self._lib.spfe_match_mutual_nn(self._ctx, q.ctypes.data_as(C.c_void_p), len(q),
+                                                   t.ctypes.data_as(C.c_void_p), len(t),
+                                                   q2t.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p)))
+        return q2t[:len(q)], dist[:len(q)]
+
+    # -- introspection
+    _DEBUG = {"conv1a": (lambda s: (s.height, s.width, 64), np.float16), "conv1b": (lambda s: (s.height // 2, s.width // 2, 64), np.float16),
+              "conv2a": (lambda s: (s.height // 2, s.width // 2, 64), np.float16), "conv2b": (lambda s: (s.height // 4, s.width // 4, 64), np.float16),
+              "conv3a": (lambda s: (s.height // 4, s.width // 4, 128), np.float16), "conv3b": (lambda s: (s.hc, s.wc, 128), np.float16),
+              "conv4a": (lambda s: (s.hc, s.wc, 128), np.float16), "conv4b": (lambda s: (s.hc, s.wc, 128), np.float16),
+              "heads": (lambda s: (s.hc, s.wc, 512), np.float16), "coarse": (lambda s: (s.hc, s.wc, 256), np.float16),
+              "score": (lambda s: (s.hc, s.wc), np.float32), "argmax": (lambda s: (s.hc, s.wc), np.uint8),
+              "semi_dust": (lambda s: (s.hc, s.wc), np.float32), "dense_dust": (lambda s: (s.hc, s.wc), np.float32),
+              "heat_log": (lambda s: (s.height, s.width), np.float32), "heat": (lambda s: (s.height, s.width), np.float32),
+              "heat_inv": (lambda s: (s.height, s.width), np.float32), "heat_minmax": (lambda s: (2,), np.float32),
+              "count": (lambda s: (), np.int32), "kp_xy": (lambda s: (s.cap, 2), np.float32), "kp_score": (lambda s: (s.cap,), np.float32),
+              "desc": (lambda s: (s.cap, 256), np.float32), "occ_grid": (lambda s: (s.hc, s.wc), np.int16)}
+
+    def debug_read(self, slot: int, name: str, batch: int) -> np.ndarray:
+        shape_fn, dt = self._DEBUG[name]
+        arr = np.empty((batch,) + tuple(shape_fn(self)), dt)
+        self._check(self._lib.spfe_debug_read(self._ctx, slot, name.encode(), arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+        return arr
+
+    def launch_count(self) -> int:
+        return int(self._lib.spfe_launch_count(self._ctx))
+
+    def profile_device(self, slot: int, d_ptr: int, batch: int):
+        st = (capi.StageTime * 32)()
+        n = self._check(self._lib.spfe_profile_device(self._ctx, slot, C.c_void_p(d_ptr), batch, st, 32))
+        return [dict(name=st[i].name.decode(), ms=st[i].ms, flop=st[i].flop, bytes=st[i].bytes) for i in range(n)]
+
+
+class SPMatcher:
+    """Mirror of ``orbslam::SPMatcher`` for the brute-force path (sp_matcher.h:16-19,48-49,86-93)."""
+
+    TH_HIGH, TH_LOW, HISTO_LENGTH = 0.7, 0.3, 30           # sp_matcher.cpp:18-20
+
+    def __init__(self, extractor: SPExtractor, nnratio: float = 0.6):
+        self._ex = extractor
+        self.mfNNratio = nnratio
+
+    @staticmethod
+    def DescriptorDistance(a: np.ndarray, b: np.ndarray) -> float:
+        a = np.ascontiguousarray(a, np.float32).ravel()
+        b = np.ascontiguousarray(b, np.float32).ravel()
+        assert a.size == 256 and b.size == 256
+        return float(capi.load().spfe_l2(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)))
+
+    def SearchByBruteForce(self, desc1: np.ndarray, valid1: np.ndarray, desc2: np.ndarray, valid2: np.ndarray | None = None):
+        """Both reference overloads on plain arrays.
+
+        (KeyFrame*, Frame&) [sp_matcher.cpp:1642-1674]: ``desc1/valid1`` = key-frame descriptors and "has a good map
+        point" flags (train side), ``desc2`` = all frame descriptors (query side), ``valid2=None``.  Returns
+        ``matches12`` of length len(desc2): index into desc1 of the matched map point, -1 = none.
+        (KeyFrame*, KeyFrame*) [sp_matcher_loop.cpp:334-376]: pass ``valid2`` too; returns ``(matches12, n)`` with
+        matches12 of length len(desc1): index into desc2, -1 = none.
+        """
+        idx_t = np.flatnonzero(valid1)
+        if valid2 is None:
+            q2t, _ = self._ex.match(desc2, desc1[idx_t])
+            out = np.full(len(desc2), -1, np.int64)
+            hit = q2t >= 0
+            out[hit] = idx_t[q2t[hit]]
+            return out
+        idx_q = np.flatnonzero(valid2)
+        q2t, _ = self._ex.match(desc2[idx_q], desc1[idx_t])
+        out = np.full(len(desc1), -1, np.int64)
+        hit = np.flatnonzero(q2t >= 0)
+        out[idx_t[q2t[hit]]] = idx_q[hit]
+        return out, int(len(hit))
