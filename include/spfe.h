@@ -54,7 +54,11 @@ enum {
 
 enum {
   SPFE_EMIT_HEAT = 1u << 0, /* produce heat / heat_inv (H x W f32 each) and copy them to the host  */
-  SPFE_EMIT_COV = 1u << 1   /* run computeCovariance (implies SPFE_EMIT_HEAT); fills kp_response from heat_inv */
+  SPFE_EMIT_COV = 1u << 1,  /* run computeCovariance (implies SPFE_EMIT_HEAT); fills kp_response from heat_inv */
+  SPFE_MATCH_PREV = 1u << 2 /* a slot is one camera stream: also match every frame against the previous frame of
+                               that slot (mutual NN, all descriptors as train set -- the BFMatcher call of
+                               Tracking::trackReferenceKeyFrameANN, tracker.cpp:372-417); frame 0 of a batch is
+                               matched against the last frame of the slot's previous batch */
 };
 
 typedef struct spfe_ctx spfe_ctx;
@@ -92,6 +96,9 @@ typedef struct spfe_frame_out {
   const float *heat_inv;   /* [H][W] or NULL                          -> heat_inv_ */
   const float *cov2;       /* [n][2] or NULL                          -> getCov() */
   const float *cov2_inv;   /* [n][2] or NULL                          -> getCov2Inv() */
+  int32_t n_prev;          /* SPFE_MATCH_PREV: keypoints of the previous frame of this stream (0 = none yet) */
+  const int32_t *match_prev; /* [n] index into the previous frame's keypoints or -1; NULL without SPFE_MATCH_PREV */
+  const float *match_dist; /* [n] L2 distance to the nearest previous descriptor */
 } spfe_frame_out;
 
 int spfe_create(const spfe_config *cfg, spfe_ctx **out);
@@ -121,11 +128,8 @@ int spfe_slot_sync(spfe_ctx *ctx, int32_t slot);
  * Thread-safe (per-call scratch), as SearchByBruteForce runs on two threads. */
 int spfe_match_mutual_nn(spfe_ctx *ctx, const float *q, int32_t nq, const float *t, int32_t nt,
                          int32_t *q2t, float *dist);
-/* Device-resident variant used by the extract+match stream path: matches the
- * descriptors of frame `fq` against those of frame `ft` of the same slot
- * (both already extracted); results in device memory, fetched by spfe_match_fetch. */
-int spfe_match_frames_device(spfe_ctx *ctx, int32_t slot, int32_t fq, int32_t ft);
-int spfe_match_fetch(spfe_ctx *ctx, int32_t slot, int32_t fq, int32_t *q2t, float *dist, int32_t *nq);
+/* SPFE_MATCH_PREV: forget the slot's previous frame (start of a new camera stream). */
+int spfe_reset_stream(spfe_ctx *ctx, int32_t slot);
 
 /* L2 distance between two 256-d descriptors (host, scalar). */
 float spfe_l2(const float *a, const float *b);
@@ -136,6 +140,13 @@ float spfe_l2(const float *a, const float *b);
  * "dense_dust", "heat_log" (f32), "argmax" (u8), "count" (i32 per frame).
  * Returns bytes copied or a negative error. */
 int64_t spfe_debug_read(spfe_ctx *ctx, int32_t slot, const char *name, void *dst, size_t dst_bytes);
+/* Device-side stopwatch on a slot's stream (CUDA events): start, enqueue any number of submits, stop.
+ * spfe_timer_stop waits for the stream and returns the elapsed milliseconds between the two events. */
+int spfe_timer_start(spfe_ctx *ctx, int32_t slot);
+int spfe_timer_stop(spfe_ctx *ctx, int32_t slot, float *ms);
+/* Parses a weight file with the library's own readers (no GPU needed).  Returns the number of
+ * parameters (1300865 for SuperPoint) or a negative error; message in err[0..errcap). */
+int64_t spfe_check_weights(const char *path, char *err, size_t errcap);
 /* Number of kernels this library has launched on the context so far. */
 int64_t spfe_launch_count(const spfe_ctx *ctx);
 /* Runs one device-resident batch with CUDA events around every stage; writes

@@ -8,12 +8,12 @@ import os
 from . import build as _build
 
 DESC_DIM = 256
-EMIT_HEAT, EMIT_COV = 1, 2
+EMIT_HEAT, EMIT_COV, MATCH_PREV = 1, 2, 4
 OK, ERR_INVALID, ERR_EMPTY, ERR_WEIGHTS, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
 
 EXPORTS = ["spfe_default_config", "spfe_create", "spfe_destroy", "spfe_last_error", "spfe_extract", "spfe_submit",
-           "spfe_wait", "spfe_submit_device", "spfe_slot_sync", "spfe_match_mutual_nn", "spfe_match_frames_device",
-           "spfe_match_fetch", "spfe_l2", "spfe_debug_read", "spfe_launch_count", "spfe_profile_device"]
+           "spfe_wait", "spfe_submit_device", "spfe_slot_sync", "spfe_match_mutual_nn", "spfe_reset_stream", "spfe_timer_start",
+           "spfe_timer_stop", "spfe_check_weights", "spfe_l2", "spfe_debug_read", "spfe_launch_count", "spfe_profile_device"]
 
 
 class Config(C.Structure):
@@ -28,7 +28,8 @@ _FP = C.POINTER(C.c_float)
 class FrameOut(C.Structure):
     _fields_ = [("n", C.c_int32), ("kp_xy", _FP), ("kp_score", _FP), ("kp_response", _FP), ("desc", _FP),
                 ("occ_grid", C.POINTER(C.c_int16)), ("dense_dust", _FP), ("semi_dust", _FP), ("heat", _FP),
-                ("heat_inv", _FP), ("cov2", _FP), ("cov2_inv", _FP)]
+                ("heat_inv", _FP), ("cov2", _FP), ("cov2_inv", _FP), ("n_prev", C.c_int32),
+                ("match_prev", C.POINTER(C.c_int32)), ("match_dist", _FP)]
 
 
 class StageTime(C.Structure):
@@ -66,8 +67,11 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.spfe_submit_device.argtypes = [vp, i32, vp, i32]
     L.spfe_slot_sync.argtypes = [vp, i32]
     L.spfe_match_mutual_nn.argtypes = [vp, vp, i32, vp, i32, vp, vp]
-    L.spfe_match_frames_device.argtypes = [vp, i32, i32, i32]
-    L.spfe_match_fetch.argtypes = [vp, i32, i32, vp, vp, C.POINTER(i32)]
+    L.spfe_reset_stream.argtypes = [vp, i32]
+    L.spfe_timer_start.argtypes = [vp, i32]
+    L.spfe_timer_stop.argtypes = [vp, i32, C.POINTER(C.c_float)]
+    L.spfe_check_weights.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+    L.spfe_check_weights.restype = i64
     L.spfe_l2.argtypes = [vp, vp]
     L.spfe_l2.restype = C.c_float
     L.spfe_debug_read.argtypes = [vp, i32, C.c_char_p, vp, C.c_size_t]

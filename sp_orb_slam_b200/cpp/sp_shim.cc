@@ -1,0 +1,92 @@
+// Implementation of the drop-in classes declared in sp_extractor.h / sp_matcher.h.
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+
+#include "sp_extractor.h"
+#include "sp_matcher.h"
+
+namespace orbslam {
+
+#ifndef SPFE_WITH_ORBSLAM_CONFIG
+namespace camera { int width = 752, height = 480; }
+namespace common { std::string model_path; }
+#endif
+
+const float SPMatcher::TH_HIGH = 0.7f;  // sp_matcher.cpp:18
+const float SPMatcher::TH_LOW = 0.3f;   // sp_matcher.cpp:19
+const int SPMatcher::HISTO_LENGTH = 30; // sp_matcher.cpp:20
+
+// Scale-pyramid bookkeeping of the reference base class (base_extractor.h:13-49).
+// SuperPoint uses one level with factor 1.0 (sp_extractor.cpp:343).
+BaseExtractor::BaseExtractor(int nfeatures_, float scale_factor, int nlevels_, int ini_th_fast, int min_th_fast)
+    : nfeatures(nfeatures_), scaleFactor(scale_factor), nlevels(nlevels_), iniThFAST(ini_th_fast), minThFAST(min_th_fast) {
+  mvScaleFactor.assign(nlevels, 1.0f);
+  mvLevelSigma2.assign(nlevels, 1.0f);
+  for (int l = 1; l < nlevels; l++) {
+    mvScaleFactor[l] = static_cast<float>(mvScaleFactor[l - 1] * scaleFactor);
+    mvLevelSigma2[l] = mvScaleFactor[l] * mvScaleFactor[l];
+  }
+  mvInvScaleFactor.resize(nlevels);
+  mvInvLevelSigma2.resize(nlevels);
+  for (int l = 0; l < nlevels; l++) {
+    mvInvScaleFactor[l] = 1.0f / mvScaleFactor[l];
+    mvInvLevelSigma2[l] = 1.0f / mvLevelSigma2[l];
+  }
+  mvImagePyramid.resize(nlevels);
+  mnFeaturesPerLevel.assign(nlevels, 0);
+  const float inv = 1.0f / static_cast<float>(scaleFactor);
+  float per_level = nlevels > 1 ? nfeatures * (1 - inv) / (1 - static_cast<float>(std::pow(static_cast<double>(inv), static_cast<double>(nlevels))))
+                                : static_cast<float>(nfeatures);
+  int used = 0;
+  for (int l = 0; l + 1 < nlevels; l++) {
+    mnFeaturesPerLevel[l] = static_cast<int>(std::lround(per_level));
+    used += mnFeaturesPerLevel[l];
+    per_level *= inv;
+  }
+  mnFeaturesPerLevel[nlevels - 1] = nfeatures - used > 0 ? nfeatures - used : 0;
+}
+
+SPExtractor::SPExtractor(int nfeatures_) : BaseExtractor(nfeatures_, 1.0f, 1, 1, 1), num_feature_(nfeatures_) {
+  spfe_config cfg;
+  spfe_default_config(&cfg, camera::height, camera::width, nfeatures_);
+  cfg.weights_path = common::model_path.c_str();
+  if (spfe_create(&cfg, &ctx_) != SPFE_OK) throw std::runtime_error(std::string("SPExtractor: ") + spfe_last_error(nullptr));
+  SPMatcher::SetBackend(ctx_);
+}
+
+SPExtractor::~SPExtractor() { spfe_destroy(ctx_); }
+
+void SPExtractor::operator()(cv::InputArray image_, cv::InputArray /*mask*/, std::vector<cv::KeyPoint> &keypoints,
+                             cv::OutputArray descriptors) {
+  const cv::Mat &image = image_.getMat();
+  if (image.empty()) throw std::runtime_error("input image is empty");  // sp_extractor.cpp:364-365
+  if (image.type() != CV_8UC1) throw std::runtime_error("SPExtractor expects CV_8UC1");  // assert at :368
+  if (image.rows != camera::height || image.cols != camera::width) throw std::runtime_error("SPExtractor: image size differs from camera::height/width");
+  spfe_frame_out o;
+  const int rc = spfe_extract(ctx_, image.data, image.step, &o);
+  if (rc == SPFE_ERR_EMPTY) throw std::runtime_error("input image is empty");
+  if (rc != SPFE_OK) throw std::runtime_error(spfe_last_error(ctx_));
+  const int hc = image.rows / 8, wc = image.cols / 8;
+  auto wrap = [](int r, int c, int type, const void *src) { return cv::Mat(r, c, type, const_cast<void *>(src)).clone(); };
+  semi_dust_ = wrap(hc, wc, CV_32FC1, o.semi_dust);
+  dense_dust_ = wrap(hc, wc, CV_32FC1, o.dense_dust);
+  occ_grid_ = wrap(hc, wc, CV_16SC1, o.occ_grid);
+  heat_ = wrap(image.rows, image.cols, CV_32FC1, o.heat);
+  heat_inv_ = wrap(image.rows, image.cols, CV_32FC1, o.heat_inv);
+  keypoints.clear();
+  keypoints.reserve(o.n);
+  cov2_.clear();
+  cov2_inv_.clear();
+  for (int i = 0; i < o.n; i++) {
+    cv::KeyPoint kp(o.kp_xy[2 * i], o.kp_xy[2 * i + 1], 1.0f);  // size 1, angle -1, octave 0 (sp_extractor.cpp:231-232)
+    kp.response = o.kp_response[i];                              // sp_extractor.cpp:271
+    keypoints.push_back(kp);
+    cov2_.emplace_back(o.cov2[2 * i], o.cov2[2 * i + 1]);
+    cov2_inv_.emplace_back(o.cov2_inv[2 * i], o.cov2_inv[2 * i + 1]);
+  }
+  descriptors.create(o.n, SPFE_DESC_DIM, CV_32FC1);  // sp_extractor.cpp:512-513
+  if (o.n > 0) memcpy(descriptors.getMat().data, o.desc, static_cast<size_t>(o.n) * SPFE_DESC_DIM * sizeof(float));
+}
+
+}  // namespace orbslam

@@ -188,48 +188,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(N);
-      uint32_t it = 0, jt = 0, tcount = 0;
-      if (WRES) mbar_wait(w_full, 0);
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, tcount++) {
-        const int acc = tcount & 1;
-        mbar_wait(t_empty(acc), ((tcount >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
-        uint32_t accumulate = 0;
-        for (int cb = 0; cb < CB; cb++)
-          for (int dx = 0; dx < NDX; dx++, it++) {
-            const int s = it % SA;
-            mbar_wait(a_full(s), (it / SA) & 1);
-            const uint32_t a_slab = smem_u32(sA + s * Cfg::SLAB_BYTES);
-            for (int dy = 0; dy < NDY; dy++) {
-              uint32_t b_blk;
-              int sb = 0;
-              if (WRES) {
-                b_blk = smem_u32(sB + ((dy * NDX + dx) * CB + cb) * Cfg::BBLK_BYTES);
-              } else {
-                sb = jt % SB;
-                mbar_wait(b_full(sb), (jt / SB) & 1);
-                b_blk = smem_u32(sB + sb * Cfg::BBLK_BYTES);
-              }
-              tc_fence_after();
-              const uint32_t a_tap = a_slab + dy * 1024;
+    // ------------------------------------------------ MMA issuer
+    // The whole warp runs the loop so that every address / descriptor stays warp-uniform (uniform
+    // datapath, no per-MMA election); one elected lane issues the tcgen05.mma / commit instructions.
+    constexpr uint32_t idesc = umma_idesc_f16(N);
+    uint32_t it = 0, jt = 0, tcount = 0;
+    if (WRES) mbar_wait(w_full, 0);
+    const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, tcount++) {
+      const uint32_t acc = tcount & 1;
+      mbar_wait(t_empty(acc), ((tcount >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+      uint32_t accumulate = 0;
+#pragma unroll 1
+      for (int cbdx = 0; cbdx < CB * NDX; cbdx++, it++) {
+        const int cb = cbdx / NDX, dx = cbdx - cb * NDX;
+        const uint32_t s = it % SA;
+        mbar_wait(a_full(s), (it / SA) & 1);
+        const uint64_t a_desc0 = umma_desc_sw128(sA_u + s * Cfg::SLAB_BYTES);
 #pragma unroll
-              for (int k = 0; k < 4; k++) {
-                umma_f16(d_tmem, umma_desc_sw128(a_tap + k * 32), umma_desc_sw128(b_blk + k * 32), idesc, accumulate);
-                accumulate = 1;
-              }
-              if (!WRES) {
-                umma_commit(b_empty(sb));
-                jt++;
-              }
-            }
-            umma_commit(a_empty(s));
+        for (int dy = 0; dy < NDY; dy++) {
+          uint32_t sb = 0;
+          uint64_t b_desc;
+          if (WRES) {
+            b_desc = umma_desc_sw128(sB_u + ((dy * NDX + dx) * CB + cb) * Cfg::BBLK_BYTES);
+          } else {
+            sb = jt % SB;
+            mbar_wait(b_full(sb), (jt / SB) & 1);
+            b_desc = umma_desc_sw128(sB_u + sb * Cfg::BBLK_BYTES);
+            jt++;
           }
-        umma_commit(t_full(acc));
+          tc_fence_after();
+          const uint64_t a_desc = a_desc0 + static_cast<uint64_t>(dy * (1024 >> 4));
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {  // +32 B per k-step == +2 in the (addr >> 4) field
+              umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accumulate | k);
+            }
+            if (!WRES) umma_commit(b_empty(sb));
+          }
+          accumulate = 1;
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit(a_empty(s));
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(t_full(acc));
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue (TMEM -> regs -> global)

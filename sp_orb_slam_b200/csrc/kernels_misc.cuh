@@ -15,54 +15,59 @@ namespace spfe {
 // conv1a: K = 9 is not a tensor-core shape and this layer is the precision-
 // critical one (|w| up to 197, SURVEY.md §7 hard part 1): fp32 FFMA on CUDA
 // cores, input scaled exactly like cv::Mat::convertTo(CV_32F, 1/255).
-// One thread = one pixel x 64 output channels; block = 32 x 8 pixels.
+// Thread = (pixel slot, 8-channel group): the 9x8 weights of the group live in
+// registers for the whole 64x16-pixel tile, inputs come from a shared patch
+// (broadcast reads), and a warp stores 4 pixels x 128 B = 512 contiguous bytes
+// per instruction.  72 FFMA per 9 LDS + 1 STG.128.
 // ---------------------------------------------------------------------------
+constexpr int C1A_TW = 64, C1A_TH = 16;
 __global__ void __launch_bounds__(256) conv1a_kernel(const uint8_t *__restrict__ in, __half *__restrict__ out,
                                                      const float *__restrict__ wgt /*[9][64]*/,
                                                      const float *__restrict__ bias /*[64]*/, int B, int H, int W) {
-  __shared__ float s_in[10][36];
-  __shared__ __align__(16) float s_w[9][64];
-  __shared__ __align__(16) float s_b[64];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8, b = blockIdx.z;
+  __shared__ float s_in[C1A_TH + 2][C1A_TW + 2];
+  const int g = threadIdx.x & 7, slot = threadIdx.x >> 3;  // channel group, pixel slot 0..31
+  const int x0 = blockIdx.x * C1A_TW, y0 = blockIdx.y * C1A_TH, b = blockIdx.z;
   const uint8_t *img = in + static_cast<size_t>(b) * H * W;
-  for (int i = threadIdx.x; i < 9 * 64; i += 256) (&s_w[0][0])[i] = wgt[i];
-  if (threadIdx.x < 64) s_b[threadIdx.x] = bias[threadIdx.x];
+  float w[9][8], bs[8];
+#pragma unroll
+  for (int t = 0; t < 9; t++) {
+    const float4 lo = *reinterpret_cast<const float4 *>(wgt + t * 64 + g * 8);
+    const float4 hi = *reinterpret_cast<const float4 *>(wgt + t * 64 + g * 8 + 4);
+    w[t][0] = lo.x; w[t][1] = lo.y; w[t][2] = lo.z; w[t][3] = lo.w;
+    w[t][4] = hi.x; w[t][5] = hi.y; w[t][6] = hi.z; w[t][7] = hi.w;
+  }
+#pragma unroll
+  for (int c = 0; c < 8; c++) bs[c] = bias[g * 8 + c];
   const float scale = 1.0f / 255.0f;
-  for (int i = threadIdx.x; i < 10 * 34; i += 256) {
-    const int r = i / 34, c = i % 34;
+  for (int i = threadIdx.x; i < (C1A_TH + 2) * (C1A_TW + 2); i += 256) {
+    const int r = i / (C1A_TW + 2), c = i - r * (C1A_TW + 2);
     const int y = y0 + r - 1, x = x0 + c - 1;
     float v = 0.f;
     if (y >= 0 && y < H && x >= 0 && x < W) v = static_cast<float>(img[static_cast<size_t>(y) * W + x]) * scale;
     s_in[r][c] = v;
   }
   __syncthreads();
-  const int x = x0 + tx, y = y0 + ty;
-  if (x >= W || y >= H) return;
-  float acc[64];
+#pragma unroll 2
+  for (int p = slot; p < C1A_TW * C1A_TH; p += 32) {
+    const int ty = p / C1A_TW, tx = p - ty * C1A_TW;
+    const int x = x0 + tx, y = y0 + ty;
+    float acc[8];
 #pragma unroll
-  for (int c = 0; c < 64; c++) acc[c] = s_b[c];
+    for (int c = 0; c < 8; c++) acc[c] = bs[c];
 #pragma unroll
-  for (int t = 0; t < 9; t++) {
-    const float xin = s_in[ty + t / 3][tx + t % 3];
+    for (int t = 0; t < 9; t++) {
+      const float xin = s_in[ty + t / 3][tx + t % 3];
 #pragma unroll
-    for (int c4 = 0; c4 < 16; c4++) {
-      const float4 w4 = *reinterpret_cast<const float4 *>(&s_w[t][c4 * 4]);
-      acc[c4 * 4 + 0] = fmaf(w4.x, xin, acc[c4 * 4 + 0]);
-      acc[c4 * 4 + 1] = fmaf(w4.y, xin, acc[c4 * 4 + 1]);
-      acc[c4 * 4 + 2] = fmaf(w4.z, xin, acc[c4 * 4 + 2]);
-      acc[c4 * 4 + 3] = fmaf(w4.w, xin, acc[c4 * 4 + 3]);
+      for (int c = 0; c < 8; c++) acc[c] = fmaf(w[t][c], xin, acc[c]);
     }
-  }
-  uint4 *dst = reinterpret_cast<uint4 *>(out + ((static_cast<size_t>(b) * H + y) * W + x) * 64);
-#pragma unroll
-  for (int g = 0; g < 8; g++) {
-    uint4 o;
-    o.x = pack_h2(fmaxf(acc[g * 8 + 0], 0.f), fmaxf(acc[g * 8 + 1], 0.f));
-    o.y = pack_h2(fmaxf(acc[g * 8 + 2], 0.f), fmaxf(acc[g * 8 + 3], 0.f));
-    o.z = pack_h2(fmaxf(acc[g * 8 + 4], 0.f), fmaxf(acc[g * 8 + 5], 0.f));
-    o.w = pack_h2(fmaxf(acc[g * 8 + 6], 0.f), fmaxf(acc[g * 8 + 7], 0.f));
-    dst[g] = o;
+    if (x < W && y < H) {
+      uint4 o;
+      o.x = pack_h2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
+      o.y = pack_h2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+      o.z = pack_h2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
+      o.w = pack_h2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+      *reinterpret_cast<uint4 *>(out + ((static_cast<size_t>(b) * H + y) * W + x) * 64 + g * 8) = o;
+    }
   }
 }
 

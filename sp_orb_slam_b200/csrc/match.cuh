@@ -40,11 +40,34 @@ __global__ void match_init_kernel(unsigned long long *rowbest, unsigned long lon
   }
 }
 
-// grid (ceil(cap/64) train tiles, ceil(cap/64) query tiles), 256 threads, 4x4 outputs per thread.
-__global__ void __launch_bounds__(256) match_dist_kernel(const float *__restrict__ q, const float *__restrict__ t,
-                                                         const int *__restrict__ nq_p, const int *__restrict__ nt_p,
-                                                         unsigned long long *rowbest, unsigned long long *colbest) {
-  const int nq = *nq_p, nt = *nt_p;
+// One matching problem per blockIdx.z.  Problem z matches query set z against
+// train set z-1; train set of problem 0 is the "carry" (last frame of the
+// previous batch of the same camera stream), or an explicit set for the
+// host-pointer API (q_stride == 0 && z == 0).
+struct MatchArgs {
+  const float *q;        // [Z][cap][256] query descriptors of frame z
+  const int *nq;         // [Z]
+  const float *t0;       // train set of problem 0
+  const int *nt0;        // its row count
+  unsigned long long *rowbest, *colbest;  // [Z][cap]
+  int *q2t;              // [Z][cap]
+  float *dist;           // [Z][cap]
+  int cap;
+};
+__device__ __forceinline__ void match_problem(const MatchArgs &a, int z, const float *&q, const float *&t, int &nq, int &nt) {
+  q = a.q + static_cast<size_t>(z) * a.cap * 256;
+  nq = a.nq[z];
+  if (z == 0) { t = a.t0; nt = *a.nt0; }
+  else { t = a.q + static_cast<size_t>(z - 1) * a.cap * 256; nt = a.nq[z - 1]; }
+}
+
+// grid (ceil(cap/64) train tiles, ceil(cap/64) query tiles, Z), 256 threads, 4x4 outputs per thread.
+__global__ void __launch_bounds__(256) match_dist_kernel(const MatchArgs ma) {
+  const float *q, *t;
+  int nq, nt;
+  match_problem(ma, blockIdx.z, q, t, nq, nt);
+  unsigned long long *rowbest = ma.rowbest + static_cast<size_t>(blockIdx.z) * ma.cap;
+  unsigned long long *colbest = ma.colbest + static_cast<size_t>(blockIdx.z) * ma.cap;
   const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
   if (i0 >= nq || j0 >= nt) return;
   __shared__ float sq[16][68], st[16][68];
@@ -125,13 +148,16 @@ __global__ void __launch_bounds__(256) match_dist_kernel(const float *__restrict
   }
 }
 
-__global__ void match_final_kernel(const unsigned long long *__restrict__ rowbest, const unsigned long long *__restrict__ colbest,
-                                   const int *__restrict__ nq_p, int *__restrict__ q2t, float *__restrict__ dist, int cap) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void match_final_kernel(const MatchArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, cap = a.cap;
   if (i >= cap) return;
+  const size_t off = static_cast<size_t>(blockIdx.y) * cap;
+  const unsigned long long *rowbest = a.rowbest + off, *colbest = a.colbest + off;
+  int *q2t = a.q2t + off;
+  float *dist = a.dist + off;
   int out = -1;
   float d = 0.f;
-  if (i < *nq_p) {
+  if (i < a.nq[blockIdx.y]) {
     const unsigned long long rb = rowbest[i];
     if (rb != ~0ull) {
       const int j = static_cast<int>(rb & 0xFFFFFFFFu);

@@ -81,12 +81,17 @@ struct Slot {
   unsigned long long *scratch = nullptr;
   CUtensorMap tmA[NLAYERS];
   MatchScratch match;
+  float *carry_desc = nullptr;  // [cap][256] last frame of the previous batch (SPFE_MATCH_PREV)
+  int *carry_count = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // pinned host mirrors
   uint8_t *h_gray = nullptr;
   int *h_count = nullptr;
   float *h_kp_xy = nullptr, *h_kp_score = nullptr, *h_desc = nullptr, *h_dense = nullptr, *h_semi = nullptr,
         *h_heat = nullptr, *h_heat_inv = nullptr;
   int16_t *h_occ = nullptr;
+  int *h_match = nullptr, *h_nprev = nullptr;
+  float *h_mdist = nullptr;
   std::vector<float> cov2, cov2_inv, resp;
 };
 
@@ -96,7 +101,7 @@ struct spfe_ctx {
   spfe_config cfg;
   std::string weights_path;
   int H = 0, W = 0, hc = 0, wc = 0, cells = 0, cap = 0, num_sms = 0;
-  bool heat = false, cov = false;
+  bool heat = false, cov = false, match_prev = false;
   EncodeTiledFn encode = nullptr;
   float *w1a = nullptr, *b1a = nullptr;  // conv1a fp32 [9][64], [64]
   Layer layers[NLAYERS];
@@ -246,6 +251,8 @@ struct StageTimer {
   }
 };
 
+int run_match(spfe_ctx *c, cudaStream_t st, const MatchArgs &a, int Z, int rows);
+
 // Enqueue the whole per-batch launch plan on the slot's stream.
 int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
   const int H = c->H, W = c->W, hc = c->hc, wc = c->wc;
@@ -257,7 +264,7 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     c->launches++;
   }
   {  // conv1a: u8 -> fp16 NHWC64
-    dim3 grid((W + 31) / 32, (H + 7) / 8, B);
+    dim3 grid((W + C1A_TW - 1) / C1A_TW, (H + C1A_TH - 1) / C1A_TH, B);
     conv1a_kernel<<<grid, 256, 0, st>>>(s.d_gray, s.a1a, c->w1a, c->b1a, B, H, W);
     c->launches++;
     CU_OK(c, cudaGetLastError());
@@ -325,6 +332,17 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     c->launches++;
     CU_OK(c, cudaGetLastError());
     mark("heat_norm", 0, 12.0 * H * W * B);
+  }
+  if (c->match_prev) {
+    // frame b vs frame b-1 (frame 0 vs the carry), all in three launches; then the last frame becomes the carry
+    MatchArgs a;
+    a.q = s.desc; a.nq = s.count; a.t0 = s.carry_desc; a.nt0 = s.carry_count;
+    a.rowbest = s.match.rowbest; a.colbest = s.match.colbest; a.q2t = s.match.q2t; a.dist = s.match.dist; a.cap = c->cap;
+    if ((rc = run_match(c, st, a, B, c->cap))) return rc;
+    CU_OK(c, cudaMemcpyAsync(s.match.dn, s.carry_count, sizeof(int), cudaMemcpyDeviceToDevice, st));  // n_prev of frame 0
+    CU_OK(c, cudaMemcpyAsync(s.carry_desc, s.desc + static_cast<size_t>(B - 1) * c->cap * 256, static_cast<size_t>(c->cap) * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CU_OK(c, cudaMemcpyAsync(s.carry_count, s.count + (B - 1), sizeof(int), cudaMemcpyDeviceToDevice, st));
+    mark("match_prev", 2.0 * 256 * c->cap * c->cap * B, 2048.0 * c->cap * B);
   }
   s.batch = B;
   return SPFE_OK;
@@ -501,7 +519,16 @@ static int create_impl(spfe_ctx *c) {
     if ((rc = dev_alloc(c, &s.match.colbest, Bm * cap))) return rc;
     if ((rc = dev_alloc(c, &s.match.q2t, Bm * cap))) return rc;
     if ((rc = dev_alloc(c, &s.match.dist, Bm * cap))) return rc;
+    if ((rc = dev_alloc(c, &s.match.dn, 2))) return rc;
     s.match.cap = static_cast<int>(cap);
+    if ((rc = dev_alloc(c, &s.carry_desc, cap * 256))) return rc;
+    if ((rc = dev_alloc(c, &s.carry_count, 1))) return rc;
+    CU_OK(c, cudaMemset(s.carry_count, 0, sizeof(int)));
+    CU_OK(c, cudaEventCreate(&s.ev0));
+    CU_OK(c, cudaEventCreate(&s.ev1));
+    if ((rc = host_alloc(c, &s.h_match, Bm * cap))) return rc;
+    if ((rc = host_alloc(c, &s.h_mdist, Bm * cap))) return rc;
+    if ((rc = host_alloc(c, &s.h_nprev, 1))) return rc;
     if ((rc = host_alloc(c, &s.h_gray, Bm * px))) return rc;
     if ((rc = host_alloc(c, &s.h_count, Bm))) return rc;
     if ((rc = host_alloc(c, &s.h_kp_xy, Bm * cap * 2))) return rc;
@@ -562,6 +589,7 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
   if (c->cap > c->cells) c->cap = c->cells;
   c->cov = (cfg->flags & SPFE_EMIT_COV) != 0;
   c->heat = c->cov || (cfg->flags & SPFE_EMIT_HEAT) != 0;
+  c->match_prev = (cfg->flags & SPFE_MATCH_PREV) != 0;
   int rc = create_impl(c);
   if (rc == SPFE_OK) rc = [&]() -> int {
     CU_OK(c, cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->cells * 6));
@@ -580,7 +608,11 @@ void spfe_destroy(spfe_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->cfg.device_id);
   cudaDeviceSynchronize();
-  for (Slot &s : c->slots) if (s.stream) cudaStreamDestroy(s.stream);
+  for (Slot &s : c->slots) {
+    if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.ev0) cudaEventDestroy(s.ev0);
+    if (s.ev1) cudaEventDestroy(s.ev1);
+  }
   if (c->match_stream) cudaStreamDestroy(c->match_stream);
   for (void *p : c->dev_allocs) cudaFree(p);
   for (void *p : c->host_allocs) cudaFreeHost(p);
@@ -606,6 +638,11 @@ static int enqueue_d2h(spfe_ctx *c, Slot &s, int B) {
   if (c->heat) {
     CU_OK(c, cudaMemcpyAsync(s.h_heat, s.heat, B * px * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU_OK(c, cudaMemcpyAsync(s.h_heat_inv, s.heat_inv, B * px * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  if (c->match_prev) {
+    CU_OK(c, cudaMemcpyAsync(s.h_match, s.match.q2t, B * cap * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_OK(c, cudaMemcpyAsync(s.h_mdist, s.match.dist, B * cap * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU_OK(c, cudaMemcpyAsync(s.h_nprev, s.match.dn, sizeof(int), cudaMemcpyDeviceToHost, st));
   }
   return SPFE_OK;
 }
@@ -655,6 +692,11 @@ int spfe_wait(spfe_ctx *c, int32_t slot, spfe_frame_out *outs) {
       o.heat = s.h_heat + b * px;
       o.heat_inv = s.h_heat_inv + b * px;
     }
+    if (c->match_prev) {
+      o.n_prev = b == 0 ? s.h_nprev[0] : s.h_count[b - 1];
+      o.match_prev = s.h_match + b * cap;
+      o.match_dist = s.h_mdist + b * cap;
+    }
     if (c->cov) {
       float *resp = s.resp.data() + b * cap, *c2 = s.cov2.data() + b * cap * 2, *c2i = s.cov2_inv.data() + b * cap * 2;
       covariance_host(o.heat_inv, c->H, c->W, o.kp_xy, o.n, resp, c2, c2i);
@@ -699,16 +741,19 @@ int spfe_slot_sync(spfe_ctx *c, int32_t slot) {
 }
 
 // ---- matcher -----------------------------------------------------------------
-static int run_match(spfe_ctx *c, cudaStream_t st, const float *dq, const float *dt, const int *dnq, const int *dnt,
-                     MatchScratch &m, int off, int cap_rows) {
-  match_init_kernel<<<(cap_rows + 255) / 256, 256, 0, st>>>(m.rowbest + off, m.colbest + off, cap_rows);
-  dim3 grid((cap_rows + 63) / 64, (cap_rows + 63) / 64);
-  match_dist_kernel<<<grid, 256, 0, st>>>(dq, dt, dnq, dnt, m.rowbest + off, m.colbest + off);
-  match_final_kernel<<<(cap_rows + 255) / 256, 256, 0, st>>>(m.rowbest + off, m.colbest + off, dnq, m.q2t + off, m.dist + off, cap_rows);
+}  // extern "C"
+namespace {
+int run_match(spfe_ctx *c, cudaStream_t st, const MatchArgs &a, int Z, int rows) {
+  match_init_kernel<<<(Z * a.cap + 255) / 256, 256, 0, st>>>(a.rowbest, a.colbest, Z * a.cap);
+  dim3 grid((rows + 63) / 64, (rows + 63) / 64, Z);
+  match_dist_kernel<<<grid, 256, 0, st>>>(a);
+  match_final_kernel<<<dim3((a.cap + 255) / 256, Z), 256, 0, st>>>(a);
   c->launches += 3;
   CU_OK(c, cudaGetLastError());
   return SPFE_OK;
 }
+}  // namespace
+extern "C" {
 
 int spfe_match_mutual_nn(spfe_ctx *c, const float *q, int32_t nq, const float *t, int32_t nt, int32_t *q2t, float *dist) {
   if (!c) return SPFE_ERR_INVALID;
@@ -730,8 +775,10 @@ int spfe_match_mutual_nn(spfe_ctx *c, const float *q, int32_t nq, const float *t
   CU_OK(c, cudaMemcpyAsync(m.dq, c->h_match_q, (size_t)nq * 256 * sizeof(float), cudaMemcpyHostToDevice, st));
   CU_OK(c, cudaMemcpyAsync(m.dt, c->h_match_t, (size_t)nt * 256 * sizeof(float), cudaMemcpyHostToDevice, st));
   CU_OK(c, cudaMemcpyAsync(m.dn, c->h_match_idx + c->match_cap, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
-  const int rows = nq > nt ? nq : nt;
-  int rc = run_match(c, st, m.dq, m.dt, m.dn, m.dn + 1, m, 0, rows);
+  MatchArgs a;
+  a.q = m.dq; a.nq = m.dn; a.t0 = m.dt; a.nt0 = m.dn + 1;
+  a.rowbest = m.rowbest; a.colbest = m.colbest; a.q2t = m.q2t; a.dist = m.dist; a.cap = c->match_cap;
+  int rc = run_match(c, st, a, 1, nq > nt ? nq : nt);
   if (rc) return rc;
   CU_OK(c, cudaMemcpyAsync(c->h_match_idx, m.q2t, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
   CU_OK(c, cudaMemcpyAsync(c->h_match_dist, m.dist, nq * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -741,31 +788,45 @@ int spfe_match_mutual_nn(spfe_ctx *c, const float *q, int32_t nq, const float *t
   return SPFE_OK;
 }
 
-int spfe_match_frames_device(spfe_ctx *c, int32_t slot, int32_t fq, int32_t ft) {
+int spfe_reset_stream(spfe_ctx *c, int32_t slot) {
   int rc = check_slot(c, slot);
   if (rc) return rc;
-  Slot &s = c->slots[slot];
-  if (fq < 0 || ft < 0 || fq >= c->cfg.max_batch || ft >= c->cfg.max_batch) return c->fail(SPFE_ERR_INVALID, "spfe_match_frames_device: frame index out of range");
   CU_OK(c, cudaSetDevice(c->cfg.device_id));
-  const size_t cap = c->cap;
-  return run_match(c, s.stream, s.desc + fq * cap * 256, s.desc + ft * cap * 256, s.count + fq, s.count + ft, s.match,
-                   (int)(fq * cap), (int)cap);
+  CU_OK(c, cudaMemsetAsync(c->slots[slot].carry_count, 0, sizeof(int), c->slots[slot].stream));
+  return SPFE_OK;
 }
 
-int spfe_match_fetch(spfe_ctx *c, int32_t slot, int32_t fq, int32_t *q2t, float *dist, int32_t *nq) {
+int spfe_timer_start(spfe_ctx *c, int32_t slot) {
   int rc = check_slot(c, slot);
   if (rc) return rc;
-  Slot &s = c->slots[slot];
-  if (fq < 0 || fq >= c->cfg.max_batch || !q2t) return c->fail(SPFE_ERR_INVALID, "spfe_match_fetch: bad arguments");
   CU_OK(c, cudaSetDevice(c->cfg.device_id));
-  const size_t cap = c->cap;
-  int n = 0;
-  CU_OK(c, cudaStreamSynchronize(s.stream));
-  CU_OK(c, cudaMemcpy(&n, s.count + fq, sizeof(int), cudaMemcpyDeviceToHost));
-  CU_OK(c, cudaMemcpy(q2t, s.match.q2t + fq * cap, n * sizeof(int), cudaMemcpyDeviceToHost));
-  if (dist) CU_OK(c, cudaMemcpy(dist, s.match.dist + fq * cap, n * sizeof(float), cudaMemcpyDeviceToHost));
-  if (nq) *nq = n;
+  CU_OK(c, cudaEventRecord(c->slots[slot].ev0, c->slots[slot].stream));
   return SPFE_OK;
+}
+
+int spfe_timer_stop(spfe_ctx *c, int32_t slot, float *ms) {
+  int rc = check_slot(c, slot);
+  if (rc) return rc;
+  if (!ms) return c->fail(SPFE_ERR_INVALID, "spfe_timer_stop: ms is NULL");
+  Slot &s = c->slots[slot];
+  CU_OK(c, cudaSetDevice(c->cfg.device_id));
+  CU_OK(c, cudaEventRecord(s.ev1, s.stream));
+  CU_OK(c, cudaEventSynchronize(s.ev1));
+  CU_OK(c, cudaEventElapsedTime(ms, s.ev0, s.ev1));
+  return SPFE_OK;
+}
+
+int64_t spfe_check_weights(const char *path, char *err, size_t errcap) {
+  WeightMap wm;
+  std::string e;
+  if (err && errcap) err[0] = 0;
+  if (!path || !load_weights(path, wm, e)) {
+    if (err && errcap) snprintf(err, errcap, "%s", path ? e.c_str() : "path is NULL");
+    return SPFE_ERR_WEIGHTS;
+  }
+  int64_t n = 0;
+  for (auto &kv : wm) n += (int64_t)kv.second.numel();
+  return n;
 }
 
 float spfe_l2(const float *a, const float *b) {
@@ -797,7 +858,8 @@ int64_t spfe_debug_read(spfe_ctx *c, int32_t slot, const char *name, void *dst, 
       {"heat_inv", s.heat_inv, B * px * 4},      {"heat_minmax", s.heat_mm_f, B * 2 * 4},
       {"count", s.count, B * 4},                 {"kp_xy", s.kp_xy, B * cap * 2 * 4},
       {"kp_score", s.kp_score, B * cap * 4},     {"desc", s.desc, B * cap * 256 * 4},
-      {"occ_grid", s.occ, B * cells * 2}};
+      {"occ_grid", s.occ, B * cells * 2},        {"match_prev", c->match_prev ? s.match.q2t : nullptr, B * cap * 4},
+      {"match_dist", c->match_prev ? s.match.dist : nullptr, B * cap * 4}};
   for (const Ent &e : tab)
     if (!strcmp(e.n, name)) {
       if (!e.p) return c->fail(SPFE_ERR_STATE, fmt("spfe_debug_read: '%s' is not produced with the current flags", name));

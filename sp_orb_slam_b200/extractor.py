@@ -38,13 +38,16 @@ class SPExtractor:
     """Drop-in mirror of ``orbslam::SPExtractor`` (blocking, batch 1) plus the batched entry points."""
 
     def __init__(self, nfeatures: int, height: int, width: int, model_path: str, *, device_id: int = 0,
-                 max_batch: int = 1, num_slots: int = 1, emit_heat: bool = True, emit_cov: bool = True):
+                 max_batch: int = 1, num_slots: int = 1, emit_heat: bool = True, emit_cov: bool = True,
+                 match_prev: bool = False):
         self._lib = capi.load()
         self._ctx = C.c_void_p()
         cfg = capi.Config()
         self._lib.spfe_default_config(C.byref(cfg), height, width, nfeatures)
         cfg.device_id, cfg.max_batch, cfg.num_slots = device_id, max_batch, num_slots
-        cfg.flags = (capi.EMIT_HEAT if emit_heat else 0) | (capi.EMIT_COV if emit_cov else 0)
+        cfg.flags = ((capi.EMIT_HEAT if emit_heat else 0) | (capi.EMIT_COV if emit_cov else 0)
+                     | (capi.MATCH_PREV if match_prev else 0))
+        self.match_prev = match_prev
         self._path = str(model_path).encode()
         cfg.weights_path = self._path
         self.cfg = cfg
@@ -95,6 +98,10 @@ class SPExtractor:
         if self.emit_heat:
             d["heat"] = _as_np(o.heat, (H, W), np.float32)
             d["heat_inv"] = _as_np(o.heat_inv, (H, W), np.float32)
+        if self.match_prev:
+            d["n_prev"] = o.n_prev
+            d["match_prev"] = (np.ctypeslib.as_array(o.match_prev, shape=(max(n, 1),))[:n].copy() if n else np.zeros(0, np.int32))
+            d["match_dist"] = _as_np(o.match_dist, (n,), np.float32)
         if self.emit_cov:
             d["kp_response"] = _as_np(o.kp_response, (n,), np.float32)
             d["cov2"] = _as_np(o.cov2, (n, 2), np.float32)
@@ -155,16 +162,16 @@ class SPExtractor:
     def sync(self, slot: int) -> None:
         self._check(self._lib.spfe_slot_sync(self._ctx, slot))
 
-    def match_frames_device(self, slot: int, fq: int, ft: int) -> None:
-        self._check(self._lib.spfe_match_frames_device(self._ctx, slot, fq, ft))
+    def reset_stream(self, slot: int) -> None:
+        self._check(self._lib.spfe_reset_stream(self._ctx, slot))
 
-    def match_fetch(self, slot: int, fq: int):
-        q2t = np.empty(self.cap, np.int32)
-        dist = np.empty(self.cap, np.float32)
-        n = C.c_int32()
-        self._check(self._lib.spfe_match_fetch(self._ctx, slot, fq, q2t.ctypes.data_as(C.c_void_p),
-                                               dist.ctypes.data_as(C.c_void_p), C.byref(n)))
-        return q2t[:n.value].copy(), dist[:n.value].copy()
+    def timer_start(self, slot: int) -> None:
+        self._check(self._lib.spfe_timer_start(self._ctx, slot))
+
+    def timer_stop(self, slot: int) -> float:
+        ms = C.c_float()
+        self._check(self._lib.spfe_timer_stop(self._ctx, slot, C.byref(ms)))
+        return float(ms.value)
 
     def match(self, q: np.ndarray, t: np.ndarray):
         q = np.ascontiguousarray(q, np.float32).reshape(-1, 256)
@@ -187,7 +194,8 @@ class SPExtractor:
               "heat_log": (lambda s: (s.height, s.width), np.float32), "heat": (lambda s: (s.height, s.width), np.float32),
               "heat_inv": (lambda s: (s.height, s.width), np.float32), "heat_minmax": (lambda s: (2,), np.float32),
               "count": (lambda s: (), np.int32), "kp_xy": (lambda s: (s.cap, 2), np.float32), "kp_score": (lambda s: (s.cap,), np.float32),
-              "desc": (lambda s: (s.cap, 256), np.float32), "occ_grid": (lambda s: (s.hc, s.wc), np.int16)}
+              "desc": (lambda s: (s.cap, 256), np.float32), "occ_grid": (lambda s: (s.hc, s.wc), np.int16),
+              "match_prev": (lambda s: (s.cap,), np.int32), "match_dist": (lambda s: (s.cap,), np.float32)}
 
     def debug_read(self, slot: int, name: str, batch: int) -> np.ndarray:
         shape_fn, dt = self._DEBUG[name]

@@ -1,0 +1,98 @@
+"""CPU tests of the C-ABI library: it loads, exports every symbol include/spfe.h
+declares, validates arguments, parses weight files and fails loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, WEIGHTS
+from sp_orb_slam_b200 import SPExtractor, SPMatcher, SpfeError, capi
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return capi.load()
+
+
+def test_exports_match_header(lib):
+    hdr = open(os.path.join(ROOT, "include", "spfe.h")).read()
+    declared = sorted(set(re.findall(r"\b(spfe_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"libspfe.so does not export {name}"
+    assert sorted(capi.EXPORTS) == declared
+
+
+def test_struct_layouts(lib):
+    cfg = capi.Config()
+    lib.spfe_default_config(C.byref(cfg), 480, 752, 800)
+    assert cfg.struct_size == C.sizeof(capi.Config)
+    assert (cfg.height, cfg.width, cfg.max_keypoints) == (480, 752, 800)
+    assert abs(cfg.score_thresh - 0.007) < 1e-9 and cfg.nms_radius == 4 and cfg.border == 8   # sp_extractor.cpp:122,502
+    assert cfg.flags == capi.EMIT_HEAT | capi.EMIT_COV
+
+
+def test_create_validates_arguments(lib):
+    ctx = C.c_void_p()
+    cfg = capi.Config()
+    lib.spfe_default_config(C.byref(cfg), 480, 750, 800)          # width not a multiple of 8
+    cfg.weights_path = WEIGHTS.encode()
+    assert lib.spfe_create(C.byref(cfg), C.byref(ctx)) == capi.ERR_INVALID
+    assert b"multiples of 8" in lib.spfe_last_error(None)
+    lib.spfe_default_config(C.byref(cfg), 480, 752, 800)
+    assert lib.spfe_create(C.byref(cfg), C.byref(ctx)) == capi.ERR_WEIGHTS   # NULL path
+    cfg.struct_size = 8
+    assert lib.spfe_create(C.byref(cfg), C.byref(ctx)) == capi.ERR_INVALID
+    assert not ctx.value
+
+
+def test_no_cpu_fallback():
+    """Without a B200 the product path must fail loudly, never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(SpfeError) as e:
+        SPExtractor(800, 480, 752, WEIGHTS)
+    assert e.value.code == capi.ERR_NO_DEVICE and "no CPU fallback" in str(e.value)
+
+
+def test_weight_readers(lib, weights):
+    err = C.create_string_buffer(256)
+    assert lib.spfe_check_weights(WEIGHTS.encode(), err, 256) == 1300865
+    assert lib.spfe_check_weights(b"/nonexistent/superpoint.pt", err, 256) == capi.ERR_WEIGHTS and b"cannot open" in err.value
+    ref = "/root/reference/orb_ros/data/models/superpoint.pt"
+    if os.path.exists(ref):                                   # the reference's own legacy archive, read by the C++ parser
+        assert lib.spfe_check_weights(ref.encode(), err, 256) == 1300865
+
+
+def test_weight_reader_rejects_garbage(lib, tmp_path):
+    err = C.create_string_buffer(256)
+    p = tmp_path / "bad.spw"
+    p.write_bytes(b"SPW1" + b"\x05\x00\x00\x00" + b"x" * 40)
+    assert lib.spfe_check_weights(str(p).encode(), err, 256) == capi.ERR_WEIGHTS
+    p.write_bytes(b"not a model file at all")
+    assert lib.spfe_check_weights(str(p).encode(), err, 256) == capi.ERR_WEIGHTS
+    from oracle import weights as OW
+    w = OW.random_weights(0)
+    del w["convDb.bias"]
+    OW.write_spw(str(p), w)
+    assert lib.spfe_check_weights(str(p).encode(), err, 256) == capi.ERR_WEIGHTS and b"convDb" in err.value
+
+
+def test_descriptor_distance_host():
+    rng = np.random.RandomState(0)
+    a, b = rng.randn(256).astype(np.float32), rng.randn(256).astype(np.float32)
+    d = SPMatcher.DescriptorDistance(a, b)
+    assert abs(d - float(np.sqrt(((a - b) ** 2).sum()))) < 1e-4
+    from oracle import sp_oracle as O
+    assert d == O.l2(a, b)                                      # same fp32 summation order
+    assert (SPMatcher.TH_HIGH, SPMatcher.TH_LOW, SPMatcher.HISTO_LENGTH) == (0.7, 0.3, 30)
+
+
+def test_shim_compiles():
+    """The C++ drop-in classes (orbslam::SPExtractor / SPMatcher) build against the C ABI."""
+    from sp_orb_slam_b200 import build
+    exe = build.build_shim()
+    assert os.path.exists(exe)

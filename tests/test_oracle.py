@@ -1,0 +1,170 @@
+"""CPU tests of the oracle itself: against the committed golden vectors (minted
+from the reference's own compiled SPFrontend), against OpenCV for the
+third-party arithmetic, and against brute-force restatements."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, WEIGHTS
+from oracle import sp_oracle as O, weights as OW
+from sp_orb_slam_b200 import synth
+
+REF_PT = "/root/reference/orb_ros/data/models/superpoint.pt"
+
+
+def test_weights_fixture_matches_reference_archive(weights):
+    if not os.path.exists(REF_PT):
+        pytest.skip("reference checkout not present (GPU box)")
+    ref = OW.read_legacy_pt(REF_PT)
+    assert list(ref) == list(weights)
+    for k in ref:
+        assert np.array_equal(ref[k], weights[k]), k
+    assert sum(v.size for v in ref.values()) == 1300865
+
+
+def test_synth_is_deterministic():
+    a = synth.make_stream(64, 96, 2, seed=3)
+    b = synth.make_stream(64, 96, 2, seed=3)
+    assert a.dtype == np.uint8 and a.shape == (2, 64, 96) and np.array_equal(a, b)
+    assert not np.array_equal(a[0], a[1])
+
+
+@pytest.mark.parametrize("name", ["g120x160", "g240x320_ragged", "g480x640"])
+def test_oracle_reproduces_golden(name, weights, golden):
+    """Golden = reference's own SPFrontend (libtorch C++) + post-processing; oracle = torch-python restatement."""
+    g = golden(name)
+    nf = int(g["nfeatures"])
+    for t in range(2):
+        o = O.extract(weights, g["frames"][t], nf, keep_forward=True)
+        f = o["forward"]
+        assert np.array_equal(f["pixels_in"].astype(np.int16), g[f"f{t}_cand_pixels"])      # candidate set: exact
+        np.testing.assert_allclose(f["score"], g[f"f{t}_cand_score"], rtol=0, atol=2e-5)
+        assert o["n"] == int(g[f"f{t}_n"])
+        assert np.array_equal(o["kp_xy"].astype(np.int16), g[f"f{t}_kp_xy"])                # keypoints: exact
+        assert np.array_equal(o["occ_grid"], g[f"f{t}_occ_grid"])
+        cos = np.sum(o["desc"] * g[f"f{t}_desc"].astype(np.float32), 1)
+        assert cos.min() > 1 - 1e-4
+        np.testing.assert_allclose(o["heat"], g[f"f{t}_heat_q"] / 255.0, atol=0.5 / 255 + 1e-4)
+        np.testing.assert_allclose(o["cov2"], g[f"f{t}_cov2"], rtol=2e-2, atol=2e-2)
+
+
+def _greedy_nms_python(pts, nf, W, H, border=8, r=4):
+    """Independent brute-force statement of sp_extractor.cpp:161-250."""
+    alive = np.ones(len(pts), bool)
+    kept = []
+    for i in range(len(pts)):
+        if not alive[i]:
+            continue
+        d = np.abs(pts - pts[i]).max(1)
+        alive &= ~(d <= r)
+        kept.append(i)
+        if len(kept) > nf:
+            break
+    kept = [i for i in kept if border <= pts[i, 0] < W - border and border <= pts[i, 1] < H - border]
+    kept.sort(key=lambda i: (pts[i, 1], pts[i, 0]))
+    return np.array(kept, np.int32)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_oracle_nms_vs_bruteforce(seed):
+    rng = np.random.RandomState(seed)
+    H, W = 96, 128
+    hc, wc = H // 8, W // 8
+    cells = np.flatnonzero(rng.rand(hc * wc) < 0.8)
+    pos = rng.randint(0, 64, len(cells))
+    pts = np.stack([(cells % wc) * 8 + pos % 8, (cells // wc) * 8 + pos // 8], 1).astype(np.float32)
+    score = rng.permutation(len(cells)).astype(np.float32)
+    order = O.sort_desc(score)
+    assert np.array_equal(score[order], np.sort(score)[::-1])
+    nf = [1000, 20, 5][seed % 3]
+    sel, occ = O.nms(pts[order], nf, W, H)
+    ref = _greedy_nms_python(pts[order], nf, W, H)
+    assert np.array_equal(sel, ref)
+    assert (occ >= 0).sum() == len(sel)
+    for k, i in enumerate(sel):
+        x, y = pts[order][i]
+        assert occ[int(y) // 8, int(x) // 8] == k
+
+
+def test_sort_desc_ties_keep_raster_order():
+    s = np.array([0.5, 0.9, 0.5, 0.9, 0.1], np.float32)
+    assert O.sort_desc(s).tolist() == [1, 3, 0, 2, 4]
+
+
+def test_to_heat_properties():
+    rng = np.random.RandomState(0)
+    x = np.log(np.clip(rng.rand(40, 56).astype(np.float32), 1e-3, None))
+    heat, heat_inv, mn, mx = O.to_heat(x)
+    assert mn == float((-x).min()) and mx == float((-x).max())
+    np.testing.assert_allclose(heat + heat_inv, 1.0, atol=1e-6)
+    assert heat.min() >= -1e-6 and heat.max() <= 1 + 1e-6
+    np.testing.assert_allclose(heat, (-x - mn) / (mx - mn), atol=1e-6)
+
+
+def test_covariance_simple_peak():
+    h = np.zeros((16, 16), np.float32)
+    h[8, 8], h[8, 7], h[8, 9], h[7, 8], h[9, 8] = 1.0, 0.5, 0.5, 0.25, 0.25
+    resp, cov2, cov2_inv = O.covariance(h, np.array([[8, 8]], np.float32))
+    assert resp[0] == 1.0
+    np.testing.assert_allclose(cov2[0], [max(1.0, 1.0 / 2.5), 1.0])     # x: (0.5+0.5)/2.5 = 0.4 -> floored to 1
+    np.testing.assert_allclose(cov2_inv[0], 1.0 / cov2[0])
+
+
+def test_matcher_vs_opencv():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.RandomState(1)
+    for nq, nt in [(300, 280), (50, 400), (1, 1), (64, 3)]:
+        q = rng.randn(nq, 256).astype(np.float32)
+        t = np.concatenate([q[: min(nq, nt)] + 0.3 * rng.randn(min(nq, nt), 256).astype(np.float32),
+                            rng.randn(max(nt - nq, 0), 256).astype(np.float32)])[:nt]
+        q /= np.linalg.norm(q, axis=1, keepdims=True)
+        t /= np.linalg.norm(t, axis=1, keepdims=True)
+        q2t, dist, _ = O.match_mutual_nn(q, t)
+        ref = -np.ones(nq, np.int32)
+        for m in cv2.BFMatcher(cv2.NORM_L2, True).match(q, t):
+            ref[m.queryIdx] = m.trainIdx
+            assert abs(m.distance - dist[m.queryIdx]) < 1e-5
+        assert np.array_equal(ref, q2t)
+    assert abs(O.l2(q[0], t[0]) - cv2.norm(q[0], t[0], cv2.NORM_L2)) < 1e-6
+
+
+def test_matcher_edge_cases():
+    q = np.eye(4, 256, dtype=np.float32)
+    q2t, _, _ = O.match_mutual_nn(q, np.zeros((0, 256), np.float32))
+    assert q2t.tolist() == [-1] * 4
+    q2t, d, _ = O.match_mutual_nn(q, q[::-1].copy())
+    assert q2t.tolist() == [3, 2, 1, 0] and np.all(d == 0)
+    dup = np.concatenate([q[:1], q[:1]])          # duplicate train rows: first index wins
+    q2t, _, _ = O.match_mutual_nn(q[:1], dup)
+    assert q2t.tolist() == [0]
+
+
+def test_reference_frontend_pins_oracle(weights):
+    """oracle/_ref = the reference's own SPFrontend compiled here; the restatement must agree with it."""
+    from oracle import ref_frontend as R
+    if not R.available():
+        pytest.skip("oracle/_ref not built (run oracle/ref_build.sh where /root/reference exists)")
+    img = synth.make_frame(120, 160, seed=11)
+    r, o = R.forward(weights, img), O.frontend_forward(weights, img)
+    assert np.array_equal(r["pixels_in"], o["pixels_in"])
+    for k, tol in [("score", 2e-5), ("semi_dust", 2e-4), ("dense_dust", 2e-5), ("heat_log", 2e-4), ("desc_sampled", 5e-6)]:
+        np.testing.assert_allclose(r[k], o[k], rtol=0, atol=tol, err_msg=k)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_fixture_self_consistency(name, golden):
+    g = golden(name)
+    nf = int(g["nfeatures"])
+    H, W = g["frames"].shape[1:]
+    for t in range(2):
+        kp = g[f"f{t}_kp_xy"].astype(int)
+        assert len(kp) == int(g[f"f{t}_n"]) <= nf + 1
+        key = kp[:, 1] * W + kp[:, 0]
+        assert np.all(np.diff(key) > 0)                                   # raster order
+        assert kp[:, 0].min() >= 8 and kp[:, 0].max() < W - 8 and kp[:, 1].min() >= 8 and kp[:, 1].max() < H - 8
+        occ = g[f"f{t}_occ_grid"]
+        assert np.array_equal(occ[kp[:, 1] // 8, kp[:, 0] // 8], np.arange(len(kp)))
+        d = np.abs(kp[:, None, :] - kp[None, :, :]).max(-1) + 100 * np.eye(len(kp), dtype=int)
+        assert d.min() > 4                                                # NMS radius
+    assert WEIGHTS.endswith(".spw")
