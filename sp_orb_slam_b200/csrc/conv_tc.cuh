@@ -20,14 +20,6 @@
 //   * weights are packed [tap][cblock][cout][64] fp16; small layers keep all
 //     of them resident in shared memory for the CTA's lifetime, large layers
 //     stream [N x 64] blocks through a second ring.
-//   * FOLD mode (Cin = 64 -> Cout = 64 layers, 52 % of the FLOPs): an N = 64 MMA is
-//     shared-memory bound (4 KB of A + 2 KB of B per 32 tensor cycles), so the three
-//     vertical taps are folded into N instead: P[pixel, (dy, cout)] with N = 192 and
-//     K = 3 dx x 64 ch -- 12 MMAs per tile instead of 36 and A is read 3x less.  The tile
-//     is stored column-major (TMA map with H and W swapped: 16 input rows x 8 columns,
-//     M index = w*16 + h) so that a warp owns two whole columns and the epilogue forms
-//     out[h] = P[h][dy0] + P[h+1][dy1] + P[h+2][dy2] with two warp shuffles; a tile then
-//     yields 14 x 8 output pixels.
 //   * persistent CTAs (1 per SM), warp-specialised: warp 0 = slab TMA
 //     producer, warp 3 = weight TMA producer, warp 1 = MMA issuer (one lane),
 //     warp 2 = TMEM allocator, warps 4-7 = epilogue.  Two TMEM accumulators so
@@ -59,17 +51,16 @@ struct ConvArgs {
   unsigned *heat_minmax;  // [B][2] ordered-uint min / max of heat_log, or nullptr
 };
 
-template <int TAPS_, int CB_, int N_, int EPI_, bool WRES_, int SA_, int SB_, bool FOLD_ = false>
+template <int TAPS_, int CB_, int N_, int EPI_, bool WRES_, int SA_, int SB_>
 struct ConvCfg {
   static constexpr int TAPS = TAPS_, CB = CB_, N = N_, EPI = EPI_, SA = SA_, SB = SB_;
-  static constexpr bool WRES = WRES_, FOLD = FOLD_;
+  static constexpr bool WRES = WRES_;
   static constexpr int NDX = TAPS == 9 ? 3 : 1;
-  static constexpr int NDY = FOLD ? 1 : NDX;          // FOLD: the three dy taps live in N
-  static constexpr int TILE_H = FOLD ? 14 : 16;        // output rows per tile
+  static constexpr int NDY = NDX;
   static constexpr int SLAB_ROWS = 16 + NDY - 1;
   static constexpr int SLAB_BYTES = SLAB_ROWS * 1024;
   static constexpr int BBLK_BYTES = N * 128;
-  static constexpr int NWB = NDX * NDY * CB;
+  static constexpr int NWB = TAPS * CB;
   static constexpr int B_BYTES = (WRES ? NWB : SB) * BBLK_BYTES;
   static constexpr int ACC_STRIDE = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
@@ -78,7 +69,6 @@ struct ConvCfg {
   static constexpr int SMEM_FIXED = 1024 + SA * SLAB_BYTES + B_BYTES + NBAR * 8 + 16;
   static constexpr int smem_bytes(int nb) { return SMEM_FIXED + nb * N * 4; }
   static_assert(N % 16 == 0 && N <= 256, "UMMA M=128 needs N % 16 == 0, N <= 256");
-  static_assert(!FOLD || (N == 192 && TAPS == 9 && (EPI == EPI_RELU || EPI == EPI_RELU_POOL)), "FOLD: 3 x 64 couts");
   static_assert(SMEM_FIXED + N * 4 <= 232448, "shared memory budget");
 };
 
@@ -153,7 +143,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int t = item / NB;
     x0 = (t % p.tiles_x) * 8;
     t /= p.tiles_x;
-    y0 = (t % p.tiles_y) * Cfg::TILE_H;
+    y0 = (t % p.tiles_y) * 16;
     b = t / p.tiles_y;
   };
 
@@ -169,11 +159,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int s = it % SA;
             mbar_wait(a_empty(s), ((it / SA) & 1) ^ 1);
             mbar_expect_tx(a_full(s), Cfg::SLAB_BYTES);
-            if constexpr (Cfg::FOLD)  // map dims are (C, H, W, B): 16 input rows x 8 columns, column-major slab
-              tma_load_4d(smem_u32(sA + s * Cfg::SLAB_BYTES), &tmA, a_full(s), p.cin_off + cb * 64, y0 - 1, x0 + dx - 1, b);
-            else
-              tma_load_4d(smem_u32(sA + s * Cfg::SLAB_BYTES), &tmA, a_full(s), p.cin_off + cb * 64,
-                          x0 + dx - (NDX == 3 ? 1 : 0), y0 - (NDY == 3 ? 1 : 0), b);
+            tma_load_4d(smem_u32(sA + s * Cfg::SLAB_BYTES), &tmA, a_full(s), p.cin_off + cb * 64,
+                        x0 + dx - (NDX == 3 ? 1 : 0), y0 - (NDY == 3 ? 1 : 0), b);
           }
       }
     }
@@ -265,62 +252,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const float *bias = sBias + nb * N;
       const int y = y0 + hl, x = x0 + wl;
 
-      if constexpr (Cfg::FOLD) {
-        // lane = (column parity)*16 + input row; out[o] = P[o][dy0] + P[o+1][dy1] + P[o+2][dy2]
-        const int hh = lane & 15, wf = wq * 2 + (lane >> 4);
-        const int xo = x0 + wf, yo = y0 + hh;
-        constexpr bool POOL = (EPI == EPI_RELU_POOL);
-        const int Ho = POOL ? (p.H >> 1) : p.H, Wo = POOL ? (p.W >> 1) : p.W;
-        const int ys = POOL ? (yo >> 1) : yo, xs = POOL ? (xo >> 1) : xo;
-        const bool valid = (hh < 14) && (yo < p.H) && (xo < p.W);
-        const int q = (lane & 1) | (((lane >> 4) & 1) << 1);  // POOL: which 4-channel slice this lane stores
-        __half *dst = p.out + ((static_cast<size_t>(b) * Ho + ys) * Wo + xs) * p.cout_stride;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 64; c0 += 16) {
-          float v[16], v1[16], v2[16];
-          tmem_ld16(taddr + c0, v);
-          tmem_ld16(taddr + 64 + c0, v1);
-          tmem_ld16(taddr + 128 + c0, v2);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; j++) {
-            v[j] += __shfl_down_sync(0xffffffffu, v1[j], 1);
-            v[j] += __shfl_down_sync(0xffffffffu, v2[j], 2);
-          }
-          if constexpr (POOL) {
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-              v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
-              v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 16));
-            }
-            float w4[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-              const float lo = (q & 1) ? v[4 + j] : v[j];
-              const float hi = (q & 1) ? v[12 + j] : v[8 + j];
-              w4[j] = fmaxf(((q & 2) ? hi : lo) + bias[c0 + q * 4 + j], 0.f);
-            }
-            if (valid) {
-              uint2 o;
-              o.x = pack_h2(w4[0], w4[1]);
-              o.y = pack_h2(w4[2], w4[3]);
-              *reinterpret_cast<uint2 *>(dst + c0 + q * 4) = o;
-            }
-          } else if (valid) {
-#pragma unroll
-            for (int g = 0; g < 2; g++) {
-              uint4 o;
-              uint32_t *ow = reinterpret_cast<uint32_t *>(&o);
-#pragma unroll
-              for (int j = 0; j < 4; j++) {
-                const int c = g * 8 + j * 2;
-                ow[j] = pack_h2(fmaxf(v[c] + bias[c0 + c], 0.f), fmaxf(v[c + 1] + bias[c0 + c + 1], 0.f));
-              }
-              *reinterpret_cast<uint4 *>(dst + c0 + g * 8) = o;
-            }
-          }
-        }
-      } else if constexpr (EPI == EPI_RELU) {
+      if constexpr (EPI == EPI_RELU) {
         const bool valid = (y < p.H) && (x < p.W);
         __half *dst = p.out + ((static_cast<size_t>(b) * p.H + y) * p.W + x) * p.cout_stride + nb * N;
 #pragma unroll 1

@@ -38,8 +38,8 @@ std::string fmt(const char *f, ...) {
 // ----------------------------------------------------------------------------
 // kernel configurations (see conv_tc.cuh)
 //                         TAPS CB  N   epilogue        resident-W  A-ring B-ring
-using CfgC64 = ConvCfg<9, 1, 192, EPI_RELU, true, 6, 1, true>;        // conv2a          (dy folded into N)
-using CfgC64P = ConvCfg<9, 1, 192, EPI_RELU_POOL, true, 6, 1, true>;  // conv1b, conv2b  (dy folded into N)
+using CfgC64 = ConvCfg<9, 1, 64, EPI_RELU, true, 6, 1>;         // conv2a
+using CfgC64P = ConvCfg<9, 1, 64, EPI_RELU_POOL, true, 6, 1>;   // conv1b, conv2b
 using CfgC3a = ConvCfg<9, 1, 128, EPI_RELU, true, 4, 1>;        // conv3a
 using CfgC128 = ConvCfg<9, 2, 128, EPI_RELU, false, 4, 8>;      // conv4a, conv4b
 using CfgC128P = ConvCfg<9, 2, 128, EPI_RELU_POOL, false, 4, 8>;  // conv3b
@@ -161,19 +161,6 @@ int make_act_map(spfe_ctx *c, CUtensorMap *tm, const void *ptr, int C, int W, in
   if (r != CUDA_SUCCESS) return c->fail(SPFE_ERR_CUDA, fmt("cuTensorMapEncodeTiled(act C=%d W=%d H=%d B=%d) -> %d", C, W, H, B, (int)r));
   return SPFE_OK;
 }
-// Same tensor with H and W swapped in the map (dims C, H, W, B): box {64 ch, 16 rows, 8 columns, 1} lands
-// column-major in shared memory (row index = w*16 + h) for the FOLD kernels.
-int make_act_map_colmajor(spfe_ctx *c, CUtensorMap *tm, const void *ptr, int C, int W, int H, int B) {
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)W, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)W * C * 2, (cuuint64_t)C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {64, 16, 8, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = c->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(ptr), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return c->fail(SPFE_ERR_CUDA, fmt("cuTensorMapEncodeTiled(colmajor act C=%d W=%d H=%d B=%d) -> %d", C, W, H, B, (int)r));
-  return SPFE_OK;
-}
 // 2-D [rows][cols] fp16 matrix -> TMA map with box {64, box_rows}, 128-B swizzle.
 int make_mat_map(spfe_ctx *c, CUtensorMap *tm, const void *ptr, int cols, int rows, int box_rows) {
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -190,33 +177,8 @@ int make_mat_map(spfe_ctx *c, CUtensorMap *tm, const void *ptr, int cols, int ro
 // Pack OIHW fp32 conv weights of one or two layers (concatenated along cout)
 // into [tap][cblock][cout_total][64] fp16; couts beyond the real ones are zero.
 int upload_layer(spfe_ctx *c, Layer &L, const std::vector<const HostTensor *> &ws, const std::vector<const HostTensor *> &bs,
-                 int n_tile, int cout_total, bool fold = false) {
+                 int n_tile, int cout_total) {
   const int ci = ws[0]->dims[1], k = ws[0]->dims[2];
-  if (fold) {
-    // FOLD layout: [dx][cblock][dy*64 + cout][64]: the three vertical taps become 3 x 64 rows of one B block.
-    const HostTensor &w = *ws[0];
-    const int co = w.dims[0];
-    L.taps = 9; L.cb = ci / 64; L.cout_total = 3 * co; L.n_tile = 3 * co;
-    std::vector<__half> packed(static_cast<size_t>(3) * L.cb * 3 * co * 64, __float2half(0.f));
-    std::vector<float> bias(3 * co, 0.f);
-    for (int o = 0; o < co; o++) {
-      bias[o] = bs[0]->data[o];
-      for (int ch = 0; ch < ci; ch++)
-        for (int dy = 0; dy < 3; dy++)
-          for (int dx = 0; dx < 3; dx++) {
-            const float v = w.data[(static_cast<size_t>(o) * ci + ch) * 9 + dy * 3 + dx];
-            const size_t wb = static_cast<size_t>(dx) * L.cb + ch / 64;
-            packed[(wb * 3 * co + dy * co + o) * 64 + (ch % 64)] = __float2half_rn(v);
-          }
-    }
-    L.flop_per_px = 2.0 * 9 * ci * co;
-    int rc;
-    if ((rc = dev_alloc(c, &L.w, packed.size()))) return rc;
-    if ((rc = dev_alloc(c, &L.bias, bias.size()))) return rc;
-    CU_OK(c, cudaMemcpy(L.w, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
-    CU_OK(c, cudaMemcpy(L.bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
-    return make_mat_map(c, &L.tm, L.w, 64, 3 * L.cb * 3 * co, 3 * co);
-  }
   L.taps = k * k;
   L.cb = ci / 64;
   L.cout_total = cout_total;
@@ -262,7 +224,7 @@ int launch_conv(spfe_ctx *c, cudaStream_t st, const CUtensorMap &tmA, const Laye
   }
   a.bias = L.bias;
   a.tiles_x = (a.W + 7) / 8;
-  a.tiles_y = (a.H + Cfg::TILE_H - 1) / Cfg::TILE_H;
+  a.tiles_y = (a.H + 15) / 16;
   a.n_items = a.B * a.tiles_x * a.tiles_y * a.NB;
   const int grid = a.n_items < c->num_sms ? a.n_items : c->num_sms;
   conv_tc_kernel<Cfg><<<grid, 256, smem, st>>>(tmA, L.tm, a);
@@ -495,17 +457,17 @@ static int create_impl(spfe_ctx *c) {
     CU_OK(c, cudaMemcpy(c->w1a, w9.data(), w9.size() * 4, cudaMemcpyHostToDevice));
     CU_OK(c, cudaMemcpy(c->b1a, b.data.data(), 64 * 4, cudaMemcpyHostToDevice));
   }
-  auto up = [&](int l, std::vector<const char *> names, int n_tile, int cout_total, bool fold = false) {
+  auto up = [&](int l, std::vector<const char *> names, int n_tile, int cout_total) {
     std::vector<const HostTensor *> ws, bs;
     for (const char *n : names) {
       ws.push_back(&wm[std::string(n) + ".weight"]);
       bs.push_back(&wm[std::string(n) + ".bias"]);
     }
-    return upload_layer(c, c->layers[l], ws, bs, n_tile, cout_total, fold);
+    return upload_layer(c, c->layers[l], ws, bs, n_tile, cout_total);
   };
-  if ((rc = up(L1B, {"conv1b"}, 192, 192, true))) return rc;
-  if ((rc = up(L2A, {"conv2a"}, 192, 192, true))) return rc;
-  if ((rc = up(L2B, {"conv2b"}, 192, 192, true))) return rc;
+  if ((rc = up(L1B, {"conv1b"}, 64, 64))) return rc;
+  if ((rc = up(L2A, {"conv2a"}, 64, 64))) return rc;
+  if ((rc = up(L2B, {"conv2b"}, 64, 64))) return rc;
   if ((rc = up(L3A, {"conv3a"}, 128, 128))) return rc;
   if ((rc = up(L3B, {"conv3b"}, 128, 128))) return rc;
   if ((rc = up(L4A, {"conv4a"}, 128, 128))) return rc;
@@ -581,9 +543,9 @@ static int create_impl(spfe_ctx *c) {
       s.resp.resize(Bm * cap);
     }
     // TMA maps of every layer's input tensor
-    if ((rc = make_act_map_colmajor(c, &s.tmA[L1B], s.a1a, 64, W, H, Bm))) return rc;
-    if ((rc = make_act_map_colmajor(c, &s.tmA[L2A], s.a1b, 64, W / 2, H / 2, Bm))) return rc;
-    if ((rc = make_act_map_colmajor(c, &s.tmA[L2B], s.a2a, 64, W / 2, H / 2, Bm))) return rc;
+    if ((rc = make_act_map(c, &s.tmA[L1B], s.a1a, 64, W, H, Bm, 18))) return rc;
+    if ((rc = make_act_map(c, &s.tmA[L2A], s.a1b, 64, W / 2, H / 2, Bm, 18))) return rc;
+    if ((rc = make_act_map(c, &s.tmA[L2B], s.a2a, 64, W / 2, H / 2, Bm, 18))) return rc;
     if ((rc = make_act_map(c, &s.tmA[L3A], s.a2b, 64, W / 4, H / 4, Bm, 18))) return rc;
     if ((rc = make_act_map(c, &s.tmA[L3B], s.a3a, 128, W / 4, H / 4, Bm, 18))) return rc;
     if ((rc = make_act_map(c, &s.tmA[L4A], s.a3b, 128, wc, hc, Bm, 18))) return rc;
