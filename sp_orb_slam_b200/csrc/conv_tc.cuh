@@ -92,6 +92,47 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   return *reinterpret_cast<uint32_t *>(&h);
 }
 
+// Epilogue: bias + ReLU + 2x2 max-pool of one 8x16-pixel accumulator tile (lane = h*8 + w), fp16 NHWC store.
+// The pool partners are lane^1 (x) and lane^8 (y), both inside the warp; each of the four lanes of a 2x2 group
+// stores one 8-channel slice of every 32-channel chunk.
+template <int N>
+__device__ __forceinline__ void epilogue_relu_pool(uint32_t taddr, const float *bias, int lane, int hl, int wl, int x0,
+                                                   int y0, int b, int nb, int H, int W, int cout_stride, __half *out) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const int yo = (y0 >> 1) + (hl >> 1), xo = (x0 >> 1) + (wl >> 1);
+  const bool valid = (yo < Ho) && (xo < Wo);
+  const int q = (lane & 1) | (((lane >> 3) & 1) << 1);
+  __half *dst = out + ((static_cast<size_t>(b) * Ho + yo) * Wo + xo) * cout_stride + nb * N + q * 8;
+#pragma unroll 1
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    float v[32];
+    tmem_ld16(taddr + c0, v);
+    tmem_ld16(taddr + c0 + 16, v + 16);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+      v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 8));
+    }
+    float w[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float lo = (q & 1) ? v[8 + j] : v[j];
+      const float hi = (q & 1) ? v[24 + j] : v[16 + j];
+      w[j] = (q & 2) ? hi : lo;
+      w[j] = fmaxf(w[j] + bias[c0 + q * 8 + j], 0.f);
+    }
+    if (valid) {
+      uint4 o;
+      o.x = pack_h2(w[0], w[1]);
+      o.y = pack_h2(w[2], w[3]);
+      o.z = pack_h2(w[4], w[5]);
+      o.w = pack_h2(w[6], w[7]);
+      *reinterpret_cast<uint4 *>(dst + c0) = o;
+    }
+  }
+}
+
 template <class Cfg>
 __global__ void __launch_bounds__(256, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const ConvArgs p) {
@@ -276,40 +317,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       } else if constexpr (EPI == EPI_RELU_POOL) {
-        // 2x2 max-pool inside the warp: partners are lane^1 (x) and lane^8 (y).
-        const int Ho = p.H >> 1, Wo = p.W >> 1;
-        const int yo = (y0 >> 1) + (hl >> 1), xo = (x0 >> 1) + (wl >> 1);
-        const bool valid = (yo < Ho) && (xo < Wo);
-        const int q = (lane & 1) | (((lane >> 3) & 1) << 1);  // which 8-channel slice this lane stores
-        __half *dst = p.out + ((static_cast<size_t>(b) * Ho + yo) * Wo + xo) * p.cout_stride + nb * N + q * 8;
-#pragma unroll 1
-        for (int c0 = 0; c0 < N; c0 += 32) {
-          float v[32];
-          tmem_ld16(taddr + c0, v);
-          tmem_ld16(taddr + c0 + 16, v + 16);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; j++) {
-            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
-            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 8));
-          }
-          float w[8];
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            const float lo = (q & 1) ? v[8 + j] : v[j];
-            const float hi = (q & 1) ? v[24 + j] : v[16 + j];
-            w[j] = (q & 2) ? hi : lo;
-            w[j] = fmaxf(w[j] + bias[c0 + q * 8 + j], 0.f);
-          }
-          if (valid) {
-            uint4 o;
-            o.x = pack_h2(w[0], w[1]);
-            o.y = pack_h2(w[2], w[3]);
-            o.z = pack_h2(w[4], w[5]);
-            o.w = pack_h2(w[6], w[7]);
-            *reinterpret_cast<uint4 *>(dst + c0) = o;
-          }
-        }
+        epilogue_relu_pool<N>(taddr, bias, lane, hl, wl, x0, y0, b, nb, p.H, p.W, p.cout_stride, p.out);
       } else if constexpr (EPI == EPI_L2NORM) {
         // convDb + channel-wise L2 normalisation (sp_extractor.cpp:100-103); N == all 256 channels.
         const bool valid = (y < p.H) && (x < p.W);

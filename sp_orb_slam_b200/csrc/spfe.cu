@@ -10,11 +10,13 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
 #include <vector>
 
+#include "conv1ab.cuh"
 #include "conv_tc.cuh"
 #include "kernels_misc.cuh"
 #include "match.cuh"
@@ -102,6 +104,7 @@ struct spfe_ctx {
   std::string weights_path;
   int H = 0, W = 0, hc = 0, wc = 0, cells = 0, cap = 0, num_sms = 0;
   bool heat = false, cov = false, match_prev = false;
+  bool fused_conv1 = false;  // SPFE_FUSED_CONV1=1 selects the fused conv1a+conv1b kernel (bit-identical, currently slower: DESIGN.md)
   EncodeTiledFn encode = nullptr;
   float *w1a = nullptr, *b1a = nullptr;  // conv1a fp32 [9][64], [64]
   Layer layers[NLAYERS];
@@ -263,14 +266,24 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     init_minmax_kernel<<<(B + 127) / 128, 128, 0, st>>>(s.heat_mm, B);
     c->launches++;
   }
-  {  // conv1a: u8 -> fp16 NHWC64
+  int rc;
+  if (c->fused_conv1) {  // conv1a + conv1b + pool in one kernel: u8 image -> fp16 [H/2][W/2][64]
+    Conv1abArgs a;
+    a.img = s.d_gray; a.w1a = c->w1a; a.b1a = c->b1a; a.b1b = c->layers[L1B].bias; a.out = s.a1b;
+    a.B = B; a.H = H; a.W = W; a.tiles_x = (W + 7) / 8; a.tiles_y = (H + 15) / 16;
+    a.n_items = B * a.tiles_x * a.tiles_y;
+    const int grid = a.n_items < c->num_sms ? a.n_items : c->num_sms;
+    conv1ab_kernel<<<grid, c1ab::THREADS, c1ab::SMEM, st>>>(c->layers[L1B].tm, a);
+    c->launches++;
+    CU_OK(c, cudaGetLastError());
+    mark("conv1a+1b", 2.0 * 9 * 64 * H * W * B + c->layers[L1B].flop_per_px * H * W * B, (1.0 + 32.0) * H * W * B);
+  } else {  // unfused path (debugging aid: materialises the conv1a activation)
     dim3 grid((W + C1A_TW - 1) / C1A_TW, (H + C1A_TH - 1) / C1A_TH, B);
     conv1a_kernel<<<grid, 256, 0, st>>>(s.d_gray, s.a1a, c->w1a, c->b1a, B, H, W);
     c->launches++;
     CU_OK(c, cudaGetLastError());
     mark("conv1a", 2.0 * 9 * 64 * H * W * B, (1.0 + 128.0) * H * W * B);
   }
-  int rc;
   auto conv_args = [&](int h, int w, int nb, int cout_stride, __half *out) {
     ConvArgs a;
     memset(&a, 0, sizeof a);
@@ -278,8 +291,10 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     return a;
   };
   auto stage_flop = [&](int l, int h, int w) { return c->layers[l].flop_per_px * h * w * B; };
-  if ((rc = launch_conv<CfgC64P>(c, st, s.tmA[L1B], c->layers[L1B], conv_args(H, W, 1, 64, s.a1b)))) return rc;
-  mark("conv1b", stage_flop(L1B, H, W), (128.0 + 32.0) * H * W * B);
+  if (!c->fused_conv1) {
+    if ((rc = launch_conv<CfgC64P>(c, st, s.tmA[L1B], c->layers[L1B], conv_args(H, W, 1, 64, s.a1b)))) return rc;
+    mark("conv1b", stage_flop(L1B, H, W), (128.0 + 32.0) * H * W * B);
+  }
   if ((rc = launch_conv<CfgC64>(c, st, s.tmA[L2A], c->layers[L2A], conv_args(H / 2, W / 2, 1, 64, s.a2a)))) return rc;
   mark("conv2a", stage_flop(L2A, H / 2, W / 2), 256.0 * (H / 2) * (W / 2) * B);
   if ((rc = launch_conv<CfgC64P>(c, st, s.tmA[L2B], c->layers[L2B], conv_args(H / 2, W / 2, 1, 64, s.a2b)))) return rc;
@@ -482,7 +497,7 @@ static int create_impl(spfe_ctx *c) {
   for (Slot &s : c->slots) {
     CU_OK(c, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     if ((rc = dev_alloc(c, &s.d_gray, Bm * px))) return rc;
-    if ((rc = dev_alloc(c, &s.a1a, Bm * px * 64))) return rc;
+    if (!c->fused_conv1 && (rc = dev_alloc(c, &s.a1a, Bm * px * 64))) return rc;
     if ((rc = dev_alloc(c, &s.a1b, Bm * px / 4 * 64))) return rc;
     if ((rc = dev_alloc(c, &s.a2a, Bm * px / 4 * 64))) return rc;
     if ((rc = dev_alloc(c, &s.a2b, Bm * px / 16 * 64))) return rc;
@@ -543,7 +558,7 @@ static int create_impl(spfe_ctx *c) {
       s.resp.resize(Bm * cap);
     }
     // TMA maps of every layer's input tensor
-    if ((rc = make_act_map(c, &s.tmA[L1B], s.a1a, 64, W, H, Bm, 18))) return rc;
+    if (!c->fused_conv1 && (rc = make_act_map(c, &s.tmA[L1B], s.a1a, 64, W, H, Bm, 18))) return rc;
     if ((rc = make_act_map(c, &s.tmA[L2A], s.a1b, 64, W / 2, H / 2, Bm, 18))) return rc;
     if ((rc = make_act_map(c, &s.tmA[L2B], s.a2a, 64, W / 2, H / 2, Bm, 18))) return rc;
     if ((rc = make_act_map(c, &s.tmA[L3A], s.a2b, 64, W / 4, H / 4, Bm, 18))) return rc;
@@ -590,9 +605,21 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
   c->cov = (cfg->flags & SPFE_EMIT_COV) != 0;
   c->heat = c->cov || (cfg->flags & SPFE_EMIT_HEAT) != 0;
   c->match_prev = (cfg->flags & SPFE_MATCH_PREV) != 0;
+  {
+    const char *e = getenv("SPFE_FUSED_CONV1");
+    c->fused_conv1 = (e && e[0] == '1');
+  }
   int rc = create_impl(c);
   if (rc == SPFE_OK) rc = [&]() -> int {
-    CU_OK(c, cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->cells * 6));
+    // the attribute is per function, not per context: only ever raise it (several extractors may coexist)
+    static std::mutex mu;
+    static int nms_smem_max = 48 * 1024;
+    std::lock_guard<std::mutex> lock(mu);
+    if (c->cells * 6 > nms_smem_max) {
+      CU_OK(c, cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->cells * 6));
+      nms_smem_max = c->cells * 6;
+    }
+    CU_OK(c, cudaFuncSetAttribute(conv1ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1ab::SMEM));
     return SPFE_OK;
   }();
   if (rc != SPFE_OK) {
@@ -847,7 +874,7 @@ int64_t spfe_debug_read(spfe_ctx *c, int32_t slot, const char *name, void *dst, 
   Slot &s = c->slots[slot];
   const size_t B = s.batch > 0 ? s.batch : 1, px = (size_t)c->H * c->W, cells = c->cells, cap = c->cap;
   struct Ent { const char *n; const void *p; size_t bytes; } tab[] = {
-      {"conv1a", s.a1a, B * px * 64 * 2},        {"conv1b", s.a1b, B * px / 4 * 64 * 2},
+      {"conv1a", c->fused_conv1 ? nullptr : s.a1a, B * px * 64 * 2},        {"conv1b", s.a1b, B * px / 4 * 64 * 2},
       {"conv2a", s.a2a, B * px / 4 * 64 * 2},    {"conv2b", s.a2b, B * px / 16 * 64 * 2},
       {"conv3a", s.a3a, B * px / 16 * 128 * 2},  {"conv3b", s.a3b, B * cells * 128 * 2},
       {"conv4a", s.a4a, B * cells * 128 * 2},    {"conv4b", s.a4b, B * cells * 128 * 2},

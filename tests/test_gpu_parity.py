@@ -70,7 +70,7 @@ def test_layers_match_oracle(H, W, weights, ex_cache):
     ex.extract_batch(list(frames))
     for b in range(2):
         fwd = O.frontend_forward(weights, frames[b], keep_layers=True)
-        for name in ["conv1a", "conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b"]:
+        for name in ["conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b"]:   # conv1a is fused into conv1b
             got = ex.debug_read(0, name, 2)[b].astype(np.float32)
             ref = fwd["layers"][name].transpose(1, 2, 0)
             assert np.abs(got - ref).max() <= LAYER_RTOL * np.abs(ref).max(), name
@@ -150,6 +150,31 @@ def test_margin_robust_keypoints_identical(weights, ex_cache):
                 miss += 1
         assert len(gs & rs) >= 0.95 * len(rs)
     assert miss <= max(2, total // 2), f"{miss} of {total} keypoint differences not explained by an eps-fragile cell"
+
+
+def test_fused_conv1_equals_unfused(weights, monkeypatch):
+    """SPFE_FUSED_CONV1=1 (conv1a computed by conv1b's producer warps straight into the swizzled shared-memory
+    slabs) must be bit-identical to the default two-kernel path, whose conv1a activation is checked against the oracle."""
+    H, W = 120, 136
+    frames = synth.make_stream(H, W, 2, seed=7, n_shapes=24)
+    plain = SPExtractor(800, H, W, WEIGHTS, max_batch=2)
+    b = plain.extract_batch(list(frames))
+    b1b = plain.debug_read(0, "conv1b", 2)
+    got = plain.debug_read(0, "conv1a", 2).astype(np.float32)
+    for t in range(2):
+        ref = O.frontend_forward(weights, frames[t], keep_layers=True)["layers"]["conv1a"].transpose(1, 2, 0)
+        assert np.abs(got[t] - ref).max() <= 1e-3 * np.abs(ref).max()          # fp32 compute, fp16 storage
+    plain.close()
+    monkeypatch.setenv("SPFE_FUSED_CONV1", "1")
+    fused = SPExtractor(800, H, W, WEIGHTS, max_batch=2)
+    a = fused.extract_batch(list(frames))
+    assert np.array_equal(b1b, fused.debug_read(0, "conv1b", 2))
+    for x, y in zip(a, b):
+        for k in ["kp_xy", "desc", "occ_grid", "dense_dust", "heat"]:
+            assert np.array_equal(x[k], y[k]), k
+    with pytest.raises(SpfeError):
+        fused.debug_read(0, "conv1a", 2)                                       # never materialised in fused mode
+    fused.close()
 
 
 def test_batch_invariance_and_determinism(ex_cache):

@@ -40,7 +40,7 @@ def layers(H, W, batch):
     for b in range(batch):
         print(f"frame {b}:", flush=True)
         fwd = O.frontend_forward(w, frames[b], keep_layers=True)
-        for name in ["conv1a", "conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b"]:
+        for name in ["conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b"]:
             got = ex.debug_read(0, name, batch)[b]
             stat(name, got, fwd["layers"][name].transpose(1, 2, 0))
         heads = ex.debug_read(0, "heads", batch)[b]
