@@ -31,7 +31,7 @@
 
 namespace spfe {
 
-enum { EPI_RELU = 0, EPI_RELU_POOL = 1, EPI_L2NORM = 2, EPI_DETECT = 3 };
+enum { EPI_RELU = 0, EPI_RELU_POOL = 1, EPI_L2NORM = 2, EPI_DETECT = 3, EPI_TOP2 = 4 };
 
 struct ConvArgs {
   int B, H, W;            // conv spatial size (input == output, before pooling)
@@ -49,10 +49,17 @@ struct ConvArgs {
   float *dense_dust;      // dustbin softmax prob
   float *heat_log;        // [B][8H][8W] log(clamp(p, 1e-3)) depth-to-space, or nullptr
   unsigned *heat_minmax;  // [B][2] ordered-uint min / max of heat_log, or nullptr
+  // EPI_TOP2 (descriptor matching as a GEMM, see match.cuh): "frame slot" s holds descriptor rows of one frame;
+  // item = (pair z, direction, 128-row tile, 256-column block): A = slot z+1-dir, B = slot z+dir
+  const int *m_count;     // [slots] valid rows per slot
+  float2 *m_cand;         // [2][Z][rows_pad][NB][2] (score, index-as-float-bits) top-2 per row and column block
+  int m_rows_pad;         // rows per slot in the fp16 descriptor tensor (multiple of 256)
+  int m_tiles;            // 128-row tiles per slot that can hold valid rows
 };
 
 template <int TAPS_, int CB_, int N_, int EPI_, bool WRES_, int SA_, int SB_>
 struct ConvCfg {
+  static constexpr bool MATCH = (EPI_ == EPI_TOP2);
   static constexpr int TAPS = TAPS_, CB = CB_, N = N_, EPI = EPI_, SA = SA_, SB = SB_;
   static constexpr bool WRES = WRES_;
   static constexpr int NDX = TAPS == 9 ? 3 : 1;
@@ -173,7 +180,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < NB * N; i += blockDim.x) sBias[i] = p.bias[i];
+  if constexpr (!Cfg::MATCH)
+    for (int i = threadIdx.x; i < NB * N; i += blockDim.x) sBias[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -182,6 +190,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto decode = [&](int item, int &nb, int &x0, int &y0, int &b) {
     nb = item % NB;
     int t = item / NB;
+    if constexpr (Cfg::MATCH) {  // rows of slot b as an [rows/8][8] "image": tile mt covers rows mt*128 .. +127
+      x0 = 0;
+      y0 = (t % p.m_tiles) * 16;
+      t /= p.m_tiles;
+      b = (t >> 1) + 1 - (t & 1);  // pair z = t >> 1, direction = t & 1
+      return;
+    }
     x0 = (t % p.tiles_x) * 8;
     t /= p.tiles_x;
     y0 = (t % p.tiles_y) * 16;
@@ -223,7 +238,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(b_empty(s), ((jt / SB) & 1) ^ 1);
                 mbar_expect_tx(b_full(s), Cfg::BBLK_BYTES);
                 const int wb = (dy * NDX + dx) * CB + cb;
-                tma_load_2d(smem_u32(sB + s * Cfg::BBLK_BYTES), &tmW, b_full(s), 0, (wb * NB + nb) * N);
+                if constexpr (Cfg::MATCH) {
+                  const int t = item / NB / p.m_tiles;  // B operand = descriptor rows of the other slot of the pair
+                  const int bslot = (t >> 1) + (t & 1);
+                  tma_load_2d(smem_u32(sB + s * Cfg::BBLK_BYTES), &tmW, b_full(s), cb * 64, bslot * p.m_rows_pad + nb * N);
+                } else {
+                  tma_load_2d(smem_u32(sB + s * Cfg::BBLK_BYTES), &tmW, b_full(s), 0, (wb * NB + nb) * N);
+                }
               }
         }
       }
@@ -318,6 +339,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       } else if constexpr (EPI == EPI_RELU_POOL) {
         epilogue_relu_pool<N>(taddr, bias, lane, hl, wl, x0, y0, b, nb, p.H, p.W, p.cout_stride, p.out);
+      } else if constexpr (EPI == EPI_TOP2) {
+        // One thread = one descriptor row of the A slot: best two dot products (first index on ties) among this
+        // item's 256 columns of the B slot.  The exact fp32 re-rank happens in match_rerank_kernel.
+        const int t = item / NB / p.m_tiles;
+        const int z = t >> 1, dir = t & 1;
+        const int n_a = p.m_count[b], n_b = p.m_count[z + dir];
+        const int row = y0 * 8 + wq * 32 + lane;
+        // Sortable 32-bit keys: ordered score bits with the low byte replaced by (255 - column) -- a larger key is a
+        // larger score, ties go to the lower column.  Dropping 8 mantissa bits (2^-15 relative) is harmless: the keys
+        // only nominate candidates.  Four independent (best, second) chains keep the dependency depth short.
+        unsigned m1[4] = {0u, 0u, 0u, 0u}, m2[4] = {0u, 0u, 0u, 0u};
+#pragma unroll 1
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          float v[32];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld16(taddr + c0 + 16, v + 16);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const int cl = c0 + j;
+            unsigned key = (f32_ordered(v[j]) & 0xFFFFFF00u) | static_cast<unsigned>(255 - cl);
+            key = (nb * N + cl < n_b) ? key : 0u;
+            const unsigned lo = min(m1[j & 3], key);
+            m1[j & 3] = max(m1[j & 3], key);
+            m2[j & 3] = max(m2[j & 3], lo);
+          }
+        }
+        unsigned b1 = 0u, b2 = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {  // merge the four chains
+          const unsigned lo = min(b1, m1[k]);
+          b1 = max(b1, m1[k]);
+          b2 = max(max(b2, lo), m2[k]);
+        }
+        if (row < n_a) {
+          float2 *dst = p.m_cand + (((static_cast<size_t>(dir) * p.B + z) * p.m_rows_pad + row) * NB + nb) * 2;
+          dst[0] = make_float2(b1 ? f32_from_ordered(b1 & 0xFFFFFF00u) : -INFINITY, __int_as_float(b1 ? nb * N + 255 - static_cast<int>(b1 & 0xFFu) : -1));
+          dst[1] = make_float2(b2 ? f32_from_ordered(b2 & 0xFFFFFF00u) : -INFINITY, __int_as_float(b2 ? nb * N + 255 - static_cast<int>(b2 & 0xFFu) : -1));
+        }
       } else if constexpr (EPI == EPI_L2NORM) {
         // convDb + channel-wise L2 normalisation (sp_extractor.cpp:100-103); N == all 256 channels.
         const bool valid = (y < p.H) && (x < p.W);

@@ -212,7 +212,8 @@ __global__ void __launch_bounds__(1024) nms_kernel(const NmsArgs p) {
 __global__ void __launch_bounds__(256) sample_desc_kernel(const __half *__restrict__ coarse /*[B][hc][wc][256]*/,
                                                           const float *__restrict__ kp_xy, const int *__restrict__ count,
                                                           float *__restrict__ desc /*[B][cap][256]*/, int hc, int wc,
-                                                          int cap) {
+                                                          int cap, __half *__restrict__ x16 /*[B][rows_pad][256] or null*/,
+                                                          int rows_pad) {
   const int b = blockIdx.y;
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= count[b]) return;
@@ -248,8 +249,18 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const __half *__restri
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   const float nrm = sqrtf(ss);
   float4 *dst = reinterpret_cast<float4 *>(desc + (static_cast<size_t>(b) * cap + i) * 256 + lane * 8);
-  dst[0] = make_float4(acc[0] / nrm, acc[1] / nrm, acc[2] / nrm, acc[3] / nrm);
-  dst[1] = make_float4(acc[4] / nrm, acc[5] / nrm, acc[6] / nrm, acc[7] / nrm);
+#pragma unroll
+  for (int j = 0; j < 8; j++) acc[j] = acc[j] / nrm;
+  dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  if (x16 != nullptr) {  // fp16 copy feeding the tensor-core matcher (candidate generation only)
+    uint4 o;
+    o.x = pack_h2(acc[0], acc[1]);
+    o.y = pack_h2(acc[2], acc[3]);
+    o.z = pack_h2(acc[4], acc[5]);
+    o.w = pack_h2(acc[6], acc[7]);
+    *reinterpret_cast<uint4 *>(x16 + (static_cast<size_t>(b) * rows_pad + i) * 256 + lane * 8) = o;
+  }
 }
 
 // ---------------------------------------------------------------------------

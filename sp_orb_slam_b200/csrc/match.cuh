@@ -169,4 +169,61 @@ __global__ void match_final_kernel(const MatchArgs a) {
   dist[i] = d;
 }
 
+
+// ---------------------------------------------------------------------------
+// Tensor-core path for the in-pipeline stream matching (SPFE_MATCH_PREV).
+// conv_tc_kernel<EPI_TOP2> computes fp16 dot products Q.T^T on the tensor core
+// and keeps, per row and per 256-column block, the two best candidates.  The
+// descriptors are unit vectors, so ranking by dot product == ranking by L2; an
+// fp16 dot product is within 2^-10 of the exact one, so every candidate whose
+// score is within MATCH_MARGIN of the row's best is re-ranked here with the
+// exact fp32 squared distance (ties -> lower index, BFMatcher's rule).
+// One warp per row; grid (ceil(cap / 8), Z pairs, 2 directions).
+// ---------------------------------------------------------------------------
+constexpr float MATCH_MARGIN = 4e-3f;
+
+struct RerankArgs {
+  const float *desc_all;   // [slots][cap][256] fp32 descriptors, slot 0 = carry, slot z+1 = frame z
+  const int *count_all;    // [slots]
+  const float2 *cand;      // [2][Z][rows_pad][NB][2]
+  unsigned long long *rowbest, *colbest;  // [Z][cap]
+  int cap, rows_pad, NB, Z;
+};
+
+__global__ void __launch_bounds__(256) match_rerank_kernel(const RerankArgs a) {
+  const int z = blockIdx.y, dir = blockIdx.z;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int self_slot = z + 1 - dir, other_slot = z + dir;
+  if (row >= a.count_all[self_slot]) return;
+  const float2 *c = a.cand + ((static_cast<size_t>(dir) * a.Z + z) * a.rows_pad + row) * a.NB * 2;
+  float best_s = -INFINITY;
+  for (int k = 0; k < a.NB * 2; k++) best_s = fmaxf(best_s, c[k].x);
+  unsigned long long best = ~0ull;
+  if (best_s > -INFINITY) {
+    const float *me = a.desc_all + (static_cast<size_t>(self_slot) * a.cap + row) * 256 + lane * 8;
+    const float4 m0 = *reinterpret_cast<const float4 *>(me), m1 = *reinterpret_cast<const float4 *>(me + 4);
+    for (int k = 0; k < a.NB * 2; k++) {
+      const float2 ck = c[k];
+      const int idx = __float_as_int(ck.y);
+      if (idx < 0 || ck.x < best_s - MATCH_MARGIN) continue;  // warp-uniform
+      const float *ot = a.desc_all + (static_cast<size_t>(other_slot) * a.cap + idx) * 256 + lane * 8;
+      const float4 o0 = *reinterpret_cast<const float4 *>(ot), o1 = *reinterpret_cast<const float4 *>(ot + 4);
+      float d, acc = 0.f;
+      d = m0.x - o0.x; acc = fmaf(d, d, acc);
+      d = m0.y - o0.y; acc = fmaf(d, d, acc);
+      d = m0.z - o0.z; acc = fmaf(d, d, acc);
+      d = m0.w - o0.w; acc = fmaf(d, d, acc);
+      d = m1.x - o1.x; acc = fmaf(d, d, acc);
+      d = m1.y - o1.y; acc = fmaf(d, d, acc);
+      d = m1.z - o1.z; acc = fmaf(d, d, acc);
+      d = m1.w - o1.w; acc = fmaf(d, d, acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(acc)) << 32) | static_cast<unsigned>(idx);
+      best = key < best ? key : best;
+    }
+  }
+  if (lane == 0) (dir == 0 ? a.rowbest : a.colbest)[static_cast<size_t>(z) * a.cap + row] = best;
+}
+
 }  // namespace spfe

@@ -48,6 +48,7 @@ using CfgC128P = ConvCfg<9, 2, 128, EPI_RELU_POOL, false, 4, 8>;  // conv3b
 using CfgHeads = ConvCfg<9, 2, 256, EPI_RELU, false, 4, 4>;     // convPa || convDa (NB = 2)
 using CfgPb = ConvCfg<1, 4, 80, EPI_DETECT, true, 4, 1>;        // convPb + detector head
 using CfgDb = ConvCfg<1, 4, 256, EPI_L2NORM, true, 4, 1>;       // convDb + L2 norm
+using CfgMatch = ConvCfg<1, 4, 256, EPI_TOP2, false, 4, 4>;     // descriptor matching: Q.T^T + top-2 per 256-column block
 
 enum { L1B = 0, L2A, L2B, L3A, L3B, L4A, L4B, LHEADS, LPB, LDB, NLAYERS };
 const char *kLayerNames[NLAYERS] = {"conv1b", "conv2a", "conv2b", "conv3a", "conv3b",
@@ -83,8 +84,13 @@ struct Slot {
   unsigned long long *scratch = nullptr;
   CUtensorMap tmA[NLAYERS];
   MatchScratch match;
-  float *carry_desc = nullptr;  // [cap][256] last frame of the previous batch (SPFE_MATCH_PREV)
-  int *carry_count = nullptr;
+  // SPFE_MATCH_PREV: descriptor "slots": slot 0 = last frame of the previous batch (carry), slot z+1 = frame z
+  float *desc_all = nullptr;    // [Bm+1][cap][256]  (desc = desc_all + cap*256)
+  int *count_all = nullptr;     // [Bm+1]            (count = count_all + 1)
+  __half *x16 = nullptr;        // [Bm+1][rows_pad][256] fp16 copies for the tensor-core candidate GEMM
+  float2 *cand = nullptr;       // [2][Bm][rows_pad][NB][2]
+  CUtensorMap tmQ, tmT;
+  Layer match_layer;            // dummy layer record for launch_conv
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // pinned host mirrors
   uint8_t *h_gray = nullptr;
@@ -103,6 +109,7 @@ struct spfe_ctx {
   spfe_config cfg;
   std::string weights_path;
   int H = 0, W = 0, hc = 0, wc = 0, cells = 0, cap = 0, num_sms = 0;
+  int rows_pad = 0, match_nb = 0, match_tiles = 0;  // tensor-core matcher geometry
   bool heat = false, cov = false, match_prev = false;
   bool fused_conv1 = false;  // SPFE_FUSED_CONV1=1 selects the fused conv1a+conv1b kernel (bit-identical, currently slower: DESIGN.md)
   EncodeTiledFn encode = nullptr;
@@ -215,7 +222,7 @@ int upload_layer(spfe_ctx *c, Layer &L, const std::vector<const HostTensor *> &w
 }
 
 template <class Cfg>
-int launch_conv(spfe_ctx *c, cudaStream_t st, const CUtensorMap &tmA, const Layer &L, ConvArgs a) {
+int launch_conv(spfe_ctx *c, cudaStream_t st, const CUtensorMap &tmA, const Layer &L, ConvArgs a, const CUtensorMap *tmB = nullptr) {
   static_assert(Cfg::TAPS == 9 || Cfg::TAPS == 1, "taps");
   if (L.taps != Cfg::TAPS || L.cb != Cfg::CB || L.n_tile != Cfg::N || (Cfg::WRES && a.NB != 1))
     return c->fail(SPFE_ERR_INVALID, "conv launch: layer / kernel configuration mismatch");
@@ -229,8 +236,9 @@ int launch_conv(spfe_ctx *c, cudaStream_t st, const CUtensorMap &tmA, const Laye
   a.tiles_x = (a.W + 7) / 8;
   a.tiles_y = (a.H + 15) / 16;
   a.n_items = a.B * a.tiles_x * a.tiles_y * a.NB;
+  if (Cfg::MATCH) a.n_items = a.B * 2 * a.m_tiles * a.NB;
   const int grid = a.n_items < c->num_sms ? a.n_items : c->num_sms;
-  conv_tc_kernel<Cfg><<<grid, 256, smem, st>>>(tmA, L.tm, a);
+  conv_tc_kernel<Cfg><<<grid, 256, smem, st>>>(tmA, tmB ? *tmB : L.tm, a);
   c->launches++;
   CU_OK(c, cudaGetLastError());
   return SPFE_OK;
@@ -336,7 +344,8 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
   }
   {
     dim3 grid((c->cap + 7) / 8, B);
-    sample_desc_kernel<<<grid, 256, 0, st>>>(s.coarse, s.kp_xy, s.count, s.desc, hc, wc, c->cap);
+    sample_desc_kernel<<<grid, 256, 0, st>>>(s.coarse, s.kp_xy, s.count, s.desc, hc, wc, c->cap,
+                                             c->match_prev ? s.x16 + static_cast<size_t>(c->rows_pad) * 256 : nullptr, c->rows_pad);
     c->launches++;
     CU_OK(c, cudaGetLastError());
     mark("sample_desc", 0, 3072.0 * c->cap * B);
@@ -349,15 +358,30 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     mark("heat_norm", 0, 12.0 * H * W * B);
   }
   if (c->match_prev) {
-    // frame b vs frame b-1 (frame 0 vs the carry), all in three launches; then the last frame becomes the carry
-    MatchArgs a;
-    a.q = s.desc; a.nq = s.count; a.t0 = s.carry_desc; a.nt0 = s.carry_count;
-    a.rowbest = s.match.rowbest; a.colbest = s.match.colbest; a.q2t = s.match.q2t; a.dist = s.match.dist; a.cap = c->cap;
-    if ((rc = run_match(c, st, a, B, c->cap))) return rc;
-    CU_OK(c, cudaMemcpyAsync(s.match.dn, s.carry_count, sizeof(int), cudaMemcpyDeviceToDevice, st));  // n_prev of frame 0
-    CU_OK(c, cudaMemcpyAsync(s.carry_desc, s.desc + static_cast<size_t>(B - 1) * c->cap * 256, static_cast<size_t>(c->cap) * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    CU_OK(c, cudaMemcpyAsync(s.carry_count, s.count + (B - 1), sizeof(int), cudaMemcpyDeviceToDevice, st));
-    mark("match_prev", 2.0 * 256 * c->cap * c->cap * B, 2048.0 * c->cap * B);
+    // frame z vs frame z-1 (frame 0 vs the carry in slot 0): fp16 candidate GEMM on the tensor core for both
+    // directions, exact fp32 re-rank of the candidates, cross-check; then the last frame becomes the carry.
+    ConvArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = B; a.H = c->rows_pad / 8; a.W = 8; a.NB = c->match_nb;
+    a.m_count = s.count_all; a.m_cand = s.cand; a.m_rows_pad = c->rows_pad; a.m_tiles = c->match_tiles;
+    if ((rc = launch_conv<CfgMatch>(c, st, s.tmQ, s.match_layer, a, &s.tmT))) return rc;
+    mark("match_gemm", 2.0 * 2 * 256 * c->cap * c->cap * B, 0);
+    RerankArgs r;
+    r.desc_all = s.desc_all; r.count_all = s.count_all; r.cand = s.cand; r.rowbest = s.match.rowbest; r.colbest = s.match.colbest;
+    r.cap = c->cap; r.rows_pad = c->rows_pad; r.NB = c->match_nb; r.Z = B;
+    match_rerank_kernel<<<dim3((c->cap + 7) / 8, B, 2), 256, 0, st>>>(r);
+    mark("match_rerank", 0, 0);
+    MatchArgs m;
+    memset(&m, 0, sizeof m);
+    m.nq = s.count; m.rowbest = s.match.rowbest; m.colbest = s.match.colbest; m.q2t = s.match.q2t; m.dist = s.match.dist; m.cap = c->cap;
+    match_final_kernel<<<dim3((c->cap + 255) / 256, B), 256, 0, st>>>(m);
+    c->launches += 2;
+    CU_OK(c, cudaGetLastError());
+    CU_OK(c, cudaMemcpyAsync(s.match.dn, s.count_all, sizeof(int), cudaMemcpyDeviceToDevice, st));  // n_prev of frame 0
+    CU_OK(c, cudaMemcpyAsync(s.desc_all, s.desc_all + static_cast<size_t>(B) * c->cap * 256, static_cast<size_t>(c->cap) * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CU_OK(c, cudaMemcpyAsync(s.x16, s.x16 + static_cast<size_t>(B) * c->rows_pad * 256, static_cast<size_t>(c->rows_pad) * 256 * sizeof(__half), cudaMemcpyDeviceToDevice, st));
+    CU_OK(c, cudaMemcpyAsync(s.count_all, s.count_all + B, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    mark("match_final", 0, 2048.0 * c->cap * B);
   }
   s.batch = B;
   return SPFE_OK;
@@ -511,15 +535,17 @@ static int create_impl(spfe_ctx *c) {
     if ((rc = dev_alloc(c, &s.argmax, Bm * cells))) return rc;
     if ((rc = dev_alloc(c, &s.semi_dust, Bm * cells))) return rc;
     if ((rc = dev_alloc(c, &s.dense_dust, Bm * cells))) return rc;
-    if ((rc = dev_alloc(c, &s.count, Bm))) return rc;
+    if ((rc = dev_alloc(c, &s.count_all, Bm + 1))) return rc;
+    s.count = s.count_all + 1;
     if ((rc = dev_alloc(c, &s.kp_xy, Bm * cap * 2))) return rc;
     if ((rc = dev_alloc(c, &s.kp_score, Bm * cap))) return rc;
-    if ((rc = dev_alloc(c, &s.desc, Bm * cap * 256))) return rc;
+    if ((rc = dev_alloc(c, &s.desc_all, (Bm + 1) * cap * 256))) return rc;
+    s.desc = s.desc_all + cap * 256;
     if ((rc = dev_alloc(c, &s.occ, Bm * cells))) return rc;
     if ((rc = dev_alloc(c, &s.scratch, Bm * cells))) return rc;
-    CU_OK(c, cudaMemset(s.count, 0, Bm * sizeof(int)));
+    CU_OK(c, cudaMemset(s.count_all, 0, (Bm + 1) * sizeof(int)));
     CU_OK(c, cudaMemset(s.kp_xy, 0, Bm * cap * 2 * sizeof(float)));
-    CU_OK(c, cudaMemset(s.desc, 0, Bm * cap * 256 * sizeof(float)));
+    CU_OK(c, cudaMemset(s.desc_all, 0, (Bm + 1) * cap * 256 * sizeof(float)));
     if (c->heat) {
       if ((rc = dev_alloc(c, &s.heat_log, Bm * px))) return rc;
       if ((rc = dev_alloc(c, &s.heat, Bm * px))) return rc;
@@ -536,9 +562,15 @@ static int create_impl(spfe_ctx *c) {
     if ((rc = dev_alloc(c, &s.match.dist, Bm * cap))) return rc;
     if ((rc = dev_alloc(c, &s.match.dn, 2))) return rc;
     s.match.cap = static_cast<int>(cap);
-    if ((rc = dev_alloc(c, &s.carry_desc, cap * 256))) return rc;
-    if ((rc = dev_alloc(c, &s.carry_count, 1))) return rc;
-    CU_OK(c, cudaMemset(s.carry_count, 0, sizeof(int)));
+    if (c->match_prev) {
+      const size_t rp = c->rows_pad, nbk = c->match_nb;
+      if ((rc = dev_alloc(c, &s.x16, (Bm + 1) * rp * 256))) return rc;
+      CU_OK(c, cudaMemset(s.x16, 0, (Bm + 1) * rp * 256 * sizeof(__half)));
+      if ((rc = dev_alloc(c, &s.cand, 2 * Bm * rp * nbk * 2))) return rc;
+      if ((rc = make_act_map(c, &s.tmQ, s.x16, 256, 8, static_cast<int>(rp / 8), Bm + 1, 16))) return rc;
+      if ((rc = make_mat_map(c, &s.tmT, s.x16, 256, static_cast<int>((Bm + 1) * rp), 256))) return rc;
+      s.match_layer.taps = 1; s.match_layer.cb = 4; s.match_layer.n_tile = 256; s.match_layer.cout_total = 256;
+    }
     CU_OK(c, cudaEventCreate(&s.ev0));
     CU_OK(c, cudaEventCreate(&s.ev1));
     if ((rc = host_alloc(c, &s.h_match, Bm * cap))) return rc;
@@ -605,6 +637,9 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
   c->cov = (cfg->flags & SPFE_EMIT_COV) != 0;
   c->heat = c->cov || (cfg->flags & SPFE_EMIT_HEAT) != 0;
   c->match_prev = (cfg->flags & SPFE_MATCH_PREV) != 0;
+  c->rows_pad = (c->cap + 255) / 256 * 256;
+  c->match_nb = c->rows_pad / 256;
+  c->match_tiles = (c->cap + 127) / 128;
   {
     const char *e = getenv("SPFE_FUSED_CONV1");
     c->fused_conv1 = (e && e[0] == '1');
@@ -819,7 +854,7 @@ int spfe_reset_stream(spfe_ctx *c, int32_t slot) {
   int rc = check_slot(c, slot);
   if (rc) return rc;
   CU_OK(c, cudaSetDevice(c->cfg.device_id));
-  CU_OK(c, cudaMemsetAsync(c->slots[slot].carry_count, 0, sizeof(int), c->slots[slot].stream));
+  CU_OK(c, cudaMemsetAsync(c->slots[slot].count_all, 0, sizeof(int), c->slots[slot].stream));
   return SPFE_OK;
 }
 
