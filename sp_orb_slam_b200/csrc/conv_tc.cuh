@@ -8,22 +8,21 @@
 //
 // GEMM view per CTA tile:  D[128 pixels, N couts] = sum over (tap, 64-channel
 // block) of A[128, 64] * W[N, 64]^T, fp16 operands, fp32 accumulation in TMEM.
-//   * activations are NHWC fp16; an output tile is 8 (x) by 16 (y) pixels, so
-//     one image row of the tile (8 pixels x 64 ch x 2 B = 1024 B) is exactly
-//     one 128B-swizzle atom.
-//   * im2col is done by TMA: for each 64-channel block and each horizontal tap
-//     offset dx a "slab" of 18 rows x 8 pixels x 64 ch is loaded by ONE
-//     cp.async.bulk.tensor.4d with out-of-bounds zero fill (= the conv's zero
-//     padding).  The three vertical taps dy are the same slab read at
-//     +dy*1024 B, so every slab byte feeds 3 taps x 4 UMMA k-steps and L2 is
-//     read 3.4x per input element instead of 9x.
-//   * weights are packed [tap][cblock][cout][64] fp16; small layers keep all
-//     of them resident in shared memory for the CTA's lifetime, large layers
-//     stream [N x 64] blocks through a second ring.
-//   * persistent CTAs (1 per SM), warp-specialised: warp 0 = slab TMA
-//     producer, warp 3 = weight TMA producer, warp 1 = MMA issuer (one lane),
-//     warp 2 = TMEM allocator, warps 4-7 = epilogue.  Two TMEM accumulators so
-//     the epilogue of tile i overlaps the MMAs of tile i+1.
+//   * activations are NHWC fp16, so a pixel's 64 channels are one 128-byte row of a 128B-swizzled UMMA operand.
+//     A work item is HALVES (1 or 2) horizontally adjacent tiles of 8 (x) by 16 (y) output pixels.
+//   * im2col is done by TMA + descriptor arithmetic: per item and 64-channel block ONE
+//     cp.async.bulk.tensor.4d loads a slab of 18 rows x PW pixels x 64 ch (PW = 8*HALVES + 8, the halo padded to
+//     a multiple of 8 pixels) with out-of-bounds zero fill (= the conv's zero padding).  The hardware applies the
+//     128B swizzle on absolute shared-memory address bits (verified by tools/umma_shift_test.cu), so the A
+//     operand of tap (dy, dx) of half h is simply the same slab addressed at +((dy*PW + h*8 + dx) * 128) bytes
+//     with a stride of PW*128 bytes between 8-row groups: every slab byte feeds up to 9 taps, L2 is read
+//     1.7x (HALVES = 2) or 2.25x (HALVES = 1) per input element instead of 9x, and a streamed weight block is
+//     used by both halves (M = 256 per weight fetch).
+//   * weights are packed [tap][cblock][cout][64] fp16; small layers keep all of them resident in shared memory
+//     for the CTA's lifetime, large layers stream [N x 64] blocks through a second ring.
+//   * persistent CTAs (1 per SM), warp-specialised: warp 0 = slab TMA producer, warp 3 = weight TMA producer,
+//     warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue.  Two TMEM accumulator sets so the
+//     epilogue of item i overlaps the MMAs of item i+1.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -57,25 +56,30 @@ struct ConvArgs {
   int m_tiles;            // 128-row tiles per slot that can hold valid rows
 };
 
-template <int TAPS_, int CB_, int N_, int EPI_, bool WRES_, int SA_, int SB_>
+template <int TAPS_, int CB_, int N_, int EPI_, bool WRES_, int SA_, int SB_, int HALVES_ = 1>
 struct ConvCfg {
   static constexpr bool MATCH = (EPI_ == EPI_TOP2);
-  static constexpr int TAPS = TAPS_, CB = CB_, N = N_, EPI = EPI_, SA = SA_, SB = SB_;
+  static constexpr int TAPS = TAPS_, CB = CB_, N = N_, EPI = EPI_, SA = SA_, SB = SB_, HALVES = HALVES_;
   static constexpr bool WRES = WRES_;
   static constexpr int NDX = TAPS == 9 ? 3 : 1;
   static constexpr int NDY = NDX;
-  static constexpr int SLAB_ROWS = 16 + NDY - 1;
-  static constexpr int SLAB_BYTES = SLAB_ROWS * 1024;
+  static constexpr int TILE_W = 8 * HALVES;                       // output pixels per item row
+  static constexpr int PW = TAPS == 9 ? 8 * HALVES + 8 : 8;       // slab pixels per image row (halo padded to x8)
+  static constexpr int SLAB_ROWS = TAPS == 9 ? 18 : 16;
+  static constexpr int SLAB_BYTES = SLAB_ROWS * PW * 128;
+  static constexpr int SBO = PW * 128;                            // bytes between 8-row groups of the A operand
   static constexpr int BBLK_BYTES = N * 128;
   static constexpr int NWB = TAPS * CB;
   static constexpr int B_BYTES = (WRES ? NWB : SB) * BBLK_BYTES;
   static constexpr int ACC_STRIDE = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
-  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int TMEM_COLS = 2 * HALVES * ACC_STRIDE;       // two accumulator sets of HALVES tiles
   static constexpr int NBAR = 2 * SA + 2 * SB + 5;
   // dynamic shared memory: [1024 align slack][A ring][B ring / resident W][barriers][tmem slot][bias NB*N f32]
   static constexpr int SMEM_FIXED = 1024 + SA * SLAB_BYTES + B_BYTES + NBAR * 8 + 16;
   static constexpr int smem_bytes(int nb) { return SMEM_FIXED + nb * N * 4; }
   static_assert(N % 16 == 0 && N <= 256, "UMMA M=128 needs N % 16 == 0, N <= 256");
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation: power of two <= 512 columns");
+  static_assert(HALVES == 1 || TAPS == 9, "tile pairs only for 3x3 convolutions");
   static_assert(SMEM_FIXED + N * 4 <= 232448, "shared memory budget");
 };
 
@@ -197,7 +201,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       b = (t >> 1) + 1 - (t & 1);  // pair z = t >> 1, direction = t & 1
       return;
     }
-    x0 = (t % p.tiles_x) * 8;
+    x0 = (t % p.tiles_x) * Cfg::TILE_W;
     t /= p.tiles_x;
     y0 = (t % p.tiles_y) * 16;
     b = t / p.tiles_y;
@@ -210,14 +214,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         int nb, x0, y0, b;
         decode(item, nb, x0, y0, b);
-        for (int cb = 0; cb < CB; cb++)
-          for (int dx = 0; dx < NDX; dx++, it++) {
-            const int s = it % SA;
-            mbar_wait(a_empty(s), ((it / SA) & 1) ^ 1);
-            mbar_expect_tx(a_full(s), Cfg::SLAB_BYTES);
-            tma_load_4d(smem_u32(sA + s * Cfg::SLAB_BYTES), &tmA, a_full(s), p.cin_off + cb * 64,
-                        x0 + dx - (NDX == 3 ? 1 : 0), y0 - (NDY == 3 ? 1 : 0), b);
-          }
+        for (int cb = 0; cb < CB; cb++, it++) {
+          const int s = it % SA;
+          mbar_wait(a_empty(s), ((it / SA) & 1) ^ 1);
+          mbar_expect_tx(a_full(s), Cfg::SLAB_BYTES);
+          tma_load_4d(smem_u32(sA + s * Cfg::SLAB_BYTES), &tmA, a_full(s), p.cin_off + cb * 64,
+                      x0 - (NDX == 3 ? 1 : 0), y0 - (NDY == 3 ? 1 : 0), b);
+        }
       }
     }
   } else if (warp == 3) {
@@ -251,53 +254,95 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer
-    // The whole warp runs the loop so that every address / descriptor stays warp-uniform (uniform
-    // datapath, no per-MMA election); one elected lane issues the tcgen05.mma / commit instructions.
+    // The whole warp runs the loop so that every address / descriptor stays warp-uniform (uniform datapath); one
+    // elected lane issues.  Entering an elected region costs ~90 cycles (measured, tools/umma_rate.cu) while an
+    // M128 x N<=128 MMA needs only 50-64, so MMAs are issued in the largest groups the buffering allows: a whole
+    // item when the weights are resident, one horizontal tap (3 dy x HALVES x 4 k-steps) when they are streamed.
     constexpr uint32_t idesc = umma_idesc_f16(N);
+    constexpr int PW = Cfg::PW, HALVES = Cfg::HALVES;
     uint32_t it = 0, jt = 0, tcount = 0;
     if (WRES) mbar_wait(w_full, 0);
     const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+    // A operand of tap (dy, dx), half h, k-step k: slab + ((dy*PW + h*8 + dx)*128 + k*32) bytes, in (addr >> 4) units
+    auto a_off = [](int dy, int dx, int h, int k) { return static_cast<uint64_t>((dy * PW + h * 8 + dx) * 8 + 2 * k); };
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, tcount++) {
       const uint32_t acc = tcount & 1;
       mbar_wait(t_empty(acc), ((tcount >> 1) & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
-      uint32_t accumulate = 0;
-#pragma unroll 1
-      for (int cbdx = 0; cbdx < CB * NDX; cbdx++, it++) {
-        const int cb = cbdx / NDX, dx = cbdx - cb * NDX;
-        const uint32_t s = it % SA;
-        mbar_wait(a_full(s), (it / SA) & 1);
-        const uint64_t a_desc0 = umma_desc_sw128(sA_u + s * Cfg::SLAB_BYTES);
+      const uint32_t d_tmem = tmem_base + acc * HALVES * Cfg::ACC_STRIDE;
+      if constexpr (WRES) {
+        static_assert(!WRES || SA >= CB, "resident-weight kernels issue a whole item at once: all its slabs must fit the ring");
+        uint32_t st[CB];
 #pragma unroll
-        for (int dy = 0; dy < NDY; dy++) {
-          uint32_t sb = 0;
-          uint64_t b_desc;
-          if (WRES) {
-            b_desc = umma_desc_sw128(sB_u + ((dy * NDX + dx) * CB + cb) * Cfg::BBLK_BYTES);
-          } else {
-            sb = jt % SB;
-            mbar_wait(b_full(sb), (jt / SB) & 1);
-            b_desc = umma_desc_sw128(sB_u + sb * Cfg::BBLK_BYTES);
-            jt++;
-          }
-          tc_fence_after();
-          const uint64_t a_desc = a_desc0 + static_cast<uint64_t>(dy * (1024 >> 4));
-          if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) {  // +32 B per k-step == +2 in the (addr >> 4) field
-              umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accumulate | k);
-            }
-            if (!WRES) umma_commit(b_empty(sb));
-          }
-          accumulate = 1;
-          __syncwarp();
+        for (int cb = 0; cb < CB; cb++) {
+          st[cb] = (it + cb) % SA;
+          mbar_wait(a_full(st[cb]), ((it + cb) / SA) & 1);
         }
-        if (elect_one()) umma_commit(a_empty(s));
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int cb = 0; cb < CB; cb++) {
+            const uint64_t a0 = umma_desc_sw128(sA_u + st[cb] * Cfg::SLAB_BYTES, Cfg::SBO);
+#pragma unroll
+            for (int dx = 0; dx < NDX; dx++)
+#pragma unroll
+              for (int dy = 0; dy < NDY; dy++) {
+                const uint64_t b0 = umma_desc_sw128(sB_u + ((dy * NDX + dx) * CB + cb) * Cfg::BBLK_BYTES, 1024);
+#pragma unroll
+                for (int h = 0; h < HALVES; h++)
+#pragma unroll
+                  for (int k = 0; k < 4; k++)
+                    umma_f16(d_tmem + h * Cfg::ACC_STRIDE, a0 + a_off(dy, dx, h, k), b0 + 2 * k, idesc, (cb | dx | dy | k) ? 1u : 0u);
+              }
+            umma_commit(a_empty(st[cb]));  // the slab is free as soon as its own MMAs retire (keeps the TMA ring busy)
+          }
+          umma_commit(t_full(acc));
+        }
         __syncwarp();
+        it += CB;
+      } else {
+        static_assert(WRES || SB >= NDY, "streamed weights: one horizontal tap's weight blocks must fit the ring");
+        // group = GDY vertical taps per elected region: all three when an MMA is short (N <= 128), one when N = 256
+        // (128 cycles per MMA dwarf the region overhead and the weight ring is only 4 blocks deep)
+        constexpr int GDY = (N >= 256 || SB < 2 * NDY) ? 1 : NDY;
+#pragma unroll 1
+        for (int cb = 0; cb < CB; cb++, it++) {
+          const uint32_t s = it % SA;
+          mbar_wait(a_full(s), (it / SA) & 1);
+          const uint64_t a0 = umma_desc_sw128(sA_u + s * Cfg::SLAB_BYTES, Cfg::SBO);
+#pragma unroll
+          for (int dx = 0; dx < NDX; dx++) {
+#pragma unroll
+            for (int g = 0; g < NDY; g += GDY) {
+              uint32_t sb[GDY];
+#pragma unroll
+              for (int d = 0; d < GDY; d++) {
+                sb[d] = (jt + d) % SB;
+                mbar_wait(b_full(sb[d]), ((jt + d) / SB) & 1);
+              }
+              tc_fence_after();
+              if (elect_one()) {
+#pragma unroll
+                for (int d = 0; d < GDY; d++) {
+                  const int dy = g + d;
+                  const uint64_t b0 = umma_desc_sw128(sB_u + sb[d] * Cfg::BBLK_BYTES, 1024);
+#pragma unroll
+                  for (int h = 0; h < HALVES; h++)
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                      umma_f16(d_tmem + h * Cfg::ACC_STRIDE, a0 + a_off(dy, dx, h, k), b0 + 2 * k, idesc, (cb | dx | dy | k) ? 1u : 0u);
+                  umma_commit(b_empty(sb[d]));
+                }
+                if (dx == NDX - 1 && g + GDY >= NDY) {
+                  umma_commit(a_empty(s));
+                  if (cb == CB - 1) umma_commit(t_full(acc));
+                }
+              }
+              __syncwarp();
+              jt += GDY;
+            }
+          }
+        }
       }
-      if (elect_one()) umma_commit(t_full(acc));
-      __syncwarp();
     }
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue (TMEM -> regs -> global)
@@ -305,13 +350,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int hl = wq * 4 + (lane >> 3), wl = lane & 7;
     uint32_t tcount = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, tcount++) {
-      int nb, x0, y0, b;
-      decode(item, nb, x0, y0, b);
+      int nb, x0_item, y0, b;
+      decode(item, nb, x0_item, y0, b);
       const int acc = tcount & 1;
       mbar_wait(t_full(acc), (tcount >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * Cfg::ACC_STRIDE;
       const float *bias = sBias + nb * N;
+#pragma unroll 1
+      for (int half = 0; half < Cfg::HALVES; half++) {  // the item's 8-pixel-wide tiles, one accumulator each
+      const int x0 = x0_item + half * 8;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + (acc * Cfg::HALVES + half) * Cfg::ACC_STRIDE;
       const int y = y0 + hl, x = x0 + wl;
 
       if constexpr (EPI == EPI_RELU) {
@@ -484,6 +532,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+      }  // half
       tc_fence_before();
       mbar_arrive(t_empty(acc));
     }

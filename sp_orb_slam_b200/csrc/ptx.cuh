@@ -126,14 +126,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, 128-byte-swizzled operand tile: rows of 128 B (64 fp16), 8-row
-// groups 1024 B apart.  `saddr` must be 1024-B aligned up to a k-offset of
-// 32/64/96 B inside the swizzle atom.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+// K-major, 128-byte-swizzled operand: rows of 128 B (64 fp16); consecutive 8-row groups are `sbo` bytes apart.
+// The swizzle acts on absolute shared-memory address bits, so `saddr` may be any 128-byte-aligned row of a
+// 1024-byte-aligned tile (plus a k-offset of 32/64/96 B); base_offset stays 0 (tools/umma_shift_test.cu).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t sbo = 1024) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);  // start address        bits [0,14)
   d |= static_cast<uint64_t>(1) << 16;                  // LBO (unused, K-major swizzled)
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;          // SBO = 1024 B         bits [32,46)
+  d |= static_cast<uint64_t>(sbo >> 4) << 32;           // SBO                  bits [32,46)
   d |= static_cast<uint64_t>(1) << 46;                  // descriptor version 1 (sm_100)
   d |= static_cast<uint64_t>(2) << 61;                  // SWIZZLE_128B
   return d;

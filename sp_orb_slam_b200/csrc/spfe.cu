@@ -40,12 +40,13 @@ std::string fmt(const char *f, ...) {
 // ----------------------------------------------------------------------------
 // kernel configurations (see conv_tc.cuh)
 //                         TAPS CB  N   epilogue        resident-W  A-ring B-ring
-using CfgC64 = ConvCfg<9, 1, 64, EPI_RELU, true, 6, 1>;         // conv2a
-using CfgC64P = ConvCfg<9, 1, 64, EPI_RELU_POOL, true, 6, 1>;   // conv1b, conv2b
-using CfgC3a = ConvCfg<9, 1, 128, EPI_RELU, true, 4, 1>;        // conv3a
-using CfgC128 = ConvCfg<9, 2, 128, EPI_RELU, false, 4, 8>;      // conv4a, conv4b
-using CfgC128P = ConvCfg<9, 2, 128, EPI_RELU_POOL, false, 4, 8>;  // conv3b
-using CfgHeads = ConvCfg<9, 2, 256, EPI_RELU, false, 4, 4>;     // convPa || convDa (NB = 2)
+//                                                                                     tile pair (HALVES = 2)
+using CfgC64 = ConvCfg<9, 1, 64, EPI_RELU, true, 2, 1, 2>;          // conv2a          slab 54 KB x2 + 72 KB weights
+using CfgC64P = ConvCfg<9, 1, 64, EPI_RELU_POOL, true, 2, 1, 2>;    // conv1b, conv2b
+using CfgC3a = ConvCfg<9, 1, 128, EPI_RELU, true, 2, 1, 1>;         // conv3a          144 KB weights: single tiles
+using CfgC128 = ConvCfg<9, 2, 128, EPI_RELU, false, 2, 6, 2>;       // conv4a, conv4b  slab 54 KB x2 + 6 x 16 KB weights
+using CfgC128P = ConvCfg<9, 2, 128, EPI_RELU_POOL, false, 2, 6, 2>; // conv3b
+using CfgHeads = ConvCfg<9, 2, 256, EPI_RELU, false, 2, 4, 1>;      // convPa || convDa (NB = 2), N = 256: single tiles
 using CfgPb = ConvCfg<1, 4, 80, EPI_DETECT, true, 4, 1>;        // convPb + detector head
 using CfgDb = ConvCfg<1, 4, 256, EPI_L2NORM, true, 4, 1>;       // convDb + L2 norm
 using CfgMatch = ConvCfg<1, 4, 256, EPI_TOP2, false, 4, 4>;     // descriptor matching: Q.T^T + top-2 per 256-column block
@@ -160,10 +161,10 @@ int host_alloc(spfe_ctx *c, T **p, size_t n) {
 }
 
 // 4-D NHWC fp16 activation tensor -> TMA map with box {64 ch, 8 px, box_rows, 1 frame}, 128-B swizzle.
-int make_act_map(spfe_ctx *c, CUtensorMap *tm, const void *ptr, int C, int W, int H, int B, int box_rows) {
+int make_act_map(spfe_ctx *c, CUtensorMap *tm, const void *ptr, int C, int W, int H, int B, int box_rows, int box_w = 8) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {64, 8, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = c->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(ptr), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -233,7 +234,7 @@ int launch_conv(spfe_ctx *c, cudaStream_t st, const CUtensorMap &tmA, const Laye
     configured.store(smem);
   }
   a.bias = L.bias;
-  a.tiles_x = (a.W + 7) / 8;
+  a.tiles_x = (a.W + Cfg::TILE_W - 1) / Cfg::TILE_W;
   a.tiles_y = (a.H + 15) / 16;
   a.n_items = a.B * a.tiles_x * a.tiles_y * a.NB;
   if (Cfg::MATCH) a.n_items = a.B * 2 * a.m_tiles * a.NB;
@@ -590,14 +591,15 @@ static int create_impl(spfe_ctx *c) {
       s.resp.resize(Bm * cap);
     }
     // TMA maps of every layer's input tensor
-    if (!c->fused_conv1 && (rc = make_act_map(c, &s.tmA[L1B], s.a1a, 64, W, H, Bm, 18))) return rc;
-    if ((rc = make_act_map(c, &s.tmA[L2A], s.a1b, 64, W / 2, H / 2, Bm, 18))) return rc;
-    if ((rc = make_act_map(c, &s.tmA[L2B], s.a2a, 64, W / 2, H / 2, Bm, 18))) return rc;
-    if ((rc = make_act_map(c, &s.tmA[L3A], s.a2b, 64, W / 4, H / 4, Bm, 18))) return rc;
-    if ((rc = make_act_map(c, &s.tmA[L3B], s.a3a, 128, W / 4, H / 4, Bm, 18))) return rc;
-    if ((rc = make_act_map(c, &s.tmA[L4A], s.a3b, 128, wc, hc, Bm, 18))) return rc;
-    if ((rc = make_act_map(c, &s.tmA[L4B], s.a4a, 128, wc, hc, Bm, 18))) return rc;
-    if ((rc = make_act_map(c, &s.tmA[LHEADS], s.a4b, 128, wc, hc, Bm, 18))) return rc;
+    // 3x3 layers: one slab of 18 rows x PW pixels per item (PW = 24 for tile pairs, 16 for single tiles)
+    if (!c->fused_conv1 && (rc = make_act_map(c, &s.tmA[L1B], s.a1a, 64, W, H, Bm, 18, CfgC64P::PW))) return rc;
+    if ((rc = make_act_map(c, &s.tmA[L2A], s.a1b, 64, W / 2, H / 2, Bm, 18, CfgC64::PW))) return rc;
+    if ((rc = make_act_map(c, &s.tmA[L2B], s.a2a, 64, W / 2, H / 2, Bm, 18, CfgC64P::PW))) return rc;
+    if ((rc = make_act_map(c, &s.tmA[L3A], s.a2b, 64, W / 4, H / 4, Bm, 18, CfgC3a::PW))) return rc;
+    if ((rc = make_act_map(c, &s.tmA[L3B], s.a3a, 128, W / 4, H / 4, Bm, 18, CfgC128P::PW))) return rc;
+    if ((rc = make_act_map(c, &s.tmA[L4A], s.a3b, 128, wc, hc, Bm, 18, CfgC128::PW))) return rc;
+    if ((rc = make_act_map(c, &s.tmA[L4B], s.a4a, 128, wc, hc, Bm, 18, CfgC128::PW))) return rc;
+    if ((rc = make_act_map(c, &s.tmA[LHEADS], s.a4b, 128, wc, hc, Bm, 18, CfgHeads::PW))) return rc;
     if ((rc = make_act_map(c, &s.tmA[LPB], s.heads, 512, wc, hc, Bm, 16))) return rc;
     if ((rc = make_act_map(c, &s.tmA[LDB], s.heads, 512, wc, hc, Bm, 16))) return rc;
   }
