@@ -9,10 +9,10 @@
 // the conv1b tcgen05 MMAs read.  The u8 image is the only tensor read from HBM.
 //
 // Warps: 0 = conv1b weight TMA (once), 1 = MMA issuer, 2 = TMEM allocator,
-// 4-7 = epilogue, 8-15 = conv1a producers.  A stage = the three dx-shifted
-// slabs of one tile (3 x 18 rows x 8 px x 64 ch); two stages and two TMEM
-// accumulators, so producers, tensor core and epilogue work on three different
-// tiles at once.
+// 4-7 = epilogue, 8-15 = conv1a producers.  A stage = the halo slab of one pair
+// of tiles (18 rows x 24 px x 64 ch, each halo pixel stored once); two stages
+// and two TMEM accumulator sets, so producers, tensor core and epilogue work on
+// three different items at once.
 #pragma once
 #include "conv_tc.cuh"
 
@@ -28,9 +28,13 @@ struct Conv1abArgs {
 };
 
 namespace c1ab {
-constexpr int SLAB = 18 * 1024, STAGE = 3 * SLAB, WBLK = 64 * 128, WBYTES = 9 * WBLK;
-constexpr int PATCH_H = 20, PATCH_W = 12, HALO_H = 18, HALO_W = 10;
+// A work item is a pair of 8x16-pixel tiles (16 x 16 outputs).  Its conv1a halo is 18 x 18 pixels, stored once in a
+// slab of 18 rows x 24 pixels (pitch padded to a multiple of 8 pixels) x 128 B; tap (dy, dx) of half h reads it at
+// +((dy*24 + h*8 + dx) * 128) bytes (the 128B swizzle acts on absolute address bits, see conv_tc.cuh).
+constexpr int PW = 24, HALO = 18, STAGE = HALO * PW * 128, WBLK = 64 * 128, WBYTES = 9 * WBLK;
+constexpr int PATCH = HALO + 2;  // image patch side (conv1a's own 3x3 support)
 constexpr int THREADS = 512, PRODUCERS = 256;
+constexpr int ITEMS = HALO * HALO * 8;  // (halo pixel, 8-channel group) work items per tile pair
 constexpr int SMEM = 1024 + 2 * STAGE + WBYTES + 9 * 8 + 16;  // dynamic part (patch + bias are static)
 }  // namespace c1ab
 
@@ -46,7 +50,7 @@ __global__ void __launch_bounds__(c1ab::THREADS, 1)
 conv1ab_kernel(const __grid_constant__ CUtensorMap tmW, const Conv1abArgs p) {
   using namespace c1ab;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ float s_patch[2][PATCH_H * PATCH_W];  // static: keeps the accesses LDS (not generic LD)
+  __shared__ float s_patch[2][PATCH * PATCH];  // static: keeps the accesses LDS (not generic LD)
   __shared__ float s_bias[64];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *sStage = smem;
@@ -75,7 +79,7 @@ conv1ab_kernel(const __grid_constant__ CUtensorMap tmW, const Conv1abArgs p) {
     tma_prefetch_desc(&tmW);
   }
   if (warp == 2) {
-    tmem_alloc(smem_u32(tmem_slot), 128);
+    tmem_alloc(smem_u32(tmem_slot), 256);  // 2 stages x 2 halves x 64 columns
     tmem_relinquish();
   }
   if (threadIdx.x < 64) sBias[threadIdx.x] = p.b1b[threadIdx.x];
@@ -85,7 +89,7 @@ conv1ab_kernel(const __grid_constant__ CUtensorMap tmW, const Conv1abArgs p) {
   const uint32_t tmem_base = *tmem_slot;
 
   auto decode = [&](int item, int &x0, int &y0, int &b) {
-    x0 = (item % p.tiles_x) * 8;
+    x0 = (item % p.tiles_x) * 16;
     const int t = item / p.tiles_x;
     y0 = (t % p.tiles_y) * 16;
     b = t / p.tiles_y;
@@ -97,7 +101,7 @@ conv1ab_kernel(const __grid_constant__ CUtensorMap tmW, const Conv1abArgs p) {
       for (int wb = 0; wb < 9; wb++) tma_load_2d(smem_u32(sW + wb * WBLK), &tmW, w_full, 0, wb * 64);
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer (warp-uniform, one elected lane issues)
+    // ------------------------------------------------ MMA issuer (warp-uniform, one elected lane issues 72 MMAs)
     constexpr uint32_t idesc = umma_idesc_f16(64);
     mbar_wait(w_full, 0);
     const uint32_t sStage_u = smem_u32(sStage), sW_u = smem_u32(sW);
@@ -107,19 +111,21 @@ conv1ab_kernel(const __grid_constant__ CUtensorMap tmW, const Conv1abArgs p) {
       mbar_wait(t_empty(st), ph ^ 1);
       mbar_wait(s_full(st), ph);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + st * 64;
+      const uint32_t d_tmem = tmem_base + st * 128;
       if (elect_one()) {
+        const uint64_t a0 = umma_desc_sw128(sStage_u + st * STAGE, PW * 128);
 #pragma unroll
-        for (int dx = 0; dx < 3; dx++) {
-          const uint64_t a0 = umma_desc_sw128(sStage_u + st * STAGE + dx * SLAB);
+        for (int dx = 0; dx < 3; dx++)
 #pragma unroll
           for (int dy = 0; dy < 3; dy++) {
-            const uint64_t a_desc = a0 + static_cast<uint64_t>(dy * (1024 >> 4));
-            const uint64_t b_desc = umma_desc_sw128(sW_u + (dy * 3 + dx) * WBLK);
+            const uint64_t b0 = umma_desc_sw128(sW_u + (dy * 3 + dx) * WBLK, 1024);
 #pragma unroll
-            for (int k = 0; k < 4; k++) umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (dx | dy | k) ? 1u : 0u);
+            for (int h = 0; h < 2; h++)
+#pragma unroll
+              for (int k = 0; k < 4; k++)
+                umma_f16(d_tmem + h * 64, a0 + static_cast<uint64_t>((dy * PW + h * 8 + dx) * 8 + 2 * k), b0 + 2 * k, idesc,
+                         (dx | dy | k) ? 1u : 0u);
           }
-        }
         umma_commit(s_empty(st));
         umma_commit(t_full(st));
       }
@@ -136,16 +142,19 @@ conv1ab_kernel(const __grid_constant__ CUtensorMap tmW, const Conv1abArgs p) {
       const uint32_t st = tcount & 1;
       mbar_wait(t_full(st), (tcount >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + st * 64;
-      epilogue_relu_pool<64>(taddr, sBias, lane, hl, wl, x0, y0, b, 0, p.H, p.W, 64, p.out);
+#pragma unroll 1
+      for (int h = 0; h < 2; h++) {
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + st * 128 + h * 64;
+        epilogue_relu_pool<64>(taddr, sBias, lane, hl, wl, x0 + h * 8, y0, b, 0, p.H, p.W, 64, p.out);
+      }
       tc_fence_before();
       mbar_arrive(t_empty(st));
     }
   } else if (warp >= 8) {
-    // ------------------------------------------------ conv1a producers (fp32 FFMA -> fp16 swizzled slabs)
-    // Thread = (pixel slot 0..31, 8-channel group g).  The halo has 18 x 10 pixels = 180 slots x 8 groups
-    // = 1440 work items, 6 rounds of 256.  The group's 9 x 8 weights stay in registers; the image patch of
-    // the NEXT tile is prefetched into a register while this tile is computed (double-buffered patch).
+    // ------------------------------------------------ conv1a producers (fp32 FFMA -> fp16 swizzled slab)
+    // Thread = (pixel slot 0..31, 8-channel group g).  The halo has 18 x 18 pixels x 8 groups = 2592 work items,
+    // 10 rounds of 256 plus 32.  The group's 9 x 8 weights stay in registers; the image patch of the NEXT item is
+    // prefetched into registers while this item is computed (double-buffered patch, one named barrier per item).
     const int ptid = threadIdx.x - 256;
     const int g = ptid & 7;  // 8 output channels == 16-byte chunk g of every 128-byte pixel row
     float w[9][8], bs[8];
@@ -160,17 +169,21 @@ conv1ab_kernel(const __grid_constant__ CUtensorMap tmW, const Conv1abArgs p) {
     for (int c = 0; c < 8; c++) bs[c] = p.b1a[g * 8 + c];
     const float scale = 1.0f / 255.0f;  // cv::Mat::convertTo(CV_32FC1, 1.f / 255.f)
     const uint32_t sStage_u = smem_u32(sStage);
-    const int pr = ptid / PATCH_W, pc = ptid - pr * PATCH_W;  // this thread's patch element (ptid < 240)
-    const int hh0 = (ptid >> 3) / HALO_W, j0 = (ptid >> 3) - hh0 * HALO_W;
-    auto load_patch = [&](int item) -> unsigned {  // raw byte; patch origin (y0-2, x0-2); 0 outside == zero padding
+    const int hh0 = (ptid >> 3) / HALO, j0 = (ptid >> 3) - hh0 * HALO;
+    // patch element(s) of this thread: 400 bytes over 256 threads (origin (y0-2, x0-2); 0 outside == zero padding)
+    auto load_patch = [&](int item, int e) -> unsigned {
       int x0, y0, b;
       decode(item, x0, y0, b);
-      const int y = y0 - 2 + pr, x = x0 - 2 + pc;
-      if (ptid < PATCH_H * PATCH_W && y >= 0 && y < p.H && x >= 0 && x < p.W)
+      const int r = e / PATCH, c = e - r * PATCH;
+      const int y = y0 - 2 + r, x = x0 - 2 + c;
+      if (e < PATCH * PATCH && y >= 0 && y < p.H && x >= 0 && x < p.W)
         return __ldg(p.img + (static_cast<size_t>(b) * p.H + y) * p.W + x);
       return 0u;
     };
-    if (blockIdx.x < p.n_items && ptid < PATCH_H * PATCH_W) s_patch[0][ptid] = static_cast<float>(load_patch(blockIdx.x)) * scale;
+    if (blockIdx.x < p.n_items) {
+      s_patch[0][ptid] = static_cast<float>(load_patch(blockIdx.x, ptid)) * scale;
+      if (ptid + 256 < PATCH * PATCH) s_patch[0][ptid + 256] = static_cast<float>(load_patch(blockIdx.x, ptid + 256)) * scale;
+    }
     named_bar_sync(1, PRODUCERS);
     uint32_t tcount = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, tcount++) {
@@ -178,25 +191,26 @@ conv1ab_kernel(const __grid_constant__ CUtensorMap tmW, const Conv1abArgs p) {
       decode(item, x0, y0, b);
       const uint32_t st = tcount & 1, ph = (tcount >> 1) & 1;
       const int next = item + gridDim.x;
-      const unsigned raw_next = next < p.n_items ? load_patch(next) : 0u;  // in flight during the compute below
+      const bool has_next = next < p.n_items;
+      const unsigned raw0 = has_next ? load_patch(next, ptid) : 0u;  // in flight during the compute below
+      const unsigned raw1 = has_next ? load_patch(next, ptid + 256) : 0u;
       const float *patch = s_patch[st];
-      mbar_wait(s_empty(st), ph ^ 1);  // the MMAs of the tile that used this stage two tiles ago are done
+      mbar_wait(s_empty(st), ph ^ 1);  // the MMAs of the item that used this stage two items ago are done
       const uint32_t stage_u = sStage_u + st * STAGE;
+      int j = j0, hh = hh0;
 #pragma unroll 2
-      for (int k = 0; k < 6; k++) {
-        if (k == 5 && ptid >= HALO_H * HALO_W * 8 - 5 * PRODUCERS) break;
-        int j = j0 + 2 * k, hh = hh0 + 3 * k;  // pixel slot + 32k  ->  (+3 rows, +2 columns) with one carry
-        if (j >= HALO_W) { j -= HALO_W; hh++; }
-        const int y = y0 - 1 + hh, x = x0 - 1 + j;  // halo pixel
+      for (int k = 0; k < 11; k++) {
+        if (k == 10 && ptid >= ITEMS - 10 * PRODUCERS) break;
+        const int y = y0 - 1 + hh, x = x0 - 1 + j;  // halo pixel (hh, j)
         uint4 o = make_uint4(0u, 0u, 0u, 0u);        // outside the image: conv1b's zero padding
         if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
           float acc[8];
 #pragma unroll
           for (int c = 0; c < 8; c++) acc[c] = bs[c];
-          const float *pp = patch + hh * PATCH_W + j;
+          const float *pp = patch + hh * PATCH + j;
 #pragma unroll
           for (int t = 0; t < 9; t++) {
-            const float xin = pp[(t / 3) * PATCH_W + t % 3];
+            const float xin = pp[(t / 3) * PATCH + t % 3];
 #pragma unroll
             for (int c = 0; c < 8; c++) acc[c] = fmaf(w[t][c], xin, acc[c]);
           }
@@ -205,17 +219,16 @@ conv1ab_kernel(const __grid_constant__ CUtensorMap tmW, const Conv1abArgs p) {
           o.z = pack_h2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
           o.w = pack_h2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
         }
-        // halo column j is column (j - dx) of slab dx; row = hh*8 + col, 16-byte chunk g XOR-swizzled by row & 7
-        const uint32_t base = stage_u + hh * 1024;
-#pragma unroll
-        for (int dx = 0; dx < 3; dx++) {
-          const int col = j - dx;
-          if (col >= 0 && col < 8) st_shared_v4(base + dx * SLAB + col * 128 + ((g ^ col) << 4), o);
-        }
+        const int row = hh * PW + j;  // 16-byte chunk g of that row, XOR-swizzled by (row & 7)
+        st_shared_v4(stage_u + row * 128 + ((g ^ (row & 7)) << 4), o);
+        j += 32 - HALO;  // next pixel slot: +32 pixels == +1 row +14 columns (HALO = 18)
+        hh += 1;
+        if (j >= HALO) { j -= HALO; hh++; }
       }
       fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
       mbar_arrive(s_full(st));
-      if (ptid < PATCH_H * PATCH_W) s_patch[st ^ 1][ptid] = static_cast<float>(raw_next) * scale;
+      s_patch[st ^ 1][ptid] = static_cast<float>(raw0) * scale;
+      if (ptid + 256 < PATCH * PATCH) s_patch[st ^ 1][ptid + 256] = static_cast<float>(raw1) * scale;
       named_bar_sync(1, PRODUCERS);  // next patch visible; everyone is done with this one
     }
   }
@@ -224,7 +237,7 @@ conv1ab_kernel(const __grid_constant__ CUtensorMap tmW, const Conv1abArgs p) {
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 128);
+    tmem_dealloc(tmem_base, 256);
   }
 }
 

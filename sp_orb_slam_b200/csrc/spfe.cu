@@ -112,7 +112,7 @@ struct spfe_ctx {
   int H = 0, W = 0, hc = 0, wc = 0, cells = 0, cap = 0, num_sms = 0;
   int rows_pad = 0, match_nb = 0, match_tiles = 0;  // tensor-core matcher geometry
   bool heat = false, cov = false, match_prev = false;
-  bool fused_conv1 = false;  // SPFE_FUSED_CONV1=1 selects the fused conv1a+conv1b kernel (bit-identical, currently slower: DESIGN.md)
+  bool fused_conv1 = true;  // SPFE_FUSED_CONV1=0 selects the two-kernel path (bit-identical; materialises conv1a for inspection)
   EncodeTiledFn encode = nullptr;
   float *w1a = nullptr, *b1a = nullptr;  // conv1a fp32 [9][64], [64]
   Layer layers[NLAYERS];
@@ -279,7 +279,7 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
   if (c->fused_conv1) {  // conv1a + conv1b + pool in one kernel: u8 image -> fp16 [H/2][W/2][64]
     Conv1abArgs a;
     a.img = s.d_gray; a.w1a = c->w1a; a.b1a = c->b1a; a.b1b = c->layers[L1B].bias; a.out = s.a1b;
-    a.B = B; a.H = H; a.W = W; a.tiles_x = (W + 7) / 8; a.tiles_y = (H + 15) / 16;
+    a.B = B; a.H = H; a.W = W; a.tiles_x = (W + 15) / 16; a.tiles_y = (H + 15) / 16;
     a.n_items = B * a.tiles_x * a.tiles_y;
     const int grid = a.n_items < c->num_sms ? a.n_items : c->num_sms;
     conv1ab_kernel<<<grid, c1ab::THREADS, c1ab::SMEM, st>>>(c->layers[L1B].tm, a);
@@ -644,7 +644,7 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
   c->match_tiles = (c->cap + 127) / 128;
   {
     const char *e = getenv("SPFE_FUSED_CONV1");
-    c->fused_conv1 = (e && e[0] == '1');
+    c->fused_conv1 = !(e && e[0] == '0');
   }
   int rc = create_impl(c);
   if (rc == SPFE_OK) rc = [&]() -> int {

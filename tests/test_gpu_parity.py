@@ -153,28 +153,29 @@ def test_margin_robust_keypoints_identical(weights, ex_cache):
 
 
 def test_fused_conv1_equals_unfused(weights, monkeypatch):
-    """SPFE_FUSED_CONV1=1 (conv1a computed by conv1b's producer warps straight into the swizzled shared-memory
-    slabs) must be bit-identical to the default two-kernel path, whose conv1a activation is checked against the oracle."""
+    """Default path: conv1a is computed by conv1b's producer warps straight into the swizzled shared-memory slab.
+    It must be bit-identical to the two-kernel path (SPFE_FUSED_CONV1=0), whose materialised conv1a activation is
+    checked against the oracle."""
     H, W = 120, 136
     frames = synth.make_stream(H, W, 2, seed=7, n_shapes=24)
+    fused = SPExtractor(800, H, W, WEIGHTS, max_batch=2)
+    a = fused.extract_batch(list(frames))
+    a1b = fused.debug_read(0, "conv1b", 2)
+    with pytest.raises(SpfeError):
+        fused.debug_read(0, "conv1a", 2)                                       # never materialised in fused mode
+    fused.close()
+    monkeypatch.setenv("SPFE_FUSED_CONV1", "0")
     plain = SPExtractor(800, H, W, WEIGHTS, max_batch=2)
     b = plain.extract_batch(list(frames))
-    b1b = plain.debug_read(0, "conv1b", 2)
+    assert np.array_equal(a1b, plain.debug_read(0, "conv1b", 2))
+    for x, y in zip(a, b):
+        for k in ["kp_xy", "desc", "occ_grid", "dense_dust", "heat"]:
+            assert np.array_equal(x[k], y[k]), k
     got = plain.debug_read(0, "conv1a", 2).astype(np.float32)
     for t in range(2):
         ref = O.frontend_forward(weights, frames[t], keep_layers=True)["layers"]["conv1a"].transpose(1, 2, 0)
         assert np.abs(got[t] - ref).max() <= 1e-3 * np.abs(ref).max()          # fp32 compute, fp16 storage
     plain.close()
-    monkeypatch.setenv("SPFE_FUSED_CONV1", "1")
-    fused = SPExtractor(800, H, W, WEIGHTS, max_batch=2)
-    a = fused.extract_batch(list(frames))
-    assert np.array_equal(b1b, fused.debug_read(0, "conv1b", 2))
-    for x, y in zip(a, b):
-        for k in ["kp_xy", "desc", "occ_grid", "dense_dust", "heat"]:
-            assert np.array_equal(x[k], y[k]), k
-    with pytest.raises(SpfeError):
-        fused.debug_read(0, "conv1a", 2)                                       # never materialised in fused mode
-    fused.close()
 
 
 def test_batch_invariance_and_determinism(ex_cache):
