@@ -28,16 +28,16 @@ __global__ void __launch_bounds__(256) conv1a_kernel(const uint8_t *__restrict__
   const int g = threadIdx.x & 7, slot = threadIdx.x >> 3;  // channel group, pixel slot 0..31
   const int x0 = blockIdx.x * C1A_TW, y0 = blockIdx.y * C1A_TH, b = blockIdx.z;
   const uint8_t *img = in + static_cast<size_t>(b) * H * W;
-  float w[9][8], bs[8];
+  float2 w[9][4], bs[4];  // channel pairs: FFMA2 does two fp32 FMAs per instruction
 #pragma unroll
   for (int t = 0; t < 9; t++) {
     const float4 lo = *reinterpret_cast<const float4 *>(wgt + t * 64 + g * 8);
     const float4 hi = *reinterpret_cast<const float4 *>(wgt + t * 64 + g * 8 + 4);
-    w[t][0] = lo.x; w[t][1] = lo.y; w[t][2] = lo.z; w[t][3] = lo.w;
-    w[t][4] = hi.x; w[t][5] = hi.y; w[t][6] = hi.z; w[t][7] = hi.w;
+    w[t][0] = make_float2(lo.x, lo.y); w[t][1] = make_float2(lo.z, lo.w);
+    w[t][2] = make_float2(hi.x, hi.y); w[t][3] = make_float2(hi.z, hi.w);
   }
 #pragma unroll
-  for (int c = 0; c < 8; c++) bs[c] = bias[g * 8 + c];
+  for (int c = 0; c < 4; c++) bs[c] = make_float2(bias[g * 8 + 2 * c], bias[g * 8 + 2 * c + 1]);
   const float scale = 1.0f / 255.0f;
   for (int i = threadIdx.x; i < (C1A_TH + 2) * (C1A_TW + 2); i += 256) {
     const int r = i / (C1A_TW + 2), c = i - r * (C1A_TW + 2);
@@ -51,21 +51,22 @@ __global__ void __launch_bounds__(256) conv1a_kernel(const uint8_t *__restrict__
   for (int p = slot; p < C1A_TW * C1A_TH; p += 32) {
     const int ty = p / C1A_TW, tx = p - ty * C1A_TW;
     const int x = x0 + tx, y = y0 + ty;
-    float acc[8];
+    float2 acc[4];
 #pragma unroll
-    for (int c = 0; c < 8; c++) acc[c] = bs[c];
+    for (int c = 0; c < 4; c++) acc[c] = bs[c];
 #pragma unroll
     for (int t = 0; t < 9; t++) {
       const float xin = s_in[ty + t / 3][tx + t % 3];
+      const float2 x2 = make_float2(xin, xin);
 #pragma unroll
-      for (int c = 0; c < 8; c++) acc[c] = fmaf(w[t][c], xin, acc[c]);
+      for (int c = 0; c < 4; c++) ffma2(acc[c], w[t][c], x2);
     }
     if (x < W && y < H) {
       uint4 o;
-      o.x = pack_h2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
-      o.y = pack_h2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
-      o.z = pack_h2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
-      o.w = pack_h2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+      o.x = pack_h2(fmaxf(acc[0].x, 0.f), fmaxf(acc[0].y, 0.f));
+      o.y = pack_h2(fmaxf(acc[1].x, 0.f), fmaxf(acc[1].y, 0.f));
+      o.z = pack_h2(fmaxf(acc[2].x, 0.f), fmaxf(acc[2].y, 0.f));
+      o.w = pack_h2(fmaxf(acc[3].x, 0.f), fmaxf(acc[3].y, 0.f));
       *reinterpret_cast<uint4 *>(out + ((static_cast<size_t>(b) * H + y) * W + x) * 64 + g * 8) = o;
     }
   }

@@ -24,6 +24,15 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Packed dual fp32 FMA (Blackwell FFMA2): d.{x,y} = a.{x,y} * b.{x,y} + d.{x,y}, each lane rounded like fmaf.
+__device__ __forceinline__ void ffma2(float2 &d, const float2 &a, const float2 &b) {
+  unsigned long long D = *reinterpret_cast<unsigned long long *>(&d);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(D)
+      : "l"(*reinterpret_cast<const unsigned long long *>(&a)), "l"(*reinterpret_cast<const unsigned long long *>(&b)));
+  d = *reinterpret_cast<float2 *>(&D);
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
