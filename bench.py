@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--nf", type=int, default=800)
     ap.add_argument("--slots", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cov", action="store_true", help="also run computeCovariance on the device (kp.response / cov2 / cov2_inv)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -186,7 +187,7 @@ def main():
     n_pool = max(4, -(-(140 << 20) // (B * H * W)))             # inputs > 126 MB L2
     pool = make_pool(H, W, B, n_pool, rank)
     ex = SPExtractor(args.nf, H, W, WEIGHTS, device_id=local_rank, max_batch=B, num_slots=S,
-                     emit_heat=False, emit_cov=False, match_prev=True)
+                     emit_heat=False, emit_cov=args.cov, match_prev=True)
     d_pool = torch.from_numpy(pool).cuda()
     stride = B * H * W
     sampler = ClockSampler(local_rank)
@@ -227,8 +228,15 @@ def main():
     conv_ms = sum(stages[n]["ms"] for n in conv_names)
     conv_flop = FLOP_PER_PIXEL * H * W * B
     step_ms = sum(d["ms"] for d in stages.values())
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/r01_traffic.json,
+    # same 32 x 752x480 launch); None for other geometries
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and (H, W, B) == (480, 752, 32):
+        tj = json.load(open(tpath))
+        traffic = tj.get({"conv1a+1b": "conv1ab_kernel"}.get(dom, dom))
     roofline = {"bound": "tensor", "kernel": dom, "achieved": dom_tf, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": dom_tf / peaks["tflops_sustained"], "traffic": None, "peak_source": peaks["src"] + " bf16 sustained",
+                "frac": dom_tf / peaks["tflops_sustained"], "traffic": traffic, "peak_source": peaks["src"] + " bf16 sustained",
                 "kernel_ms": stages[dom]["ms"], "kernel_share_of_step": stages[dom]["ms"] / step_ms,
                 "conv_stack": {"achieved": conv_flop / (conv_ms * 1e-3) / 1e12, "frac": conv_flop / (conv_ms * 1e-3) / 1e12 / peaks["tflops_sustained"],
                                "frac_of_burst": conv_flop / (conv_ms * 1e-3) / 1e12 / peaks["tflops_burst"], "gflop_per_frame": conv_flop / B / 1e9},
@@ -259,7 +267,7 @@ def main():
     e2e_frames, e2e_ms_all = sharding.aggregate_throughput(Ke * B, e2e_ms)
     cap, cells = ex.cap, ex.hc * ex.wc
     h2d = B * H * W
-    d2h = B * (4 + cap * (8 + 4 + 1024 + 8) + cells * (2 + 4 + 4)) + 4
+    d2h = B * (4 + cap * (8 + 4 + 1024 + 8 + (20 if args.cov else 0)) + cells * (2 + 4 + 4)) + 8
     clocks = sampler.stop(windows)
 
     if rank == 0:
@@ -270,7 +278,10 @@ def main():
             "config": {"workload": f"synthetic {W}x{H} u8 camera stream per GPU (BASELINE configs[1] geometry + configs[2] matching): "
                                    f"extract + mutual-NN match to previous frame, nfeatures {args.nf}",
                        "frames_per_step": B, "slots": S, "weights": "superpoint_v1 (reference weights, tests/golden)",
-                       "outputs": "keypoints, scores, descriptors, occ_grid, dust maps, matches (heat/cov off in throughput mode)",
+                       "outputs": "everything Frame::ExtractORB reads except the heat images: keypoints (+response), descriptors, occ_grid, "
+                                  "dust maps, cov2/cov2_inv (computeCovariance on the device), matches to the previous frame; "
+                                  "heat_/heat_inv_ stay on the device (SPFE_EMIT_HEAT off)" if args.cov else
+                                  "keypoints, scores, descriptors, occ_grid, dust maps, matches (heat/cov off)",
                        "l2": f"inputs rotate over {n_pool} batches = {n_pool * stride >> 20} MiB > 126 MB L2; activations per step {B * H * W * 128 * 2 >> 20}+ MiB",
                        "parallelism": f"{world} independent streams, one per GPU, no data-path collective"},
             "e2e": {"value": e2e_frames / (e2e_ms_all * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

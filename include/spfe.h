@@ -53,8 +53,9 @@ enum {
 };
 
 enum {
-  SPFE_EMIT_HEAT = 1u << 0, /* produce heat / heat_inv (H x W f32 each) and copy them to the host  */
-  SPFE_EMIT_COV = 1u << 1,  /* run computeCovariance (implies SPFE_EMIT_HEAT); fills kp_response from heat_inv */
+  SPFE_EMIT_HEAT = 1u << 0, /* copy heat_ / heat_inv_ (H x W f32 each) to the host  */
+  SPFE_EMIT_COV = 1u << 1,  /* run computeCovariance (on the device; the heat maps need not leave it): fills
+                               kp_response (heat_inv at the keypoint), cov2, cov2_inv */
   SPFE_MATCH_PREV = 1u << 2 /* a slot is one camera stream: also match every frame against the previous frame of
                                that slot (mutual NN, all descriptors as train set -- the BFMatcher call of
                                Tracking::trackReferenceKeyFrameANN, tracker.cpp:372-417); frame 0 of a batch is

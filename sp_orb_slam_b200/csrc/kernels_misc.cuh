@@ -294,8 +294,9 @@ __global__ void __launch_bounds__(256) heat_norm_kernel(const float *__restrict_
   float4 *d0 = reinterpret_cast<float4 *>(heat + off), *d1 = reinterpret_cast<float4 *>(heat_inv + off);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_per_frame / 4; i += gridDim.x * blockDim.x) {
     const float4 v = src[i];
-    d0[i] = make_float4(__fadd_rn(__fmul_rn(v.x, a0), b0), __fadd_rn(__fmul_rn(v.y, a0), b0),
-                        __fadd_rn(__fmul_rn(v.z, a0), b0), __fadd_rn(__fmul_rn(v.w, a0), b0));
+    if (heat != nullptr)  // heat_ is only materialised when it is copied to the host (SPFE_EMIT_HEAT)
+      d0[i] = make_float4(__fadd_rn(__fmul_rn(v.x, a0), b0), __fadd_rn(__fmul_rn(v.y, a0), b0),
+                          __fadd_rn(__fmul_rn(v.z, a0), b0), __fadd_rn(__fmul_rn(v.w, a0), b0));
     d1[i] = make_float4(__fadd_rn(__fmul_rn(v.x, a1), b1), __fadd_rn(__fmul_rn(v.y, a1), b1),
                         __fadd_rn(__fmul_rn(v.z, a1), b1), __fadd_rn(__fmul_rn(v.w, a1), b1));
   }

@@ -18,6 +18,7 @@
 
 #include "conv1ab.cuh"
 #include "conv_tc.cuh"
+#include "cov.cuh"
 #include "kernels_misc.cuh"
 #include "match.cuh"
 #include "weights.h"
@@ -101,7 +102,13 @@ struct Slot {
   int16_t *h_occ = nullptr;
   int *h_match = nullptr, *h_nprev = nullptr;
   float *h_mdist = nullptr;
-  std::vector<float> cov2, cov2_inv, resp;
+  // covariance (device)
+  int *cov_owner = nullptr, *cov_qlen = nullptr, *cov_overflow = nullptr, *cov_frame_flag = nullptr, *cov_n_replay = nullptr;
+  uint32_t *cov_visited = nullptr;
+  uint32_t *cov_queue = nullptr;
+  float *resp = nullptr, *cov2 = nullptr, *cov2_inv = nullptr;
+  float *h_resp = nullptr, *h_cov2 = nullptr, *h_cov2_inv = nullptr;
+  int *h_cov_overflow = nullptr;
 };
 
 }  // namespace
@@ -111,7 +118,8 @@ struct spfe_ctx {
   std::string weights_path;
   int H = 0, W = 0, hc = 0, wc = 0, cells = 0, cap = 0, num_sms = 0;
   int rows_pad = 0, match_nb = 0, match_tiles = 0;  // tensor-core matcher geometry
-  bool heat = false, cov = false, match_prev = false;
+  bool heat = false, cov = false, match_prev = false;  // heat: heat maps computed on the device (EMIT_HEAT or EMIT_COV)
+  bool heat_host = false;                              // EMIT_HEAT: heat_ / heat_inv_ are also copied to the host
   bool fused_conv1 = true;  // SPFE_FUSED_CONV1=0 selects the two-kernel path (bit-identical; materialises conv1a for inspection)
   EncodeTiledFn encode = nullptr;
   float *w1a = nullptr, *b1a = nullptr;  // conv1a fp32 [9][64], [64]
@@ -353,10 +361,32 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
   }
   if (c->heat) {
     dim3 grid(64, B);
-    heat_norm_kernel<<<grid, 256, 0, st>>>(s.heat_log, s.heat_mm, s.heat, s.heat_inv, s.heat_mm_f, H * W);
+    heat_norm_kernel<<<grid, 256, 0, st>>>(s.heat_log, s.heat_mm, c->heat_host ? s.heat : nullptr, s.heat_inv, s.heat_mm_f, H * W);
     c->launches++;
     CU_OK(c, cudaGetLastError());
-    mark("heat_norm", 0, 12.0 * H * W * B);
+    mark("heat_norm", 0, (c->heat_host ? 12.0 : 8.0) * H * W * B);
+  }
+  if (c->cov) {  // computeCovariance on the device (cov.cuh): parallel floods, then sequential replay of the conflicted few
+    const size_t px = static_cast<size_t>(H) * W;
+    CU_OK(c, cudaMemsetAsync(s.cov_owner, 0x7F, B * px * sizeof(int), st));
+    const size_t vis_words = (px + 31) / 32;
+    CU_OK(c, cudaMemsetAsync(s.cov_visited, 0, B * vis_words * sizeof(uint32_t), st));
+    CU_OK(c, cudaMemsetAsync(s.cov_frame_flag, 0, B * sizeof(int), st));
+    CovArgs a;
+    a.heat_inv = s.heat_inv; a.kp_xy = s.kp_xy; a.count = s.count; a.owner = s.cov_owner; a.visited = s.cov_visited;
+    a.queue = s.cov_queue; a.qlen = s.cov_qlen; a.response = s.resp; a.cov2 = s.cov2; a.cov2_inv = s.cov2_inv;
+    a.overflow = s.cov_overflow; a.H = H; a.W = W; a.cap = c->cap;
+    a.frame_flag = s.cov_frame_flag; a.n_replay = s.cov_n_replay; a.vis_words = static_cast<int>(vis_words);
+    dim3 grid((c->cap + 127) / 128, B);
+    mark("cov_memset", 0, 5.0 * px * B);
+    cov_flood_kernel<<<dim3((c->cap + COV_TPB - 1) / COV_TPB, B), COV_TPB, COV_SMEM, st>>>(a);
+    mark("cov_flood", 0, 0);
+    cov_finish_kernel<<<grid, 128, 0, st>>>(a);
+    mark("cov_finish", 0, 0);
+    cov_replay_kernel<<<B, 32, (COV_SEQ_QCAP + COV_SEQ_BITMAP_WORDS) * sizeof(uint32_t), st>>>(a);
+    c->launches += 3;
+    CU_OK(c, cudaGetLastError());
+    mark("cov_replay", 0, 0);
   }
   if (c->match_prev) {
     // frame z vs frame z-1 (frame 0 vs the carry in slot 0): fp16 candidate GEMM on the tensor core for both
@@ -386,53 +416,6 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
   }
   s.batch = B;
   return SPFE_OK;
-}
-
-// computeCovariance (sp_extractor.cpp:252-340) on the host, from the device's
-// heat_inv: breadth-first descent from each keypoint over 4-neighbours whose
-// value is positive and strictly below the popped pixel's, sharing one
-// "unvisited" mask across all keypoints of the frame (marked on pop).
-void covariance_host(const float *heat_inv, int H, int W, const float *kp_xy, int n, float *resp, float *cov2,
-                     float *cov2_inv) {
-  std::vector<uint8_t> unvisited(static_cast<size_t>(H) * W, 1);
-  std::vector<int> fifo;
-  for (int k = 0; k < n; k++) {
-    const int cu = static_cast<int>(kp_xy[2 * k]), cv = static_cast<int>(kp_xy[2 * k + 1]);
-    resp[k] = heat_inv[static_cast<size_t>(cv) * W + cu];
-    fifo.clear();
-    fifo.push_back(cv * W + cu);
-    // gather the basin in pop order (duplicates included, as in the reference), then weight by value / sum
-    size_t head = 0;
-    while (head < fifo.size()) {
-      const int pix = fifo[head++];
-      unvisited[pix] = 0;
-      const int u = pix % W, v = pix / W;
-      const float here = heat_inv[pix];
-      const int cand[4] = {u - 1 > 0 ? pix - 1 : -1, v - 1 > 0 ? pix - W : -1, u + 1 < W ? pix + 1 : -1,
-                           v + 1 < H ? pix + W : -1};
-      for (int t = 0; t < 4; t++) {
-        if (cand[t] < 0) continue;
-        const float hv = heat_inv[cand[t]];
-        if (unvisited[cand[t]] && hv > 0.0f && hv < here) fifo.push_back(cand[t]);
-      }
-    }
-    float total = 0.0f;
-    for (int pix : fifo) total += heat_inv[pix];
-    float sx = 0.0f, sy = 0.0f;
-    for (int pix : fifo) {
-      const float du = static_cast<float>(pix % W) - static_cast<float>(cu);
-      const float dv = static_cast<float>(pix / W) - static_cast<float>(cv);
-      const float wgt = heat_inv[pix] / total;
-      sx += wgt * (du * du);
-      sy += wgt * (dv * dv);
-    }
-    if (sx < 1.0f) sx = 1.0f;
-    if (sy < 1.0f) sy = 1.0f;
-    cov2[2 * k] = sx;
-    cov2[2 * k + 1] = sy;
-    cov2_inv[2 * k] = 1.0f / sx;
-    cov2_inv[2 * k + 1] = 1.0f / sy;
-  }
 }
 
 }  // namespace
@@ -553,8 +536,27 @@ static int create_impl(spfe_ctx *c) {
       if ((rc = dev_alloc(c, &s.heat_inv, Bm * px))) return rc;
       if ((rc = dev_alloc(c, &s.heat_mm, Bm * 2))) return rc;
       if ((rc = dev_alloc(c, &s.heat_mm_f, Bm * 2))) return rc;
-      if ((rc = host_alloc(c, &s.h_heat, Bm * px))) return rc;
-      if ((rc = host_alloc(c, &s.h_heat_inv, Bm * px))) return rc;
+      if (c->heat_host) {
+        if ((rc = host_alloc(c, &s.h_heat, Bm * px))) return rc;
+        if ((rc = host_alloc(c, &s.h_heat_inv, Bm * px))) return rc;
+      }
+    }
+    if (c->cov) {
+      if ((rc = dev_alloc(c, &s.cov_owner, Bm * px))) return rc;
+      if ((rc = dev_alloc(c, &s.cov_visited, Bm * ((px + 31) / 32)))) return rc;
+      if ((rc = dev_alloc(c, &s.cov_queue, Bm * cap * COV_QCAP))) return rc;
+      if ((rc = dev_alloc(c, &s.cov_qlen, Bm * cap))) return rc;
+      if ((rc = dev_alloc(c, &s.cov_overflow, 1))) return rc;
+      if ((rc = dev_alloc(c, &s.cov_frame_flag, Bm))) return rc;
+      if ((rc = dev_alloc(c, &s.cov_n_replay, Bm * 2))) return rc;
+      CU_OK(c, cudaMemset(s.cov_overflow, 0, sizeof(int)));
+      if ((rc = dev_alloc(c, &s.resp, Bm * cap))) return rc;
+      if ((rc = dev_alloc(c, &s.cov2, Bm * cap * 2))) return rc;
+      if ((rc = dev_alloc(c, &s.cov2_inv, Bm * cap * 2))) return rc;
+      if ((rc = host_alloc(c, &s.h_resp, Bm * cap))) return rc;
+      if ((rc = host_alloc(c, &s.h_cov2, Bm * cap * 2))) return rc;
+      if ((rc = host_alloc(c, &s.h_cov2_inv, Bm * cap * 2))) return rc;
+      if ((rc = host_alloc(c, &s.h_cov_overflow, 1))) return rc;
     }
     // matcher scratch (device-resident frame-vs-frame matching inside a slot)
     if ((rc = dev_alloc(c, &s.match.rowbest, Bm * cap))) return rc;
@@ -585,11 +587,6 @@ static int create_impl(spfe_ctx *c) {
     if ((rc = host_alloc(c, &s.h_dense, Bm * cells))) return rc;
     if ((rc = host_alloc(c, &s.h_semi, Bm * cells))) return rc;
     if ((rc = host_alloc(c, &s.h_occ, Bm * cells))) return rc;
-    if (c->cov) {
-      s.cov2.resize(Bm * cap * 2);
-      s.cov2_inv.resize(Bm * cap * 2);
-      s.resp.resize(Bm * cap);
-    }
     // TMA maps of every layer's input tensor
     // 3x3 layers: one slab of 18 rows x PW pixels per item (PW = 24 for tile pairs, 16 for single tiles)
     if (!c->fused_conv1 && (rc = make_act_map(c, &s.tmA[L1B], s.a1a, 64, W, H, Bm, 18, CfgC64P::PW))) return rc;
@@ -637,7 +634,8 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
   c->cap = cfg->max_keypoints + 1;
   if (c->cap > c->cells) c->cap = c->cells;
   c->cov = (cfg->flags & SPFE_EMIT_COV) != 0;
-  c->heat = c->cov || (cfg->flags & SPFE_EMIT_HEAT) != 0;
+  c->heat_host = (cfg->flags & SPFE_EMIT_HEAT) != 0;
+  c->heat = c->cov || c->heat_host;
   c->match_prev = (cfg->flags & SPFE_MATCH_PREV) != 0;
   c->rows_pad = (c->cap + 255) / 256 * 256;
   c->match_nb = c->rows_pad / 256;
@@ -657,6 +655,8 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
       nms_smem_max = c->cells * 6;
     }
     CU_OK(c, cudaFuncSetAttribute(conv1ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1ab::SMEM));
+    CU_OK(c, cudaFuncSetAttribute(cov_flood_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_SMEM));
+    CU_OK(c, cudaFuncSetAttribute(cov_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (COV_SEQ_QCAP + COV_SEQ_BITMAP_WORDS) * (int)sizeof(uint32_t)));
     return SPFE_OK;
   }();
   if (rc != SPFE_OK) {
@@ -699,9 +699,15 @@ static int enqueue_d2h(spfe_ctx *c, Slot &s, int B) {
   CU_OK(c, cudaMemcpyAsync(s.h_occ, s.occ, B * cells * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
   CU_OK(c, cudaMemcpyAsync(s.h_dense, s.dense_dust, B * cells * sizeof(float), cudaMemcpyDeviceToHost, st));
   CU_OK(c, cudaMemcpyAsync(s.h_semi, s.semi_dust, B * cells * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (c->heat) {
+  if (c->heat_host) {
     CU_OK(c, cudaMemcpyAsync(s.h_heat, s.heat, B * px * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU_OK(c, cudaMemcpyAsync(s.h_heat_inv, s.heat_inv, B * px * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  if (c->cov) {
+    CU_OK(c, cudaMemcpyAsync(s.h_resp, s.resp, B * cap * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU_OK(c, cudaMemcpyAsync(s.h_cov2, s.cov2, B * cap * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU_OK(c, cudaMemcpyAsync(s.h_cov2_inv, s.cov2_inv, B * cap * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU_OK(c, cudaMemcpyAsync(s.h_cov_overflow, s.cov_overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
   }
   if (c->match_prev) {
     CU_OK(c, cudaMemcpyAsync(s.h_match, s.match.q2t, B * cap * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -740,6 +746,7 @@ int spfe_wait(spfe_ctx *c, int32_t slot, spfe_frame_out *outs) {
   if (!s.pending || !s.on_host) return c->fail(SPFE_ERR_STATE, "spfe_wait: nothing submitted on this slot");
   CU_OK(c, cudaStreamSynchronize(s.stream));
   s.pending = false;
+  if (c->cov && s.h_cov_overflow[0]) return c->fail(SPFE_ERR_STATE, "covariance flood queue overflow (more than 32768 queued pixels in one keypoint basin)");
   if (!outs) return SPFE_OK;
   const size_t px = (size_t)c->H * c->W, cells = c->cells, cap = c->cap;
   for (int b = 0; b < s.batch; b++) {
@@ -752,7 +759,7 @@ int spfe_wait(spfe_ctx *c, int32_t slot, spfe_frame_out *outs) {
     o.occ_grid = s.h_occ + b * cells;
     o.dense_dust = s.h_dense + b * cells;
     o.semi_dust = s.h_semi + b * cells;
-    if (c->heat) {
+    if (c->heat_host) {
       o.heat = s.h_heat + b * px;
       o.heat_inv = s.h_heat_inv + b * px;
     }
@@ -762,11 +769,9 @@ int spfe_wait(spfe_ctx *c, int32_t slot, spfe_frame_out *outs) {
       o.match_dist = s.h_mdist + b * cap;
     }
     if (c->cov) {
-      float *resp = s.resp.data() + b * cap, *c2 = s.cov2.data() + b * cap * 2, *c2i = s.cov2_inv.data() + b * cap * 2;
-      covariance_host(o.heat_inv, c->H, c->W, o.kp_xy, o.n, resp, c2, c2i);
-      o.kp_response = resp;
-      o.cov2 = c2;
-      o.cov2_inv = c2i;
+      o.kp_response = s.h_resp + b * cap;
+      o.cov2 = s.h_cov2 + b * cap * 2;
+      o.cov2_inv = s.h_cov2_inv + b * cap * 2;
     }
   }
   return SPFE_OK;
@@ -923,7 +928,8 @@ int64_t spfe_debug_read(spfe_ctx *c, int32_t slot, const char *name, void *dst, 
       {"count", s.count, B * 4},                 {"kp_xy", s.kp_xy, B * cap * 2 * 4},
       {"kp_score", s.kp_score, B * cap * 4},     {"desc", s.desc, B * cap * 256 * 4},
       {"occ_grid", s.occ, B * cells * 2},        {"match_prev", c->match_prev ? s.match.q2t : nullptr, B * cap * 4},
-      {"match_dist", c->match_prev ? s.match.dist : nullptr, B * cap * 4}};
+      {"match_dist", c->match_prev ? s.match.dist : nullptr, B * cap * 4},
+      {"cov_qlen", s.cov_qlen, B * cap * 4},     {"cov_replayed", s.cov_n_replay, B * 2 * 4}};
   for (const Ent &e : tab)
     if (!strcmp(e.n, name)) {
       if (!e.p) return c->fail(SPFE_ERR_STATE, fmt("spfe_debug_read: '%s' is not produced with the current flags", name));

@@ -59,7 +59,7 @@ class SPExtractor:
         self.height, self.width, self.nfeatures = height, width, nfeatures
         self.hc, self.wc = height // 8, width // 8
         self.max_batch, self.num_slots = max_batch, num_slots
-        self.emit_heat, self.emit_cov = emit_heat or emit_cov, emit_cov
+        self.emit_heat, self.emit_cov = emit_heat, emit_cov
         self.cap = min(nfeatures + 1, self.hc * self.wc)
         # side outputs of the last operator() call (sp_extractor.h:69-77)
         self.semi_dust_ = self.dense_dust_ = self.heat_ = self.heat_inv_ = self.occ_grid_ = self.mask_ = None
@@ -195,7 +195,8 @@ class SPExtractor:
               "heat_inv": (lambda s: (s.height, s.width), np.float32), "heat_minmax": (lambda s: (2,), np.float32),
               "count": (lambda s: (), np.int32), "kp_xy": (lambda s: (s.cap, 2), np.float32), "kp_score": (lambda s: (s.cap,), np.float32),
               "desc": (lambda s: (s.cap, 256), np.float32), "occ_grid": (lambda s: (s.hc, s.wc), np.int16),
-              "match_prev": (lambda s: (s.cap,), np.int32), "match_dist": (lambda s: (s.cap,), np.float32)}
+              "match_prev": (lambda s: (s.cap,), np.int32), "match_dist": (lambda s: (s.cap,), np.float32),
+              "cov_qlen": (lambda s: (s.cap,), np.int32), "cov_replayed": (lambda s: (2,), np.int32)}
 
     def debug_read(self, slot: int, name: str, batch: int) -> np.ndarray:
         shape_fn, dt = self._DEBUG[name]

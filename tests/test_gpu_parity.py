@@ -298,8 +298,9 @@ def test_stream_matching_match_prev(ex_cache):
 
 
 def test_covariance_vs_oracle_on_same_heat(ex_cache):
-    """computeCovariance is order- and comparison-dependent: check it bit-exactly against the oracle run on the
-    GPU's own heat_inv and keypoints (isolates the host restatement from network rounding)."""
+    """computeCovariance is order- and comparison-dependent (shared visited map, FIFO floods).  The device version
+    (parallel floods + sequential replay of conflicted keypoints, csrc/cov.cuh) must be bit-exact against the oracle's
+    sequential C restatement run on the GPU's own heat_inv and keypoints."""
     H, W = 240, 320
     ex = ex_cache(H, W, 800, max_batch=4)
     o = ex.extract(synth.make_frame(H, W, seed=23))
@@ -309,6 +310,27 @@ def test_covariance_vs_oracle_on_same_heat(ex_cache):
     assert np.all(o["cov2"] >= 1.0)
     heat, heat_inv, _, _ = O.to_heat(ex.debug_read(0, "heat_log", 1)[0])
     assert np.array_equal(o["heat"], heat) and np.array_equal(o["heat_inv"], heat_inv)     # to_heat: bit-exact
+
+
+def test_covariance_dense_full_size_and_device_only(ex_cache):
+    """Dense 752x480 scenes (hundreds of keypoints 5 px apart -> overlapping floods that must be replayed in order),
+    a batch of them, and the mode where the heat maps never leave the device."""
+    H, W = 480, 752
+    ex = ex_cache(H, W, 800, max_batch=3)
+    frames = synth.make_stream(H, W, 3, seed=77, n_shapes=1500)
+    outs = ex.extract_batch(list(frames))
+    qlen = ex.debug_read(0, "cov_qlen", 3)
+    for t, o in enumerate(outs):
+        resp, cov2, cov2_inv = O.covariance(o["heat_inv"], o["kp_xy"])
+        assert np.array_equal(o["kp_response"], resp), t
+        assert np.array_equal(o["cov2"], cov2) and np.array_equal(o["cov2_inv"], cov2_inv), t
+        assert np.all(qlen[t, :o["n"]] > 0)                                                # every flood completed
+    dev = ex_cache(H, W, 800, max_batch=3, emit_heat=False, emit_cov=True)
+    outs2 = dev.extract_batch(list(frames))
+    for o, o2 in zip(outs, outs2):
+        assert "heat" not in o2
+        for k in ["kp_xy", "kp_response", "cov2", "cov2_inv", "desc"]:
+            assert np.array_equal(o[k], o2[k]), k
 
 
 def test_operator_call_mirrors_reference(ex_cache):
