@@ -22,6 +22,7 @@ struct Conv1abArgs {
   const uint8_t *img;  // [B][H][W]
   const float *w1a;    // [9][64]
   const float *b1a;    // [64]
+  const void *w1m;     // conv1ab_mma.cuh: conv1a weights + bias as hi | lo fp16 UMMA operands (4096 B)
   const float *b1b;    // [64]
   __half *out;         // [B][H/2][W/2][64]
   int B, H, W, tiles_x, tiles_y, n_items;

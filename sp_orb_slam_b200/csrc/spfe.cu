@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "conv1ab.cuh"
+#include "conv1ab_mma.cuh"
 #include "conv_tc.cuh"
 #include "cov.cuh"
 #include "kernels_misc.cuh"
@@ -120,7 +121,11 @@ struct spfe_ctx {
   int rows_pad = 0, match_nb = 0, match_tiles = 0;  // tensor-core matcher geometry
   bool heat = false, cov = false, match_prev = false;  // heat: heat maps computed on the device (EMIT_HEAT or EMIT_COV)
   bool heat_host = false;                              // EMIT_HEAT: heat_ / heat_inv_ are also copied to the host
-  bool fused_conv1 = true;  // SPFE_FUSED_CONV1=0 selects the two-kernel path (bit-identical; materialises conv1a for inspection)
+  // conv1a + conv1b: 2 = one kernel, both layers on the tensor core (default); 1 = one kernel, conv1a on the CUDA cores
+  // (SPFE_CONV1=ffma); 0 = two kernels (SPFE_CONV1=unfused or SPFE_FUSED_CONV1=0; materialises conv1a for inspection)
+  int conv1_mode = 2;
+  bool fused_conv1 = true;
+  void *w1m = nullptr;  // conv1a weights as hi | lo fp16 UMMA operands (conv1ab_mma.cuh)
   EncodeTiledFn encode = nullptr;
   float *w1a = nullptr, *b1a = nullptr;  // conv1a fp32 [9][64], [64]
   Layer layers[NLAYERS];
@@ -286,11 +291,12 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
   int rc;
   if (c->fused_conv1) {  // conv1a + conv1b + pool in one kernel: u8 image -> fp16 [H/2][W/2][64]
     Conv1abArgs a;
-    a.img = s.d_gray; a.w1a = c->w1a; a.b1a = c->b1a; a.b1b = c->layers[L1B].bias; a.out = s.a1b;
+    a.img = s.d_gray; a.w1a = c->w1a; a.b1a = c->b1a; a.w1m = c->w1m; a.b1b = c->layers[L1B].bias; a.out = s.a1b;
     a.B = B; a.H = H; a.W = W; a.tiles_x = (W + 15) / 16; a.tiles_y = (H + 15) / 16;
     a.n_items = B * a.tiles_x * a.tiles_y;
     const int grid = a.n_items < c->num_sms ? a.n_items : c->num_sms;
-    conv1ab_kernel<<<grid, c1ab::THREADS, c1ab::SMEM, st>>>(c->layers[L1B].tm, a);
+    if (c->conv1_mode == 2) conv1ab_mma_kernel<<<grid, c1m::THREADS, c1m::SMEM, st>>>(c->layers[L1B].tm, a);
+    else conv1ab_kernel<<<grid, c1ab::THREADS, c1ab::SMEM, st>>>(c->layers[L1B].tm, a);
     c->launches++;
     CU_OK(c, cudaGetLastError());
     mark("conv1a+1b", 2.0 * 9 * 64 * H * W * B + c->layers[L1B].flop_per_px * H * W * B, (1.0 + 32.0) * H * W * B);
@@ -479,6 +485,22 @@ static int create_impl(spfe_ctx *c) {
     if ((rc = dev_alloc(c, &c->b1a, 64))) return rc;
     CU_OK(c, cudaMemcpy(c->w1a, w9.data(), w9.size() * 4, cudaMemcpyHostToDevice));
     CU_OK(c, cudaMemcpy(c->b1a, b.data.data(), 64 * 4, cudaMemcpyHostToDevice));
+    // conv1ab_mma.cuh: W1[part][64 couts][16 k] fp16, part 0 = hi, 1 = lo = fp16(v - hi); k = tap 0..8, k = 9 is the bias
+    // (its im2col column holds 255, the conv1a epilogue scales by 1/255).  Un-swizzled K-major canonical layout:
+    // 8-row x 16-byte core matrices, K chunks 128 B apart, 8-row groups 256 B apart.
+    std::vector<__half> img(2 * 64 * 16, __float2half(0.f));
+    for (int o = 0; o < 64; o++)
+      for (int k = 0; k < 10; k++) {
+        const float v = k < 9 ? w.data[o * 9 + k] : b.data[o];
+        if (!(std::fabs(v) < 60000.f)) return c->fail(SPFE_ERR_WEIGHTS, "conv1a weight / bias outside the fp16 range");
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        const size_t off = static_cast<size_t>(o >> 3) * 128 + (k >> 3) * 64 + (o & 7) * 8 + (k & 7);  // in fp16 elements
+        img[off] = hi;
+        img[64 * 16 + off] = lo;
+      }
+    if ((rc = dev_alloc(c, reinterpret_cast<__half **>(&c->w1m), img.size()))) return rc;
+    CU_OK(c, cudaMemcpy(c->w1m, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
   }
   auto up = [&](int l, std::vector<const char *> names, int n_tile, int cout_total) {
     std::vector<const HostTensor *> ws, bs;
@@ -641,8 +663,10 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
   c->match_nb = c->rows_pad / 256;
   c->match_tiles = (c->cap + 127) / 128;
   {
-    const char *e = getenv("SPFE_FUSED_CONV1");
-    c->fused_conv1 = !(e && e[0] == '0');
+    const char *e = getenv("SPFE_FUSED_CONV1"), *m = getenv("SPFE_CONV1");
+    if (m && !strcmp(m, "ffma")) c->conv1_mode = 1;
+    if ((m && !strcmp(m, "unfused")) || (e && e[0] == '0')) c->conv1_mode = 0;
+    c->fused_conv1 = c->conv1_mode != 0;
   }
   int rc = create_impl(c);
   if (rc == SPFE_OK) rc = [&]() -> int {
@@ -655,6 +679,7 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
       nms_smem_max = c->cells * 6;
     }
     CU_OK(c, cudaFuncSetAttribute(conv1ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1ab::SMEM));
+    CU_OK(c, cudaFuncSetAttribute(conv1ab_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1m::SMEM));
     CU_OK(c, cudaFuncSetAttribute(cov_flood_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_SMEM));
     CU_OK(c, cudaFuncSetAttribute(cov_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (COV_SEQ_QCAP + COV_SEQ_BITMAP_WORDS) * (int)sizeof(uint32_t)));
     return SPFE_OK;

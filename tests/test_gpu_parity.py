@@ -152,25 +152,41 @@ def test_margin_robust_keypoints_identical(weights, ex_cache):
     assert miss <= max(2, total // 2), f"{miss} of {total} keypoint differences not explained by an eps-fragile cell"
 
 
-def test_fused_conv1_equals_unfused(weights, monkeypatch):
-    """Default path: conv1a is computed by conv1b's producer warps straight into the swizzled shared-memory slab.
-    It must be bit-identical to the two-kernel path (SPFE_FUSED_CONV1=0), whose materialised conv1a activation is
-    checked against the oracle."""
+@pytest.mark.parametrize("mode", ["mma", "ffma"])
+def test_fused_conv1_equals_unfused(mode, weights, monkeypatch):
+    """conv1a never touches HBM on the default path: it is computed inside the conv1b kernel, straight into the swizzled
+    shared-memory slab.  SPFE_CONV1=ffma (conv1a by fp32 FFMA on the CUDA cores) must be bit-identical to the two-kernel
+    path (SPFE_CONV1=unfused), whose materialised conv1a activation is checked against the oracle.  The default,
+    SPFE_CONV1=mma (conv1a on the tensor core: exact u8 pixels x hi/lo-split fp16 weights, fp32 accumulation), sums in a
+    different order, so single fp16 roundings of conv1a may flip: conv1b must agree within 2e-3 of the layer's max with
+    fewer than 2 % of its elements differing at all, and the keypoint sets must still coincide almost everywhere."""
     H, W = 120, 136
     frames = synth.make_stream(H, W, 2, seed=7, n_shapes=24)
+    monkeypatch.setenv("SPFE_CONV1", mode)
     fused = SPExtractor(800, H, W, WEIGHTS, max_batch=2)
     a = fused.extract_batch(list(frames))
     a1b = fused.debug_read(0, "conv1b", 2)
     with pytest.raises(SpfeError):
         fused.debug_read(0, "conv1a", 2)                                       # never materialised in fused mode
     fused.close()
-    monkeypatch.setenv("SPFE_FUSED_CONV1", "0")
+    monkeypatch.setenv("SPFE_CONV1", "unfused")
     plain = SPExtractor(800, H, W, WEIGHTS, max_batch=2)
     b = plain.extract_batch(list(frames))
-    assert np.array_equal(a1b, plain.debug_read(0, "conv1b", 2))
-    for x, y in zip(a, b):
-        for k in ["kp_xy", "desc", "occ_grid", "dense_dust", "heat"]:
-            assert np.array_equal(x[k], y[k]), k
+    p1b = plain.debug_read(0, "conv1b", 2)
+    if mode == "ffma":
+        assert np.array_equal(a1b, p1b)
+        for x, y in zip(a, b):
+            for k in ["kp_xy", "desc", "occ_grid", "dense_dust", "heat"]:
+                assert np.array_equal(x[k], y[k]), k
+    else:
+        d = np.abs(a1b.astype(np.float32) - p1b.astype(np.float32))
+        assert d.max() <= 2e-3 * np.abs(p1b.astype(np.float32)).max()
+        assert (d > 0).mean() < 0.02
+        for x, y in zip(a, b):
+            xs = {(int(u), int(v)) for u, v in x["kp_xy"]}
+            ys = {(int(u), int(v)) for u, v in y["kp_xy"]}
+            assert len(xs & ys) >= 0.98 * len(xs | ys)
+            np.testing.assert_allclose(x["dense_dust"], y["dense_dust"], atol=2e-3)
     got = plain.debug_read(0, "conv1a", 2).astype(np.float32)
     for t in range(2):
         ref = O.frontend_forward(weights, frames[t], keep_layers=True)["layers"]["conv1a"].transpose(1, 2, 0)
