@@ -113,9 +113,19 @@ int spfe_extract(spfe_ctx *ctx, const uint8_t *gray, size_t row_stride, spfe_fra
 
 /* Throughput mode: enqueue `batch` frames (host pointers) on `slot` and return
  * immediately; spfe_wait blocks until that slot's results are on the host and
- * fills outs[0..batch).  Different slots overlap copies and kernels. */
+ * fills outs[0..batch).  The H2D copies, the kernels and the D2H copies of all slots run on three in-order queues
+ * chained by events, so with >= 2 slots in flight the copies of one batch hide behind the kernels of another while
+ * the persistent kernels of consecutive batches never compete for SMs.  (SPFE_SLOT_STREAMS=1 in the environment
+ * gives every slot one private stream instead.) */
 int spfe_submit(spfe_ctx *ctx, int32_t slot, const uint8_t *const *grays, int32_t batch, size_t row_stride);
 int spfe_wait(spfe_ctx *ctx, int32_t slot, spfe_frame_out *outs);
+/* Zero-staging variant of spfe_submit for a capture pipeline that already owns page-locked memory: `frames` is
+ * [batch][H][W] u8, dense, and is DMA'd to the device straight from the caller's buffer (no host memcpy), so it must
+ * stay valid and unmodified until spfe_wait returns for this slot.  Works with pageable memory too, only slower.
+ * spfe_host_alloc / spfe_host_free hand out page-locked memory without the caller needing the CUDA headers. */
+int spfe_submit_pinned(spfe_ctx *ctx, int32_t slot, const uint8_t *frames, int32_t batch);
+void *spfe_host_alloc(size_t bytes);
+void spfe_host_free(void *p);
 
 /* Same pipeline on frames that already live in device memory ([batch][H][W] u8,
  * dense).  Results stay on the device; no host copies.  Asynchronous on the

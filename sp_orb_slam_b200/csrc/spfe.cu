@@ -14,6 +14,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "conv1ab.cuh"
@@ -70,7 +71,11 @@ struct Layer {
 };
 
 struct Slot {
-  cudaStream_t stream = nullptr;
+  // kernels / H2D / D2H queues of this slot.  By default all slots share the context's three streams (one in-order
+  // compute queue: the persistent kernels of consecutive batches never fight for SMs; copies overlap on their own
+  // engines); SPFE_SLOT_STREAMS=1 gives every slot a private stream for all three instead.
+  cudaStream_t stream = nullptr, in_stream = nullptr, out_stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
   int batch = 0;
   bool pending = false, on_host = false;
   // device activations (NHWC fp16)
@@ -135,6 +140,8 @@ struct spfe_ctx {
   std::string error;
   std::mutex match_mu;
   cudaStream_t match_stream = nullptr;
+  cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;
+  bool slot_streams = false;
   MatchScratch match;  // for spfe_match_mutual_nn (host pointers)
   float *h_match_q = nullptr, *h_match_t = nullptr;
   int *h_match_idx = nullptr;
@@ -523,9 +530,26 @@ static int create_impl(spfe_ctx *c) {
 
   // ---- per-slot buffers
   c->slots.resize(cfg.num_slots);
+  {
+    const char *e = getenv("SPFE_SLOT_STREAMS");
+    c->slot_streams = e && e[0] == '1';
+    if (!c->slot_streams) {
+      CU_OK(c, cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
+      CU_OK(c, cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+      CU_OK(c, cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+    }
+  }
   const size_t px = static_cast<size_t>(H) * W, cells = c->cells, cap = c->cap;
   for (Slot &s : c->slots) {
-    CU_OK(c, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    if (c->slot_streams) {
+      CU_OK(c, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+      s.in_stream = s.out_stream = s.stream;
+    } else {
+      s.stream = c->compute; s.in_stream = c->copy_in; s.out_stream = c->copy_out;
+    }
+    CU_OK(c, cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+    CU_OK(c, cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    CU_OK(c, cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
     if ((rc = dev_alloc(c, &s.d_gray, Bm * px))) return rc;
     if (!c->fused_conv1 && (rc = dev_alloc(c, &s.a1a, Bm * px * 64))) return rc;
     if ((rc = dev_alloc(c, &s.a1b, Bm * px / 4 * 64))) return rc;
@@ -698,11 +722,13 @@ void spfe_destroy(spfe_ctx *c) {
   cudaSetDevice(c->cfg.device_id);
   cudaDeviceSynchronize();
   for (Slot &s : c->slots) {
-    if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.stream && c->slot_streams) cudaStreamDestroy(s.stream);
+    for (cudaEvent_t e : {s.ev_in, s.ev_done, s.ev_out}) if (e) cudaEventDestroy(e);
     if (s.ev0) cudaEventDestroy(s.ev0);
     if (s.ev1) cudaEventDestroy(s.ev1);
   }
   if (c->match_stream) cudaStreamDestroy(c->match_stream);
+  for (cudaStream_t st : {c->compute, c->copy_in, c->copy_out}) if (st) cudaStreamDestroy(st);
   for (void *p : c->dev_allocs) cudaFree(p);
   for (void *p : c->host_allocs) cudaFreeHost(p);
   delete c;
@@ -716,7 +742,7 @@ static int check_slot(spfe_ctx *c, int32_t slot) {
 
 static int enqueue_d2h(spfe_ctx *c, Slot &s, int B) {
   const size_t px = (size_t)c->H * c->W, cells = c->cells, cap = c->cap;
-  cudaStream_t st = s.stream;
+  cudaStream_t st = s.out_stream;
   CU_OK(c, cudaMemcpyAsync(s.h_count, s.count, B * sizeof(int), cudaMemcpyDeviceToHost, st));
   CU_OK(c, cudaMemcpyAsync(s.h_kp_xy, s.kp_xy, B * cap * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
   CU_OK(c, cudaMemcpyAsync(s.h_kp_score, s.kp_score, B * cap * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -742,6 +768,41 @@ static int enqueue_d2h(spfe_ctx *c, Slot &s, int B) {
   return SPFE_OK;
 }
 
+// pageable -> pinned staging of one batch; frames are independent, so large batches are copied by a few threads
+static void stage_frames(spfe_ctx *c, Slot &s, const uint8_t *const *grays, int batch, size_t row_stride) {
+  const size_t px = (size_t)c->H * c->W;
+  auto copy_range = [&](int b0, int b1) {
+    for (int b = b0; b < b1; b++) {
+      if (row_stride == (size_t)c->W) memcpy(s.h_gray + b * px, grays[b], px);
+      else for (int y = 0; y < c->H; y++) memcpy(s.h_gray + b * px + (size_t)y * c->W, grays[b] + y * row_stride, c->W);
+    }
+  };
+  const int nthr = (batch * px >= (size_t)(4u << 20)) ? (batch < 4 ? batch : 4) : 1;
+  if (nthr <= 1) return copy_range(0, batch);
+  std::vector<std::thread> th;
+  for (int t = 1; t < nthr; t++) th.emplace_back(copy_range, batch * t / nthr, batch * (t + 1) / nthr);
+  copy_range(0, batch / nthr);
+  for (auto &t : th) t.join();
+}
+
+static int submit_host(spfe_ctx *c, Slot &s, const uint8_t *src, int batch) {
+  int rc;
+  // copy-in queue -> compute queue -> copy-out queue, chained by events (one and the same stream with SPFE_SLOT_STREAMS=1)
+  CU_OK(c, cudaMemcpyAsync(s.d_gray, src, batch * (size_t)c->H * c->W, cudaMemcpyHostToDevice, s.in_stream));
+  if (s.in_stream != s.stream) {
+    CU_OK(c, cudaEventRecord(s.ev_in, s.in_stream));
+    CU_OK(c, cudaStreamWaitEvent(s.stream, s.ev_in, 0));
+  }
+  if ((rc = run_pipeline(c, s, batch, nullptr))) return rc;
+  CU_OK(c, cudaEventRecord(s.ev_done, s.stream));
+  if (s.out_stream != s.stream) CU_OK(c, cudaStreamWaitEvent(s.out_stream, s.ev_done, 0));
+  if ((rc = enqueue_d2h(c, s, batch))) return rc;
+  CU_OK(c, cudaEventRecord(s.ev_out, s.out_stream));
+  s.pending = true;
+  s.on_host = true;
+  return SPFE_OK;
+}
+
 int spfe_submit(spfe_ctx *c, int32_t slot, const uint8_t *const *grays, int32_t batch, size_t row_stride) {
   int rc = check_slot(c, slot);
   if (rc) return rc;
@@ -750,18 +811,29 @@ int spfe_submit(spfe_ctx *c, int32_t slot, const uint8_t *const *grays, int32_t 
   Slot &s = c->slots[slot];
   if (s.pending) return c->fail(SPFE_ERR_STATE, "spfe_submit: slot still has an un-waited batch");
   CU_OK(c, cudaSetDevice(c->cfg.device_id));
-  const size_t px = (size_t)c->H * c->W;
-  for (int b = 0; b < batch; b++) {
+  for (int b = 0; b < batch; b++)
     if (!grays[b]) return c->fail(SPFE_ERR_EMPTY, "input image is empty");
-    if (row_stride == (size_t)c->W) memcpy(s.h_gray + b * px, grays[b], px);
-    else for (int y = 0; y < c->H; y++) memcpy(s.h_gray + b * px + (size_t)y * c->W, grays[b] + y * row_stride, c->W);
-  }
-  CU_OK(c, cudaMemcpyAsync(s.d_gray, s.h_gray, batch * px, cudaMemcpyHostToDevice, s.stream));
-  if ((rc = run_pipeline(c, s, batch, nullptr))) return rc;
-  if ((rc = enqueue_d2h(c, s, batch))) return rc;
-  s.pending = true;
-  s.on_host = true;
-  return SPFE_OK;
+  stage_frames(c, s, grays, batch, row_stride);
+  return submit_host(c, s, s.h_gray, batch);
+}
+
+int spfe_submit_pinned(spfe_ctx *c, int32_t slot, const uint8_t *frames, int32_t batch) {
+  int rc = check_slot(c, slot);
+  if (rc) return rc;
+  if (batch < 1 || batch > c->cfg.max_batch) return c->fail(SPFE_ERR_INVALID, "spfe_submit_pinned: bad batch");
+  if (!frames) return c->fail(SPFE_ERR_EMPTY, "input image is empty");
+  Slot &s = c->slots[slot];
+  if (s.pending) return c->fail(SPFE_ERR_STATE, "spfe_submit_pinned: slot still has an un-waited batch");
+  CU_OK(c, cudaSetDevice(c->cfg.device_id));
+  return submit_host(c, s, frames, batch);
+}
+
+void *spfe_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  return cudaMallocHost(&p, bytes ? bytes : 1) == cudaSuccess ? p : nullptr;
+}
+void spfe_host_free(void *p) {
+  if (p) cudaFreeHost(p);
 }
 
 int spfe_wait(spfe_ctx *c, int32_t slot, spfe_frame_out *outs) {
@@ -769,7 +841,7 @@ int spfe_wait(spfe_ctx *c, int32_t slot, spfe_frame_out *outs) {
   if (rc) return rc;
   Slot &s = c->slots[slot];
   if (!s.pending || !s.on_host) return c->fail(SPFE_ERR_STATE, "spfe_wait: nothing submitted on this slot");
-  CU_OK(c, cudaStreamSynchronize(s.stream));
+  CU_OK(c, cudaEventSynchronize(s.ev_out));
   s.pending = false;
   if (c->cov && s.h_cov_overflow[0]) return c->fail(SPFE_ERR_STATE, "covariance flood queue overflow (more than 32768 queued pixels in one keypoint basin)");
   if (!outs) return SPFE_OK;
@@ -824,13 +896,15 @@ int spfe_submit_device(spfe_ctx *c, int32_t slot, const void *d_gray, int32_t ba
   s.d_gray = saved;
   s.pending = false;
   s.on_host = false;
-  return rc;
+  if (rc) return rc;
+  CU_OK(c, cudaEventRecord(s.ev_done, s.stream));
+  return SPFE_OK;
 }
 
 int spfe_slot_sync(spfe_ctx *c, int32_t slot) {
   int rc = check_slot(c, slot);
   if (rc) return rc;
-  CU_OK(c, cudaStreamSynchronize(c->slots[slot].stream));
+  CU_OK(c, cudaEventSynchronize(c->slots[slot].ev_done));  // the slot's last submit; other slots may still be running
   return SPFE_OK;
 }
 

@@ -78,6 +78,9 @@ class SPExtractor:
         if getattr(self, "_ctx", None) and self._ctx.value:
             self._lib.spfe_destroy(self._ctx)
             self._ctx = C.c_void_p()
+            for p in getattr(self, "_pinned", []):
+                self._lib.spfe_host_free(p)
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -145,6 +148,22 @@ class SPExtractor:
         self._keep = frames
         ptrs = (C.c_void_p * len(frames))(*[f.ctypes.data for f in frames])
         self._check(self._lib.spfe_submit(self._ctx, slot, ptrs, len(frames), self.width))
+
+    def submit_pinned(self, slot: int, frames: np.ndarray) -> None:
+        """``frames``: C-contiguous [batch][H][W] u8, ideally page-locked (``pinned_frames``); DMA'd as is, so it must stay
+        untouched until ``wait(slot)`` returns."""
+        assert frames.dtype == np.uint8 and frames.flags.c_contiguous and frames.shape[1:] == (self.height, self.width)
+        self._keep = frames
+        self._check(self._lib.spfe_submit_pinned(self._ctx, slot, C.c_void_p(frames.ctypes.data), frames.shape[0]))
+
+    def pinned_frames(self, n: int) -> np.ndarray:
+        """Page-locked [n][H][W] u8 buffer (spfe_host_alloc); freed with the extractor."""
+        nbytes = n * self.height * self.width
+        p = self._lib.spfe_host_alloc(nbytes)
+        if not p:
+            raise SpfeError(capi.ERR_CUDA, "spfe_host_alloc failed")
+        self._pinned = getattr(self, "_pinned", []) + [p]
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nbytes,)).reshape(n, self.height, self.width)
 
     def wait(self, slot: int, n_frames: int, unpack: bool = True):
         outs = (capi.FrameOut * n_frames)()

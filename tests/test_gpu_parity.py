@@ -392,6 +392,14 @@ def test_slots_pipeline(ex_cache):
         assert np.array_equal(r["kp_xy"], o["kp_xy"]) and np.array_equal(r["desc"], o["desc"])
     single.close()
     assert ex.launch_count() > 0
+    # zero-staging entry: frames DMA'd straight from the caller's page-locked buffer give the same results
+    pinned = ex.pinned_frames(6)
+    pinned[:] = frames
+    for s in range(3):
+        ex.submit_pinned(s, pinned[2 * s: 2 * s + 2])
+    res2 = [o for s in range(3) for o in ex.wait(s, 2)]
+    for o, o2 in zip(res, res2):
+        assert np.array_equal(o["kp_xy"], o2["kp_xy"]) and np.array_equal(o["desc"], o2["desc"])
 
 
 def test_cpp_shim_selftest(tmp_path, ex_cache):

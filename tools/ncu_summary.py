@@ -1,0 +1,51 @@
+"""Summarise an `ncu --set full` report into profiles/: a markdown table per kernel and the per-launch DRAM traffic
+JSON that bench.py reads for `roofline.traffic`.
+
+    python tools/ncu_summary.py gpurun_out/prof_conv.ncu-rep profiles/r01_ncu_conv_summary.md profiles/r01_traffic.json
+"""
+import csv
+import io
+import json
+import re
+import subprocess
+import sys
+
+METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+           "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+           "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active",
+           "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+           "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+           "l1tex__m_xbar2l1tex_read_bytes.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+           "sm__cycles_elapsed.max", "launch__registers_per_thread", "launch__grid_size", "launch__block_size"]
+TO_BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def main(rep, md_out, json_out, title):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    kcol = hdr.index("Kernel Name")
+    out = [f"# {title}", "",
+           "Workload: `python tools/bringup.py profile 480 752 32` = 32 frames of 752x480 per launch. ncu replays each kernel "
+           "~40x cold-cache and serialised: compare shares and ratios, not absolute times.", ""]
+    traffic = {}
+    for r in rows[2:]:
+        name = r[kcol]
+        out += [f"### `{name}`", "", "| metric | value | unit |", "|---|---|---|"]
+        by = 0.0
+        for m in METRICS:
+            if m in hdr:
+                i = hdr.index(m)
+                out.append(f"| {m} | {r[i]} | {units[i]} |")
+                if m.startswith("dram__bytes"):
+                    by += float(r[i].replace(",", "")) * TO_BYTES.get(units[i], 1.0)
+        out.append("")
+        key = re.sub(r"^void ", "", name).split("(")[0]
+        traffic.setdefault(key, by)
+    open(md_out, "w").write("\n".join(out))
+    json.dump(traffic, open(json_out, "w"), indent=1)
+    print(json.dumps(traffic, indent=1))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "ncu --set full (--clock-control none)")
