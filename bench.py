@@ -173,7 +173,8 @@ def main():
     ap.add_argument("--nf", type=int, default=800)
     ap.add_argument("--slots", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cov", action="store_true", help="also run computeCovariance on the device (kp.response / cov2 / cov2_inv)")
+    ap.add_argument("--lean", action="store_true", help="skip computeCovariance and the heat_ image (keypoints, descriptors, "
+                    "occ_grid, dust maps and matches only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -186,31 +187,45 @@ def main():
     H, W, B, K, S = args.height, args.width, args.batch, args.steps, args.slots
     n_pool = max(4, -(-(140 << 20) // (B * H * W)))             # inputs > 126 MB L2
     pool = make_pool(H, W, B, n_pool, rank)
+    # default workload = everything Frame::ExtractORB (frame.cpp:296-314) reads from the extractor: keypoints with
+    # response, descriptors, occ_grid_, dense_dust_ / semi_dust_, heat_, cov2 / cov2_inv (computeCovariance), plus the
+    # match against the previous frame.  heat_inv_ (= 1 - heat_, read by nothing outside computeCovariance) stays on
+    # the device.  --lean drops computeCovariance and the heat_ image.
+    full = not args.lean
     ex = SPExtractor(args.nf, H, W, WEIGHTS, device_id=local_rank, max_batch=B, num_slots=S,
-                     emit_heat=False, emit_cov=args.cov, match_prev=True)
+                     emit_heat=full, emit_heat_inv=False, emit_cov=full, match_prev=True)
     d_pool = torch.from_numpy(pool).cuda()
     stride = B * H * W
     sampler = ClockSampler(local_rank)
     windows = []
 
     # ---------------- device-resident throughput (`value`)
-    for i in range(args.warmup):
-        ex.submit_device(0, d_pool.data_ptr() + (i % n_pool) * stride, B)
-    ex.sync(0)
-    sharding.barrier()
-    torch.cuda.synchronize()
-    l0 = ex.launch_count()
-    w0 = time.time()
-    ex.timer_start(0)
-    for i in range(K):
-        ex.submit_device(0, d_pool.data_ptr() + (i % n_pool) * stride, B)
-    ms = ex.timer_stop(0)
-    torch.cuda.synchronize()
-    windows.append((w0, time.time()))
-    launches = ex.launch_count() - l0
-    sharding.barrier()
-    frames_all, ms_all = sharding.aggregate_throughput(K * B, ms)
-    value = frames_all / (ms_all * 1e-3)
+    def run_device(e):
+        for i in range(args.warmup):
+            e.submit_device(0, d_pool.data_ptr() + (i % n_pool) * stride, B)
+        e.sync(0)
+        sharding.barrier()
+        torch.cuda.synchronize()
+        l0 = e.launch_count()
+        w0 = time.time()
+        e.timer_start(0)
+        for i in range(K):
+            e.submit_device(0, d_pool.data_ptr() + (i % n_pool) * stride, B)
+        ms = e.timer_stop(0)
+        torch.cuda.synchronize()
+        windows.append((w0, time.time()))
+        n_launch = e.launch_count() - l0
+        sharding.barrier()
+        frames_all, ms_all = sharding.aggregate_throughput(K * B, ms)
+        return frames_all / (ms_all * 1e-3), ms_all, n_launch
+
+    value, ms_all, launches = run_device(ex)
+    lean_value = None
+    if full:                                                     # the same stream without computeCovariance / heat_, for comparison
+        lean = SPExtractor(args.nf, H, W, WEIGHTS, device_id=local_rank, max_batch=B, num_slots=1,
+                           emit_heat=False, emit_heat_inv=False, emit_cov=False, match_prev=True)
+        lean_value = run_device(lean)[0]
+        lean.close()
 
     # ---------------- per-kernel device times (roofline), CUDA events between stages on the library's stream
     stages = {}
@@ -276,7 +291,7 @@ def main():
     pg_frames, pg_ms_all = run_e2e(lambda s, p: ex.submit(s, host_batches[p]), Ke)
     cap, cells = ex.cap, ex.hc * ex.wc
     h2d = B * H * W
-    d2h = B * (4 + cap * (8 + 4 + 1024 + 8 + (20 if args.cov else 0)) + cells * (2 + 4 + 4)) + 8
+    d2h = B * (4 + cap * (8 + 4 + 1024 + 8 + (20 if full else 0)) + cells * (2 + 4 + 4) + (H * W * 4 if full else 0)) + 8
     clocks = sampler.stop(windows)
 
     if rank == 0:
@@ -287,16 +302,17 @@ def main():
             "config": {"workload": f"synthetic {W}x{H} u8 camera stream per GPU (BASELINE configs[1] geometry + configs[2] matching): "
                                    f"extract + mutual-NN match to previous frame, nfeatures {args.nf}",
                        "frames_per_step": B, "slots": S, "weights": "superpoint_v1 (reference weights, tests/golden)",
-                       "outputs": "everything Frame::ExtractORB reads except the heat images: keypoints (+response), descriptors, occ_grid, "
-                                  "dust maps, cov2/cov2_inv (computeCovariance on the device), matches to the previous frame; "
-                                  "heat_/heat_inv_ stay on the device (SPFE_EMIT_HEAT off)" if args.cov else
-                                  "keypoints, scores, descriptors, occ_grid, dust maps, matches (heat/cov off)",
+                       "outputs": "everything Frame::ExtractORB reads: keypoints (+response), descriptors, occ_grid_, dust maps, "
+                                  "heat_, cov2/cov2_inv (computeCovariance on the device), matches to the previous frame; "
+                                  "only heat_inv_ (= 1 - heat_) stays on the device" if full else
+                                  "keypoints, scores, descriptors, occ_grid, dust maps, matches (--lean: no computeCovariance, no heat_)",
                        "l2": f"inputs rotate over {n_pool} batches = {n_pool * stride >> 20} MiB > 126 MB L2; activations per step {B * H * W * 128 * 2 >> 20}+ MiB",
                        "parallelism": f"{world} independent streams, one per GPU, no data-path collective"},
             "e2e": {"value": e2e_frames / (e2e_ms_all * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "ms_per_step": e2e_ms_all / Ke, "input": "page-locked host frames (spfe_submit_pinned)",
                     "pageable_input_value": pg_frames / (pg_ms_all * 1e-3)},
             "gpu_launches": int(launches),
+            "lean_value": lean_value,
             "clocks": clocks,
             "roofline": roofline,
         }

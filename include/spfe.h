@@ -53,9 +53,11 @@ enum {
 };
 
 enum {
-  SPFE_EMIT_HEAT = 1u << 0, /* copy heat_ / heat_inv_ (H x W f32 each) to the host  */
+  SPFE_EMIT_HEAT = 1u << 0, /* copy heat_ (H x W f32; read by Frame::ExtractORB, frame.cpp:304) to the host */
   SPFE_EMIT_COV = 1u << 1,  /* run computeCovariance (on the device; the heat maps need not leave it): fills
                                kp_response (heat_inv at the keypoint), cov2, cov2_inv */
+  SPFE_EMIT_HEAT_INV = 1u << 3, /* copy heat_inv_ (H x W f32 = 1 - heat_; a public member of SPExtractor that nothing outside
+                               computeCovariance reads) to the host as well */
   SPFE_MATCH_PREV = 1u << 2 /* a slot is one camera stream: also match every frame against the previous frame of
                                that slot (mutual NN, all descriptors as train set -- the BFMatcher call of
                                Tracking::trackReferenceKeyFrameANN, tracker.cpp:372-417); frame 0 of a batch is
@@ -94,7 +96,7 @@ typedef struct spfe_frame_out {
   const float *dense_dust; /* [H/8][W/8] softmax dustbin probability  -> dense_dust_ */
   const float *semi_dust;  /* [H/8][W/8] raw dustbin logit            -> semi_dust_ */
   const float *heat;       /* [H][W] or NULL                          -> heat_ */
-  const float *heat_inv;   /* [H][W] or NULL                          -> heat_inv_ */
+  const float *heat_inv;   /* [H][W] or NULL (SPFE_EMIT_HEAT_INV)     -> heat_inv_ */
   const float *cov2;       /* [n][2] or NULL                          -> getCov() */
   const float *cov2_inv;   /* [n][2] or NULL                          -> getCov2Inv() */
   int32_t n_prev;          /* SPFE_MATCH_PREV: keypoints of the previous frame of this stream (0 = none yet) */

@@ -8,7 +8,7 @@ import os
 from . import build as _build
 
 DESC_DIM = 256
-EMIT_HEAT, EMIT_COV, MATCH_PREV = 1, 2, 4
+EMIT_HEAT, EMIT_COV, MATCH_PREV, EMIT_HEAT_INV = 1, 2, 4, 8
 OK, ERR_INVALID, ERR_EMPTY, ERR_WEIGHTS, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
 
 EXPORTS = ["spfe_default_config", "spfe_create", "spfe_destroy", "spfe_last_error", "spfe_extract", "spfe_submit",

@@ -110,6 +110,7 @@ struct Slot {
   float *h_mdist = nullptr;
   // covariance (device)
   int *cov_owner = nullptr, *cov_qlen = nullptr, *cov_overflow = nullptr, *cov_frame_flag = nullptr, *cov_n_replay = nullptr;
+  int *cov_done = nullptr, *cov_ctr = nullptr, *cov_big = nullptr, *cov_pend = nullptr;
   uint32_t *cov_visited = nullptr;
   uint32_t *cov_queue = nullptr;
   float *resp = nullptr, *cov2 = nullptr, *cov2_inv = nullptr;
@@ -125,7 +126,7 @@ struct spfe_ctx {
   int H = 0, W = 0, hc = 0, wc = 0, cells = 0, cap = 0, num_sms = 0;
   int rows_pad = 0, match_nb = 0, match_tiles = 0;  // tensor-core matcher geometry
   bool heat = false, cov = false, match_prev = false;  // heat: heat maps computed on the device (EMIT_HEAT or EMIT_COV)
-  bool heat_host = false;                              // EMIT_HEAT: heat_ / heat_inv_ are also copied to the host
+  bool heat_host = false, heat_inv_host = false;       // EMIT_HEAT / EMIT_HEAT_INV: heat_ / heat_inv_ are also copied to the host
   // conv1a + conv1b: 2 = one kernel, both layers on the tensor core (default); 1 = one kernel, conv1a on the CUDA cores
   // (SPFE_CONV1=ffma); 0 = two kernels (SPFE_CONV1=unfused or SPFE_FUSED_CONV1=0; materialises conv1a for inspection)
   int conv1_mode = 2;
@@ -385,19 +386,28 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     const size_t vis_words = (px + 31) / 32;
     CU_OK(c, cudaMemsetAsync(s.cov_visited, 0, B * vis_words * sizeof(uint32_t), st));
     CU_OK(c, cudaMemsetAsync(s.cov_frame_flag, 0, B * sizeof(int), st));
+    CU_OK(c, cudaMemsetAsync(s.cov_ctr, 0, COV_NCTR * sizeof(int), st));
     CovArgs a;
     a.heat_inv = s.heat_inv; a.kp_xy = s.kp_xy; a.count = s.count; a.owner = s.cov_owner; a.visited = s.cov_visited;
     a.queue = s.cov_queue; a.qlen = s.cov_qlen; a.response = s.resp; a.cov2 = s.cov2; a.cov2_inv = s.cov2_inv;
-    a.overflow = s.cov_overflow; a.H = H; a.W = W; a.cap = c->cap;
+    a.overflow = s.cov_overflow; a.H = H; a.W = W; a.cap = c->cap; a.B = B; a.round = 0;
+    a.done = s.cov_done; a.ctr = s.cov_ctr; a.big = s.cov_big; a.pend = s.cov_pend;
     a.frame_flag = s.cov_frame_flag; a.n_replay = s.cov_n_replay; a.vis_words = static_cast<int>(vis_words);
-    dim3 grid((c->cap + 127) / 128, B);
     mark("cov_memset", 0, 5.0 * px * B);
-    cov_flood_kernel<<<dim3((c->cap + COV_TPB - 1) / COV_TPB, B), COV_TPB, COV_SMEM, st>>>(a);
+    cov_flood_kernel<COV_S_WIN, COV_S_QCAP, COV_S_WARPS, false><<<c->num_sms, COV_S_WARPS * 32, COV_S_SMEM, st>>>(a);
+    cov_flood_kernel<COV_WIN, COV_QCAP, COV_B_WARPS, true><<<32, COV_B_WARPS * 32, COV_B_SMEM, st>>>(a);
     mark("cov_flood", 0, 0);
-    cov_finish_kernel<<<grid, 128, 0, st>>>(a);
-    mark("cov_finish", 0, 0);
+    cov_resolve0_kernel<<<(B * c->cap + 7) / 8, 256, 0, st>>>(a);
+    mark("cov_resolve0", 0, 0);
+    for (int r = 1; r <= COV_ROUNDS; r++) {
+      a.round = r;
+      cov_claim_kernel<<<c->num_sms, 256, 0, st>>>(a);
+      cov_resolve_kernel<COV_S_WIN, COV_S_QCAP, COV_S_WARPS, false><<<c->num_sms, COV_S_WARPS * 32, COV_S_SMEM, st>>>(a);
+      cov_resolve_kernel<COV_WIN, COV_QCAP, COV_B_WARPS, true><<<32, COV_B_WARPS * 32, COV_B_SMEM, st>>>(a);
+    }
+    mark("cov_rounds", 0, 0);
     cov_replay_kernel<<<B, 32, (COV_SEQ_QCAP + COV_SEQ_BITMAP_WORDS) * sizeof(uint32_t), st>>>(a);
-    c->launches += 3;
+    c->launches += 4 + 3 * COV_ROUNDS;
     CU_OK(c, cudaGetLastError());
     mark("cov_replay", 0, 0);
   }
@@ -451,7 +461,7 @@ void spfe_default_config(spfe_config *cfg, int32_t height, int32_t width, int32_
   cfg->device_id = 0;
   cfg->max_batch = 1;
   cfg->num_slots = 1;
-  cfg->flags = SPFE_EMIT_HEAT | SPFE_EMIT_COV;  // what SPExtractor::operator() always produces
+  cfg->flags = SPFE_EMIT_HEAT | SPFE_EMIT_HEAT_INV | SPFE_EMIT_COV;  // what SPExtractor::operator() always produces
   cfg->weights_path = nullptr;
 }
 
@@ -582,10 +592,8 @@ static int create_impl(spfe_ctx *c) {
       if ((rc = dev_alloc(c, &s.heat_inv, Bm * px))) return rc;
       if ((rc = dev_alloc(c, &s.heat_mm, Bm * 2))) return rc;
       if ((rc = dev_alloc(c, &s.heat_mm_f, Bm * 2))) return rc;
-      if (c->heat_host) {
-        if ((rc = host_alloc(c, &s.h_heat, Bm * px))) return rc;
-        if ((rc = host_alloc(c, &s.h_heat_inv, Bm * px))) return rc;
-      }
+      if (c->heat_host && (rc = host_alloc(c, &s.h_heat, Bm * px))) return rc;
+      if (c->heat_inv_host && (rc = host_alloc(c, &s.h_heat_inv, Bm * px))) return rc;
     }
     if (c->cov) {
       if ((rc = dev_alloc(c, &s.cov_owner, Bm * px))) return rc;
@@ -595,6 +603,10 @@ static int create_impl(spfe_ctx *c) {
       if ((rc = dev_alloc(c, &s.cov_overflow, 1))) return rc;
       if ((rc = dev_alloc(c, &s.cov_frame_flag, Bm))) return rc;
       if ((rc = dev_alloc(c, &s.cov_n_replay, Bm * 2))) return rc;
+      if ((rc = dev_alloc(c, &s.cov_done, Bm * cap))) return rc;
+      if ((rc = dev_alloc(c, &s.cov_ctr, COV_NCTR))) return rc;
+      if ((rc = dev_alloc(c, &s.cov_big, Bm * cap))) return rc;
+      if ((rc = dev_alloc(c, &s.cov_pend, Bm * cap))) return rc;
       CU_OK(c, cudaMemset(s.cov_overflow, 0, sizeof(int)));
       if ((rc = dev_alloc(c, &s.resp, Bm * cap))) return rc;
       if ((rc = dev_alloc(c, &s.cov2, Bm * cap * 2))) return rc;
@@ -681,7 +693,8 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
   if (c->cap > c->cells) c->cap = c->cells;
   c->cov = (cfg->flags & SPFE_EMIT_COV) != 0;
   c->heat_host = (cfg->flags & SPFE_EMIT_HEAT) != 0;
-  c->heat = c->cov || c->heat_host;
+  c->heat_inv_host = (cfg->flags & SPFE_EMIT_HEAT_INV) != 0;
+  c->heat = c->cov || c->heat_host || c->heat_inv_host;
   c->match_prev = (cfg->flags & SPFE_MATCH_PREV) != 0;
   c->rows_pad = (c->cap + 255) / 256 * 256;
   c->match_nb = c->rows_pad / 256;
@@ -704,7 +717,10 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
     }
     CU_OK(c, cudaFuncSetAttribute(conv1ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1ab::SMEM));
     CU_OK(c, cudaFuncSetAttribute(conv1ab_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1m::SMEM));
-    CU_OK(c, cudaFuncSetAttribute(cov_flood_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_SMEM));
+    CU_OK(c, cudaFuncSetAttribute(cov_flood_kernel<COV_S_WIN, COV_S_QCAP, COV_S_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_S_SMEM));
+    CU_OK(c, cudaFuncSetAttribute(cov_flood_kernel<COV_WIN, COV_QCAP, COV_B_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_B_SMEM));
+    CU_OK(c, cudaFuncSetAttribute(cov_resolve_kernel<COV_S_WIN, COV_S_QCAP, COV_S_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_S_SMEM));
+    CU_OK(c, cudaFuncSetAttribute(cov_resolve_kernel<COV_WIN, COV_QCAP, COV_B_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_B_SMEM));
     CU_OK(c, cudaFuncSetAttribute(cov_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (COV_SEQ_QCAP + COV_SEQ_BITMAP_WORDS) * (int)sizeof(uint32_t)));
     return SPFE_OK;
   }();
@@ -750,10 +766,8 @@ static int enqueue_d2h(spfe_ctx *c, Slot &s, int B) {
   CU_OK(c, cudaMemcpyAsync(s.h_occ, s.occ, B * cells * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
   CU_OK(c, cudaMemcpyAsync(s.h_dense, s.dense_dust, B * cells * sizeof(float), cudaMemcpyDeviceToHost, st));
   CU_OK(c, cudaMemcpyAsync(s.h_semi, s.semi_dust, B * cells * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (c->heat_host) {
-    CU_OK(c, cudaMemcpyAsync(s.h_heat, s.heat, B * px * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CU_OK(c, cudaMemcpyAsync(s.h_heat_inv, s.heat_inv, B * px * sizeof(float), cudaMemcpyDeviceToHost, st));
-  }
+  if (c->heat_host) CU_OK(c, cudaMemcpyAsync(s.h_heat, s.heat, B * px * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (c->heat_inv_host) CU_OK(c, cudaMemcpyAsync(s.h_heat_inv, s.heat_inv, B * px * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (c->cov) {
     CU_OK(c, cudaMemcpyAsync(s.h_resp, s.resp, B * cap * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU_OK(c, cudaMemcpyAsync(s.h_cov2, s.cov2, B * cap * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -856,10 +870,8 @@ int spfe_wait(spfe_ctx *c, int32_t slot, spfe_frame_out *outs) {
     o.occ_grid = s.h_occ + b * cells;
     o.dense_dust = s.h_dense + b * cells;
     o.semi_dust = s.h_semi + b * cells;
-    if (c->heat_host) {
-      o.heat = s.h_heat + b * px;
-      o.heat_inv = s.h_heat_inv + b * px;
-    }
+    if (c->heat_host) o.heat = s.h_heat + b * px;
+    if (c->heat_inv_host) o.heat_inv = s.h_heat_inv + b * px;
     if (c->match_prev) {
       o.n_prev = b == 0 ? s.h_nprev[0] : s.h_count[b - 1];
       o.match_prev = s.h_match + b * cap;
@@ -1028,7 +1040,8 @@ int64_t spfe_debug_read(spfe_ctx *c, int32_t slot, const char *name, void *dst, 
       {"kp_score", s.kp_score, B * cap * 4},     {"desc", s.desc, B * cap * 256 * 4},
       {"occ_grid", s.occ, B * cells * 2},        {"match_prev", c->match_prev ? s.match.q2t : nullptr, B * cap * 4},
       {"match_dist", c->match_prev ? s.match.dist : nullptr, B * cap * 4},
-      {"cov_qlen", s.cov_qlen, B * cap * 4},     {"cov_replayed", s.cov_n_replay, B * 2 * 4}};
+      {"cov_qlen", s.cov_qlen, B * cap * 4},     {"cov_done", s.cov_done, B * cap * 4},
+      {"cov_counters", s.cov_ctr, COV_NCTR * 4},     {"cov_replayed", s.cov_n_replay, B * 2 * 4}};
   for (const Ent &e : tab)
     if (!strcmp(e.n, name)) {
       if (!e.p) return c->fail(SPFE_ERR_STATE, fmt("spfe_debug_read: '%s' is not produced with the current flags", name));

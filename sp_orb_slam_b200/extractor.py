@@ -39,14 +39,16 @@ class SPExtractor:
 
     def __init__(self, nfeatures: int, height: int, width: int, model_path: str, *, device_id: int = 0,
                  max_batch: int = 1, num_slots: int = 1, emit_heat: bool = True, emit_cov: bool = True,
-                 match_prev: bool = False):
+                 match_prev: bool = False, emit_heat_inv: bool | None = None):
         self._lib = capi.load()
         self._ctx = C.c_void_p()
         cfg = capi.Config()
         self._lib.spfe_default_config(C.byref(cfg), height, width, nfeatures)
         cfg.device_id, cfg.max_batch, cfg.num_slots = device_id, max_batch, num_slots
+        emit_heat_inv = emit_heat if emit_heat_inv is None else emit_heat_inv
         cfg.flags = ((capi.EMIT_HEAT if emit_heat else 0) | (capi.EMIT_COV if emit_cov else 0)
-                     | (capi.MATCH_PREV if match_prev else 0))
+                     | (capi.MATCH_PREV if match_prev else 0) | (capi.EMIT_HEAT_INV if emit_heat_inv else 0))
+        self.emit_heat_inv = emit_heat_inv
         self.match_prev = match_prev
         self._path = str(model_path).encode()
         cfg.weights_path = self._path
@@ -100,6 +102,7 @@ class SPExtractor:
                  dense_dust=_as_np(o.dense_dust, (hc, wc), np.float32), semi_dust=_as_np(o.semi_dust, (hc, wc), np.float32))
         if self.emit_heat:
             d["heat"] = _as_np(o.heat, (H, W), np.float32)
+        if self.emit_heat_inv:
             d["heat_inv"] = _as_np(o.heat_inv, (H, W), np.float32)
         if self.match_prev:
             d["n_prev"] = o.n_prev
@@ -215,7 +218,8 @@ class SPExtractor:
               "count": (lambda s: (), np.int32), "kp_xy": (lambda s: (s.cap, 2), np.float32), "kp_score": (lambda s: (s.cap,), np.float32),
               "desc": (lambda s: (s.cap, 256), np.float32), "occ_grid": (lambda s: (s.hc, s.wc), np.int16),
               "match_prev": (lambda s: (s.cap,), np.int32), "match_dist": (lambda s: (s.cap,), np.float32),
-              "cov_qlen": (lambda s: (s.cap,), np.int32), "cov_replayed": (lambda s: (2,), np.int32)}
+              "cov_qlen": (lambda s: (s.cap,), np.int32), "cov_done": (lambda s: (s.cap,), np.int32),
+              "cov_counters": (lambda s: (4,), np.int32), "cov_replayed": (lambda s: (2,), np.int32)}
 
     def debug_read(self, slot: int, name: str, batch: int) -> np.ndarray:
         shape_fn, dt = self._DEBUG[name]

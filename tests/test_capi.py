@@ -31,7 +31,7 @@ def test_struct_layouts(lib):
     assert cfg.struct_size == C.sizeof(capi.Config)
     assert (cfg.height, cfg.width, cfg.max_keypoints) == (480, 752, 800)
     assert abs(cfg.score_thresh - 0.007) < 1e-9 and cfg.nms_radius == 4 and cfg.border == 8   # sp_extractor.cpp:122,502
-    assert cfg.flags == capi.EMIT_HEAT | capi.EMIT_COV
+    assert cfg.flags == capi.EMIT_HEAT | capi.EMIT_HEAT_INV | capi.EMIT_COV   # everything operator() fills
 
 
 def test_create_validates_arguments(lib):

@@ -315,7 +315,7 @@ def test_stream_matching_match_prev(ex_cache):
 
 def test_covariance_vs_oracle_on_same_heat(ex_cache):
     """computeCovariance is order- and comparison-dependent (shared visited map, FIFO floods).  The device version
-    (parallel floods + sequential replay of conflicted keypoints, csrc/cov.cuh) must be bit-exact against the oracle's
+    (parallel lone floods, ordered conflict-resolution rounds, sequential remainder; csrc/cov.cuh) must be bit-exact against the oracle's
     sequential C restatement run on the GPU's own heat_inv and keypoints."""
     H, W = 240, 320
     ex = ex_cache(H, W, 800, max_batch=4)
@@ -336,11 +336,14 @@ def test_covariance_dense_full_size_and_device_only(ex_cache):
     frames = synth.make_stream(H, W, 3, seed=77, n_shapes=1500)
     outs = ex.extract_batch(list(frames))
     qlen = ex.debug_read(0, "cov_qlen", 3)
+    done = ex.debug_read(0, "cov_done", 3)
+    ctr = ex.debug_read(0, "cov_counters", 1)[0]
+    assert ctr[2] > 0                                     # some keypoints conflicted and went through the ordered rounds
     for t, o in enumerate(outs):
         resp, cov2, cov2_inv = O.covariance(o["heat_inv"], o["kp_xy"])
         assert np.array_equal(o["kp_response"], resp), t
         assert np.array_equal(o["cov2"], cov2) and np.array_equal(o["cov2_inv"], cov2_inv), t
-        assert np.all(qlen[t, :o["n"]] > 0)                                                # every flood completed
+        assert np.all(qlen[t, :o["n"]] > 0) and np.all(done[t, :o["n"]] == 1)             # every flood completed
     dev = ex_cache(H, W, 800, max_batch=3, emit_heat=False, emit_cov=True)
     outs2 = dev.extract_batch(list(frames))
     for o, o2 in zip(outs, outs2):
