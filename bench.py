@@ -167,7 +167,7 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=752)
     ap.add_argument("--nf", type=int, default=800)
@@ -244,12 +244,13 @@ def main():
     conv_flop = FLOP_PER_PIXEL * H * W * B
     step_ms = sum(d["ms"] for d in stages.values())
     # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/r01_traffic.json,
-    # same 32 x 752x480 launch); None for other geometries
+    # same frames-per-launch x 752x480 shape); None for other geometries
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath) and (H, W, B) == (480, 752, 32):
+    if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        traffic = tj.get({"conv1a+1b": "conv1ab_mma_kernel"}.get(dom, dom))
+        if (H, W, B) == (480, 752, tj.get("frames_per_launch")):
+            traffic = tj.get({"conv1a+1b": "conv1ab_mma_kernel"}.get(dom, dom))
     roofline = {"bound": "tensor", "kernel": dom, "achieved": dom_tf, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": dom_tf / peaks["tflops_sustained"], "traffic": traffic, "peak_source": peaks["src"] + " bf16 sustained",
                 "kernel_ms": stages[dom]["ms"], "kernel_share_of_step": stages[dom]["ms"] / step_ms,

@@ -36,9 +36,10 @@ constexpr int COV_QCAP = 2048;   // big flood: queue entries == stride of the pe
 constexpr int COV_B_WARPS = 4;   // big floods (warps) per block
 constexpr int COV_B_SMEM = COV_B_WARPS * (COV_WIN * COV_WIN + COV_QCAP) * 2;  // 136 KB
 constexpr int COV_S_WIN = 64;    // small flood (the common case)
-constexpr int COV_S_QCAP = 512;
+constexpr int COV_S_QCAP = 1024;
 constexpr int COV_S_WARPS = 16;  // small floods (warps) per block
-constexpr int COV_S_SMEM = COV_S_WARPS * (COV_S_WIN * COV_S_WIN + COV_S_QCAP) * 2;  // 144 KB
+constexpr int COV_S_SMEM = COV_S_WARPS * (COV_S_WIN * COV_S_WIN + COV_S_QCAP) * 2;  // 160 KB
+constexpr int COV_R_BIG_BLOCKS = 32;  // cov_resolve_kernel: blocks (of COV_B_WARPS active warps) that take the big floods
 constexpr int COV_ROUNDS = 3;    // parallel conflict-resolution rounds before the sequential remainder
 constexpr int COV_SEQ_QCAP = 32 * 1024;  // queue entries of the sequential path (128 KB of shared memory)
 constexpr int COV_SEQ_BITMAP_WORDS = 16 * 1024;  // + 64 KB: the frame's visited bitmap if H*W <= 524288 pixels
@@ -56,6 +57,7 @@ struct CovArgs {
   uint32_t *queue;        // [B][cap][COV_QCAP] pop list (pixel indices, duplicates included) of every LONE flood
   int *qlen;              // [B][cap]   its length
   int *done;              // [B][cap]   1 = response / cov2 / cov2_inv are final
+  int *isbig;             // [B][cap]   1 = the lone flood needed the big limits
   int *ctr;               // [COV_NCTR]
   int *big;               // [B*cap]    keypoints (b*cap + k) whose lone flood needs the big limits
   int *pend;              // [B*cap]    keypoints not clean in round 0
@@ -252,7 +254,10 @@ __global__ void __launch_bounds__(WARPS * 32) cov_flood_kernel(const CovArgs a) 
       const int idx = sq[i];
       q[i] = static_cast<uint32_t>((oy + idx / WIN) * W + ox + (idx & (WIN - 1)));
     }
-    if (lane == 0) a.qlen[ki] = n;
+    if (lane == 0) {
+      a.qlen[ki] = n;
+      a.isbig[ki] = BIG;
+    }
     __syncwarp();
   }
 }
@@ -305,37 +310,27 @@ __global__ void __launch_bounds__(256) cov_claim_kernel(const CovArgs a) {
 }
 
 // Round r, step 2: a pending keypoint that owns all its pixels has no unfinished lower-indexed neighbour: flood it
-// against the visited map (seeded into fp on the pixels of the lone flood, the only ones it can reach).  BIG selects
-// which keypoints a launch handles: those whose lone flood fits the small window / queue, or the others.
-template <int WIN, int QCAP, int WARPS, bool BIG>
-__global__ void __launch_bounds__(WARPS * 32) cov_resolve_kernel(const CovArgs a) {
-  extern __shared__ uint8_t cov_smem[];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, n_pend = a.ctr[2];
-  if (BIG && a.ctr[1] == 0) return;  // no lone flood needed the big limits
-  uint16_t *fp = reinterpret_cast<uint16_t *>(cov_smem) + static_cast<size_t>(w) * (WIN * WIN + QCAP);
-  uint16_t *sq = fp + WIN * WIN;
-  const int W = a.W, H = a.H;
-  for (int e = blockIdx.x * WARPS + w; e < n_pend; e += gridDim.x * WARPS) {
+// against the visited map (seeded into fp on the pixels of the lone flood, the only ones it can reach).
+template <int WIN, int QCAP>
+__device__ __forceinline__ void cov_resolve_warp(const CovArgs &a, uint16_t *fp, uint16_t *sq, int lane, int first, int stride, bool big) {
+  const int W = a.W, H = a.H, n_pend = a.ctr[2];
+  for (int e = first; e < n_pend; e += stride) {
     const int ki = a.pend[e];
     if (a.done[ki]) continue;
     const int b = ki / a.cap, k = ki - b * a.cap;
     if (a.frame_flag[b]) continue;
+    if ((a.isbig[ki] != 0) != big) continue;  // the blocks of the other kind handle it
     const size_t px = static_cast<size_t>(H) * W;
     const float *heat = a.heat_inv + b * px;
     const int *owner = a.owner + b * px;
     uint32_t *visited = a.visited + static_cast<size_t>(b) * a.vis_words;
     const uint32_t *q = a.queue + static_cast<size_t>(ki) * COV_QCAP;
     const int n = a.qlen[ki], mine = cov_tag(a.round, k);
+    bool blocked = false;
+    for (int i = lane; i < n; i += 32) blocked |= (owner[q[i]] != mine);
+    if (__any_sync(0xffffffffu, blocked)) continue;
     const float *xy = a.kp_xy + static_cast<size_t>(ki) * 2;
     const int cu = static_cast<int>(xy[0]), cv = static_cast<int>(xy[1]);
-    bool blocked = false, small = n <= COV_S_QCAP;
-    for (int i = lane; i < n; i += 32) {
-      const int pix = static_cast<int>(q[i]), v = pix / W, u = pix - v * W;
-      blocked |= (owner[pix] != mine);
-      small &= (abs(u - cu) < COV_S_WIN / 2 - 1) && (abs(v - cv) < COV_S_WIN / 2 - 1);
-    }
-    if (__any_sync(0xffffffffu, blocked)) continue;
-    if (__all_sync(0xffffffffu, small) == BIG) continue;  // the other launch of this round handles it
     const int ox = cu - WIN / 2, oy = cv - WIN / 2;
     cov_fp_init<WIN>(fp, lane);
     for (int i = lane; i < n; i += 32) {
@@ -360,6 +355,23 @@ __global__ void __launch_bounds__(WARPS * 32) cov_resolve_kernel(const CovArgs a
     }
     if (lane == 0) a.done[ki] = 1;
     __syncwarp();
+  }
+}
+
+// One launch per round: the last COV_R_BIG_BLOCKS blocks take the keypoints whose lone flood needed the big limits
+// (COV_B_WARPS warps of the block work, with the big window / queue), all other blocks the common small ones.
+__global__ void __launch_bounds__(COV_S_WARPS * 32) cov_resolve_kernel(const CovArgs a) {
+  extern __shared__ uint8_t cov_smem[];
+  static_assert(COV_B_SMEM <= COV_S_SMEM, "both kinds of block use the same launch configuration");
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int n_small = static_cast<int>(gridDim.x) - COV_R_BIG_BLOCKS;
+  if (static_cast<int>(blockIdx.x) < n_small) {
+    uint16_t *fp = reinterpret_cast<uint16_t *>(cov_smem) + static_cast<size_t>(w) * (COV_S_WIN * COV_S_WIN + COV_S_QCAP);
+    cov_resolve_warp<COV_S_WIN, COV_S_QCAP>(a, fp, fp + COV_S_WIN * COV_S_WIN, lane, blockIdx.x * COV_S_WARPS + w, n_small * COV_S_WARPS, false);
+  } else if (w < COV_B_WARPS && a.ctr[1] > 0) {
+    uint16_t *fp = reinterpret_cast<uint16_t *>(cov_smem) + static_cast<size_t>(w) * (COV_WIN * COV_WIN + COV_QCAP);
+    cov_resolve_warp<COV_WIN, COV_QCAP>(a, fp, fp + COV_WIN * COV_WIN, lane, (blockIdx.x - n_small) * COV_B_WARPS + w,
+                                        COV_R_BIG_BLOCKS * COV_B_WARPS, true);
   }
 }
 

@@ -110,7 +110,7 @@ struct Slot {
   float *h_mdist = nullptr;
   // covariance (device)
   int *cov_owner = nullptr, *cov_qlen = nullptr, *cov_overflow = nullptr, *cov_frame_flag = nullptr, *cov_n_replay = nullptr;
-  int *cov_done = nullptr, *cov_ctr = nullptr, *cov_big = nullptr, *cov_pend = nullptr;
+  int *cov_done = nullptr, *cov_ctr = nullptr, *cov_big = nullptr, *cov_pend = nullptr, *cov_isbig = nullptr;
   uint32_t *cov_visited = nullptr;
   uint32_t *cov_queue = nullptr;
   float *resp = nullptr, *cov2 = nullptr, *cov2_inv = nullptr;
@@ -391,7 +391,7 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     a.heat_inv = s.heat_inv; a.kp_xy = s.kp_xy; a.count = s.count; a.owner = s.cov_owner; a.visited = s.cov_visited;
     a.queue = s.cov_queue; a.qlen = s.cov_qlen; a.response = s.resp; a.cov2 = s.cov2; a.cov2_inv = s.cov2_inv;
     a.overflow = s.cov_overflow; a.H = H; a.W = W; a.cap = c->cap; a.B = B; a.round = 0;
-    a.done = s.cov_done; a.ctr = s.cov_ctr; a.big = s.cov_big; a.pend = s.cov_pend;
+    a.done = s.cov_done; a.isbig = s.cov_isbig; a.ctr = s.cov_ctr; a.big = s.cov_big; a.pend = s.cov_pend;
     a.frame_flag = s.cov_frame_flag; a.n_replay = s.cov_n_replay; a.vis_words = static_cast<int>(vis_words);
     mark("cov_memset", 0, 5.0 * px * B);
     cov_flood_kernel<COV_S_WIN, COV_S_QCAP, COV_S_WARPS, false><<<c->num_sms, COV_S_WARPS * 32, COV_S_SMEM, st>>>(a);
@@ -402,12 +402,11 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     for (int r = 1; r <= COV_ROUNDS; r++) {
       a.round = r;
       cov_claim_kernel<<<c->num_sms, 256, 0, st>>>(a);
-      cov_resolve_kernel<COV_S_WIN, COV_S_QCAP, COV_S_WARPS, false><<<c->num_sms, COV_S_WARPS * 32, COV_S_SMEM, st>>>(a);
-      cov_resolve_kernel<COV_WIN, COV_QCAP, COV_B_WARPS, true><<<32, COV_B_WARPS * 32, COV_B_SMEM, st>>>(a);
+      cov_resolve_kernel<<<c->num_sms > 2 * COV_R_BIG_BLOCKS ? c->num_sms : 2 * COV_R_BIG_BLOCKS, COV_S_WARPS * 32, COV_S_SMEM, st>>>(a);
     }
     mark("cov_rounds", 0, 0);
     cov_replay_kernel<<<B, 32, (COV_SEQ_QCAP + COV_SEQ_BITMAP_WORDS) * sizeof(uint32_t), st>>>(a);
-    c->launches += 4 + 3 * COV_ROUNDS;
+    c->launches += 4 + 2 * COV_ROUNDS;
     CU_OK(c, cudaGetLastError());
     mark("cov_replay", 0, 0);
   }
@@ -605,6 +604,7 @@ static int create_impl(spfe_ctx *c) {
       if ((rc = dev_alloc(c, &s.cov_n_replay, Bm * 2))) return rc;
       if ((rc = dev_alloc(c, &s.cov_done, Bm * cap))) return rc;
       if ((rc = dev_alloc(c, &s.cov_ctr, COV_NCTR))) return rc;
+      if ((rc = dev_alloc(c, &s.cov_isbig, Bm * cap))) return rc;
       if ((rc = dev_alloc(c, &s.cov_big, Bm * cap))) return rc;
       if ((rc = dev_alloc(c, &s.cov_pend, Bm * cap))) return rc;
       CU_OK(c, cudaMemset(s.cov_overflow, 0, sizeof(int)));
@@ -719,8 +719,7 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
     CU_OK(c, cudaFuncSetAttribute(conv1ab_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1m::SMEM));
     CU_OK(c, cudaFuncSetAttribute(cov_flood_kernel<COV_S_WIN, COV_S_QCAP, COV_S_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_S_SMEM));
     CU_OK(c, cudaFuncSetAttribute(cov_flood_kernel<COV_WIN, COV_QCAP, COV_B_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_B_SMEM));
-    CU_OK(c, cudaFuncSetAttribute(cov_resolve_kernel<COV_S_WIN, COV_S_QCAP, COV_S_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_S_SMEM));
-    CU_OK(c, cudaFuncSetAttribute(cov_resolve_kernel<COV_WIN, COV_QCAP, COV_B_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_B_SMEM));
+    CU_OK(c, cudaFuncSetAttribute(cov_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_S_SMEM));
     CU_OK(c, cudaFuncSetAttribute(cov_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (COV_SEQ_QCAP + COV_SEQ_BITMAP_WORDS) * (int)sizeof(uint32_t)));
     return SPFE_OK;
   }();

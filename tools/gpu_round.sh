@@ -9,6 +9,6 @@ if [ "${1:-}" = "ncu" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv1ab|conv_tc" -s 10 -c 5 -o gpurun_out/prof_conv \
-      python tools/bringup.py profile 480 752 32 > gpurun_out/ncu_full.log 2>&1
+      python tools/bringup.py profile 480 752 64 > gpurun_out/ncu_full.log 2>&1
   ls -la gpurun_out/
 fi

@@ -1,7 +1,7 @@
 """Summarise an `ncu --set full` report into profiles/: a markdown table per kernel and the per-launch DRAM traffic
 JSON that bench.py reads for `roofline.traffic`.
 
-    python tools/ncu_summary.py gpurun_out/prof_conv.ncu-rep profiles/r01_ncu_conv_summary.md profiles/r01_traffic.json
+    python tools/ncu_summary.py gpurun_out/prof_conv.ncu-rep profiles/r01_ncu_conv_summary.md profiles/r01_traffic.json [title] [frames]
 """
 import csv
 import io
@@ -20,15 +20,15 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
 TO_BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
-def main(rep, md_out, json_out, title):
+def main(rep, md_out, json_out, title, frames):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     kcol = hdr.index("Kernel Name")
     out = [f"# {title}", "",
-           "Workload: `python tools/bringup.py profile 480 752 32` = 32 frames of 752x480 per launch. ncu replays each kernel "
+           f"Workload: `python tools/bringup.py profile 480 752 {frames}` = {frames} frames of 752x480 per launch. ncu replays each kernel "
            "~40x cold-cache and serialised: compare shares and ratios, not absolute times.", ""]
-    traffic = {}
+    traffic = {"frames_per_launch": frames}
     for r in rows[2:]:
         name = r[kcol]
         out += [f"### `{name}`", "", "| metric | value | unit |", "|---|---|---|"]
@@ -48,4 +48,5 @@ def main(rep, md_out, json_out, title):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "ncu --set full (--clock-control none)")
+    main(sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "ncu --set full (--clock-control none)",
+         int(sys.argv[5]) if len(sys.argv) > 5 else 64)
