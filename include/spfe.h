@@ -141,6 +141,42 @@ int spfe_slot_sync(spfe_ctx *ctx, int32_t slot);
  * Thread-safe (per-call scratch), as SearchByBruteForce runs on two threads. */
 int spfe_match_mutual_nn(spfe_ctx *ctx, const float *q, int32_t nq, const float *t, int32_t nt,
                          int32_t *q2t, float *dist);
+/* Guided (cell-grid) searches -- the greedy candidate loops of
+ *   SPMatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, th_dist)   orb_slam2/src/cv/sp_matcher.cpp:344-432
+ *   SPMatcher::SearchByProjection(Frame &Cur, const Frame &Last, th, bMono)        orb_slam2/src/cv/sp_matcher.cpp:1439-1543
+ *   the patch-wise association of dust tracking                                    orb_slam2/src/tracking/tracker_dust.cpp:112-172
+ * with the per-object tests hoisted into flat arrays by the caller.  For every query (map
+ * point) i, in order: candidates = Frame::GetFeaturesInArea(qxy[i], qradius[i]) over occ_grid (frame.cpp:382-420;
+ * SPFE_GUIDED_AREA) or the 2 x 2 occ_grid cells at floor(qxy[i]) in cell units (SPFE_GUIDED_DUST_CELLS); candidates
+ * with kp_taken set are skipped; the nearest descriptor (first on ties, distances below best_init only) is accepted if
+ *   dist <= th_le  ||  dist < (c2_adaptive > 0 ? 1.2f * c2_adaptive / (c2_adaptive + |kp_un - qxy|^2) : th_lt)
+ * and, if qblocks[i], becomes unavailable to the queries that follow.  Results are those of the sequential loop.
+ *   SearchByProjection(F, MPs):     best_init 256, th_le = th_dist, th_lt = 0.7 (or c2_adaptive = tracking::dust::c2_thresh)
+ *   SearchByProjection(Cur, Last):  best_init FLT_MAX, th_le = TH_HIGH (0.7), th_lt = -INFINITY
+ *   dust-track association:         best_init 0.75, th_le = -INFINITY, th_lt = 0.75, qblocks = NULL
+ * q2kp[i] = matched keypoint or -1, qdist[i] = its distance; kp_taken_out (may be NULL) = kp_taken after the loop.
+ * Thread-safe like spfe_match_mutual_nn. */
+enum { SPFE_GUIDED_AREA = 0, SPFE_GUIDED_DUST_CELLS = 1 };
+typedef struct spfe_guided_search {
+  int32_t struct_size;      /* = sizeof(spfe_guided_search) */
+  int32_t mode;             /* SPFE_GUIDED_* */
+  int32_t m;                /* queries, in the reference's iteration order */
+  int32_t n;                /* keypoints of the frame */
+  const float *qdesc;       /* [m][256] MapPoint::getDescTrack() */
+  const float *qxy;         /* [m][2] projection: pixels (AREA) or occ_grid cell units (DUST_CELLS) */
+  const float *qradius;     /* [m] search radius in pixels (AREA); ignored for DUST_CELLS */
+  const uint8_t *qvalid;    /* [m] or NULL: 0 = the reference's loop `continue`s before searching */
+  const uint8_t *qblocks;   /* [m] or NULL (= all 1): pMP->Observations() > 0 */
+  const float *kdesc;       /* [n][256] Frame::mDescriptors */
+  const float *kp_un;       /* [n][2] Frame::mvKeysUn (x, y); may be NULL for DUST_CELLS */
+  const int16_t *occ_grid;  /* [grid_rows][grid_cols] Frame::occ_grid (keypoint index or -1) */
+  int32_t grid_rows, grid_cols;
+  const uint8_t *kp_taken;  /* [n] or NULL: keypoint already carries an observed map point */
+  float min_x, min_y;       /* Frame::mnMinX / mnMinY */
+  float best_init, th_le, th_lt, c2_adaptive;
+} spfe_guided_search;
+int spfe_search_guided(spfe_ctx *ctx, const spfe_guided_search *g, int32_t *q2kp, float *qdist, uint8_t *kp_taken_out);
+
 /* SPFE_MATCH_PREV: forget the slot's previous frame (start of a new camera stream). */
 int spfe_reset_stream(spfe_ctx *ctx, int32_t slot);
 

@@ -210,3 +210,69 @@ def match_mutual_nn(q: np.ndarray, t: np.ndarray):
     _lib().orc_match_mutual(_p(q, C.c_float), len(q), _p(t, C.c_float), len(t), 256,
                             _p(q2t, C.c_int32), _p(dist, C.c_float), _p(sec, C.c_float))
     return q2t, dist, sec
+
+
+# ----------------------------------------------------------------------------
+# guided (cell-grid) searches -- SURVEY.md section 8(f) rank 2
+# ----------------------------------------------------------------------------
+FLT_MAX = float(np.finfo(np.float32).max)
+TH_HIGH, TH_LOW = 0.7, 0.3      # sp_matcher.cpp:18-19
+
+
+def features_in_area(occ: np.ndarray, kp_un: np.ndarray, x: float, y: float, r: float, min_x: float = 0.0, min_y: float = 0.0):
+    """Frame::GetFeaturesInArea (frame.cpp:382-420) -> keypoint indices in the reference's order."""
+    occ = np.ascontiguousarray(occ, np.int16)
+    kp_un = np.ascontiguousarray(kp_un, np.float32).reshape(-1, 2)
+    out = np.empty(occ.size + 4, np.int32)
+    L = _lib()
+    L.orc_features_in_area.restype = C.c_int
+    n = L.orc_features_in_area(_p(occ, C.c_int16), occ.shape[0], occ.shape[1], _p(kp_un, C.c_float), C.c_float(x), C.c_float(y),
+                               C.c_float(r), C.c_float(min_x), C.c_float(min_y), _p(out, C.c_int32))
+    return out[:n].copy()
+
+
+def search_guided(qdesc, qxy, qr, occ, kp_un, kdesc, *, mode: int, best_init: float, th_le: float, th_lt: float, c2: float = 0.0,
+                  qvalid=None, qblocks=None, kp_taken=None, min_x: float = 0.0, min_y: float = 0.0):
+    """Generic greedy guided search (orc_search_guided).  -> (q2kp int32[m], qdist f32[m], kp_taken_after u8[n])."""
+    qdesc = np.ascontiguousarray(qdesc, np.float32).reshape(-1, 256)
+    m = len(qdesc)
+    qxy = np.ascontiguousarray(qxy, np.float32).reshape(m, 2)
+    qr = np.ascontiguousarray(np.broadcast_to(np.asarray(qr, np.float32), (m,)))
+    occ = np.ascontiguousarray(occ, np.int16)
+    kp_un = np.ascontiguousarray(kp_un, np.float32).reshape(-1, 2)
+    kdesc = np.ascontiguousarray(kdesc, np.float32).reshape(-1, 256)
+    n = len(kdesc)
+    qvalid = np.ones(m, np.uint8) if qvalid is None else np.ascontiguousarray(qvalid, np.uint8)
+    qblocks = np.ones(m, np.uint8) if qblocks is None else np.ascontiguousarray(qblocks, np.uint8)
+    taken = np.zeros(n, np.uint8) if kp_taken is None else np.array(kp_taken, np.uint8)
+    q2kp = np.empty(max(m, 1), np.int32)
+    qdist = np.empty(max(m, 1), np.float32)
+    _lib().orc_search_guided(m, _p(qdesc, C.c_float), _p(qvalid, C.c_uint8), _p(qblocks, C.c_uint8), _p(qxy, C.c_float),
+                             _p(qr, C.c_float), mode, _p(occ, C.c_int16), occ.shape[0], occ.shape[1], _p(kp_un, C.c_float),
+                             _p(kdesc, C.c_float), n, _p(taken, C.c_uint8), C.c_float(min_x), C.c_float(min_y),
+                             C.c_float(best_init), C.c_float(th_le), C.c_float(th_lt), C.c_float(c2),
+                             _p(q2kp, C.c_int32), _p(qdist, C.c_float))
+    return q2kp[:m], qdist[:m], taken
+
+
+def search_by_projection_map_points(qdesc, proj_xy, radius, occ, kp_un, kdesc, *, th_dist: float, in_view=None, observed=None,
+                                    kp_taken=None, c2_adaptive: float = 0.0):
+    """SPMatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, th_dist), sp_matcher.cpp:344-432.
+    radius[i] = RadiusByViewingCos(mTrackViewCos) * th * mvScaleFactors[level] (host-side, :362-374)."""
+    return search_guided(qdesc, proj_xy, radius, occ, kp_un, kdesc, mode=0, best_init=256.0, th_le=th_dist, th_lt=0.7,
+                         c2=c2_adaptive, qvalid=in_view, qblocks=observed, kp_taken=kp_taken)
+
+
+def search_by_projection_last_frame(qdesc, proj_xy, radius, occ, kp_un, kdesc, *, valid=None, observed=None, kp_taken=None):
+    """SPMatcher::SearchByProjection(Frame &Cur, const Frame &Last, th, bMono), sp_matcher.cpp:1439-1543 (monocular:
+    mvuRight < 0, so the stereo test at :1512-1517 never fires)."""
+    return search_guided(qdesc, proj_xy, radius, occ, kp_un, kdesc, mode=0, best_init=FLT_MAX, th_le=TH_HIGH, th_lt=-np.inf,
+                         qvalid=valid, qblocks=observed, kp_taken=kp_taken)
+
+
+def dust_associate(qdesc, proj_uv_cells, occ, kdesc, *, in_view=None):
+    """Patch-wise association of dust tracking, tracker_dust.cpp:112-172: 2x2 occ_grid cells at floor(dust_proj),
+    best descriptor distance < 0.75, the matched cell is cleared."""
+    n = len(np.asarray(kdesc).reshape(-1, 256))
+    return search_guided(qdesc, proj_uv_cells, 0.0, occ, np.zeros((n, 2), np.float32), kdesc, mode=1, best_init=0.75,
+                         th_le=-np.inf, th_lt=0.75, qvalid=in_view)

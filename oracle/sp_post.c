@@ -185,3 +185,94 @@ void orc_match_mutual(const float *q, int nq, const float *t, int nt, int d,
     if (q2t[i] < 0 || t2q[q2t[i]] != i) q2t[i] = -1;
   free(t2q); free(tbest);
 }
+
+/* ---------------------------------------------------------------------------
+ * Guided (cell-grid) searches -- SURVEY.md section 8(f) rank 2.
+ *
+ *   orc_features_in_area <- Frame::GetFeaturesInArea, orb_slam2/src/type/frame.cpp:382-420: the live code walks the
+ *                           extractor's occ_grid (8-px cells, ix outer / iy inner) and keeps the keypoints with
+ *                           |dx| < r && |dy| < r; minLevel / maxLevel are ignored by it.
+ *   orc_search_guided    <- the greedy loops of
+ *        SPMatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, th_dist)  sp_matcher.cpp:344-432   (mode 0)
+ *        SPMatcher::SearchByProjection(Frame &Cur, const Frame &Last, th, bMono)       sp_matcher.cpp:1439-1543 (mode 0)
+ *        the dust-track patch association of Tracking                                  tracker_dust.cpp:112-172 (mode 1)
+ *   with the per-object tests hoisted into flat arrays: qvalid[i] = the loop's `continue` tests passed
+ *   (mbTrackInView && !isBad(), pMP && !mvbOutlier && projected inside the image, in_view && !isBad()), qblocks[i] =
+ *   the matched keypoint becomes unavailable to later queries (pMP->Observations() > 0; always for mode 1, which
+ *   clears the occ_grid cell), kp_taken[idx] = the keypoint already carries an observed map point on entry.
+ *   Acceptance: best <= th_le  ||  best < (c2 > 0 ? 1.2f * c2 / (c2 + duv) : th_lt).
+ *   The reference dereferences mvKeysUn[-1] when every candidate of a map point is skipped (sp_matcher.cpp:416-417,
+ *   undefined behaviour); here that is "no match".  Mode 1 reads occ_grid without a bounds check upstream; here
+ *   out-of-range cells are skipped.
+ * ------------------------------------------------------------------------- */
+int orc_features_in_area(const int16_t *occ, int grid_rows, int grid_cols, const float *kp_un, float x, float y, float r,
+                         float min_x, float min_y, int32_t *out) {
+  int n = 0;
+  int c0 = (int)floorf((x - min_x - r) / 8.0f); if (c0 < 0) c0 = 0;
+  if (c0 >= grid_cols) return 0;
+  int c1 = (int)ceilf((x - min_x + r) / 8.0f); if (c1 > grid_cols - 1) c1 = grid_cols - 1;
+  if (c1 < 0) return 0;
+  int r0 = (int)floorf((y - min_y - r) / 8.0f); if (r0 < 0) r0 = 0;
+  if (r0 >= grid_rows) return 0;
+  int r1 = (int)ceilf((y - min_y + r) / 8.0f); if (r1 > grid_rows - 1) r1 = grid_rows - 1;
+  if (r1 < 0) return 0;
+  for (int ix = c0; ix <= c1; ix++)
+    for (int iy = r0; iy <= r1; iy++) {
+      const int16_t idx = occ[iy * grid_cols + ix];
+      if (idx == -1) continue;
+      const float dx = kp_un[2 * idx] - x, dy = kp_un[2 * idx + 1] - y;
+      if (fabsf(dx) < r && fabsf(dy) < r) out[n++] = idx;
+    }
+  return n;
+}
+
+void orc_search_guided(int m, const float *qdesc, const uint8_t *qvalid, const uint8_t *qblocks, const float *qxy,
+                       const float *qr, int mode, const int16_t *occ, int grid_rows, int grid_cols, const float *kp_un,
+                       const float *kdesc, int n, uint8_t *kp_taken, float min_x, float min_y, float best_init,
+                       float th_le, float th_lt, float c2, int32_t *q2kp, float *qdist) {
+  int32_t *cand = (int32_t *)malloc(sizeof(int32_t) * (size_t)(grid_rows * grid_cols + 4));
+  (void)n;
+  for (int i = 0; i < m; i++) {
+    q2kp[i] = -1;
+    qdist[i] = 0.0f;
+    if (qvalid && !qvalid[i]) continue;
+    const float x = qxy[2 * i], y = qxy[2 * i + 1];
+    int nc = 0;
+    if (mode == 0) {
+      nc = orc_features_in_area(occ, grid_rows, grid_cols, kp_un, x, y, qr[i], min_x, min_y, cand);
+    } else {
+      const int u = (int)floorf(x), v = (int)floorf(y);
+      for (int du = 0; du < 2; du++)
+        for (int dv = 0; dv < 2; dv++) {
+          const int uu = u + du, vv = v + dv;
+          if (uu < 0 || uu >= grid_cols || vv < 0 || vv >= grid_rows) continue;
+          const int16_t idx = occ[vv * grid_cols + uu];
+          if (idx != -1) cand[nc++] = idx;
+        }
+    }
+    float best = best_init;
+    int best_idx = -1;
+    for (int c = 0; c < nc; c++) {
+      const int idx = cand[c];
+      if (kp_taken[idx]) continue;
+      const float d = orc_l2(qdesc + (size_t)i * 256, kdesc + (size_t)idx * 256, 256);
+      if (d < best) { best = d; best_idx = idx; }
+    }
+    if (best_idx < 0) continue;
+    int accept = best <= th_le;
+    if (!accept) {
+      float thr = th_lt;
+      if (c2 > 0.0f) {
+        const float du = kp_un[2 * best_idx] - x, dv = kp_un[2 * best_idx + 1] - y;
+        const float duv = du * du + dv * dv;
+        thr = 1.2f * c2 / (c2 + duv);
+      }
+      accept = best < thr;
+    }
+    if (!accept) continue;
+    q2kp[i] = best_idx;
+    qdist[i] = best;
+    if (!qblocks || qblocks[i]) kp_taken[best_idx] = 1;
+  }
+  free(cand);
+}

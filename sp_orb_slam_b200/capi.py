@@ -12,7 +12,7 @@ EMIT_HEAT, EMIT_COV, MATCH_PREV, EMIT_HEAT_INV = 1, 2, 4, 8
 OK, ERR_INVALID, ERR_EMPTY, ERR_WEIGHTS, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
 
 EXPORTS = ["spfe_default_config", "spfe_create", "spfe_destroy", "spfe_last_error", "spfe_extract", "spfe_submit",
-           "spfe_wait", "spfe_submit_pinned", "spfe_host_alloc", "spfe_host_free", "spfe_submit_device", "spfe_slot_sync", "spfe_match_mutual_nn", "spfe_reset_stream", "spfe_timer_start",
+           "spfe_wait", "spfe_submit_pinned", "spfe_host_alloc", "spfe_host_free", "spfe_submit_device", "spfe_slot_sync", "spfe_match_mutual_nn", "spfe_search_guided", "spfe_reset_stream", "spfe_timer_start",
            "spfe_timer_stop", "spfe_check_weights", "spfe_l2", "spfe_debug_read", "spfe_launch_count", "spfe_profile_device"]
 
 
@@ -30,6 +30,18 @@ class FrameOut(C.Structure):
                 ("occ_grid", C.POINTER(C.c_int16)), ("dense_dust", _FP), ("semi_dust", _FP), ("heat", _FP),
                 ("heat_inv", _FP), ("cov2", _FP), ("cov2_inv", _FP), ("n_prev", C.c_int32),
                 ("match_prev", C.POINTER(C.c_int32)), ("match_dist", _FP)]
+
+
+class GuidedSearch(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("mode", C.c_int32), ("m", C.c_int32), ("n", C.c_int32),
+                ("qdesc", C.c_void_p), ("qxy", C.c_void_p), ("qradius", C.c_void_p), ("qvalid", C.c_void_p),
+                ("qblocks", C.c_void_p), ("kdesc", C.c_void_p), ("kp_un", C.c_void_p), ("occ_grid", C.c_void_p),
+                ("grid_rows", C.c_int32), ("grid_cols", C.c_int32), ("kp_taken", C.c_void_p),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("best_init", C.c_float), ("th_le", C.c_float),
+                ("th_lt", C.c_float), ("c2_adaptive", C.c_float)]
+
+
+GUIDED_AREA, GUIDED_DUST_CELLS = 0, 1
 
 
 class StageTime(C.Structure):
@@ -72,6 +84,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.spfe_submit_device.argtypes = [vp, i32, vp, i32]
     L.spfe_slot_sync.argtypes = [vp, i32]
     L.spfe_match_mutual_nn.argtypes = [vp, vp, i32, vp, i32, vp, vp]
+    L.spfe_search_guided.argtypes = [vp, C.POINTER(GuidedSearch), vp, vp, vp]
     L.spfe_reset_stream.argtypes = [vp, i32]
     L.spfe_timer_start.argtypes = [vp, i32]
     L.spfe_timer_stop.argtypes = [vp, i32, C.POINTER(C.c_float)]

@@ -11,12 +11,24 @@
 
 using namespace orbslam;
 
-struct MapPoint { bool bad = false; bool isBad() const { return bad; } };
+struct MapPoint {
+  bool bad = false; bool isBad() const { return bad; }
+  // the fields SearchByProjection(Frame&, MapPoints) / the dust association read (map_point.h)
+  bool mbTrackInView = true, in_view = true, dust_match = false;
+  float mTrackProjX = 0, mTrackProjY = 0, mTrackViewCos = 1.f, dust_proj_u = 0, dust_proj_v = 0;
+  int mnTrackScaleLevel = 0, nobs = 1;
+  cv::Mat desc;
+  int Observations() const { return nobs; }
+  cv::Mat getDescTrack() const { return desc; }
+};
 struct KeyFrame {
   cv::Mat mDescriptors; std::vector<MapPoint *> mps;
   std::vector<MapPoint *> GetMapPointMatches() { return mps; }
 };
-struct Frame { cv::Mat mDescriptors; int N = 0; };
+struct Frame {
+  cv::Mat mDescriptors, occ_grid; int N = 0;
+  std::vector<cv::KeyPoint> mvKeysUn; std::vector<MapPoint *> mvpMapPoints; std::vector<float> mvScaleFactors{1.0f};
+};
 
 static cv::Mat read_raw(const char *path, int H, int W) {
   cv::Mat m(H, W, CV_8UC1);
@@ -57,8 +69,34 @@ int main(int argc, char **argv) {
   int n2 = matcher.SearchByBruteForce(&kf, &kf2, mkk);
   printf("SearchByBruteForce(KF,Frame) %d matches; (KF,KF) %d matches; d(0,0)=%.6f\n", n, n2,
          ka.empty() || kb.empty() ? 0.f : SPMatcher::DescriptorDistance(da.row(0), db.row(0)));
+  // guided searches: map points = frame A's keypoints projected where they were seen, searched in frame B
+  std::vector<MapPoint> mp3(ka.size());
+  std::vector<MapPoint *> vmp;
+  for (size_t i = 0; i < ka.size(); i++) {
+    mp3[i].desc = da.row(static_cast<int>(i)).clone();
+    mp3[i].mTrackProjX = ka[i].pt.x; mp3[i].mTrackProjY = ka[i].pt.y;
+    mp3[i].dust_proj_u = (ka[i].pt.x - 3.5f) / 8.0f; mp3[i].dust_proj_v = (ka[i].pt.y - 3.5f) / 8.0f;
+    mp3[i].mTrackViewCos = (i % 2) ? 0.9995f : 0.99f;
+    mp3[i].mbTrackInView = mp3[i].in_view = (i % 7 != 6);
+    mp3[i].nobs = (i % 5 == 4) ? 0 : 2;
+    vmp.push_back(&mp3[i]);
+  }
+  (*ex)(b, cv::Mat(), kb, db);  // occ_grid_ of frame B
+  fr.occ_grid = sp->occ_grid_.clone(); fr.mvKeysUn = kb; fr.mvpMapPoints.assign(kb.size(), nullptr);
+  const int n3 = matcher.SearchByProjection(fr, vmp, 3.0f, 0.7f);
+  std::vector<MapPoint *> proj_assign = fr.mvpMapPoints;
+  fr.mvpMapPoints.assign(kb.size(), nullptr);
+  const int n4 = matcher.DustAssociate(fr, vmp);
+  printf("SearchByProjection(F,MPs) %d matches; dust association %d matches\n", n3, n4);
   // dump for the python-side check
   std::string pre = argv[6];
+  {
+    FILE *g = fopen((pre + "_guided.txt").c_str(), "w");
+    for (size_t k = 0; k < kb.size(); k++)
+      fprintf(g, "%ld %ld\n", proj_assign[k] ? static_cast<long>(proj_assign[k] - mp3.data()) : -1L,
+              fr.mvpMapPoints[k] ? static_cast<long>(fr.mvpMapPoints[k] - mp3.data()) : -1L);
+    fclose(g);
+  }
   FILE *f = fopen((pre + "_kf_frame.txt").c_str(), "w");
   for (size_t q = 0; q < m12.size(); q++) fprintf(f, "%ld\n", m12[q] ? static_cast<long>(m12[q] - store.data()) : -1L);
   fclose(f);

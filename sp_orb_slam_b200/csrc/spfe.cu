@@ -21,6 +21,7 @@
 #include "conv1ab_mma.cuh"
 #include "conv_tc.cuh"
 #include "cov.cuh"
+#include "guided.cuh"
 #include "kernels_misc.cuh"
 #include "match.cuh"
 #include "weights.h"
@@ -148,6 +149,9 @@ struct spfe_ctx {
   int *h_match_idx = nullptr;
   float *h_match_dist = nullptr;
   int match_cap = 0;
+  // spfe_search_guided scratch (device, grown on demand; guarded by match_mu)
+  void *guided_buf = nullptr;
+  size_t guided_bytes = 0;
 
   int fail(int code, const std::string &msg) {
     error = msg;
@@ -743,6 +747,7 @@ void spfe_destroy(spfe_ctx *c) {
     if (s.ev1) cudaEventDestroy(s.ev1);
   }
   if (c->match_stream) cudaStreamDestroy(c->match_stream);
+  if (c->guided_buf) cudaFree(c->guided_buf);
   for (cudaStream_t st : {c->compute, c->copy_in, c->copy_out}) if (st) cudaStreamDestroy(st);
   for (void *p : c->dev_allocs) cudaFree(p);
   for (void *p : c->host_allocs) cudaFreeHost(p);
@@ -964,6 +969,79 @@ int spfe_match_mutual_nn(spfe_ctx *c, const float *q, int32_t nq, const float *t
   CU_OK(c, cudaStreamSynchronize(st));
   memcpy(q2t, c->h_match_idx, nq * sizeof(int));
   if (dist) memcpy(dist, c->h_match_dist, nq * sizeof(float));
+  return SPFE_OK;
+}
+
+int spfe_search_guided(spfe_ctx *c, const spfe_guided_search *g, int32_t *q2kp, float *qdist, uint8_t *kp_taken_out) {
+  if (!c) return SPFE_ERR_INVALID;
+  if (!g || g->struct_size != (int32_t)sizeof(spfe_guided_search)) return c->fail(SPFE_ERR_INVALID, "spfe_search_guided: bad struct pointer / struct_size");
+  const int m = g->m, n = g->n, cells = g->grid_rows * g->grid_cols;
+  if (m < 0 || n < 0 || m >= (1 << 20) || g->grid_rows <= 0 || g->grid_cols <= 0 || (g->mode != SPFE_GUIDED_AREA && g->mode != SPFE_GUIDED_DUST_CELLS))
+    return c->fail(SPFE_ERR_INVALID, "spfe_search_guided: bad m / n / grid / mode");
+  if (m > 0 && (!g->qdesc || !g->qxy || !q2kp || !qdist || !g->occ_grid || (g->mode == SPFE_GUIDED_AREA && !g->qradius)))
+    return c->fail(SPFE_ERR_INVALID, "spfe_search_guided: NULL query / output / occ_grid pointer");
+  if (n > 0 && (!g->kdesc || (!g->kp_un && (g->mode == SPFE_GUIDED_AREA || g->c2_adaptive > 0.0f))))
+    return c->fail(SPFE_ERR_INVALID, "spfe_search_guided: NULL keypoint pointer");
+  if (m == 0) {
+    if (kp_taken_out && n > 0) { if (g->kp_taken) memcpy(kp_taken_out, g->kp_taken, n); else memset(kp_taken_out, 0, n); }
+    return SPFE_OK;
+  }
+  std::lock_guard<std::mutex> lock(c->match_mu);
+  CU_OK(c, cudaSetDevice(c->cfg.device_id));
+  cudaStream_t st = c->match_stream;
+  // one device block, carved into 256-byte aligned pieces
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const size_t nn = n > 0 ? n : 1;
+  const size_t o_qdesc = carve((size_t)m * 1024), o_qxy = carve((size_t)m * 8), o_qr = carve((size_t)m * 4), o_qvalid = carve(m),
+               o_qblocks = carve(m), o_kdesc = carve(nn * 1024), o_kpun = carve(nn * 8), o_occ = carve((size_t)cells * 2),
+               o_taken = carve(nn), o_kpmin = carve(nn * 4), o_cand = carve((size_t)m * GUIDED_CAND * 4),
+               o_cdist = carve((size_t)m * GUIDED_CAND * 4), o_ncand = carve((size_t)m * 4), o_dec = carve(m),
+               o_q2kp = carve((size_t)m * 4), o_qdist = carve((size_t)m * 4), o_over = carve(4);
+  if (off > c->guided_bytes) {
+    if (c->guided_buf) cudaFree(c->guided_buf);
+    c->guided_buf = nullptr;
+    c->guided_bytes = 0;
+    CU_OK(c, cudaMalloc(&c->guided_buf, off + off / 2));
+    c->guided_bytes = off + off / 2;
+  }
+  uint8_t *base = static_cast<uint8_t *>(c->guided_buf);
+  auto up = [&](size_t o, const void *src, size_t bytes) { return src ? cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess; };
+  CU_OK(c, up(o_qdesc, g->qdesc, (size_t)m * 1024));
+  CU_OK(c, up(o_qxy, g->qxy, (size_t)m * 8));
+  CU_OK(c, up(o_qr, g->qradius, (size_t)m * 4));
+  CU_OK(c, up(o_qvalid, g->qvalid, m));
+  CU_OK(c, up(o_qblocks, g->qblocks, m));
+  CU_OK(c, up(o_kdesc, g->kdesc, (size_t)n * 1024));
+  CU_OK(c, up(o_kpun, g->kp_un, (size_t)n * 8));
+  CU_OK(c, up(o_occ, g->occ_grid, (size_t)cells * 2));
+  if (g->kp_taken) CU_OK(c, up(o_taken, g->kp_taken, n));
+  else CU_OK(c, cudaMemsetAsync(base + o_taken, 0, nn, st));
+  CU_OK(c, cudaMemsetAsync(base + o_kpmin, 0x7F, nn * 4, st));
+  CU_OK(c, cudaMemsetAsync(base + o_over, 0, 4, st));
+  GuidedArgs a;
+  a.mode = g->mode; a.m = m; a.n = n; a.grid_rows = g->grid_rows; a.grid_cols = g->grid_cols;
+  a.qdesc = reinterpret_cast<float *>(base + o_qdesc); a.qxy = reinterpret_cast<float *>(base + o_qxy);
+  a.qr = reinterpret_cast<float *>(base + o_qr);
+  a.qvalid = g->qvalid ? base + o_qvalid : nullptr; a.qblocks = g->qblocks ? base + o_qblocks : nullptr;
+  a.kdesc = reinterpret_cast<float *>(base + o_kdesc); a.kp_un = reinterpret_cast<float *>(base + o_kpun);
+  a.occ = reinterpret_cast<int16_t *>(base + o_occ); a.taken = base + o_taken; a.kpmin = reinterpret_cast<int *>(base + o_kpmin);
+  a.cand = reinterpret_cast<int *>(base + o_cand); a.cdist = reinterpret_cast<float *>(base + o_cdist);
+  a.ncand = reinterpret_cast<int *>(base + o_ncand); a.decided = base + o_dec;
+  a.q2kp = reinterpret_cast<int *>(base + o_q2kp); a.qdist = reinterpret_cast<float *>(base + o_qdist);
+  a.overflow = reinterpret_cast<int *>(base + o_over);
+  a.min_x = g->min_x; a.min_y = g->min_y; a.best_init = g->best_init; a.th_le = g->th_le; a.th_lt = g->th_lt; a.c2 = g->c2_adaptive;
+  guided_cand_kernel<<<(m + 7) / 8, 256, 0, st>>>(a);
+  guided_resolve_kernel<<<1, 1024, 0, st>>>(a);
+  c->launches += 2;
+  CU_OK(c, cudaGetLastError());
+  int over = 0;
+  CU_OK(c, cudaMemcpyAsync(q2kp, base + o_q2kp, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+  CU_OK(c, cudaMemcpyAsync(qdist, base + o_qdist, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+  if (kp_taken_out && n > 0) CU_OK(c, cudaMemcpyAsync(kp_taken_out, base + o_taken, n, cudaMemcpyDeviceToHost, st));
+  CU_OK(c, cudaMemcpyAsync(&over, base + o_over, 4, cudaMemcpyDeviceToHost, st));
+  CU_OK(c, cudaStreamSynchronize(st));
+  if (over) return c->fail(SPFE_ERR_INVALID, fmt("spfe_search_guided: a query has more than %d candidate keypoints (radius too large)", GUIDED_CAND));
   return SPFE_OK;
 }
 

@@ -205,6 +205,33 @@ class SPExtractor:
                                                    q2t.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p)))
         return q2t[:len(q)], dist[:len(q)]
 
+    def search_guided(self, qdesc, qxy, qradius, occ, kp_un, kdesc, *, mode: int, best_init: float, th_le: float, th_lt: float,
+                      c2_adaptive: float = 0.0, qvalid=None, qblocks=None, kp_taken=None, min_x: float = 0.0, min_y: float = 0.0):
+        """spfe_search_guided on plain arrays -> (q2kp int32[m], qdist f32[m], kp_taken_after u8[n])."""
+        qdesc = np.ascontiguousarray(qdesc, np.float32).reshape(-1, 256)
+        m = len(qdesc)
+        kdesc = np.ascontiguousarray(kdesc, np.float32).reshape(-1, 256)
+        n = len(kdesc)
+        qxy = np.ascontiguousarray(qxy, np.float32).reshape(m, 2)
+        qr = np.ascontiguousarray(np.broadcast_to(np.asarray(qradius, np.float32), (m,)))
+        occ = np.ascontiguousarray(occ, np.int16)
+        kp_un = None if kp_un is None else np.ascontiguousarray(kp_un, np.float32).reshape(n, 2)
+        opt = [None if a is None else np.ascontiguousarray(a, np.uint8) for a in (qvalid, qblocks, kp_taken)]
+        g = capi.GuidedSearch()
+        g.struct_size, g.mode, g.m, g.n = C.sizeof(capi.GuidedSearch), mode, m, n
+        ptr = lambda a: None if a is None or a.size == 0 else a.ctypes.data
+        g.qdesc, g.qxy, g.qradius = ptr(qdesc), ptr(qxy), ptr(qr)
+        g.qvalid, g.qblocks, g.kp_taken = ptr(opt[0]), ptr(opt[1]), ptr(opt[2])
+        g.kdesc, g.kp_un, g.occ_grid = ptr(kdesc), ptr(kp_un), ptr(occ)
+        g.grid_rows, g.grid_cols = occ.shape
+        g.min_x, g.min_y, g.best_init, g.th_le, g.th_lt, g.c2_adaptive = min_x, min_y, best_init, th_le, th_lt, c2_adaptive
+        q2kp = np.empty(max(m, 1), np.int32)
+        qdist = np.empty(max(m, 1), np.float32)
+        taken = np.zeros(max(n, 1), np.uint8)
+        self._check(self._lib.spfe_search_guided(self._ctx, C.byref(g), q2kp.ctypes.data_as(C.c_void_p),
+                                                 qdist.ctypes.data_as(C.c_void_p), taken.ctypes.data_as(C.c_void_p)))
+        return q2kp[:m], qdist[:m], taken[:n]
+
     # -- introspection
     _DEBUG = {"conv1a": (lambda s: (s.height, s.width, 64), np.float16), "conv1b": (lambda s: (s.height // 2, s.width // 2, 64), np.float16),
               "conv2a": (lambda s: (s.height // 2, s.width // 2, 64), np.float16), "conv2b": (lambda s: (s.height // 4, s.width // 4, 64), np.float16),
@@ -251,6 +278,42 @@ class SPMatcher:
         b = np.ascontiguousarray(b, np.float32).ravel()
         assert a.size == 256 and b.size == 256
         return float(capi.load().spfe_l2(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)))
+
+    @staticmethod
+    def RadiusByViewingCos(view_cos):
+        """sp_matcher.cpp:434-439."""
+        return np.where(np.asarray(view_cos, np.float32) > np.float32(0.998), np.float32(2.5), np.float32(4.0))
+
+    def SearchByProjectionMapPoints(self, frame: dict, mp_desc, proj_xy, view_cos, *, th: float = 1.0, th_dist: float = 0.7,
+                                    in_view=None, observed=None, c2_adaptive: float = 0.0):
+        """``SearchByProjection(Frame &F, const vector<MapPoint*>&, th, th_dist)`` (sp_matcher.cpp:344-432) on arrays.
+        ``frame``: dict with ``desc`` [n,256], ``kp_un`` [n,2] (mvKeysUn), ``occ_grid``, optional ``taken`` [n] (keypoints
+        that already carry an observed map point).  Per map point: ``mp_desc`` (getDescTrack), ``proj_xy`` (mTrackProjX/Y),
+        ``view_cos`` (mTrackViewCos), ``in_view`` (mbTrackInView && !isBad()), ``observed`` (Observations() > 0);
+        ``c2_adaptive`` = tracking::dust::c2_thresh when tracking::map::match_adaptive.  Returns (mp2kp, nmatches):
+        F.mvpMapPoints[mp2kp[i]] = vpMapPoints[i] for mp2kp[i] >= 0, applied in order."""
+        r = self.RadiusByViewingCos(view_cos)
+        if th != 1.0:
+            r = r * np.float32(th)
+        q2kp, _, _ = self._ex.search_guided(mp_desc, proj_xy, r, frame["occ_grid"], frame["kp_un"], frame["desc"],
+                                            mode=capi.GUIDED_AREA, best_init=256.0, th_le=th_dist, th_lt=0.7,
+                                            c2_adaptive=c2_adaptive, qvalid=in_view, qblocks=observed, kp_taken=frame.get("taken"))
+        return q2kp, int((q2kp >= 0).sum())
+
+    def SearchByProjectionLastFrame(self, frame: dict, last_desc, proj_xy, *, th: float, valid=None, observed=None):
+        """``SearchByProjection(Frame &Cur, const Frame &Last, th, bMono)`` (sp_matcher.cpp:1439-1543), monocular: the
+        caller projects the last frame's map points into the current frame (:1464-1482, ``valid`` = has a map point,
+        not an outlier, in front of the camera, inside the image); radius = th * mvScaleFactors[0] = th."""
+        q2kp, _, _ = self._ex.search_guided(last_desc, proj_xy, np.float32(th), frame["occ_grid"], frame["kp_un"], frame["desc"],
+                                            mode=capi.GUIDED_AREA, best_init=float(np.finfo(np.float32).max), th_le=self.TH_HIGH,
+                                            th_lt=-np.inf, qvalid=valid, qblocks=observed, kp_taken=frame.get("taken"))
+        return q2kp, int((q2kp >= 0).sum())
+
+    def DustAssociate(self, frame: dict, mp_desc, dust_proj_uv, *, in_view=None):
+        """Patch-wise association of dust tracking (tracker_dust.cpp:112-172): ``dust_proj_uv`` in occ_grid cell units."""
+        q2kp, _, _ = self._ex.search_guided(mp_desc, dust_proj_uv, np.float32(0), frame["occ_grid"], None, frame["desc"],
+                                            mode=capi.GUIDED_DUST_CELLS, best_init=0.75, th_le=-np.inf, th_lt=0.75, qvalid=in_view)
+        return q2kp, int((q2kp >= 0).sum())
 
     def SearchByBruteForce(self, desc1: np.ndarray, valid1: np.ndarray, desc2: np.ndarray, valid2: np.ndarray | None = None):
         """Both reference overloads on plain arrays.

@@ -428,3 +428,19 @@ def test_cpp_shim_selftest(tmp_path, ex_cache):
     exp = SPMatcher(ex).SearchByBruteForce(a["desc"], valid, b["desc"])
     got = np.loadtxt(pre + "_kf_frame.txt", dtype=np.int64).reshape(-1)
     assert np.array_equal(got, exp)
+    # guided searches through the C++ templates == the Python mirror (both over spfe_search_guided; the device result is
+    # checked against the oracle in tests/test_guided.py)
+    i = np.arange(a["n"])
+    frame_b = dict(desc=b["desc"], kp_un=b["kp_xy"], occ_grid=b["occ_grid"])
+    cos = np.where(i % 2 == 1, 0.9995, 0.99).astype(np.float32)
+    in_view, observed = (i % 7 != 6).astype(np.uint8), (i % 5 != 4).astype(np.uint8)
+    M = SPMatcher(ex)
+    mp2kp, n3 = M.SearchByProjectionMapPoints(frame_b, a["desc"], a["kp_xy"], cos, th=3.0, th_dist=0.7, in_view=in_view, observed=observed)
+    dust2kp, n4 = M.DustAssociate(frame_b, a["desc"], ((a["kp_xy"] - 3.5) / 8.0).astype(np.float32), in_view=in_view)
+    assert f"SearchByProjection(F,MPs) {n3} matches; dust association {n4} matches" in r.stdout and n3 > 50 and n4 > 50
+    exp_g = -np.ones((b["n"], 2), np.int64)
+    for col, q2kp in enumerate((mp2kp, dust2kp)):
+        for mp, kp in enumerate(q2kp):                       # applied in map-point order: later assignments overwrite
+            if kp >= 0:
+                exp_g[kp, col] = mp
+    assert np.array_equal(np.loadtxt(pre + "_guided.txt", dtype=np.int64).reshape(-1, 2), exp_g)

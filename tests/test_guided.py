@@ -1,0 +1,178 @@
+"""Guided (cell-grid) searches, SURVEY.md section 8(f) rank 2: the oracle's restatement of the reference's greedy loops
+(CPU tests) and the device version against it (GPU tests, through the C ABI).  Index work is compared bit-exactly."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import WEIGHTS
+from oracle import sp_oracle as O
+from sp_orb_slam_b200 import SPExtractor, SPMatcher, capi, synth
+
+
+def random_frame(rng, hc=30, wc=40, fill=0.45):
+    """A fake extractor output: at most one keypoint per 8x8 cell, raster order, occ_grid, unit descriptors."""
+    pts = []
+    for cy in range(hc):
+        for cx in range(wc):
+            if rng.rand() < fill:
+                pts.append((cx * 8 + rng.randint(8), cy * 8 + rng.randint(8)))
+    pts = sorted(pts, key=lambda p: (p[1], p[0]))
+    kp = np.array(pts, np.float32).reshape(-1, 2)
+    occ = -np.ones((hc, wc), np.int16)
+    for i, (x, y) in enumerate(pts):
+        occ[y // 8, x // 8] = i
+    d = rng.randn(len(pts), 256).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return dict(kp_un=kp, occ_grid=occ, desc=d)
+
+
+def test_features_in_area_matches_bruteforce():
+    rng = np.random.RandomState(3)
+    f = random_frame(rng)
+    H, W = f["occ_grid"].shape[0] * 8, f["occ_grid"].shape[1] * 8
+    for _ in range(200):
+        x, y = rng.uniform(-20, W + 20), rng.uniform(-20, H + 20)
+        r = rng.choice([2.5, 4.0, 7.0, 15.0])
+        got = O.features_in_area(f["occ_grid"], f["kp_un"], x, y, r)
+        # frame.cpp:387-416: cells clamp(floor((x - r) / 8)) .. clamp(ceil((x + r) / 8)), ix outer / iy inner, |dx| < r && |dy| < r
+        x0, x1 = max(0, int(np.floor(np.float32(x - r) / 8))), min(f["occ_grid"].shape[1] - 1, int(np.ceil(np.float32(x + r) / 8)))
+        y0, y1 = max(0, int(np.floor(np.float32(y - r) / 8))), min(f["occ_grid"].shape[0] - 1, int(np.ceil(np.float32(y + r) / 8)))
+        ref = []
+        for ix in range(x0, x1 + 1):
+            for iy in range(y0, y1 + 1):
+                i = f["occ_grid"][iy, ix]
+                if i >= 0 and abs(f["kp_un"][i, 0] - np.float32(x)) < r and abs(f["kp_un"][i, 1] - np.float32(y)) < r:
+                    ref.append(i)
+        assert list(got) == ref
+
+
+def test_greedy_order_semantics():
+    """Two map points compete for one keypoint: the first in order takes it, the second falls back to its next-best
+    (or to nothing); an unobserved map point (qblocks = 0) does not block; kp_taken on entry is skipped."""
+    rng = np.random.RandomState(5)
+    f = random_frame(rng, 6, 6, 1.0)
+    k0 = int(f["occ_grid"][2, 2])
+    q = np.stack([f["desc"][k0], f["desc"][k0], f["desc"][k0]]) + 1e-3 * rng.randn(3, 256).astype(np.float32)
+    xy = np.tile(f["kp_un"][k0], (3, 1))
+    q2kp, dist, taken = O.search_by_projection_last_frame(q, xy, 12.0, f["occ_grid"], f["kp_un"], f["desc"])
+    assert q2kp[0] == k0 and q2kp[1] == -1 and q2kp[2] == -1 and taken[k0] == 1    # others are > TH_HIGH away (random descriptors)
+    q2kp, _, taken = O.search_by_projection_last_frame(q, xy, 12.0, f["occ_grid"], f["kp_un"], f["desc"], observed=[0, 1, 1])
+    assert list(q2kp) == [k0, k0, -1]                                               # an unobserved map point does not block
+    pre = np.zeros(len(f["desc"]), np.uint8)
+    pre[k0] = 1
+    q2kp, _, _ = O.search_by_projection_last_frame(q, xy, 12.0, f["occ_grid"], f["kp_un"], f["desc"], kp_taken=pre)
+    assert np.all(q2kp == -1)
+    # SearchByProjection(F, MPs): best <= th_dist, else the 0.7 / adaptive rule (sp_matcher.cpp:404-427)
+    far = f["desc"][k0] + 0.05 * rng.randn(256).astype(np.float32)
+    d = O.l2(far, f["desc"][k0])
+    assert 0.5 < d < 1.0
+    for th_dist, c2, expect in [(d + 0.01, 0.0, k0), (0.1, 0.0, k0 if d < 0.7 else -1), (0.1, 1e-6, -1)]:
+        xy1 = f["kp_un"][k0][None] + np.float32([[1.0, 1.0]])
+        got, _, _ = O.search_by_projection_map_points(far[None], xy1, 4.0, f["occ_grid"], f["kp_un"], f["desc"], th_dist=th_dist, c2_adaptive=c2)
+        assert got[0] == expect, (th_dist, c2, d)
+    # dust association: 2 x 2 cells at floor(proj), strict < 0.75, matched cell cleared (tracker_dust.cpp:118-166)
+    cell = np.float32([[2.0 - 0.5, 2.0 - 0.5]])                                     # floor -> (1, 1): cells (1..2, 1..2)
+    got, _, taken = O.dust_associate(np.stack([q[0], q[1]]), np.tile(cell, (2, 1)), f["occ_grid"], f["desc"])
+    assert got[0] == k0 and got[1] == -1 and taken[k0] == 1
+
+
+def test_guided_struct_matches_header():
+    import re
+    import os
+    from conftest import ROOT
+    hdr = open(os.path.join(ROOT, "include", "spfe.h")).read()
+    body = re.search(r"typedef struct spfe_guided_search \{(.*?)\} spfe_guided_search;", hdr, re.S).group(1)
+    names = []
+    for decl in re.sub(r"/\*.*?\*/", "", body, flags=re.S).split(";"):
+        if decl.strip():
+            parts = decl.strip().split(",")
+            names += [parts[0].split()[-1].lstrip("*")] + [q.strip().lstrip("*") for q in parts[1:]]
+    assert names == [f[0] for f in capi.GuidedSearch._fields_]
+
+
+# ------------------------------------------------------------------------------------------------------------ GPU
+def _scenario(rng, fr, m, jitter, dup_frac=0.3, noise=0.02):
+    """Map points around the frame's own keypoints: noisy copies of their descriptors, projections jittered by a few
+    pixels, a share of duplicates (several map points competing for one keypoint) and random validity / observation flags."""
+    n = len(fr["desc"])
+    src = rng.randint(0, n, m)
+    dup = rng.rand(m) < dup_frac
+    src[dup] = src[rng.randint(0, m, dup.sum())]
+    qdesc = fr["desc"][src] + noise * rng.randn(m, 256).astype(np.float32)
+    qxy = fr["kp_xy"][src] + rng.uniform(-jitter, jitter, (m, 2)).astype(np.float32)
+    return qdesc.astype(np.float32), qxy.astype(np.float32), (rng.rand(m) < 0.9).astype(np.uint8), (rng.rand(m) < 0.8).astype(np.uint8)
+
+
+@pytest.fixture(scope="module")
+def gpu_frame():
+    H, W = 480, 752
+    ex = SPExtractor(800, H, W, WEIGHTS, emit_heat=False, emit_cov=False)
+    fr = ex.extract(synth.make_frame(H, W, seed=91, n_shapes=400))
+    yield ex, fr
+    ex.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,m,jitter", [(0, 600, 3.0), (1, 2000, 6.0), (2, 120, 1.0)])
+def test_search_by_projection_matches_oracle(gpu_frame, seed, m, jitter):
+    ex, fr = gpu_frame
+    rng = np.random.RandomState(seed)
+    frame = dict(desc=fr["desc"], kp_un=fr["kp_xy"], occ_grid=fr["occ_grid"], taken=(rng.rand(fr["n"]) < 0.1).astype(np.uint8))
+    qdesc, qxy, valid, observed = _scenario(rng, fr, m, jitter)
+    M = SPMatcher(ex)
+    # (Frame, MapPoints): radius from the viewing cosine, adaptive threshold on and off
+    cos = rng.uniform(0.99, 1.0, m).astype(np.float32)
+    for th, th_dist, c2 in [(1.0, 0.7, 0.0), (3.0, 0.5, 25.0)]:
+        got, nm = M.SearchByProjectionMapPoints(frame, qdesc, qxy, cos, th=th, th_dist=th_dist, in_view=valid, observed=observed, c2_adaptive=c2)
+        r = M.RadiusByViewingCos(cos) * (np.float32(th) if th != 1.0 else np.float32(1))
+        ref, rd, _ = O.search_by_projection_map_points(qdesc, qxy, r, fr["occ_grid"], fr["kp_xy"], fr["desc"], th_dist=th_dist, in_view=valid,
+                                                       observed=observed, kp_taken=frame["taken"], c2_adaptive=c2)
+        assert np.array_equal(got, ref) and nm == int((ref >= 0).sum()) and nm > 50
+    # (Cur, Last)
+    got, nm = M.SearchByProjectionLastFrame(frame, qdesc, qxy, th=7.0, valid=valid, observed=observed)
+    ref, rd, taken_ref = O.search_by_projection_last_frame(qdesc, qxy, 7.0, fr["occ_grid"], fr["kp_xy"], fr["desc"], valid=valid,
+                                                           observed=observed, kp_taken=frame["taken"])
+    assert np.array_equal(got, ref)
+    q2kp, qd, taken = ex.search_guided(qdesc, qxy, 7.0, fr["occ_grid"], fr["kp_xy"], fr["desc"], mode=capi.GUIDED_AREA,
+                                       best_init=O.FLT_MAX, th_le=0.7, th_lt=-np.inf, qvalid=valid, qblocks=observed, kp_taken=frame["taken"])
+    assert np.array_equal(taken, taken_ref)
+    np.testing.assert_allclose(qd[ref >= 0], rd[ref >= 0], rtol=2e-6)
+
+
+@pytest.mark.gpu
+def test_dust_association_matches_oracle(gpu_frame):
+    ex, fr = gpu_frame
+    rng = np.random.RandomState(7)
+    qdesc, qxy, valid, _ = _scenario(rng, fr, 1200, 4.0, dup_frac=0.4)
+    uv = ((qxy - 3.5) / 8.0).astype(np.float32)                # dust_proj in cell units (tracker_dust.cpp:107-110 geometry)
+    got, nm = SPMatcher(ex).DustAssociate(dict(desc=fr["desc"], occ_grid=fr["occ_grid"]), qdesc, uv, in_view=valid)
+    ref, _, _ = O.dust_associate(qdesc, uv, fr["occ_grid"], fr["desc"], in_view=valid)
+    assert np.array_equal(got, ref) and nm > 50
+    assert len(set(got[got >= 0])) == (got >= 0).sum()         # every keypoint matched at most once (its cell is cleared)
+
+
+@pytest.mark.gpu
+def test_guided_deep_conflict_chain_and_edges(gpu_frame):
+    """600 map points projecting onto the same spot: every one depends on all before it (more rounds than the parallel
+    resolver runs -> sequential remainder); empty inputs; radius too large is an error, not a wrong answer."""
+    ex, fr = gpu_frame
+    rng = np.random.RandomState(11)
+    k0 = fr["n"] // 2
+    m = 600
+    qdesc = fr["desc"][rng.randint(0, fr["n"], m)] + 0.3 * rng.randn(m, 256).astype(np.float32)
+    qxy = np.tile(fr["kp_xy"][k0], (m, 1)).astype(np.float32)
+    for blocks in (np.zeros(m, np.uint8), np.ones(m, np.uint8)):     # unobserved map points never free a later one from waiting
+        got, _, taken = ex.search_guided(qdesc, qxy, 20.0, fr["occ_grid"], fr["kp_xy"], fr["desc"], mode=capi.GUIDED_AREA,
+                                         best_init=256.0, th_le=10.0, th_lt=0.0, qblocks=blocks)
+        ref, _, taken_ref = O.search_guided(qdesc, qxy, 20.0, fr["occ_grid"], fr["kp_xy"], fr["desc"], mode=0, best_init=256.0,
+                                            th_le=10.0, th_lt=0.0, qblocks=blocks)
+        assert np.array_equal(got, ref) and np.array_equal(taken, taken_ref)
+        assert (ref >= 0).sum() == (m if blocks[0] == 0 else taken_ref.sum()) and taken_ref.sum() == (0 if blocks[0] == 0 else (ref >= 0).sum())
+    e, _, _ = ex.search_guided(np.zeros((0, 256), np.float32), np.zeros((0, 2), np.float32), 4.0, fr["occ_grid"], fr["kp_xy"], fr["desc"],
+                               mode=capi.GUIDED_AREA, best_init=256.0, th_le=0.7, th_lt=0.7)
+    assert len(e) == 0
+    from sp_orb_slam_b200 import SpfeError
+    with pytest.raises(SpfeError):
+        ex.search_guided(qdesc[:4], qxy[:4], 200.0, fr["occ_grid"], fr["kp_xy"], fr["desc"], mode=capi.GUIDED_AREA,
+                         best_init=256.0, th_le=0.7, th_lt=0.7)
