@@ -141,6 +141,13 @@ int spfe_slot_sync(spfe_ctx *ctx, int32_t slot);
  * Thread-safe (per-call scratch), as SearchByBruteForce runs on two threads. */
 int spfe_match_mutual_nn(spfe_ctx *ctx, const float *q, int32_t nq, const float *t, int32_t nt,
                          int32_t *q2t, float *dist);
+/* Exact 2 nearest neighbours under L2 of every query row among the train rows (host pointers): idx[i][0..1] = best /
+ * second-best train row (first index on ties, -1 if there is none), dist[i][0..1] = their L2 distances.  This is
+ * cv::DescriptorMatcher::knnMatch(query, matches, 2) as called on the key frame's FLANN index by
+ * SPMatcher::SearchForTriByFlann / SearchByFlann (orb_slam2/src/cv/sp_matcher.cpp:183-200, :262-270) -- exact where the
+ * reference's KD-tree search is approximate; the ratio test (0.7, :203-206) stays with the caller.  Thread-safe. */
+int spfe_match_knn2(spfe_ctx *ctx, const float *q, int32_t nq, const float *t, int32_t nt, int32_t *idx, float *dist);
+
 /* Guided (cell-grid) searches -- the greedy candidate loops of
  *   SPMatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, th_dist)   orb_slam2/src/cv/sp_matcher.cpp:344-432
  *   SPMatcher::SearchByProjection(Frame &Cur, const Frame &Last, th, bMono)        orb_slam2/src/cv/sp_matcher.cpp:1439-1543

@@ -276,3 +276,13 @@ def dust_associate(qdesc, proj_uv_cells, occ, kdesc, *, in_view=None):
     n = len(np.asarray(kdesc).reshape(-1, 256))
     return search_guided(qdesc, proj_uv_cells, 0.0, occ, np.zeros((n, 2), np.float32), kdesc, mode=1, best_init=0.75,
                          th_le=-np.inf, th_lt=0.75, qvalid=in_view)
+
+
+def knn2(q: np.ndarray, t: np.ndarray):
+    """Exact 2-NN under L2 (orc_knn2) -> (idx int32[nq,2], dist f32[nq,2])."""
+    q = np.ascontiguousarray(q, np.float32).reshape(-1, 256)
+    t = np.ascontiguousarray(t, np.float32).reshape(-1, 256) if np.size(t) else np.zeros((0, 256), np.float32)
+    idx = np.empty((max(len(q), 1), 2), np.int32)
+    dist = np.empty((max(len(q), 1), 2), np.float32)
+    _lib().orc_knn2(_p(q, C.c_float), len(q), _p(t, C.c_float), len(t), 256, _p(idx, C.c_int32), _p(dist, C.c_float))
+    return idx[:len(q)], dist[:len(q)]

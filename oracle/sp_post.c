@@ -276,3 +276,19 @@ void orc_search_guided(int m, const float *qdesc, const uint8_t *qvalid, const u
   }
   free(cand);
 }
+
+/* Exact 2 nearest neighbours (first index on ties): the result FLANN's KD-tree search approximates in
+ * SPMatcher::SearchForTriByFlann / SearchByFlann (sp_matcher.cpp:197-206, :266-270); == cv::BFMatcher(NORM_L2).knnMatch(q, t, 2). */
+void orc_knn2(const float *q, int nq, const float *t, int nt, int d, int32_t *idx, float *dist) {
+  for (int i = 0; i < nq; i++) {
+    float b0 = FLT_MAX, b1 = FLT_MAX;
+    int j0 = -1, j1 = -1;
+    for (int j = 0; j < nt; j++) {
+      const float dd = orc_l2(q + (size_t)i * d, t + (size_t)j * d, d);
+      if (dd < b0) { b1 = b0; j1 = j0; b0 = dd; j0 = j; }
+      else if (dd < b1) { b1 = dd; j1 = j; }
+    }
+    idx[2 * i] = j0; idx[2 * i + 1] = j1;
+    dist[2 * i] = j0 >= 0 ? b0 : 0.0f; dist[2 * i + 1] = j1 >= 0 ? b1 : 0.0f;
+  }
+}

@@ -53,6 +53,9 @@ struct MatchArgs {
   int *q2t;              // [Z][cap]
   float *dist;           // [Z][cap]
   int cap;
+  // k-NN pass 2 (spfe_match_knn2): skip each row's best column (low word of excl[i]), write the row minima of the rest
+  // into rowbest, leave the column minima alone
+  const unsigned long long *excl;
 };
 __device__ __forceinline__ void match_problem(const MatchArgs &a, int z, const float *&q, const float *&t, int &nq, int &nt) {
   q = a.q + static_cast<size_t>(z) * a.cap * 256;
@@ -105,10 +108,13 @@ __global__ void __launch_bounds__(256) match_dist_kernel(const MatchArgs ma) {
 #pragma unroll
   for (int r = 0; r < 4; r++) {
     unsigned long long best = ~0ull;
+    unsigned skip = 0xFFFFFFFFu;
+    if (ma.excl != nullptr && i0 + ty * 4 + r < nq)
+      skip = static_cast<unsigned>(ma.excl[static_cast<size_t>(blockIdx.z) * ma.cap + i0 + ty * 4 + r] & 0xFFFFFFFFu);
 #pragma unroll
     for (int cidx = 0; cidx < 4; cidx++) {
       const int j = j0 + tx * 4 + cidx;
-      if (j < nt) {
+      if (j < nt && static_cast<unsigned>(j) != skip) {
         const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(acc[r][cidx])) << 32) | static_cast<unsigned>(j);
         best = key < best ? key : best;
       }
@@ -121,6 +127,7 @@ __global__ void __launch_bounds__(256) match_dist_kernel(const MatchArgs ma) {
     const int i = i0 + ty * 4 + r;
     if (tx == 0 && i < nq) atomicMin(rowbest + i, best);
   }
+  if (ma.excl != nullptr) return;  // block-uniform
   // column minima: per-thread over its 4 rows, then across the 16 ty groups through shared memory
 #pragma unroll
   for (int cidx = 0; cidx < 4; cidx++) {
@@ -169,6 +176,18 @@ __global__ void match_final_kernel(const MatchArgs a) {
   dist[i] = d;
 }
 
+
+// Exact 2-NN of every query row: best / second-best keys -> idx[i][2], dist[i][2] (-1 / 0 where there is no such row).
+__global__ void knn2_final_kernel(const unsigned long long *first, const unsigned long long *second, int nq, int *idx, float *dist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const unsigned long long k[2] = {first[i], second[i]};
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    idx[2 * i + r] = k[r] == ~0ull ? -1 : static_cast<int>(k[r] & 0xFFFFFFFFu);
+    dist[2 * i + r] = k[r] == ~0ull ? 0.f : sqrtf(__uint_as_float(static_cast<unsigned>(k[r] >> 32)));
+  }
+}
 
 // ---------------------------------------------------------------------------
 // Tensor-core path for the in-pipeline stream matching (SPFE_MATCH_PREV).

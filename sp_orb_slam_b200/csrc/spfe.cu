@@ -960,6 +960,7 @@ int spfe_match_mutual_nn(spfe_ctx *c, const float *q, int32_t nq, const float *t
   CU_OK(c, cudaMemcpyAsync(m.dt, c->h_match_t, (size_t)nt * 256 * sizeof(float), cudaMemcpyHostToDevice, st));
   CU_OK(c, cudaMemcpyAsync(m.dn, c->h_match_idx + c->match_cap, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
   MatchArgs a;
+  memset(&a, 0, sizeof a);
   a.q = m.dq; a.nq = m.dn; a.t0 = m.dt; a.nt0 = m.dn + 1;
   a.rowbest = m.rowbest; a.colbest = m.colbest; a.q2t = m.q2t; a.dist = m.dist; a.cap = c->match_cap;
   int rc = run_match(c, st, a, 1, nq > nt ? nq : nt);
@@ -969,6 +970,52 @@ int spfe_match_mutual_nn(spfe_ctx *c, const float *q, int32_t nq, const float *t
   CU_OK(c, cudaStreamSynchronize(st));
   memcpy(q2t, c->h_match_idx, nq * sizeof(int));
   if (dist) memcpy(dist, c->h_match_dist, nq * sizeof(float));
+  return SPFE_OK;
+}
+
+int spfe_match_knn2(spfe_ctx *c, const float *q, int32_t nq, const float *t, int32_t nt, int32_t *idx, float *dist) {
+  if (!c) return SPFE_ERR_INVALID;
+  if (nq < 0 || nt < 0 || (nq > 0 && (!q || !idx || !dist)) || (nt > 0 && !t)) return c->fail(SPFE_ERR_INVALID, "spfe_match_knn2: bad arguments");
+  if (nq > c->match_cap || nt > c->match_cap) return c->fail(SPFE_ERR_INVALID, fmt("spfe_match_knn2: more than %d rows", c->match_cap));
+  if (nq == 0) return SPFE_OK;
+  if (nt == 0) {
+    for (int i = 0; i < 2 * nq; i++) { idx[i] = -1; dist[i] = 0.f; }
+    return SPFE_OK;
+  }
+  std::lock_guard<std::mutex> lock(c->match_mu);
+  CU_OK(c, cudaSetDevice(c->cfg.device_id));
+  cudaStream_t st = c->match_stream;
+  MatchScratch &m = c->match;
+  memcpy(c->h_match_q, q, (size_t)nq * 256 * sizeof(float));
+  memcpy(c->h_match_t, t, (size_t)nt * 256 * sizeof(float));
+  c->h_match_idx[c->match_cap] = nq;
+  c->h_match_idx[c->match_cap + 1] = nt;
+  CU_OK(c, cudaMemcpyAsync(m.dq, c->h_match_q, (size_t)nq * 256 * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU_OK(c, cudaMemcpyAsync(m.dt, c->h_match_t, (size_t)nt * 256 * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU_OK(c, cudaMemcpyAsync(m.dn, c->h_match_idx + c->match_cap, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
+  MatchArgs a;
+  memset(&a, 0, sizeof a);
+  a.q = m.dq; a.nq = m.dn; a.t0 = m.dt; a.nt0 = m.dn + 1;
+  a.rowbest = m.rowbest; a.colbest = m.colbest; a.q2t = m.q2t; a.dist = m.dist; a.cap = c->match_cap;
+  const int rows = nq > nt ? nq : nt;
+  dim3 grid((rows + 63) / 64, (rows + 63) / 64, 1);
+  match_init_kernel<<<(a.cap + 255) / 256, 256, 0, st>>>(a.rowbest, a.colbest, a.cap);
+  match_dist_kernel<<<grid, 256, 0, st>>>(a);                        // pass 1: nearest row of every query (and of every train row)
+  match_init_kernel<<<(a.cap + 255) / 256, 256, 0, st>>>(m.colbest, m.colbest, a.cap);
+  MatchArgs b = a;
+  b.excl = m.rowbest;
+  b.rowbest = m.colbest;                                             // pass 2: nearest among the others -> second best
+  match_dist_kernel<<<grid, 256, 0, st>>>(b);
+  // q2t / dist scratch hold >= 2 * cap entries only if cap >= 2 * nq: use the staging descriptors' space instead
+  int *d_idx = reinterpret_cast<int *>(m.dq);
+  float *d_dist = reinterpret_cast<float *>(m.dq) + 2 * (size_t)nq;
+  knn2_final_kernel<<<(nq + 255) / 256, 256, 0, st>>>(m.rowbest, m.colbest, nq, d_idx, d_dist);
+  c->launches += 5;
+  CU_OK(c, cudaGetLastError());
+  CU_OK(c, cudaMemcpyAsync(c->h_match_q, d_idx, (size_t)nq * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU_OK(c, cudaStreamSynchronize(st));
+  memcpy(idx, c->h_match_q, (size_t)nq * 2 * sizeof(int));
+  memcpy(dist, reinterpret_cast<float *>(c->h_match_q) + 2 * (size_t)nq, (size_t)nq * 2 * sizeof(float));
   return SPFE_OK;
 }
 

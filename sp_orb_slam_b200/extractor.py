@@ -205,6 +205,16 @@ class SPExtractor:
                                                    q2t.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p)))
         return q2t[:len(q)], dist[:len(q)]
 
+    def knn2(self, q: np.ndarray, t: np.ndarray):
+        """Exact 2-NN (spfe_match_knn2) -> (idx int32[nq,2], dist f32[nq,2]); -1 / 0 where no such row exists."""
+        q = np.ascontiguousarray(q, np.float32).reshape(-1, 256)
+        t = np.ascontiguousarray(t, np.float32).reshape(-1, 256)
+        idx = np.empty((max(len(q), 1), 2), np.int32)
+        dist = np.empty((max(len(q), 1), 2), np.float32)
+        self._check(self._lib.spfe_match_knn2(self._ctx, q.ctypes.data_as(C.c_void_p), len(q), t.ctypes.data_as(C.c_void_p), len(t),
+                                              idx.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p)))
+        return idx[:len(q)], dist[:len(q)]
+
     def search_guided(self, qdesc, qxy, qradius, occ, kp_un, kdesc, *, mode: int, best_init: float, th_le: float, th_lt: float,
                       c2_adaptive: float = 0.0, qvalid=None, qblocks=None, kp_taken=None, min_x: float = 0.0, min_y: float = 0.0):
         """spfe_search_guided on plain arrays -> (q2kp int32[m], qdist f32[m], kp_taken_after u8[n])."""
@@ -278,6 +288,13 @@ class SPMatcher:
         b = np.ascontiguousarray(b, np.float32).ravel()
         assert a.size == 256 and b.size == 256
         return float(capi.load().spfe_l2(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)))
+
+    def KnnMatchRatio(self, query_desc: np.ndarray, train_desc: np.ndarray, ratio: float = 0.7):
+        """``flann->knnMatch(query, matches, 2)`` + the ratio test of SearchForTriByFlann / SearchByFlann
+        (sp_matcher.cpp:197-206, :266-270) with an exact 2-NN.  -> (train index or -1 per query row, idx[nq,2], dist[nq,2])."""
+        idx, dist = self._ex.knn2(query_desc, train_desc)
+        good = (idx[:, 0] >= 0) & (idx[:, 1] >= 0) & (dist[:, 0] < np.float32(ratio) * dist[:, 1])
+        return np.where(good, idx[:, 0], -1), idx, dist
 
     @staticmethod
     def RadiusByViewingCos(view_cos):

@@ -176,3 +176,40 @@ def test_guided_deep_conflict_chain_and_edges(gpu_frame):
     with pytest.raises(SpfeError):
         ex.search_guided(qdesc[:4], qxy[:4], 200.0, fr["occ_grid"], fr["kp_xy"], fr["desc"], mode=capi.GUIDED_AREA,
                          best_init=256.0, th_le=0.7, th_lt=0.7)
+
+
+# ------------------------------------------------------------------------------------------------ exact 2-NN (rank 3)
+def _knn_sets(rng, nq, nt, noise=0.25):
+    t = rng.randn(nt, 256).astype(np.float32)
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    q = t[rng.randint(0, max(nt, 1), nq)] + noise / 16 * rng.randn(nq, 256).astype(np.float32) if nt else rng.randn(nq, 256).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    return q.astype(np.float32), t
+
+
+def test_knn2_oracle_vs_opencv():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.RandomState(4)
+    q, t = _knn_sets(rng, 200, 333)
+    idx, dist = O.knn2(q, t)
+    for i, ms in enumerate(cv2.BFMatcher(cv2.NORM_L2).knnMatch(q, t, k=2)):
+        assert [m.trainIdx for m in ms] == list(idx[i])
+        np.testing.assert_allclose([m.distance for m in ms], dist[i], rtol=1e-5)
+    i1, d1 = O.knn2(q[:3], t[:1])
+    assert list(i1[:, 1]) == [-1] * 3 and np.all(i1[:, 0] == 0)
+
+
+@pytest.mark.gpu
+def test_knn2_matches_oracle(gpu_frame):
+    ex, fr = gpu_frame
+    rng = np.random.RandomState(9)
+    for nq, nt in [(700, 801), (33, 2000), (5, 1), (4, 0), (1500, 64)]:
+        q, t = _knn_sets(rng, nq, nt)
+        idx, dist = ex.knn2(q, t)
+        ridx, rdist = O.knn2(q, t)
+        assert np.array_equal(idx, ridx)
+        np.testing.assert_allclose(dist, rdist, rtol=2e-6, atol=1e-7)
+    q, t = _knn_sets(rng, 400, 500, noise=0.5)
+    good, idx, dist = SPMatcher(ex).KnnMatchRatio(q, t, 0.7)
+    ridx, rdist = O.knn2(q, t)
+    assert np.array_equal(good, np.where(rdist[:, 0] < np.float32(0.7) * rdist[:, 1], ridx[:, 0], -1)) and (good >= 0).sum() > 100
