@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(1024) nms_kernel(const NmsArgs p) {
   const int cells = p.hc * p.wc;
   float *s_sc = reinterpret_cast<float *>(nms_smem);
   uint8_t *s_pos = reinterpret_cast<uint8_t *>(s_sc + cells);
-  volatile uint8_t *s_st = s_pos + cells;
+  uint8_t *s_st = s_pos + cells;
+  uint8_t *s_new = s_st + cells;  // next state of the undecided cells (Jacobi iteration: reads and writes never race)
   __shared__ int s_cnt, s_cnt2;
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const float *score = p.score + static_cast<size_t>(b) * cells;
@@ -150,10 +151,12 @@ __global__ void __launch_bounds__(1024) nms_kernel(const NmsArgs p) {
           }
         }
       }
-      if (any_kept) s_st[c] = ST_SUPP;
-      else if (all_supp) s_st[c] = ST_KEPT;
-      else undecided = 1;
+      s_new[c] = any_kept ? ST_SUPP : (all_supp ? ST_KEPT : ST_UNDEC);
+      if (!any_kept && !all_supp) undecided = 1;
     }
+    __syncthreads();
+    for (int c = tid; c < cells; c += nt)
+      if (s_st[c] == ST_UNDEC) s_st[c] = s_new[c];
     if (!__syncthreads_or(undecided)) break;
   }
 

@@ -364,7 +364,7 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     n.score = s.score; n.argmax = s.argmax; n.hc = hc; n.wc = wc; n.thresh = c->cfg.score_thresh;
     n.radius = c->cfg.nms_radius; n.border = c->cfg.border; n.cap = c->cap;
     n.count = s.count; n.kp_xy = s.kp_xy; n.kp_score = s.kp_score; n.occ = s.occ; n.scratch = s.scratch;
-    nms_kernel<<<B, 1024, c->cells * 6, st>>>(n);
+    nms_kernel<<<B, 1024, c->cells * 7, st>>>(n);
     c->launches++;
     CU_OK(c, cudaGetLastError());
     mark("nms", 0, 7.0 * c->cells * B);
@@ -686,7 +686,7 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
   if (!cfg || !out || cfg->struct_size != (int32_t)sizeof(spfe_config)) { g_create_error = "spfe_create: bad config pointer / struct_size"; return SPFE_ERR_INVALID; }
   if (cfg->height <= 0 || cfg->width <= 0 || cfg->height % 8 || cfg->width % 8) { g_create_error = "spfe_create: height/width must be positive multiples of 8 (sp_extractor.cpp:70)"; return SPFE_ERR_INVALID; }
   if (cfg->max_keypoints < 1 || cfg->max_batch < 1 || cfg->num_slots < 1 || cfg->nms_radius < 0 || cfg->nms_radius > 8 || cfg->border < 0) { g_create_error = "spfe_create: bad max_keypoints / max_batch / num_slots / nms_radius / border"; return SPFE_ERR_INVALID; }
-  if ((size_t)(cfg->height / 8) * (cfg->width / 8) > 37000) { g_create_error = "spfe_create: more than 37000 cells (NMS shared-memory budget)"; return SPFE_ERR_INVALID; }
+  if ((size_t)(cfg->height / 8) * (cfg->width / 8) > 33000) { g_create_error = "spfe_create: more than 33000 cells (NMS shared-memory budget)"; return SPFE_ERR_INVALID; }
   if (!cfg->weights_path) { g_create_error = "spfe_create: weights_path is NULL"; return SPFE_ERR_WEIGHTS; }
   spfe_ctx *c = new spfe_ctx();
   c->cfg = *cfg;
@@ -715,9 +715,9 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
     static std::mutex mu;
     static int nms_smem_max = 48 * 1024;
     std::lock_guard<std::mutex> lock(mu);
-    if (c->cells * 6 > nms_smem_max) {
-      CU_OK(c, cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->cells * 6));
-      nms_smem_max = c->cells * 6;
+    if (c->cells * 7 > nms_smem_max) {
+      CU_OK(c, cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->cells * 7));
+      nms_smem_max = c->cells * 7;
     }
     CU_OK(c, cudaFuncSetAttribute(conv1ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1ab::SMEM));
     CU_OK(c, cudaFuncSetAttribute(conv1ab_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1m::SMEM));
