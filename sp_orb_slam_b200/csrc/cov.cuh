@@ -29,16 +29,18 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace spfe {
 
 constexpr int COV_WIN = 128;     // big flood: window side around the keypoint (pixels)
 constexpr int COV_QCAP = 2048;   // big flood: queue entries == stride of the per-keypoint pop lists in global memory
 constexpr int COV_B_WARPS = 4;   // big floods (warps) per block
-constexpr int COV_B_SMEM = COV_B_WARPS * (COV_WIN * COV_WIN + COV_QCAP) * 2;  // 136 KB
+constexpr int COV_B_SMEM = COV_B_WARPS * (COV_WIN * COV_WIN * 2 + COV_QCAP * 2);  // 144 KB (two-byte first-position map)
 constexpr int COV_S_WIN = 64;    // small flood (the common case)
 constexpr int COV_S_QCAP = 1024;
-constexpr int COV_S_WARPS = 16;  // small floods (warps) per block
-constexpr int COV_S_SMEM = COV_S_WARPS * (COV_S_WIN * COV_S_WIN + COV_S_QCAP) * 2;  // 160 KB
+constexpr int COV_S_WARPS = 32;  // small floods (warps) per block
+constexpr int COV_S_SMEM = COV_S_WARPS * (COV_S_WIN * COV_S_WIN + COV_S_QCAP * 2);  // 192 KB (one-byte first-position map)
 constexpr int COV_R_BIG_BLOCKS = 32;  // cov_resolve_kernel: blocks (of COV_B_WARPS active warps) that take the big floods
 constexpr int COV_ROUNDS = 3;    // parallel conflict-resolution rounds before the sequential remainder
 constexpr int COV_SEQ_QCAP = 32 * 1024;  // queue entries of the sequential path (128 KB of shared memory)
@@ -148,19 +150,33 @@ __device__ __forceinline__ void cov_moments_warp(const float *heat, int n, int W
 // A long flood costs one memory round trip per LEVEL (tens) instead of per pop (hundreds).
 // Queue entry = wy * WIN + wx in a WIN x WIN window centred on the keypoint.  Returns the number of pops or -1 if the
 // flood leaves the window or the queue.  fp must be initialised by the caller.
-template <int WIN, int QCAP>
-__device__ __forceinline__ int cov_warp_flood(const float *heat, int W, int H, int ox, int oy, uint16_t *fp, uint16_t *sq, int lane,
-                                              int *owner, int claim) {
+// Two encodings of the first-position map: absolute (uint16_t: position, 0xFFFF = unset, 0 = visited before the flood)
+// for the big limits, and REL8 (uint8_t: 0 = unset, 1 = popped in an earlier level or visited before the flood,
+// 2 + k = k-th entry of the level being expanded; a level of more than 253 entries does not fit) -- half the shared
+// memory per flood, so twice as many floods in flight.
+template <int WIN, bool REL8>
+struct CovFp {
+  using T = typename std::conditional<REL8, uint8_t, uint16_t>::type;
+  static constexpr int BYTES = WIN * WIN * static_cast<int>(sizeof(T));
+  static constexpr int UNSET = REL8 ? 0 : 0xFFFF;
+  static constexpr int SEEN = REL8 ? 1 : 0;
+};
+
+template <int WIN, int QCAP, bool REL8>
+__device__ __forceinline__ int cov_warp_flood(const float *heat, int W, int H, int ox, int oy, typename CovFp<WIN, REL8>::T *fp,
+                                              uint16_t *sq, int lane, int *owner, int claim) {
+  using FpT = typename CovFp<WIN, REL8>::T;
   if (lane == 0) sq[0] = static_cast<uint16_t>((WIN / 2) * WIN + WIN / 2);
   __syncwarp();
   int lo = 0, hi = 1;
   while (lo < hi) {
+    if (REL8 && hi - lo > 253) return -1;
     for (int c0 = lo; c0 < hi; c0 += 32) {  // (1) first pop position of every pixel of this level
       const int i = c0 + lane;
       const bool act = i < hi;
       const int idx = act ? sq[i] : -1 - lane;
       const unsigned m = __match_any_sync(0xffffffffu, idx);
-      if (act && (__ffs(m) - 1) == lane && fp[idx] == 0xFFFFu) fp[idx] = static_cast<uint16_t>(i);
+      if (act && (__ffs(m) - 1) == lane && fp[idx] == CovFp<WIN, REL8>::UNSET) fp[idx] = static_cast<FpT>(REL8 ? 2 + i - lo : i);
       __syncwarp();
     }
     int tail = hi;
@@ -186,7 +202,8 @@ __device__ __forceinline__ int cov_warp_flood(const float *heat, int W, int H, i
           nidx[d] = idx + didx[d];
           if (!ok[d] || !(hv[d] > 0.0f && hv[d] < here)) continue;
           if (!inwin[d]) { over = true; continue; }
-          push[d] = fp[nidx[d]] > i;
+          const int f = fp[nidx[d]];
+          push[d] = REL8 ? (f == 0 || (f >= 2 && f - 2 + lo > i)) : (f > i);
         }
       }
       const int cnt = static_cast<int>(push[0]) + push[1] + push[2] + push[3];
@@ -205,16 +222,21 @@ __device__ __forceinline__ int cov_warp_flood(const float *heat, int W, int H, i
       tail += total;
       __syncwarp();
     }
+    if (REL8) {  // the level is done: its pixels are "popped in an earlier level" from now on
+      for (int i = lo + lane; i < hi; i += 32) fp[sq[i]] = 1;
+      __syncwarp();
+    }
     lo = hi;
     hi = tail;
   }
   return hi;
 }
 
-template <int WIN>
-__device__ __forceinline__ void cov_fp_init(uint16_t *fp, int lane) {
+template <int WIN, bool REL8>
+__device__ __forceinline__ void cov_fp_init(typename CovFp<WIN, REL8>::T *fp, int lane) {
   uint4 *p = reinterpret_cast<uint4 *>(fp);
-  for (int i = lane; i < WIN * WIN / 8; i += 32) p[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+  const unsigned v = REL8 ? 0u : ~0u;
+  for (int i = lane; i < CovFp<WIN, REL8>::BYTES / 16; i += 32) p[i] = make_uint4(v, v, v, v);
   __syncwarp();
 }
 
@@ -223,9 +245,11 @@ __device__ __forceinline__ void cov_fp_init(uint16_t *fp, int lane) {
 template <int WIN, int QCAP, int WARPS, bool BIG>
 __global__ void __launch_bounds__(WARPS * 32) cov_flood_kernel(const CovArgs a) {
   extern __shared__ uint8_t cov_smem[];
+  constexpr bool REL8 = !BIG;
+  using Fp = CovFp<WIN, REL8>;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint16_t *fp = reinterpret_cast<uint16_t *>(cov_smem) + static_cast<size_t>(w) * (WIN * WIN + QCAP);
-  uint16_t *sq = fp + WIN * WIN;
+  typename Fp::T *fp = reinterpret_cast<typename Fp::T *>(cov_smem + static_cast<size_t>(w) * (Fp::BYTES + QCAP * 2));
+  uint16_t *sq = reinterpret_cast<uint16_t *>(cov_smem + static_cast<size_t>(w) * (Fp::BYTES + QCAP * 2) + Fp::BYTES);
   const int W = a.W, H = a.H, total = BIG ? a.ctr[1] : a.B * a.cap;
   const size_t px = static_cast<size_t>(H) * W;
   for (;;) {
@@ -238,8 +262,8 @@ __global__ void __launch_bounds__(WARPS * 32) cov_flood_kernel(const CovArgs a) 
     if (k >= a.count[b]) continue;
     const float *xy = a.kp_xy + static_cast<size_t>(ki) * 2;
     const int ox = static_cast<int>(xy[0]) - WIN / 2, oy = static_cast<int>(xy[1]) - WIN / 2;
-    cov_fp_init<WIN>(fp, lane);
-    const int n = cov_warp_flood<WIN, QCAP>(a.heat_inv + b * px, W, H, ox, oy, fp, sq, lane, a.owner + b * px, cov_tag(0, k));
+    cov_fp_init<WIN, REL8>(fp, lane);
+    const int n = cov_warp_flood<WIN, QCAP, REL8>(a.heat_inv + b * px, W, H, ox, oy, fp, sq, lane, a.owner + b * px, cov_tag(0, k));
     __syncwarp();
     if (n < 0) {
       if (lane == 0) {
@@ -311,8 +335,9 @@ __global__ void __launch_bounds__(256) cov_claim_kernel(const CovArgs a) {
 
 // Round r, step 2: a pending keypoint that owns all its pixels has no unfinished lower-indexed neighbour: flood it
 // against the visited map (seeded into fp on the pixels of the lone flood, the only ones it can reach).
-template <int WIN, int QCAP>
-__device__ __forceinline__ void cov_resolve_warp(const CovArgs &a, uint16_t *fp, uint16_t *sq, int lane, int first, int stride, bool big) {
+template <int WIN, int QCAP, bool REL8>
+__device__ __forceinline__ void cov_resolve_warp(const CovArgs &a, typename CovFp<WIN, REL8>::T *fp, uint16_t *sq, int lane, int first,
+                                                 int stride, bool big) {
   const int W = a.W, H = a.H, n_pend = a.ctr[2];
   for (int e = first; e < n_pend; e += stride) {
     const int ki = a.pend[e];
@@ -332,13 +357,13 @@ __device__ __forceinline__ void cov_resolve_warp(const CovArgs &a, uint16_t *fp,
     const float *xy = a.kp_xy + static_cast<size_t>(ki) * 2;
     const int cu = static_cast<int>(xy[0]), cv = static_cast<int>(xy[1]);
     const int ox = cu - WIN / 2, oy = cv - WIN / 2;
-    cov_fp_init<WIN>(fp, lane);
+    cov_fp_init<WIN, REL8>(fp, lane);
     for (int i = lane; i < n; i += 32) {
       const int pix = static_cast<int>(q[i]), v = pix / W, u = pix - v * W;
-      if ((__ldcg(visited + (pix >> 5)) >> (pix & 31)) & 1u) fp[(v - oy) * WIN + (u - ox)] = 0;
+      if ((__ldcg(visited + (pix >> 5)) >> (pix & 31)) & 1u) fp[(v - oy) * WIN + (u - ox)] = CovFp<WIN, REL8>::SEEN;
     }
     __syncwarp();
-    const int tail = cov_warp_flood<WIN, QCAP>(heat, W, H, ox, oy, fp, sq, lane, nullptr, 0);
+    const int tail = cov_warp_flood<WIN, QCAP, REL8>(heat, W, H, ox, oy, fp, sq, lane, nullptr, 0);
     __syncwarp();
     if (tail <= 0) continue;  // does not fit: left to the sequential remainder
     cov_moments_warp(heat, tail, W, cu, cv, lane, a.cov2 + static_cast<size_t>(ki) * 2, a.cov2_inv + static_cast<size_t>(ki) * 2,
@@ -366,12 +391,15 @@ __global__ void __launch_bounds__(COV_S_WARPS * 32) cov_resolve_kernel(const Cov
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int n_small = static_cast<int>(gridDim.x) - COV_R_BIG_BLOCKS;
   if (static_cast<int>(blockIdx.x) < n_small) {
-    uint16_t *fp = reinterpret_cast<uint16_t *>(cov_smem) + static_cast<size_t>(w) * (COV_S_WIN * COV_S_WIN + COV_S_QCAP);
-    cov_resolve_warp<COV_S_WIN, COV_S_QCAP>(a, fp, fp + COV_S_WIN * COV_S_WIN, lane, blockIdx.x * COV_S_WARPS + w, n_small * COV_S_WARPS, false);
+    using Fp = CovFp<COV_S_WIN, true>;
+    uint8_t *base = cov_smem + static_cast<size_t>(w) * (Fp::BYTES + COV_S_QCAP * 2);
+    cov_resolve_warp<COV_S_WIN, COV_S_QCAP, true>(a, base, reinterpret_cast<uint16_t *>(base + Fp::BYTES), lane, blockIdx.x * COV_S_WARPS + w,
+                                                  n_small * COV_S_WARPS, false);
   } else if (w < COV_B_WARPS && a.ctr[1] > 0) {
-    uint16_t *fp = reinterpret_cast<uint16_t *>(cov_smem) + static_cast<size_t>(w) * (COV_WIN * COV_WIN + COV_QCAP);
-    cov_resolve_warp<COV_WIN, COV_QCAP>(a, fp, fp + COV_WIN * COV_WIN, lane, (blockIdx.x - n_small) * COV_B_WARPS + w,
-                                        COV_R_BIG_BLOCKS * COV_B_WARPS, true);
+    using Fp = CovFp<COV_WIN, false>;
+    uint8_t *base = cov_smem + static_cast<size_t>(w) * (Fp::BYTES + COV_QCAP * 2);
+    cov_resolve_warp<COV_WIN, COV_QCAP, false>(a, reinterpret_cast<uint16_t *>(base), reinterpret_cast<uint16_t *>(base + Fp::BYTES), lane,
+                                               (blockIdx.x - n_small) * COV_B_WARPS + w, COV_R_BIG_BLOCKS * COV_B_WARPS, true);
   }
 }
 
