@@ -56,8 +56,12 @@ struct ConvArgs {
   int m_tiles;            // 128-row tiles per slot that can hold valid rows
 };
 
-template <int TAPS_, int CB_, int N_, int EPI_, bool WRES_, int SA_, int SB_, int HALVES_ = 1>
+template <int TAPS_, int CB_, int N_, int EPI_, bool WRES_, int SA_, int SB_, int HALVES_ = 1, int EG_ = 1>
 struct ConvCfg {
+  // EG = epilogue warp groups (4 warps each).  With 2, group g drains accumulator set g, so the epilogues of two
+  // consecutive items run side by side: for the layers whose epilogue (softmax / log / norm), not the MMAs, paces the CTA.
+  static constexpr int EG = EG_, THREADS = 128 + 128 * EG_;
+  static_assert(EG_ == 1 || EG_ == 2, "one or two epilogue groups");
   static constexpr bool MATCH = (EPI_ == EPI_TOP2);
   static constexpr int TAPS = TAPS_, CB = CB_, N = N_, EPI = EPI_, SA = SA_, SB = SB_, HALVES = HALVES_;
   static constexpr bool WRES = WRES_;
@@ -145,7 +149,7 @@ __device__ __forceinline__ void epilogue_relu_pool(uint32_t taddr, const float *
 }
 
 template <class Cfg>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const ConvArgs p) {
   constexpr int N = Cfg::N, CB = Cfg::CB, SA = Cfg::SA, SB = Cfg::SB;
   const int NB = p.NB;  // resident weights (WRES) require NB == 1 (checked on the host)
@@ -348,8 +352,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------ epilogue (TMEM -> regs -> global)
     const int wq = warp & 3;
     const int hl = wq * 4 + (lane >> 3), wl = lane & 7;
+    const uint32_t egroup = static_cast<uint32_t>(warp - 4) >> 2;
     uint32_t tcount = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, tcount++) {
+      if (Cfg::EG == 2 && (tcount & 1) != egroup) continue;  // the other group's accumulator set
       int nb, x0_item, y0, b;
       decode(item, nb, x0_item, y0, b);
       const int acc = tcount & 1;

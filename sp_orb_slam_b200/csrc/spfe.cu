@@ -51,9 +51,9 @@ using CfgC3a = ConvCfg<9, 1, 128, EPI_RELU, true, 2, 1, 1>;         // conv3a   
 using CfgC128 = ConvCfg<9, 2, 128, EPI_RELU, false, 2, 6, 2>;       // conv4a, conv4b  slab 54 KB x2 + 6 x 16 KB weights
 using CfgC128P = ConvCfg<9, 2, 128, EPI_RELU_POOL, false, 2, 6, 2>; // conv3b
 using CfgHeads = ConvCfg<9, 2, 256, EPI_RELU, false, 2, 4, 1>;      // convPa || convDa (NB = 2), N = 256: single tiles
-using CfgPb = ConvCfg<1, 4, 80, EPI_DETECT, true, 4, 1>;        // convPb + detector head
-using CfgDb = ConvCfg<1, 4, 256, EPI_L2NORM, true, 4, 1>;       // convDb + L2 norm
-using CfgMatch = ConvCfg<1, 4, 256, EPI_TOP2, false, 4, 4>;     // descriptor matching: Q.T^T + top-2 per 256-column block
+using CfgPb = ConvCfg<1, 4, 80, EPI_DETECT, true, 4, 1, 1, 2>;  // convPb + detector head   (epilogue-bound: two epilogue groups)
+using CfgDb = ConvCfg<1, 4, 256, EPI_L2NORM, true, 4, 1, 1, 2>; // convDb + L2 norm
+using CfgMatch = ConvCfg<1, 4, 256, EPI_TOP2, false, 4, 4, 1, 2>;  // descriptor matching: Q.T^T + top-2 per 256-column block
 
 enum { L1B = 0, L2A, L2B, L3A, L3B, L4A, L4B, LHEADS, LPB, LDB, NLAYERS };
 const char *kLayerNames[NLAYERS] = {"conv1b", "conv2a", "conv2b", "conv3a", "conv3b",
@@ -264,7 +264,7 @@ int launch_conv(spfe_ctx *c, cudaStream_t st, const CUtensorMap &tmA, const Laye
   a.n_items = a.B * a.tiles_x * a.tiles_y * a.NB;
   if (Cfg::MATCH) a.n_items = a.B * 2 * a.m_tiles * a.NB;
   const int grid = a.n_items < c->num_sms ? a.n_items : c->num_sms;
-  conv_tc_kernel<Cfg><<<grid, 256, smem, st>>>(tmA, tmB ? *tmB : L.tm, a);
+  conv_tc_kernel<Cfg><<<grid, Cfg::THREADS, smem, st>>>(tmA, tmB ? *tmB : L.tm, a);
   c->launches++;
   CU_OK(c, cudaGetLastError());
   return SPFE_OK;
