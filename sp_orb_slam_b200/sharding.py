@@ -39,10 +39,13 @@ def init_distributed(backend: str | None = None):
     os.environ.setdefault("MASTER_PORT", "29533")
     if backend is None:
         backend = "nccl" if torch.cuda.is_available() else "gloo"
+    kw = {}
     if backend == "nccl":
         torch.cuda.set_device(local_rank)
+        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep NCCL's version banner off stdout (one JSON line only)
+        kw["device_id"] = torch.device("cuda", local_rank)
     if not dist.is_initialized():
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
     return rank, local_rank, world
 
 
