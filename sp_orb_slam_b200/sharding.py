@@ -12,6 +12,7 @@ tests) is used only for (i) the barrier + max-over-ranks timing of the bench and
 from __future__ import annotations
 
 import os
+import sys
 
 import numpy as np
 
@@ -42,10 +43,23 @@ def init_distributed(backend: str | None = None):
     kw = {}
     if backend == "nccl":
         torch.cuda.set_device(local_rank)
-        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep NCCL's version banner off stdout (one JSON line only)
         kw["device_id"] = torch.device("cuda", local_rank)
     if not dist.is_initialized():
-        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+        # NCCL prints its version banner on stdout when the first communicator is created; bench.py must print exactly
+        # one JSON line there, so stdout points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+            if backend == "nccl":
+                t = torch.zeros(1, device=kw["device_id"])
+                dist.all_reduce(t)
+                torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     return rank, local_rank, world
 
 
