@@ -115,6 +115,7 @@ conv1ab_mma_kernel(const __grid_constant__ CUtensorMap tmW, const Conv1abArgs p)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();  // conv2a's CTAs may take over an SM (and load their weights) as soon as this CTA leaves it
 
   auto decode = [&](int item, int &x0, int &y0, int &b) {
     x0 = (item % p.tiles_x) * 16;

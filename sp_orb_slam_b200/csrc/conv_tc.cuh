@@ -194,6 +194,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barriers, TMEM, bias) and the resident-weight loads below do not
+  // depend on the previous kernel of the stream, so this CTA may have started while that kernel was still draining;
+  // the roles that touch its output (activation loads, global stores) wait for it first.
+  griddep_launch_dependents();
 
   auto decode = [&](int item, int &nb, int &x0, int &y0, int &b) {
     nb = item % NB;
@@ -214,6 +218,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ------------------------------------------------ activation slab producer
     if (lane == 0) {
+      griddep_wait();
       uint32_t it = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         int nb, x0, y0, b;
@@ -235,6 +240,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int wb = 0; wb < Cfg::NWB; wb++)
           tma_load_2d(smem_u32(sB + wb * Cfg::BBLK_BYTES), &tmW, w_full, 0, wb * N);
       } else {
+        if constexpr (Cfg::MATCH) griddep_wait();  // the B operand is the previous kernel's output here, not constant weights
         uint32_t jt = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
           const int nb = item % NB;
@@ -353,6 +359,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int wq = warp & 3;
     const int hl = wq * 4 + (lane >> 3), wl = lane & 7;
     const uint32_t egroup = static_cast<uint32_t>(warp - 4) >> 2;
+    griddep_wait();
     uint32_t tcount = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, tcount++) {
       if (Cfg::EG == 2 && (tcount & 1) != egroup) continue;  // the other group's accumulator set

@@ -33,6 +33,13 @@ __device__ __forceinline__ void ffma2(float2 &d, const float2 &a, const float2 &
   d = *reinterpret_cast<float2 *>(&D);
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream still runs; griddep_wait() blocks until that predecessor has completed and its writes are visible.
+// griddep_launch_dependents() lets the successor's CTAs be scheduled as soon as SMs free up.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

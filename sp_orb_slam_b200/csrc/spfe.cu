@@ -130,6 +130,7 @@ struct spfe_ctx {
   bool heat_host = false, heat_inv_host = false;       // EMIT_HEAT / EMIT_HEAT_INV: heat_ / heat_inv_ are also copied to the host
   // conv1a + conv1b: 2 = one kernel, both layers on the tensor core (default); 1 = one kernel, conv1a on the CUDA cores
   // (SPFE_CONV1=ffma); 0 = two kernels (SPFE_CONV1=unfused or SPFE_FUSED_CONV1=0; materialises conv1a for inspection)
+  bool pdl = false;  // SPFE_PDL=1: programmatic dependent launch of the tensor-core kernels (measured: no gain, the board is power-capped)
   int conv1_mode = 2;
   bool fused_conv1 = true;
   void *w1m = nullptr;  // conv1a weights as hi | lo fp16 UMMA operands (conv1ab_mma.cuh)
@@ -264,7 +265,17 @@ int launch_conv(spfe_ctx *c, cudaStream_t st, const CUtensorMap &tmA, const Laye
   a.n_items = a.B * a.tiles_x * a.tiles_y * a.NB;
   if (Cfg::MATCH) a.n_items = a.B * 2 * a.m_tiles * a.NB;
   const int grid = a.n_items < c->num_sms ? a.n_items : c->num_sms;
-  conv_tc_kernel<Cfg><<<grid, Cfg::THREADS, smem, st>>>(tmA, tmB ? *tmB : L.tm, a);
+  if (c->pdl) {  // programmatic dependent launch: overlap this kernel's prologue with the previous kernel's tail
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(Cfg::THREADS); lc.dynamicSmemBytes = smem; lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    CU_OK(c, cudaLaunchKernelEx(&lc, conv_tc_kernel<Cfg>, tmA, tmB ? *tmB : L.tm, a));
+  } else {
+    conv_tc_kernel<Cfg><<<grid, Cfg::THREADS, smem, st>>>(tmA, tmB ? *tmB : L.tm, a);
+  }
   c->launches++;
   CU_OK(c, cudaGetLastError());
   return SPFE_OK;
@@ -708,6 +719,8 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
     if (m && !strcmp(m, "ffma")) c->conv1_mode = 1;
     if ((m && !strcmp(m, "unfused")) || (e && e[0] == '0')) c->conv1_mode = 0;
     c->fused_conv1 = c->conv1_mode != 0;
+    const char *pd = getenv("SPFE_PDL");
+    c->pdl = pd && pd[0] == '1';
   }
   int rc = create_impl(c);
   if (rc == SPFE_OK) rc = [&]() -> int {
