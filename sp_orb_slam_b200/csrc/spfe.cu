@@ -254,10 +254,15 @@ int launch_conv(spfe_ctx *c, cudaStream_t st, const CUtensorMap &tmA, const Laye
   if (L.taps != Cfg::TAPS || L.cb != Cfg::CB || L.n_tile != Cfg::N || (Cfg::WRES && a.NB != 1))
     return c->fail(SPFE_ERR_INVALID, "conv launch: layer / kernel configuration mismatch");
   const int smem = Cfg::smem_bytes(a.NB);
-  static std::atomic<int> configured{0};
-  if (configured.load() < smem) {
-    CU_OK(c, cudaFuncSetAttribute(conv_tc_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured.store(smem);
+  {  // function attributes are per device: remember what this instantiation was granted on the context's device
+    static std::mutex mu;
+    static int granted[64] = {0};
+    std::lock_guard<std::mutex> lock(mu);
+    int &g = granted[c->cfg.device_id & 63];
+    if (g < smem) {
+      CU_OK(c, cudaFuncSetAttribute(conv_tc_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      g = smem;
+    }
   }
   a.bias = L.bias;
   a.tiles_x = (a.W + Cfg::TILE_W - 1) / Cfg::TILE_W;
@@ -724,10 +729,12 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
   }
   int rc = create_impl(c);
   if (rc == SPFE_OK) rc = [&]() -> int {
-    // the attribute is per function, not per context: only ever raise it (several extractors may coexist)
+    // the attribute is per function and device, not per context: only ever raise it (several extractors may coexist)
     static std::mutex mu;
-    static int nms_smem_max = 48 * 1024;
+    static int nms_granted[64] = {0};  // per device
     std::lock_guard<std::mutex> lock(mu);
+    int &nms_smem_max = nms_granted[c->cfg.device_id & 63];
+    if (nms_smem_max == 0) nms_smem_max = 48 * 1024;
     if (c->cells * 7 > nms_smem_max) {
       CU_OK(c, cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->cells * 7));
       nms_smem_max = c->cells * 7;
