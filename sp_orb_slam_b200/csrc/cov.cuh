@@ -70,6 +70,7 @@ struct CovArgs {
   int *overflow;          // [1] set if even the sequential queue overflowed (reported as an error)
   int *n_replay;          // [B][2] statistics: keypoints / pixels replayed sequentially
   int H, W, cap, B, round;
+  int force;              // test hook (SPFE_COV_FORCE): bit 0 = every small flood "does not fit", bit 1 = every big flood neither
 };
 
 __device__ __forceinline__ int cov_tag(int round, int k) { return ((64 - round) << 16) | k; }
@@ -263,7 +264,8 @@ __global__ void __launch_bounds__(WARPS * 32) cov_flood_kernel(const CovArgs a) 
     const float *xy = a.kp_xy + static_cast<size_t>(ki) * 2;
     const int ox = static_cast<int>(xy[0]) - WIN / 2, oy = static_cast<int>(xy[1]) - WIN / 2;
     cov_fp_init<WIN, REL8>(fp, lane);
-    const int n = cov_warp_flood<WIN, QCAP, REL8>(a.heat_inv + b * px, W, H, ox, oy, fp, sq, lane, a.owner + b * px, cov_tag(0, k));
+    int n = cov_warp_flood<WIN, QCAP, REL8>(a.heat_inv + b * px, W, H, ox, oy, fp, sq, lane, a.owner + b * px, cov_tag(0, k));
+    if (a.force & (BIG ? 2 : 1)) n = -1;
     __syncwarp();
     if (n < 0) {
       if (lane == 0) {

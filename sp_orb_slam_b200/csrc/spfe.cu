@@ -130,6 +130,7 @@ struct spfe_ctx {
   bool heat_host = false, heat_inv_host = false;       // EMIT_HEAT / EMIT_HEAT_INV: heat_ / heat_inv_ are also copied to the host
   // conv1a + conv1b: 2 = one kernel, both layers on the tensor core (default); 1 = one kernel, conv1a on the CUDA cores
   // (SPFE_CONV1=ffma); 0 = two kernels (SPFE_CONV1=unfused or SPFE_FUSED_CONV1=0; materialises conv1a for inspection)
+  int cov_force = 0;  // SPFE_COV_FORCE (test hook): push floods down the big / sequential fallback paths
   bool pdl = false;  // SPFE_PDL=1: programmatic dependent launch of the tensor-core kernels (measured: no gain, the board is power-capped)
   int conv1_mode = 2;
   bool fused_conv1 = true;
@@ -411,6 +412,7 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     a.heat_inv = s.heat_inv; a.kp_xy = s.kp_xy; a.count = s.count; a.owner = s.cov_owner; a.visited = s.cov_visited;
     a.queue = s.cov_queue; a.qlen = s.cov_qlen; a.response = s.resp; a.cov2 = s.cov2; a.cov2_inv = s.cov2_inv;
     a.overflow = s.cov_overflow; a.H = H; a.W = W; a.cap = c->cap; a.B = B; a.round = 0;
+    a.force = c->cov_force;
     a.done = s.cov_done; a.isbig = s.cov_isbig; a.ctr = s.cov_ctr; a.big = s.cov_big; a.pend = s.cov_pend;
     a.frame_flag = s.cov_frame_flag; a.n_replay = s.cov_n_replay; a.vis_words = static_cast<int>(vis_words);
     mark("cov_memset", 0, 5.0 * px * B);
@@ -726,6 +728,8 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
     c->fused_conv1 = c->conv1_mode != 0;
     const char *pd = getenv("SPFE_PDL");
     c->pdl = pd && pd[0] == '1';
+    const char *cf = getenv("SPFE_COV_FORCE");
+    c->cov_force = cf ? atoi(cf) : 0;
   }
   int rc = create_impl(c);
   if (rc == SPFE_OK) rc = [&]() -> int {

@@ -352,6 +352,25 @@ def test_covariance_vs_oracle_on_same_heat(ex_cache):
     assert np.array_equal(o["heat"], heat) and np.array_equal(o["heat_inv"], heat_inv)     # to_heat: bit-exact
 
 
+@pytest.mark.parametrize("force", [1, 3])
+def test_covariance_fallback_paths(force, monkeypatch):
+    """The paths real frames rarely take: SPFE_COV_FORCE=1 sends every lone flood through the big-limit kernel (and the
+    big-limit blocks of the rounds), =3 additionally fails those, so the whole frame is replayed sequentially."""
+    H, W = 240, 320
+    monkeypatch.setenv("SPFE_COV_FORCE", str(force))
+    ex = SPExtractor(800, H, W, WEIGHTS, max_batch=2)
+    frames = synth.make_stream(H, W, 2, seed=23, n_shapes=300)
+    for o in ex.extract_batch(list(frames)):
+        resp, cov2, cov2_inv = O.covariance(o["heat_inv"], o["kp_xy"])
+        assert o["n"] > 100 and np.array_equal(o["kp_response"], resp)
+        assert np.array_equal(o["cov2"], cov2) and np.array_equal(o["cov2_inv"], cov2_inv)
+    ctr = ex.debug_read(0, "cov_counters", 1)[0]
+    replayed = ex.debug_read(0, "cov_replayed", 2)
+    assert ctr[1] > 100                                        # every flood went to the big list
+    assert (replayed[:, 0].min() > 100) == (force == 3)        # ... and, with force = 3, to the sequential replay
+    ex.close()
+
+
 def test_covariance_dense_full_size_and_device_only(ex_cache):
     """Dense 752x480 scenes (hundreds of keypoints 5 px apart -> overlapping floods that must be replayed in order),
     a batch of them, and the mode where the heat maps never leave the device."""
