@@ -56,8 +56,14 @@ struct ConvArgs {
   int m_tiles;            // 128-row tiles per slot that can hold valid rows
 };
 
-template <int TAPS_, int CB_, int N_, int EPI_, bool WRES_, int SA_, int SB_, int HALVES_ = 1, int EG_ = 1>
+template <int TAPS_, int CB_, int N_, int EPI_, bool WRES_, int SA_, int SB_, int HALVES_ = 1, int EG_ = 1, bool PAIR_ = false>
 struct ConvCfg {
+  // PAIR: two CTAs of a cluster run every MMA together (cta_group::2, M = 256): each works on its own item (its own
+  // slabs, accumulators and epilogue) but holds only half of the weights, so the shared-memory operand reads per SM and
+  // MMA drop from A + B to A + B/2 -- the limiter of the N = 64 layers (tools/umma2_rate.cu).  The leader (rank 0)
+  // issues the MMAs for both; items 2q and 2q+1 go to ranks 0 and 1 of pair q mod (grid / 2).
+  static constexpr bool PAIR = PAIR_;
+  static_assert(!PAIR_ || (WRES_ && CB_ == 1 && N_ % 32 == 0), "pairs: resident weights, one channel block");
   // EG = epilogue warp groups (4 warps each).  With 2, group g drains accumulator set g, so the epilogues of two
   // consecutive items run side by side: for the layers whose epilogue (softmax / log / norm), not the MMAs, paces the CTA.
   static constexpr int EG = EG_, THREADS = 128 + 128 * EG_;
@@ -72,7 +78,7 @@ struct ConvCfg {
   static constexpr int SLAB_ROWS = TAPS == 9 ? 18 : 16;
   static constexpr int SLAB_BYTES = SLAB_ROWS * PW * 128;
   static constexpr int SBO = PW * 128;                            // bytes between 8-row groups of the A operand
-  static constexpr int BBLK_BYTES = N * 128;
+  static constexpr int BBLK_BYTES = (PAIR_ ? N_ / 2 : N_) * 128;  // a pair member holds N/2 rows of every weight block
   static constexpr int NWB = TAPS * CB;
   static constexpr int B_BYTES = (WRES ? NWB : SB) * BBLK_BYTES;
   static constexpr int ACC_STRIDE = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
@@ -178,15 +184,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < SA; s++) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < SB; s++) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    for (int s = 0; s < 2; s++) { mbar_init(t_full(s), 1); mbar_init(t_empty(s), 128); }
+    for (int s = 0; s < 2; s++) { mbar_init(t_full(s), 1); mbar_init(t_empty(s), Cfg::PAIR ? 8 : 128); }
     mbar_init(w_full, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
   }
+  if constexpr (Cfg::PAIR) cluster_sync_all();  // both CTAs' barriers exist before anything can signal across the pair
   if (warp == 2) {
-    tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (Cfg::PAIR) { tmem_alloc_pair(smem_u32(tmem_slot), Cfg::TMEM_COLS); tmem_relinquish_pair(); }
+    else { tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS); tmem_relinquish(); }
   }
   if constexpr (!Cfg::MATCH)
     for (int i = threadIdx.x; i < NB * N; i += blockDim.x) sBias[i] = p.bias[i];
@@ -198,6 +205,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // depend on the previous kernel of the stream, so this CTA may have started while that kernel was still draining;
   // the roles that touch its output (activation loads, global stores) wait for it first.
   griddep_launch_dependents();
+  const uint32_t rank = Cfg::PAIR ? cluster_ctarank() : 0u;
+  // Work distribution.  Plain: CTA b takes items b, b + grid, ...  Pair: pair j = b / 2 takes item pairs j, j + grid / 2, ...;
+  // rank r works on item 2q + r (clamped: with an odd item count the last item is computed by both ranks, which write
+  // identical results).
+  const int q_first = Cfg::PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int q_step = Cfg::PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int q_end = Cfg::PAIR ? (p.n_items + 1) >> 1 : p.n_items;
+  auto item_of = [&](int q) { return Cfg::PAIR ? min(2 * q + static_cast<int>(rank), p.n_items - 1) : q; };
+  if constexpr (Cfg::PAIR) {  // each rank loads its half of the resident weights; nobody starts before both halves are in
+    if (warp == 3) {
+      if (lane == 0) {
+        mbar_expect_tx(w_full, Cfg::NWB * Cfg::BBLK_BYTES);
+        for (int wb = 0; wb < Cfg::NWB; wb++)
+          tma_load_2d(smem_u32(sB + wb * Cfg::BBLK_BYTES), &tmW, w_full, 0, wb * N + static_cast<int>(rank) * (N / 2));
+      }
+      mbar_wait(w_full, 0);
+    }
+    cluster_sync_all();
+  }
 
   auto decode = [&](int item, int &nb, int &x0, int &y0, int &b) {
     nb = item % NB;
@@ -220,21 +246,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       griddep_wait();
       uint32_t it = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int q = q_first; q < q_end; q += q_step) {
         int nb, x0, y0, b;
-        decode(item, nb, x0, y0, b);
+        decode(item_of(q), nb, x0, y0, b);
         for (int cb = 0; cb < CB; cb++, it++) {
           const int s = it % SA;
           mbar_wait(a_empty(s), ((it / SA) & 1) ^ 1);
-          mbar_expect_tx(a_full(s), Cfg::SLAB_BYTES);
-          tma_load_4d(smem_u32(sA + s * Cfg::SLAB_BYTES), &tmA, a_full(s), p.cin_off + cb * 64,
-                      x0 - (NDX == 3 ? 1 : 0), y0 - (NDY == 3 ? 1 : 0), b);
+          if constexpr (Cfg::PAIR) {  // both ranks' slabs complete on the leader's barrier (the leader issues the MMAs)
+            if (rank == 0) mbar_expect_tx(a_full(s), 2 * Cfg::SLAB_BYTES);
+            tma_load_4d_pair(smem_u32(sA + s * Cfg::SLAB_BYTES), &tmA, mapa_shared(a_full(s), 0), p.cin_off + cb * 64,
+                             x0 - (NDX == 3 ? 1 : 0), y0 - (NDY == 3 ? 1 : 0), b);
+          } else {
+            mbar_expect_tx(a_full(s), Cfg::SLAB_BYTES);
+            tma_load_4d(smem_u32(sA + s * Cfg::SLAB_BYTES), &tmA, a_full(s), p.cin_off + cb * 64,
+                        x0 - (NDX == 3 ? 1 : 0), y0 - (NDY == 3 ? 1 : 0), b);
+          }
         }
       }
     }
   } else if (warp == 3) {
     // ------------------------------------------------ weight producer
-    if (lane == 0) {
+    if (lane == 0 && !Cfg::PAIR) {
       if (WRES) {
         mbar_expect_tx(w_full, Cfg::NWB * Cfg::BBLK_BYTES);
         for (int wb = 0; wb < Cfg::NWB; wb++)
@@ -242,7 +274,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       } else {
         if constexpr (Cfg::MATCH) griddep_wait();  // the B operand is the previous kernel's output here, not constant weights
         uint32_t jt = 0;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {  // (never a pair: pairs keep their weights resident)
           const int nb = item % NB;
           for (int cb = 0; cb < CB; cb++)
             for (int dx = 0; dx < NDX; dx++)
@@ -268,14 +300,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // elected lane issues.  Entering an elected region costs ~90 cycles (measured, tools/umma_rate.cu) while an
     // M128 x N<=128 MMA needs only 50-64, so MMAs are issued in the largest groups the buffering allows: a whole
     // item when the weights are resident, one horizontal tap (3 dy x HALVES x 4 k-steps) when they are streamed.
-    constexpr uint32_t idesc = umma_idesc_f16(N);
+    constexpr uint32_t idesc = Cfg::PAIR ? umma_idesc_f16_pair(N) : umma_idesc_f16(N);
     constexpr int PW = Cfg::PW, HALVES = Cfg::HALVES;
     uint32_t it = 0, jt = 0, tcount = 0;
     if (WRES) mbar_wait(w_full, 0);
     const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
     // A operand of tap (dy, dx), half h, k-step k: slab + ((dy*PW + h*8 + dx)*128 + k*32) bytes, in (addr >> 4) units
     auto a_off = [](int dy, int dx, int h, int k) { return static_cast<uint64_t>((dy * PW + h * 8 + dx) * 8 + 2 * k); };
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, tcount++) {
+    for (int q = q_first; q < q_end && rank == 0; q += q_step, tcount++) {  // in a pair only the leader issues
       const uint32_t acc = tcount & 1;
       mbar_wait(t_empty(acc), ((tcount >> 1) & 1) ^ 1);
       const uint32_t d_tmem = tmem_base + acc * HALVES * Cfg::ACC_STRIDE;
@@ -300,12 +332,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int h = 0; h < HALVES; h++)
 #pragma unroll
-                  for (int k = 0; k < 4; k++)
-                    umma_f16(d_tmem + h * Cfg::ACC_STRIDE, a0 + a_off(dy, dx, h, k), b0 + 2 * k, idesc, (cb | dx | dy | k) ? 1u : 0u);
+                  for (int k = 0; k < 4; k++) {
+                    if constexpr (Cfg::PAIR)
+                      umma_f16_pair(d_tmem + h * Cfg::ACC_STRIDE, a0 + a_off(dy, dx, h, k), b0 + 2 * k, idesc, (cb | dx | dy | k) ? 1u : 0u);
+                    else
+                      umma_f16(d_tmem + h * Cfg::ACC_STRIDE, a0 + a_off(dy, dx, h, k), b0 + 2 * k, idesc, (cb | dx | dy | k) ? 1u : 0u);
+                  }
               }
-            umma_commit(a_empty(st[cb]));  // the slab is free as soon as its own MMAs retire (keeps the TMA ring busy)
+            // the slab is free as soon as its own MMAs retire (keeps the TMA ring busy); in a pair both ranks are told
+            if constexpr (Cfg::PAIR) umma_commit_pair(a_empty(st[cb])); else umma_commit(a_empty(st[cb]));
           }
-          umma_commit(t_full(acc));
+          if constexpr (Cfg::PAIR) umma_commit_pair(t_full(acc)); else umma_commit(t_full(acc));
         }
         __syncwarp();
         it += CB;
@@ -361,8 +398,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t egroup = static_cast<uint32_t>(warp - 4) >> 2;
     griddep_wait();
     uint32_t tcount = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, tcount++) {
+    for (int q = q_first; q < q_end; q += q_step, tcount++) {
       if (Cfg::EG == 2 && (tcount & 1) != egroup) continue;  // the other group's accumulator set
+      const int item = item_of(q);
       int nb, x0_item, y0, b;
       decode(item, nb, x0_item, y0, b);
       const int acc = tcount & 1;
@@ -547,15 +585,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       }  // half
       tc_fence_before();
-      mbar_arrive(t_empty(acc));
+      if constexpr (Cfg::PAIR) {  // the leader's MMA warp waits for both epilogues: one cluster-scope arrival per warp
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_shared(t_empty(acc), 0));
+      } else {
+        mbar_arrive(t_empty(acc));
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (Cfg::PAIR) cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (Cfg::PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 

@@ -47,6 +47,8 @@ std::string fmt(const char *f, ...) {
 //                                                                                     tile pair (HALVES = 2)
 using CfgC64 = ConvCfg<9, 1, 64, EPI_RELU, true, 2, 1, 2>;          // conv2a          slab 54 KB x2 + 72 KB weights
 using CfgC64P = ConvCfg<9, 1, 64, EPI_RELU_POOL, true, 2, 1, 2>;    // conv1b, conv2b
+using CfgC64X = ConvCfg<9, 1, 64, EPI_RELU, true, 3, 1, 2, 1, true>;        // the same as CTA pairs (cta_group::2): default
+using CfgC64PX = ConvCfg<9, 1, 64, EPI_RELU_POOL, true, 3, 1, 2, 1, true>;
 using CfgC3a = ConvCfg<9, 1, 128, EPI_RELU, true, 2, 1, 1>;         // conv3a          144 KB weights: single tiles
 using CfgC128 = ConvCfg<9, 2, 128, EPI_RELU, false, 2, 6, 2>;       // conv4a, conv4b  slab 54 KB x2 + 6 x 16 KB weights
 using CfgC128P = ConvCfg<9, 2, 128, EPI_RELU_POOL, false, 2, 6, 2>; // conv3b
@@ -67,6 +69,7 @@ struct Layer {
   __half *w = nullptr;  // packed [tap][cblock][cout_total][64]
   float *bias = nullptr;
   CUtensorMap tm;
+  CUtensorMap tm_half;  // box of n_tile / 2 rows: what one member of a CTA pair loads
   int taps = 0, cb = 0, cout_total = 0, n_tile = 0;
   double flop_per_px = 0;  // 2 * taps * cin * cout (real couts)
 };
@@ -130,6 +133,8 @@ struct spfe_ctx {
   bool heat_host = false, heat_inv_host = false;       // EMIT_HEAT / EMIT_HEAT_INV: heat_ / heat_inv_ are also copied to the host
   // conv1a + conv1b: 2 = one kernel, both layers on the tensor core (default); 1 = one kernel, conv1a on the CUDA cores
   // (SPFE_CONV1=ffma); 0 = two kernels (SPFE_CONV1=unfused or SPFE_FUSED_CONV1=0; materialises conv1a for inspection)
+  bool pair = true;   // SPFE_PAIR=0: single-CTA MMAs for the 64 -> 64 layers as well
+  bool pair_conv2a = false;  // SPFE_PAIR=2: conv2a as pairs too
   int cov_force = 0;  // SPFE_COV_FORCE (test hook): push floods down the big / sequential fallback paths
   bool pdl = false;  // SPFE_PDL=1: programmatic dependent launch of the tensor-core kernels (measured: no gain, the board is power-capped)
   int conv1_mode = 2;
@@ -246,6 +251,7 @@ int upload_layer(spfe_ctx *c, Layer &L, const std::vector<const HostTensor *> &w
   if ((rc = dev_alloc(c, &L.bias, bias.size()))) return rc;
   CU_OK(c, cudaMemcpy(L.w, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
   CU_OK(c, cudaMemcpy(L.bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (int rc2 = make_mat_map(c, &L.tm_half, L.w, 64, L.taps * L.cb * cout_total, n_tile / 2)) return rc2;
   return make_mat_map(c, &L.tm, L.w, 64, L.taps * L.cb * cout_total, n_tile);
 }
 
@@ -270,8 +276,17 @@ int launch_conv(spfe_ctx *c, cudaStream_t st, const CUtensorMap &tmA, const Laye
   a.tiles_y = (a.H + 15) / 16;
   a.n_items = a.B * a.tiles_x * a.tiles_y * a.NB;
   if (Cfg::MATCH) a.n_items = a.B * 2 * a.m_tiles * a.NB;
-  const int grid = a.n_items < c->num_sms ? a.n_items : c->num_sms;
-  if (c->pdl) {  // programmatic dependent launch: overlap this kernel's prologue with the previous kernel's tail
+  int grid = a.n_items < c->num_sms ? a.n_items : c->num_sms;
+  if (Cfg::PAIR) {  // clusters of two CTAs; every pair works on two items at a time
+    const int pairs = (a.n_items + 1) / 2 < c->num_sms / 2 ? (a.n_items + 1) / 2 : c->num_sms / 2;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(2 * pairs); lc.blockDim = dim3(Cfg::THREADS); lc.dynamicSmemBytes = smem; lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    CU_OK(c, cudaLaunchKernelEx(&lc, conv_tc_kernel<Cfg>, tmA, L.tm_half, a));
+  } else if (c->pdl) {  // programmatic dependent launch: overlap this kernel's prologue with the previous kernel's tail
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(grid); lc.blockDim = dim3(Cfg::THREADS); lc.dynamicSmemBytes = smem; lc.stream = st;
     cudaLaunchAttribute at[1];
@@ -347,9 +362,14 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     if ((rc = launch_conv<CfgC64P>(c, st, s.tmA[L1B], c->layers[L1B], conv_args(H, W, 1, 64, s.a1b)))) return rc;
     mark("conv1b", stage_flop(L1B, H, W), (128.0 + 32.0) * H * W * B);
   }
-  if ((rc = launch_conv<CfgC64>(c, st, s.tmA[L2A], c->layers[L2A], conv_args(H / 2, W / 2, 1, 64, s.a2a)))) return rc;
+  // conv2a stays single-CTA: its epilogue (full-resolution 128-byte stores), not the MMAs, paces it (pairs measured 6 % slower)
+  if (c->pair_conv2a) rc = launch_conv<CfgC64X>(c, st, s.tmA[L2A], c->layers[L2A], conv_args(H / 2, W / 2, 1, 64, s.a2a));
+  else rc = launch_conv<CfgC64>(c, st, s.tmA[L2A], c->layers[L2A], conv_args(H / 2, W / 2, 1, 64, s.a2a));
+  if (rc) return rc;
   mark("conv2a", stage_flop(L2A, H / 2, W / 2), 256.0 * (H / 2) * (W / 2) * B);
-  if ((rc = launch_conv<CfgC64P>(c, st, s.tmA[L2B], c->layers[L2B], conv_args(H / 2, W / 2, 1, 64, s.a2b)))) return rc;
+  if (c->pair) rc = launch_conv<CfgC64PX>(c, st, s.tmA[L2B], c->layers[L2B], conv_args(H / 2, W / 2, 1, 64, s.a2b));
+  else rc = launch_conv<CfgC64P>(c, st, s.tmA[L2B], c->layers[L2B], conv_args(H / 2, W / 2, 1, 64, s.a2b));
+  if (rc) return rc;
   mark("conv2b", stage_flop(L2B, H / 2, W / 2), 160.0 * (H / 2) * (W / 2) * B);
   if ((rc = launch_conv<CfgC3a>(c, st, s.tmA[L3A], c->layers[L3A], conv_args(H / 4, W / 4, 1, 128, s.a3a)))) return rc;
   mark("conv3a", stage_flop(L3A, H / 4, W / 4), 384.0 * (H / 4) * (W / 4) * B);
@@ -728,6 +748,9 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
     c->fused_conv1 = c->conv1_mode != 0;
     const char *pd = getenv("SPFE_PDL");
     c->pdl = pd && pd[0] == '1';
+    const char *pr = getenv("SPFE_PAIR");
+    c->pair = !(pr && pr[0] == '0');
+    c->pair_conv2a = pr && pr[0] == '2';
     const char *cf = getenv("SPFE_COV_FORCE");
     c->cov_force = cf ? atoi(cf) : 0;
   }
