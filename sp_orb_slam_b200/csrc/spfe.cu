@@ -135,6 +135,7 @@ struct spfe_ctx {
   // (SPFE_CONV1=ffma); 0 = two kernels (SPFE_CONV1=unfused or SPFE_FUSED_CONV1=0; materialises conv1a for inspection)
   bool pair = true;   // SPFE_PAIR=0: single-CTA MMAs for the 64 -> 64 layers as well
   bool pair_conv2a = false;  // SPFE_PAIR=2: conv2a as pairs too
+  bool pair_conv1 = false;   // SPFE_PAIR_CONV1=1: the fused conv1a+1b kernel as pairs
   int cov_force = 0;  // SPFE_COV_FORCE (test hook): push floods down the big / sequential fallback paths
   bool pdl = false;  // SPFE_PDL=1: programmatic dependent launch of the tensor-core kernels (measured: no gain, the board is power-capped)
   int conv1_mode = 2;
@@ -339,7 +340,16 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     a.B = B; a.H = H; a.W = W; a.tiles_x = (W + 15) / 16; a.tiles_y = (H + 15) / 16;
     a.n_items = B * a.tiles_x * a.tiles_y;
     const int grid = a.n_items < c->num_sms ? a.n_items : c->num_sms;
-    if (c->conv1_mode == 2) conv1ab_mma_kernel<<<grid, c1m::THREADS, c1m::SMEM, st>>>(c->layers[L1B].tm, a);
+    if (c->conv1_mode == 2 && c->pair_conv1) {  // CTA pairs: every pair works on two items at a time
+      const int pairs = (a.n_items + 1) / 2 < c->num_sms / 2 ? (a.n_items + 1) / 2 : c->num_sms / 2;
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = dim3(2 * pairs); lc.blockDim = dim3(c1m::THREADS); lc.dynamicSmemBytes = c1m::SMEM; lc.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      lc.attrs = at; lc.numAttrs = 1;
+      CU_OK(c, cudaLaunchKernelEx(&lc, conv1ab_mma_kernel<true>, c->layers[L1B].tm_half, a));
+    } else if (c->conv1_mode == 2) conv1ab_mma_kernel<false><<<grid, c1m::THREADS, c1m::SMEM, st>>>(c->layers[L1B].tm, a);
     else conv1ab_kernel<<<grid, c1ab::THREADS, c1ab::SMEM, st>>>(c->layers[L1B].tm, a);
     c->launches++;
     CU_OK(c, cudaGetLastError());
@@ -751,6 +761,8 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
     const char *pr = getenv("SPFE_PAIR");
     c->pair = !(pr && pr[0] == '0');
     c->pair_conv2a = pr && pr[0] == '2';
+    const char *p1 = getenv("SPFE_PAIR_CONV1");
+    c->pair_conv1 = c->pair && p1 && p1[0] == '1';
     const char *cf = getenv("SPFE_COV_FORCE");
     c->cov_force = cf ? atoi(cf) : 0;
   }
@@ -767,7 +779,8 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
       nms_smem_max = c->cells * 7;
     }
     CU_OK(c, cudaFuncSetAttribute(conv1ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1ab::SMEM));
-    CU_OK(c, cudaFuncSetAttribute(conv1ab_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1m::SMEM));
+    CU_OK(c, cudaFuncSetAttribute(conv1ab_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c1m::SMEM));
+    CU_OK(c, cudaFuncSetAttribute(conv1ab_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c1m::SMEM));
     CU_OK(c, cudaFuncSetAttribute(cov_flood_kernel<COV_S_WIN, COV_S_QCAP, COV_S_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_S_SMEM));
     CU_OK(c, cudaFuncSetAttribute(cov_flood_kernel<COV_WIN, COV_QCAP, COV_B_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_B_SMEM));
     CU_OK(c, cudaFuncSetAttribute(cov_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_S_SMEM));
