@@ -26,13 +26,21 @@
 //
 // PAIR: two CTAs of a cluster run every MMA together (cta_group::2, see conv_tc.cuh / ptx.cuh): each rank keeps its own
 // item (patch, im2col, slab, accumulators, epilogues) but only half of the conv1b and conv1a weights (32 couts); the
-// leader issues all MMAs, so every "ready" barrier lives in the leader and is armed by both ranks (one arrival per warp,
-// cluster-scope release where shared-memory data is handed over), while the "done" barriers are signalled in both CTAs
-// by multicast commits.
+// leader issues all MMAs, so every "ready" barrier lives in the leader and is armed by both ranks (one arrival per
+// warp), while the "done" barriers are signalled in both CTAs by multicast commits.
 #pragma once
 #include "conv1ab.cuh"
 
 namespace spfe {
+
+#ifdef SPFE_C1M_TRACE
+// [n][0] MMA warp: c1a(n) issued, [1] warp 8: c_full(n) seen, [2] s_empty seen, [3] work done, [4] arrived,
+// [5] MMA warp: e1_done(n) seen, [6] c1b(n) issued; [7] peer CTA warp 8: work duration, [8] peer: c_full wait, [9] peer arrive duration
+__device__ long long g_c1m_trace[16][10];
+#define C1M_T(n, k) do { if ((n) >= 200 && (n) < 216 && blockIdx.x == 0 && lane == 0) g_c1m_trace[(n) - 200][k] = clock64(); } while (0)
+#else
+#define C1M_T(n, k) do { } while (0)
+#endif
 
 namespace c1m {
 constexpr int PW = c1ab::PW, HALO = c1ab::HALO, STAGE = c1ab::STAGE, WBLK = c1ab::WBLK, WBYTES = c1ab::WBYTES;
@@ -153,15 +161,15 @@ conv1ab_mma_kernel(const __grid_constant__ CUtensorMap tmW, const Conv1abArgs p)
     y0 = (t % p.tiles_y) * 16;
     b = t / p.tiles_y;
   };
-  // "ready" barriers live in the leader of a pair: one arrival per warp; `data`: shared-memory contents are handed over
-  // (cluster-scope release; only for warps without global stores in flight, see ptx.cuh)
-  auto arrive_ready = [&](uint32_t bar, bool data) {
+  // "ready" barriers live in the leader of a pair: one remote arrival per warp.  Where shared-memory contents are
+  // handed over (A1, slab), the writers run fence.proxy.async first and the arrival is the plain CTA-scope-release one,
+  // exactly CUTLASS's 2-SM hand-off (ClusterBarrier::arrive after fence_view_async_shared): each rank's tensor core reads
+  // its OWN shared memory, written by its own warps before the arrival left the SM.  A cluster-scope release here costs
+  // 900 - 1800 cycles per arrival (traced) and puts the conv1a chain back on the critical path.
+  auto arrive_ready = [&](uint32_t bar) {
     if constexpr (PAIR) {
       __syncwarp();
-      if (lane == 0) {
-        if (data) mbar_arrive_cluster_release(mapa_shared(bar, 0));
-        else mbar_arrive_cluster(mapa_shared(bar, 0));
-      }
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(bar, 0));
     } else {
       mbar_arrive(bar);
     }
@@ -179,10 +187,7 @@ conv1ab_mma_kernel(const __grid_constant__ CUtensorMap tmW, const Conv1abArgs p)
         if constexpr (PAIR) umma_commit_pair(bar);
         else umma_commit(bar);
       };
-      auto wait_ready = [&](uint32_t bar, uint32_t parity) {
-        if constexpr (PAIR) mbar_wait_cluster(bar, parity);
-        else mbar_wait(bar, parity);
-      };
+      auto wait_ready = [&](uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); };
       const uint32_t sStage_u = smem_u32(sStage), sW_u = smem_u32(sW), sA1_u = smem_u32(sA1), sW1_u = smem_u32(sW1);
       auto issue_c1a = [&](uint32_t n) {  // conv1a of the n-th item: 3 M-tiles x (hi, lo); its accumulators are free (e1_done(n-1))
         const uint32_t buf = n & 1;
@@ -200,12 +205,14 @@ conv1ab_mma_kernel(const __grid_constant__ CUtensorMap tmW, const Conv1abArgs p)
           commit(c_full);
         }
         __syncwarp();
+        C1M_T(static_cast<int>(n), 0);
       };
       mbar_wait(w_full, 0);
       if (n_mine > 0) issue_c1a(0);
       for (int n = 0; n < n_mine; n++) {
         const uint32_t st = n & 1, ph = (n >> 1) & 1;
         wait_ready(e1_done(st), ph);  // slab of item n written, conv1a accumulators free again
+        C1M_T(n, 5);
         if (n + 1 < n_mine) issue_c1a(n + 1);
         wait_ready(t_empty(st), ph ^ 1);
         tc_fence_after();
@@ -227,6 +234,7 @@ conv1ab_mma_kernel(const __grid_constant__ CUtensorMap tmW, const Conv1abArgs p)
           commit(t_full(st));
         }
         __syncwarp();
+        C1M_T(n, 6);
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -245,7 +253,7 @@ conv1ab_mma_kernel(const __grid_constant__ CUtensorMap tmW, const Conv1abArgs p)
         epilogue_relu_pool<64>(taddr, s_bias, lane, hl, wl, x0 + h * 8, y0, b, 0, p.H, p.W, 64, p.out);
       }
       tc_fence_before();
-      arrive_ready(t_empty(st), false);  // (these warps have global stores in flight: no cluster-scope release)
+      arrive_ready(t_empty(st));
     }
   } else if (warp >= 8) {
     // ------------------------------------------------ conv1a epilogue, channels 32 * half .. +32:
@@ -255,8 +263,16 @@ conv1ab_mma_kernel(const __grid_constant__ CUtensorMap tmW, const Conv1abArgs p)
     const uint32_t sStage_u = smem_u32(sStage);
     for (int n = 0; n < n_mine; n++) {
       const uint32_t st = n & 1, ph = (n >> 1) & 1;
+#ifdef SPFE_C1M_TRACE
+      const long long pt0 = clock64();
+#endif
       mbar_wait(c_full, n & 1);
+      if (warp == 8) C1M_T(n, 1);
+#ifdef SPFE_C1M_TRACE
+      const long long pt1 = clock64();
+#endif
       mbar_wait(s_empty(st), ph ^ 1);  // the conv1b MMAs that read this slab two items ago are done
+      if (warp == 8) C1M_T(n, 2);
       tc_fence_after();
       const uint32_t stage_u = sStage_u + st * STAGE;
 #pragma unroll 1
@@ -286,7 +302,17 @@ conv1ab_mma_kernel(const __grid_constant__ CUtensorMap tmW, const Conv1abArgs p)
       }
       tc_fence_before();
       fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
-      arrive_ready(e1_done(st), true);
+      if (warp == 8) C1M_T(n, 3);
+#ifdef SPFE_C1M_TRACE
+      const long long pt2 = clock64();
+#endif
+      arrive_ready(e1_done(st));
+      if (warp == 8) C1M_T(n, 4);
+#ifdef SPFE_C1M_TRACE
+      if (blockIdx.x == 1 && warp == 8 && lane == 0 && n >= 200 && n < 216) {
+        g_c1m_trace[n - 200][7] = pt2 - pt1; g_c1m_trace[n - 200][8] = pt1 - pt0; g_c1m_trace[n - 200][9] = clock64() - pt2;
+      }
+#endif
     }
   } else {
     // ------------------------------------------------ im2col producers (warps 0, 2, 3): u8 patch -> A1 rows (9 taps, 255, zeros)
@@ -322,6 +348,11 @@ conv1ab_mma_kernel(const __grid_constant__ CUtensorMap tmW, const Conv1abArgs p)
       for (int k = 0; k < PER_T; k++)
         if (ptid + k * NPROD < PATCH * PATCH) s_patch[buf][ptid + k * NPROD] = __ushort2half_rn(static_cast<unsigned short>(raw[k]));
       named_bar_sync(1, NPROD);
+      if (n + 1 < n_mine) {  // next item's patch: in flight during the im2col below, published by the next iteration
+        const int next = item_of(n + 1);
+#pragma unroll
+        for (int k = 0; k < PER_T; k++) raw[k] = load_patch(next, ptid + k * NPROD);
+      }
       const unsigned short *patch = reinterpret_cast<const unsigned short *>(s_patch[buf]);
       mbar_wait(a_empty(buf), ph ^ 1);  // the conv1a MMAs that read this buffer two items ago are done
       for (int q = ptid; q < NPIX; q += NPROD) {
@@ -343,13 +374,7 @@ conv1ab_mma_kernel(const __grid_constant__ CUtensorMap tmW, const Conv1abArgs p)
         st_shared_v4(row_addr(buf, q) + 128, c1);
       }
       fence_proxy_async_smem();
-      arrive_ready(a_full(buf), true);
-      // next item's patch: issued after the arrival (whose cluster-scope release would otherwise wait for these loads)
-      if (n + 1 < n_mine) {
-        const int next = item_of(n + 1);
-#pragma unroll
-        for (int k = 0; k < PER_T; k++) raw[k] = load_patch(next, ptid + k * NPROD);
-      }
+      arrive_ready(a_full(buf));
     }
   }
 

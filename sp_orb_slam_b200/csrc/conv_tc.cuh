@@ -114,42 +114,54 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 }
 
 // Epilogue: bias + ReLU + 2x2 max-pool of one 8x16-pixel accumulator tile (lane = h*8 + w), fp16 NHWC store.
-// The pool partners are lane^1 (x) and lane^8 (y), both inside the warp; each of the four lanes of a 2x2 group
-// stores one 8-channel slice of every 32-channel chunk.
+// The pool partners are lane^1 (x) and lane^8 (y), both inside the warp.  The 2x2 maximum is a reduce-scatter: every
+// 32-channel chunk is first halved with the x partner (each lane keeps the 16 channels whose bit 3 equals its x parity
+// and receives the partner's values for them), then halved again with the y partner (bit 4 / y parity), so each of the
+// four lanes of a 2x2 group ends up with the 8-channel slice it stores -- 24 shuffles per chunk instead of 64 (this
+// epilogue, not the MMAs, paced the pooled 64 -> 64 layers).  max is exact, so the result does not depend on the order.
+// All TMEM loads of the tile are issued before the first wait.
 template <int N>
 __device__ __forceinline__ void epilogue_relu_pool(uint32_t taddr, const float *bias, int lane, int hl, int wl, int x0,
                                                    int y0, int b, int nb, int H, int W, int cout_stride, __half *out) {
+  static_assert(N == 64 || N == 128, "pooled layers have 64 or 128 output channels");
   const int Ho = H >> 1, Wo = W >> 1;
   const int yo = (y0 >> 1) + (hl >> 1), xo = (x0 >> 1) + (wl >> 1);
   const bool valid = (yo < Ho) && (xo < Wo);
+  const bool px = lane & 1, py = (lane >> 3) & 1;
   const int q = (lane & 1) | (((lane >> 3) & 1) << 1);
   __half *dst = out + ((static_cast<size_t>(b) * Ho + yo) * Wo + xo) * cout_stride + nb * N + q * 8;
 #pragma unroll 1
-  for (int c0 = 0; c0 < N; c0 += 32) {
-    float v[32];
+  for (int c0 = 0; c0 < N; c0 += 64) {
+    float v[64];
     tmem_ld16(taddr + c0, v);
     tmem_ld16(taddr + c0 + 16, v + 16);
+    tmem_ld16(taddr + c0 + 32, v + 32);
+    tmem_ld16(taddr + c0 + 48, v + 48);
     tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; j++) {
-      v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
-      v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 8));
-    }
-    float w[8];
+    for (int ch = 0; ch < 64; ch += 32) {
+      float u[16];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const float lo = (q & 1) ? v[8 + j] : v[j];
-      const float hi = (q & 1) ? v[24 + j] : v[16 + j];
-      w[j] = (q & 2) ? hi : lo;
-      w[j] = fmaxf(w[j] + bias[c0 + q * 8 + j], 0.f);
-    }
-    if (valid) {
-      uint4 o;
-      o.x = pack_h2(w[0], w[1]);
-      o.y = pack_h2(w[2], w[3]);
-      o.z = pack_h2(w[4], w[5]);
-      o.w = pack_h2(w[6], w[7]);
-      *reinterpret_cast<uint4 *>(dst + c0) = o;
+      for (int j = 0; j < 16; j++) {  // x partner: channels (j >> 3) * 16 + px * 8 + (j & 7) of this chunk
+        const int ca = ch + (j >> 3) * 16 + (j & 7), cb = ca + 8;
+        const float keep = px ? v[cb] : v[ca], send = px ? v[ca] : v[cb];
+        u[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+      }
+      float w[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {   // y partner: channels py * 16 + px * 8 + j == q * 8 + j
+        const float keep = py ? u[8 + j] : u[j], send = py ? u[j] : u[8 + j];
+        w[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+        w[j] = fmaxf(w[j] + bias[c0 + ch + q * 8 + j], 0.f);
+      }
+      if (valid) {
+        uint4 o;
+        o.x = pack_h2(w[0], w[1]);
+        o.y = pack_h2(w[2], w[3]);
+        o.z = pack_h2(w[4], w[5]);
+        o.w = pack_h2(w[6], w[7]);
+        *reinterpret_cast<uint4 *>(dst + c0 + ch) = o;
+      }
     }
   }
 }

@@ -135,7 +135,7 @@ struct spfe_ctx {
   // (SPFE_CONV1=ffma); 0 = two kernels (SPFE_CONV1=unfused or SPFE_FUSED_CONV1=0; materialises conv1a for inspection)
   bool pair = true;   // SPFE_PAIR=0: single-CTA MMAs for the 64 -> 64 layers as well
   bool pair_conv2a = false;  // SPFE_PAIR=2: conv2a as pairs too
-  bool pair_conv1 = false;   // SPFE_PAIR_CONV1=1: the fused conv1a+1b kernel as pairs
+  bool pair_conv1 = true;    // SPFE_PAIR_CONV1=0: the fused conv1a+1b kernel single-CTA
   int cov_force = 0;  // SPFE_COV_FORCE (test hook): push floods down the big / sequential fallback paths
   bool pdl = false;  // SPFE_PDL=1: programmatic dependent launch of the tensor-core kernels (measured: no gain, the board is power-capped)
   int conv1_mode = 2;
@@ -498,6 +498,9 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
 // C ABI
 // ============================================================================
 extern "C" {
+#ifdef SPFE_C1M_TRACE
+void *spfe_c1m_trace_ptr = nullptr;  // device address of g_c1m_trace (tools/c1m_trace.py)
+#endif
 
 void spfe_default_config(spfe_config *cfg, int32_t height, int32_t width, int32_t max_keypoints) {
   if (!cfg) return;
@@ -725,6 +728,9 @@ static int create_impl(spfe_ctx *c) {
   if ((rc = host_alloc(c, &c->h_match_t, static_cast<size_t>(c->match_cap) * 256))) return rc;
   if ((rc = host_alloc(c, &c->h_match_idx, c->match_cap + 2))) return rc;
   if ((rc = host_alloc(c, &c->h_match_dist, c->match_cap))) return rc;
+#ifdef SPFE_C1M_TRACE
+  CU_OK(c, cudaGetSymbolAddress(&spfe_c1m_trace_ptr, g_c1m_trace));
+#endif
   CU_OK(c, cudaDeviceSynchronize());
   return SPFE_OK;
 }
@@ -762,7 +768,7 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
     c->pair = !(pr && pr[0] == '0');
     c->pair_conv2a = pr && pr[0] == '2';
     const char *p1 = getenv("SPFE_PAIR_CONV1");
-    c->pair_conv1 = c->pair && p1 && p1[0] == '1';
+    c->pair_conv1 = c->pair && !(p1 && p1[0] == '0');
     const char *cf = getenv("SPFE_COV_FORCE");
     c->cov_force = cf ? atoi(cf) : 0;
   }
