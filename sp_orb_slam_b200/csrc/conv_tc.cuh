@@ -434,17 +434,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld16(taddr + c0, v);
           tmem_ld16(taddr + c0 + 16, v + 16);
           tmem_ld_wait();
-          if (valid) {
+          if (valid) {  // 64 bytes of this pixel: two 32-byte stores (full sectors)
 #pragma unroll
-            for (int g = 0; g < 4; g++) {
-              uint4 o;
-              uint32_t *ow = reinterpret_cast<uint32_t *>(&o);
+            for (int g = 0; g < 4; g += 2) {
+              uint4 o[2];
+              uint32_t *ow = reinterpret_cast<uint32_t *>(o);
 #pragma unroll
-              for (int j = 0; j < 4; j++) {
+              for (int j = 0; j < 8; j++) {
                 const int c = g * 8 + j * 2;
                 ow[j] = pack_h2(fmaxf(v[c] + bias[c0 + c], 0.f), fmaxf(v[c + 1] + bias[c0 + c + 1], 0.f));
               }
-              *reinterpret_cast<uint4 *>(dst + c0 + g * 8) = o;
+              st_global_v8(dst + c0 + g * 8, o[0], o[1]);
             }
           }
         }
@@ -515,15 +515,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld_wait();
           if (valid) {
 #pragma unroll
-            for (int g = 0; g < 4; g++) {
-              uint4 o;
-              uint32_t *ow = reinterpret_cast<uint32_t *>(&o);
+            for (int g = 0; g < 4; g += 2) {
+              uint4 o[2];
+              uint32_t *ow = reinterpret_cast<uint32_t *>(o);
 #pragma unroll
-              for (int j = 0; j < 4; j++) {
+              for (int j = 0; j < 8; j++) {
                 const int c = g * 8 + j * 2;
                 ow[j] = pack_h2((v[c] + bias[c0 + c]) * inv, (v[c + 1] + bias[c0 + c + 1]) * inv);
               }
-              *reinterpret_cast<uint4 *>(dst + c0 + g * 8) = o;
+              st_global_v8(dst + c0 + g * 8, o[0], o[1]);
             }
           }
         }

@@ -33,6 +33,13 @@ __device__ __forceinline__ void ffma2(float2 &d, const float2 &a, const float2 &
   d = *reinterpret_cast<float2 *>(&D);
 }
 
+// 32-byte global store (sm_100): one full sector per thread and instruction.
+__device__ __forceinline__ void st_global_v8(void *ptr, const uint4 &a, const uint4 &b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch
 // A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
 // stream still runs; griddep_wait() blocks until that predecessor has completed and its writes are visible.

@@ -134,7 +134,7 @@ struct spfe_ctx {
   // conv1a + conv1b: 2 = one kernel, both layers on the tensor core (default); 1 = one kernel, conv1a on the CUDA cores
   // (SPFE_CONV1=ffma); 0 = two kernels (SPFE_CONV1=unfused or SPFE_FUSED_CONV1=0; materialises conv1a for inspection)
   bool pair = true;   // SPFE_PAIR=0: single-CTA MMAs for the 64 -> 64 layers as well
-  bool pair_conv2a = false;  // SPFE_PAIR=2: conv2a as pairs too
+  bool pair_conv2a = true;   // SPFE_PAIR_CONV2A=0: conv2a single-CTA
   bool pair_conv1 = true;    // SPFE_PAIR_CONV1=0: the fused conv1a+1b kernel single-CTA
   int cov_force = 0;  // SPFE_COV_FORCE (test hook): push floods down the big / sequential fallback paths
   bool pdl = false;  // SPFE_PDL=1: programmatic dependent launch of the tensor-core kernels (measured: no gain, the board is power-capped)
@@ -372,7 +372,6 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     if ((rc = launch_conv<CfgC64P>(c, st, s.tmA[L1B], c->layers[L1B], conv_args(H, W, 1, 64, s.a1b)))) return rc;
     mark("conv1b", stage_flop(L1B, H, W), (128.0 + 32.0) * H * W * B);
   }
-  // conv2a stays single-CTA: its epilogue (full-resolution 128-byte stores), not the MMAs, paces it (pairs measured 6 % slower)
   if (c->pair_conv2a) rc = launch_conv<CfgC64X>(c, st, s.tmA[L2A], c->layers[L2A], conv_args(H / 2, W / 2, 1, 64, s.a2a));
   else rc = launch_conv<CfgC64>(c, st, s.tmA[L2A], c->layers[L2A], conv_args(H / 2, W / 2, 1, 64, s.a2a));
   if (rc) return rc;
@@ -766,7 +765,8 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
     c->pdl = pd && pd[0] == '1';
     const char *pr = getenv("SPFE_PAIR");
     c->pair = !(pr && pr[0] == '0');
-    c->pair_conv2a = pr && pr[0] == '2';
+    const char *p2 = getenv("SPFE_PAIR_CONV2A");
+    c->pair_conv2a = c->pair && !(p2 && p2[0] == '0');
     const char *p1 = getenv("SPFE_PAIR_CONV1");
     c->pair_conv1 = c->pair && !(p1 && p1[0] == '0');
     const char *cf = getenv("SPFE_COV_FORCE");
