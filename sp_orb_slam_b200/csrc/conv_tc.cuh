@@ -63,7 +63,7 @@ struct ConvCfg {
   // MMA drop from A + B to A + B/2 -- the limiter of the N = 64 layers (tools/umma2_rate.cu).  The leader (rank 0)
   // issues the MMAs for both; items 2q and 2q+1 go to ranks 0 and 1 of pair q mod (grid / 2).
   static constexpr bool PAIR = PAIR_;
-  static_assert(!PAIR_ || (WRES_ && CB_ == 1 && N_ % 32 == 0), "pairs: resident weights, one channel block");
+  static_assert(!PAIR_ || (N_ % 32 == 0 && EPI_ != EPI_TOP2), "pairs: convolution layers with N a multiple of 32");
   // EG = epilogue warp groups (4 warps each).  With 2, group g drains accumulator set g, so the epilogues of two
   // consecutive items run side by side: for the layers whose epilogue (softmax / log / norm), not the MMAs, paces the CTA.
   static constexpr int EG = EG_, THREADS = 128 + 128 * EG_;
@@ -219,13 +219,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   griddep_launch_dependents();
   const uint32_t rank = Cfg::PAIR ? cluster_ctarank() : 0u;
   // Work distribution.  Plain: CTA b takes items b, b + grid, ...  Pair: pair j = b / 2 takes item pairs j, j + grid / 2, ...;
-  // rank r works on item 2q + r (clamped: with an odd item count the last item is computed by both ranks, which write
+  // rank r works on tile 2q + r (clamped: with an odd tile count the last tile is computed by both ranks, which write
   // identical results).
+  // With several cout blocks (NB > 1) the two ranks take the same block nb of two neighbouring tiles, so that they share B.
   const int q_first = Cfg::PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int q_step = Cfg::PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const int q_end = Cfg::PAIR ? (p.n_items + 1) >> 1 : p.n_items;
-  auto item_of = [&](int q) { return Cfg::PAIR ? min(2 * q + static_cast<int>(rank), p.n_items - 1) : q; };
-  if constexpr (Cfg::PAIR) {  // each rank loads its half of the resident weights; nobody starts before both halves are in
+  const int n_tiles = p.n_items / NB;
+  const int q_end = Cfg::PAIR ? ((n_tiles + 1) >> 1) * NB : p.n_items;
+  auto item_of = [&](int q) {
+    if constexpr (!Cfg::PAIR) return q;
+    const int tq = q / NB, nb = q - tq * NB;
+    return min(2 * tq + static_cast<int>(rank), n_tiles - 1) * NB + nb;
+  };
+  if constexpr (Cfg::PAIR && WRES) {  // each rank loads its half of the resident weights; nobody starts before both halves are in
     if (warp == 3) {
       if (lane == 0) {
         mbar_expect_tx(w_full, Cfg::NWB * Cfg::BBLK_BYTES);
@@ -278,7 +284,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 3) {
     // ------------------------------------------------ weight producer
-    if (lane == 0 && !Cfg::PAIR) {
+    if (lane == 0 && !(Cfg::PAIR && WRES)) {
       if (WRES) {
         mbar_expect_tx(w_full, Cfg::NWB * Cfg::BBLK_BYTES);
         for (int wb = 0; wb < Cfg::NWB; wb++)
@@ -286,15 +292,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       } else {
         if constexpr (Cfg::MATCH) griddep_wait();  // the B operand is the previous kernel's output here, not constant weights
         uint32_t jt = 0;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {  // (never a pair: pairs keep their weights resident)
-          const int nb = item % NB;
+        for (int q = q_first; q < q_end; q += q_step) {
+          const int item = item_of(q);
+          const int nb = item % NB;  // (a pair's two items share nb: NB divides 2 or is 1, see the host-side check)
           for (int cb = 0; cb < CB; cb++)
             for (int dx = 0; dx < NDX; dx++)
               for (int dy = 0; dy < NDY; dy++, jt++) {
                 const int s = jt % SB;
                 mbar_wait(b_empty(s), ((jt / SB) & 1) ^ 1);
-                mbar_expect_tx(b_full(s), Cfg::BBLK_BYTES);
                 const int wb = (dy * NDX + dx) * CB + cb;
+                if constexpr (Cfg::PAIR) {  // each rank streams its N/2 rows of the block; both halves complete on the leader's barrier
+                  if (rank == 0) mbar_expect_tx(b_full(s), 2 * Cfg::BBLK_BYTES);
+                  tma_load_2d_pair(smem_u32(sB + s * Cfg::BBLK_BYTES), &tmW, mapa_shared(b_full(s), 0), 0,
+                                   (wb * NB + nb) * N + static_cast<int>(rank) * (N / 2));
+                  continue;
+                }
+                mbar_expect_tx(b_full(s), Cfg::BBLK_BYTES);
                 if constexpr (Cfg::MATCH) {
                   const int t = item / NB / p.m_tiles;  // B operand = descriptor rows of the other slot of the pair
                   const int bslot = (t >> 1) + (t & 1);
@@ -387,13 +400,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                   for (int h = 0; h < HALVES; h++)
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                      umma_f16(d_tmem + h * Cfg::ACC_STRIDE, a0 + a_off(dy, dx, h, k), b0 + 2 * k, idesc, (cb | dx | dy | k) ? 1u : 0u);
-                  umma_commit(b_empty(sb[d]));
+                    for (int k = 0; k < 4; k++) {
+                      if constexpr (Cfg::PAIR)
+                        umma_f16_pair(d_tmem + h * Cfg::ACC_STRIDE, a0 + a_off(dy, dx, h, k), b0 + 2 * k, idesc, (cb | dx | dy | k) ? 1u : 0u);
+                      else
+                        umma_f16(d_tmem + h * Cfg::ACC_STRIDE, a0 + a_off(dy, dx, h, k), b0 + 2 * k, idesc, (cb | dx | dy | k) ? 1u : 0u);
+                    }
+                  if constexpr (Cfg::PAIR) umma_commit_pair(b_empty(sb[d])); else umma_commit(b_empty(sb[d]));
                 }
                 if (dx == NDX - 1 && g + GDY >= NDY) {
-                  umma_commit(a_empty(s));
-                  if (cb == CB - 1) umma_commit(t_full(acc));
+                  if constexpr (Cfg::PAIR) umma_commit_pair(a_empty(s)); else umma_commit(a_empty(s));
+                  if (cb == CB - 1) { if constexpr (Cfg::PAIR) umma_commit_pair(t_full(acc)); else umma_commit(t_full(acc)); }
                 }
               }
               __syncwarp();

@@ -53,6 +53,12 @@ using CfgC3a = ConvCfg<9, 1, 128, EPI_RELU, true, 2, 1, 1>;         // conv3a   
 using CfgC128 = ConvCfg<9, 2, 128, EPI_RELU, false, 2, 6, 2>;       // conv4a, conv4b  slab 54 KB x2 + 6 x 16 KB weights
 using CfgC128P = ConvCfg<9, 2, 128, EPI_RELU_POOL, false, 2, 6, 2>; // conv3b
 using CfgHeads = ConvCfg<9, 2, 256, EPI_RELU, false, 2, 4, 1>;      // convPa || convDa (NB = 2), N = 256: single tiles
+// CTA-pair variants of the streamed-weight layers: each rank streams half of every weight block (half the L2 -> SM
+// traffic that bounds these layers) and conv3a keeps half of its weights, which makes room for tile pairs
+using CfgC3aX = ConvCfg<9, 1, 128, EPI_RELU, true, 2, 1, 2, 1, true>;
+using CfgC128X = ConvCfg<9, 2, 128, EPI_RELU, false, 2, 9, 2, 1, true>;
+using CfgC128PX = ConvCfg<9, 2, 128, EPI_RELU_POOL, false, 2, 9, 2, 1, true>;
+using CfgHeadsX = ConvCfg<9, 2, 256, EPI_RELU, false, 2, 8, 1, 1, true>;
 using CfgPb = ConvCfg<1, 4, 80, EPI_DETECT, true, 4, 1, 1, 2>;  // convPb + detector head   (epilogue-bound: two epilogue groups)
 using CfgDb = ConvCfg<1, 4, 256, EPI_L2NORM, true, 4, 1, 1, 2>; // convDb + L2 norm
 using CfgMatch = ConvCfg<1, 4, 256, EPI_TOP2, false, 4, 4, 1, 2>;  // descriptor matching: Q.T^T + top-2 per 256-column block
@@ -95,6 +101,7 @@ struct Slot {
   int16_t *occ = nullptr;
   unsigned long long *scratch = nullptr;
   CUtensorMap tmA[NLAYERS];
+  CUtensorMap tmA3aX;  // conv3a as a CTA pair works on tile pairs (slab of 24 pixels per row instead of 16)
   MatchScratch match;
   // SPFE_MATCH_PREV: descriptor "slots": slot 0 = last frame of the previous batch (carry), slot z+1 = frame z
   float *desc_all = nullptr;    // [Bm+1][cap][256]  (desc = desc_all + cap*256)
@@ -135,6 +142,7 @@ struct spfe_ctx {
   // (SPFE_CONV1=ffma); 0 = two kernels (SPFE_CONV1=unfused or SPFE_FUSED_CONV1=0; materialises conv1a for inspection)
   bool pair = true;   // SPFE_PAIR=0: single-CTA MMAs for the 64 -> 64 layers as well
   bool pair_conv2a = true;   // SPFE_PAIR_CONV2A=0: conv2a single-CTA
+  bool pair_stream = true;   // SPFE_PAIR_STREAM=0: conv3a .. convPa|Da single-CTA
   bool pair_conv1 = true;    // SPFE_PAIR_CONV1=0: the fused conv1a+1b kernel single-CTA
   int cov_force = 0;  // SPFE_COV_FORCE (test hook): push floods down the big / sequential fallback paths
   bool pdl = false;  // SPFE_PDL=1: programmatic dependent launch of the tensor-core kernels (measured: no gain, the board is power-capped)
@@ -279,7 +287,8 @@ int launch_conv(spfe_ctx *c, cudaStream_t st, const CUtensorMap &tmA, const Laye
   if (Cfg::MATCH) a.n_items = a.B * 2 * a.m_tiles * a.NB;
   int grid = a.n_items < c->num_sms ? a.n_items : c->num_sms;
   if (Cfg::PAIR) {  // clusters of two CTAs; every pair works on two items at a time
-    const int pairs = (a.n_items + 1) / 2 < c->num_sms / 2 ? (a.n_items + 1) / 2 : c->num_sms / 2;
+    const int pair_items = (a.n_items / a.NB + 1) / 2 * a.NB;
+    const int pairs = pair_items < c->num_sms / 2 ? pair_items : c->num_sms / 2;
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(2 * pairs); lc.blockDim = dim3(Cfg::THREADS); lc.dynamicSmemBytes = smem; lc.stream = st;
     cudaLaunchAttribute at[1];
@@ -380,15 +389,25 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
   else rc = launch_conv<CfgC64P>(c, st, s.tmA[L2B], c->layers[L2B], conv_args(H / 2, W / 2, 1, 64, s.a2b));
   if (rc) return rc;
   mark("conv2b", stage_flop(L2B, H / 2, W / 2), 160.0 * (H / 2) * (W / 2) * B);
-  if ((rc = launch_conv<CfgC3a>(c, st, s.tmA[L3A], c->layers[L3A], conv_args(H / 4, W / 4, 1, 128, s.a3a)))) return rc;
+  if (c->pair_stream) rc = launch_conv<CfgC3aX>(c, st, s.tmA3aX, c->layers[L3A], conv_args(H / 4, W / 4, 1, 128, s.a3a));
+  else rc = launch_conv<CfgC3a>(c, st, s.tmA[L3A], c->layers[L3A], conv_args(H / 4, W / 4, 1, 128, s.a3a));
+  if (rc) return rc;
   mark("conv3a", stage_flop(L3A, H / 4, W / 4), 384.0 * (H / 4) * (W / 4) * B);
-  if ((rc = launch_conv<CfgC128P>(c, st, s.tmA[L3B], c->layers[L3B], conv_args(H / 4, W / 4, 1, 128, s.a3b)))) return rc;
+  if (c->pair_stream) rc = launch_conv<CfgC128PX>(c, st, s.tmA[L3B], c->layers[L3B], conv_args(H / 4, W / 4, 1, 128, s.a3b));
+  else rc = launch_conv<CfgC128P>(c, st, s.tmA[L3B], c->layers[L3B], conv_args(H / 4, W / 4, 1, 128, s.a3b));
+  if (rc) return rc;
   mark("conv3b", stage_flop(L3B, H / 4, W / 4), 320.0 * (H / 4) * (W / 4) * B);
-  if ((rc = launch_conv<CfgC128>(c, st, s.tmA[L4A], c->layers[L4A], conv_args(hc, wc, 1, 128, s.a4a)))) return rc;
+  if (c->pair_stream) rc = launch_conv<CfgC128X>(c, st, s.tmA[L4A], c->layers[L4A], conv_args(hc, wc, 1, 128, s.a4a));
+  else rc = launch_conv<CfgC128>(c, st, s.tmA[L4A], c->layers[L4A], conv_args(hc, wc, 1, 128, s.a4a));
+  if (rc) return rc;
   mark("conv4a", stage_flop(L4A, hc, wc), 512.0 * hc * wc * B);
-  if ((rc = launch_conv<CfgC128>(c, st, s.tmA[L4B], c->layers[L4B], conv_args(hc, wc, 1, 128, s.a4b)))) return rc;
+  if (c->pair_stream) rc = launch_conv<CfgC128X>(c, st, s.tmA[L4B], c->layers[L4B], conv_args(hc, wc, 1, 128, s.a4b));
+  else rc = launch_conv<CfgC128>(c, st, s.tmA[L4B], c->layers[L4B], conv_args(hc, wc, 1, 128, s.a4b));
+  if (rc) return rc;
   mark("conv4b", stage_flop(L4B, hc, wc), 512.0 * hc * wc * B);
-  if ((rc = launch_conv<CfgHeads>(c, st, s.tmA[LHEADS], c->layers[LHEADS], conv_args(hc, wc, 2, 512, s.heads)))) return rc;
+  if (c->pair_stream) rc = launch_conv<CfgHeadsX>(c, st, s.tmA[LHEADS], c->layers[LHEADS], conv_args(hc, wc, 2, 512, s.heads));
+  else rc = launch_conv<CfgHeads>(c, st, s.tmA[LHEADS], c->layers[LHEADS], conv_args(hc, wc, 2, 512, s.heads));
+  if (rc) return rc;
   mark("convPa|Da", stage_flop(LHEADS, hc, wc), (256.0 + 1024.0) * hc * wc * B);
   {
     ConvArgs a = conv_args(hc, wc, 1, 0, nullptr);
@@ -705,6 +724,7 @@ static int create_impl(spfe_ctx *c) {
     if ((rc = make_act_map(c, &s.tmA[L2A], s.a1b, 64, W / 2, H / 2, Bm, 18, CfgC64::PW))) return rc;
     if ((rc = make_act_map(c, &s.tmA[L2B], s.a2a, 64, W / 2, H / 2, Bm, 18, CfgC64P::PW))) return rc;
     if ((rc = make_act_map(c, &s.tmA[L3A], s.a2b, 64, W / 4, H / 4, Bm, 18, CfgC3a::PW))) return rc;
+    if ((rc = make_act_map(c, &s.tmA3aX, s.a2b, 64, W / 4, H / 4, Bm, 18, CfgC3aX::PW))) return rc;
     if ((rc = make_act_map(c, &s.tmA[L3B], s.a3a, 128, W / 4, H / 4, Bm, 18, CfgC128P::PW))) return rc;
     if ((rc = make_act_map(c, &s.tmA[L4A], s.a3b, 128, wc, hc, Bm, 18, CfgC128::PW))) return rc;
     if ((rc = make_act_map(c, &s.tmA[L4B], s.a4a, 128, wc, hc, Bm, 18, CfgC128::PW))) return rc;
@@ -767,6 +787,8 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
     c->pair = !(pr && pr[0] == '0');
     const char *p2 = getenv("SPFE_PAIR_CONV2A");
     c->pair_conv2a = c->pair && !(p2 && p2[0] == '0');
+    const char *p3 = getenv("SPFE_PAIR_STREAM");
+    c->pair_stream = c->pair && !(p3 && p3[0] == '0');
     const char *p1 = getenv("SPFE_PAIR_CONV1");
     c->pair_conv1 = c->pair && !(p1 && p1[0] == '0');
     const char *cf = getenv("SPFE_COV_FORCE");
