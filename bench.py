@@ -250,7 +250,8 @@ def main():
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         if (H, W, B) == (480, 752, tj.get("frames_per_launch")):
-            traffic = tj.get({"conv1a+1b": "conv1ab_mma_kernel"}.get(dom, dom))
+            want = {"conv1a+1b": "conv1ab_mma_kernel"}.get(dom, dom)
+            traffic = next((v for k, v in tj.items() if k.startswith(want)), None)
     roofline = {"bound": "tensor", "kernel": dom, "achieved": dom_tf, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": dom_tf / peaks["tflops_sustained"], "traffic": traffic, "peak_source": peaks["src"] + " bf16 sustained",
                 "kernel_ms": stages[dom]["ms"], "kernel_share_of_step": stages[dom]["ms"] / step_ms,

@@ -594,9 +594,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 hmin = fminf(hmin, h[c]);
                 hmax = fmaxf(hmax, h[c]);
               }
-              float4 *d4 = reinterpret_cast<float4 *>(hrow + static_cast<size_t>(r) * Wf);
-              d4[0] = make_float4(h[0], h[1], h[2], h[3]);
-              d4[1] = make_float4(h[4], h[5], h[6], h[7]);
+              st_global_v8(hrow + static_cast<size_t>(r) * Wf,  // the cell's 8 pixels of this row: one 32-byte store
+                           make_uint4(__float_as_uint(h[0]), __float_as_uint(h[1]), __float_as_uint(h[2]), __float_as_uint(h[3])),
+                           make_uint4(__float_as_uint(h[4]), __float_as_uint(h[5]), __float_as_uint(h[6]), __float_as_uint(h[7])));
             }
           }
         }

@@ -40,7 +40,8 @@ def main(rep, md_out, json_out, title, frames):
                 if m.startswith("dram__bytes"):
                     by += float(r[i].replace(",", "")) * TO_BYTES.get(units[i], 1.0)
         out.append("")
-        key = re.sub(r"^void ", "", name).split("(")[0]
+        key = re.sub(r"^void ", "", name)
+        key = key[:key.rindex("(")] if "(" in key else key      # drop the parameter list, keep template arguments
         traffic.setdefault(key, by)
     open(md_out, "w").write("\n".join(out))
     json.dump(traffic, open(json_out, "w"), indent=1)
