@@ -64,9 +64,6 @@ using CfgDb = ConvCfg<1, 4, 256, EPI_L2NORM, true, 4, 1, 1, 2>; // convDb + L2 n
 using CfgMatch = ConvCfg<1, 4, 256, EPI_TOP2, false, 4, 4, 1, 2>;  // descriptor matching: Q.T^T + top-2 per 256-column block
 
 enum { L1B = 0, L2A, L2B, L3A, L3B, L4A, L4B, LHEADS, LPB, LDB, NLAYERS };
-const char *kLayerNames[NLAYERS] = {"conv1b", "conv2a", "conv2b", "conv3a", "conv3b",
-                                    "conv4a", "conv4b", "heads",  "convPb", "convDb"};
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
