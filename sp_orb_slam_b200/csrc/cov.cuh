@@ -70,10 +70,14 @@ struct CovArgs {
   int *overflow;          // [1] set if even the sequential queue overflowed (reported as an error)
   int *n_replay;          // [B][2] statistics: keypoints / pixels replayed sequentially
   int H, W, cap, B, round;
+  int epoch_tag;          // (508 - batches since the owner map was cleared) << 22
   int force;              // test hook (SPFE_COV_FORCE): bit 0 = every small flood "does not fit", bit 1 = every big flood neither
 };
 
-__device__ __forceinline__ int cov_tag(int round, int k) { return ((64 - round) << 16) | k; }
+// Claim value: smaller wins (atomicMin).  Later rounds of a batch override earlier ones, and later batches override
+// earlier batches (epoch_tag falls from 508 << 22 to 0 over 509 batches), so the owner map is cleared only every 509
+// batches instead of every batch; a stale claim of an older batch never equals a current one.
+__device__ __forceinline__ int cov_tag(int epoch_tag, int round, int k) { return epoch_tag | ((64 - round) << 16) | k; }
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // Moments of a popped-pixel list, in the reference's order of operations (sp_extractor.cpp:316-333); one thread.
@@ -264,7 +268,7 @@ __global__ void __launch_bounds__(WARPS * 32) cov_flood_kernel(const CovArgs a) 
     const float *xy = a.kp_xy + static_cast<size_t>(ki) * 2;
     const int ox = static_cast<int>(xy[0]) - WIN / 2, oy = static_cast<int>(xy[1]) - WIN / 2;
     cov_fp_init<WIN, REL8>(fp, lane);
-    int n = cov_warp_flood<WIN, QCAP, REL8>(a.heat_inv + b * px, W, H, ox, oy, fp, sq, lane, a.owner + b * px, cov_tag(0, k));
+    int n = cov_warp_flood<WIN, QCAP, REL8>(a.heat_inv + b * px, W, H, ox, oy, fp, sq, lane, a.owner + b * px, cov_tag(a.epoch_tag, 0, k));
     if (a.force & (BIG ? 2 : 1)) n = -1;
     __syncwarp();
     if (n < 0) {
@@ -306,7 +310,7 @@ __global__ void __launch_bounds__(256) cov_resolve0_kernel(const CovArgs a) {
     a.done[ki] = 0;
   }
   if (a.frame_flag[b]) return;  // whole frame goes through the sequential path
-  const int n = a.qlen[ki], mine = cov_tag(0, k);
+  const int n = a.qlen[ki], mine = cov_tag(a.epoch_tag, 0, k);
   bool dirty = false;
   for (int i = lane; i < n; i += 32) dirty |= (owner[q[i]] != mine);
   if (__any_sync(0xffffffffu, dirty)) {
@@ -330,7 +334,7 @@ __global__ void __launch_bounds__(256) cov_claim_kernel(const CovArgs a) {
     if (a.frame_flag[b]) continue;
     int *owner = a.owner + static_cast<size_t>(b) * a.H * a.W;
     const uint32_t *q = a.queue + static_cast<size_t>(ki) * COV_QCAP;
-    const int n = a.qlen[ki], mine = cov_tag(a.round, k);
+    const int n = a.qlen[ki], mine = cov_tag(a.epoch_tag, a.round, k);
     for (int i = lane; i < n; i += 32) atomicMin(owner + q[i], mine);
   }
 }
@@ -352,7 +356,7 @@ __device__ __forceinline__ void cov_resolve_warp(const CovArgs &a, typename CovF
     const int *owner = a.owner + b * px;
     uint32_t *visited = a.visited + static_cast<size_t>(b) * a.vis_words;
     const uint32_t *q = a.queue + static_cast<size_t>(ki) * COV_QCAP;
-    const int n = a.qlen[ki], mine = cov_tag(a.round, k);
+    const int n = a.qlen[ki], mine = cov_tag(a.epoch_tag, a.round, k);
     bool blocked = false;
     for (int i = lane; i < n; i += 32) blocked |= (owner[q[i]] != mine);
     if (__any_sync(0xffffffffu, blocked)) continue;

@@ -118,6 +118,7 @@ struct Slot {
   float *h_mdist = nullptr;
   // covariance (device)
   int *cov_owner = nullptr, *cov_qlen = nullptr, *cov_overflow = nullptr, *cov_frame_flag = nullptr, *cov_n_replay = nullptr;
+  unsigned long long cov_epoch = 0;  // batches run on this slot (see cov_tag)
   int *cov_done = nullptr, *cov_ctr = nullptr, *cov_big = nullptr, *cov_pend = nullptr, *cov_isbig = nullptr;
   uint32_t *cov_visited = nullptr;
   uint32_t *cov_queue = nullptr;
@@ -448,7 +449,8 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
   }
   if (c->cov) {  // computeCovariance on the device (cov.cuh): parallel floods, then sequential replay of the conflicted few
     const size_t px = static_cast<size_t>(H) * W;
-    CU_OK(c, cudaMemsetAsync(s.cov_owner, 0x7F, B * px * sizeof(int), st));
+    if (s.cov_epoch % 509 == 0)  // claims carry a falling batch tag (cov_tag): the 4-byte-per-pixel map needs no clearing in between
+      CU_OK(c, cudaMemsetAsync(s.cov_owner, 0x7F, static_cast<size_t>(c->cfg.max_batch) * px * sizeof(int), st));
     const size_t vis_words = (px + 31) / 32;
     CU_OK(c, cudaMemsetAsync(s.cov_visited, 0, B * vis_words * sizeof(uint32_t), st));
     CU_OK(c, cudaMemsetAsync(s.cov_frame_flag, 0, B * sizeof(int), st));
@@ -458,6 +460,8 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     a.queue = s.cov_queue; a.qlen = s.cov_qlen; a.response = s.resp; a.cov2 = s.cov2; a.cov2_inv = s.cov2_inv;
     a.overflow = s.cov_overflow; a.H = H; a.W = W; a.cap = c->cap; a.B = B; a.round = 0;
     a.force = c->cov_force;
+    a.epoch_tag = (508 - static_cast<int>(s.cov_epoch % 509)) << 22;  // every tag stays below the cleared value 0x7F7F7F7F
+    s.cov_epoch++;
     a.done = s.cov_done; a.isbig = s.cov_isbig; a.ctr = s.cov_ctr; a.big = s.cov_big; a.pend = s.cov_pend;
     a.frame_flag = s.cov_frame_flag; a.n_replay = s.cov_n_replay; a.vis_words = static_cast<int>(vis_words);
     mark("cov_memset", 0, 5.0 * px * B);
