@@ -34,6 +34,11 @@ SMI_FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdo
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
 
+def workload_name(W, H, nf):
+    return (f"synthetic {W}x{H} u8 camera stream per GPU (BASELINE configs[1] geometry + configs[2] matching): "
+            f"extract + mutual-NN match to previous frame, nfeatures {nf}")
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -154,8 +159,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"synthetic {args.width}x{args.height} u8 stream, extract + match to previous frame, nfeatures {args.nf}",
-                   "frames_per_step": per_step},
+        "config": {"workload": workload_name(args.width, args.height, args.nf), "frames_per_step": per_step,
+                   "outputs": "everything SPExtractor::operator() fills (heat, NMS, computeCovariance) + the match to the previous frame"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -301,8 +306,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": ms_all / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic",
-            "config": {"workload": f"synthetic {W}x{H} u8 camera stream per GPU (BASELINE configs[1] geometry + configs[2] matching): "
-                                   f"extract + mutual-NN match to previous frame, nfeatures {args.nf}",
+            "config": {"workload": workload_name(W, H, args.nf),
                        "frames_per_step": B, "slots": S, "weights": "superpoint_v1 (reference weights, tests/golden)",
                        "outputs": "everything Frame::ExtractORB reads: keypoints (+response), descriptors, occ_grid_, dust maps, "
                                   "heat_, cov2/cov2_inv (computeCovariance on the device), matches to the previous frame; "
