@@ -94,6 +94,7 @@ struct NmsArgs {
   float *kp_score;          // [B][cap]
   int16_t *occ;             // [B][cells]
   unsigned long long *scratch;  // [B][cells] key list
+  int list_smem;                // 1: the key list lives behind the cell arrays in dynamic shared memory (cells * 8 more bytes)
 };
 
 enum { ST_NONE = 0, ST_UNDEC = 1, ST_KEPT = 2, ST_SUPP = 3 };
@@ -110,7 +111,9 @@ __global__ void __launch_bounds__(1024) nms_kernel(const NmsArgs p) {
   const float *score = p.score + static_cast<size_t>(b) * cells;
   const uint8_t *amax = p.argmax + static_cast<size_t>(b) * cells;
   int16_t *occ = p.occ + static_cast<size_t>(b) * cells;
-  unsigned long long *list = p.scratch + static_cast<size_t>(b) * cells;
+  // key lists of the two counting sorts: in shared memory when the launch provided room for them (p.list_smem), else in global scratch
+  unsigned long long *list = p.list_smem ? reinterpret_cast<unsigned long long *>(nms_smem + ((cells * 7 + 7) & ~7))
+                                         : p.scratch + static_cast<size_t>(b) * cells;
   const int W = p.wc * 8, H = p.hc * 8;
 
   if (tid == 0) { s_cnt = 0; s_cnt2 = 0; }
@@ -161,11 +164,18 @@ __global__ void __launch_bounds__(1024) nms_kernel(const NmsArgs p) {
   }
 
   // ---- cap: keep the `cap` best survivors (score desc, ties by cell index asc)
-  for (int c = tid; c < cells; c += nt)
-    if (s_st[c] == ST_KEPT) {
-      const int slot = atomicAdd(&s_cnt, 1);
-      list[slot] = (static_cast<unsigned long long>(__float_as_uint(s_sc[c])) << 32) | (0xFFFFFFFFu - static_cast<unsigned>(c));
-    }
+  // (list appends are warp-aggregated: one shared-memory atomic per warp instead of one per survivor)
+  const unsigned lane_lt = (1u << (tid & 31)) - 1u;
+  for (int c0 = 0; c0 < cells; c0 += nt) {
+    const int c = c0 + tid;
+    const bool kept = c < cells && s_st[c] == ST_KEPT;
+    const unsigned m = __ballot_sync(0xffffffffu, kept);
+    int base = 0;
+    if ((tid & 31) == 0 && m) base = atomicAdd(&s_cnt, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (kept)
+      list[base + __popc(m & lane_lt)] = (static_cast<unsigned long long>(__float_as_uint(s_sc[c])) << 32) | (0xFFFFFFFFu - static_cast<unsigned>(c));
+  }
   __syncthreads();
   const int K = s_cnt;
   if (K > p.cap) {
@@ -179,15 +189,22 @@ __global__ void __launch_bounds__(1024) nms_kernel(const NmsArgs p) {
   __syncthreads();
 
   // ---- border filter + raster (v outer, u inner) ordering
-  for (int c = tid; c < cells; c += nt)
-    if (s_st[c] == ST_KEPT) {
+  for (int c0 = 0; c0 < cells; c0 += nt) {
+    const int c = c0 + tid;
+    bool in = false;
+    int px = 0, py = 0;
+    if (c < cells && s_st[c] == ST_KEPT) {
       const int cy = c / p.wc, cx = c - cy * p.wc;
-      const int px = cx * 8 + (s_pos[c] & 7), py = cy * 8 + (s_pos[c] >> 3);
-      if (px >= p.border && px < W - p.border && py >= p.border && py < H - p.border) {
-        const int slot = atomicAdd(&s_cnt2, 1);
-        list[slot] = (static_cast<unsigned long long>(py * W + px) << 32) | static_cast<unsigned>(c);
-      }
+      px = cx * 8 + (s_pos[c] & 7);
+      py = cy * 8 + (s_pos[c] >> 3);
+      in = px >= p.border && px < W - p.border && py >= p.border && py < H - p.border;
     }
+    const unsigned m = __ballot_sync(0xffffffffu, in);
+    int base = 0;
+    if ((tid & 31) == 0 && m) base = atomicAdd(&s_cnt2, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (in) list[base + __popc(m & lane_lt)] = (static_cast<unsigned long long>(py * W + px) << 32) | static_cast<unsigned>(c);
+  }
   __syncthreads();
   const int Nk = s_cnt2;
   float *kp_xy = p.kp_xy + static_cast<size_t>(b) * p.cap * 2;

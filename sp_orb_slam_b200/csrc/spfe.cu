@@ -142,6 +142,7 @@ struct spfe_ctx {
   bool pair_conv2a = true;   // SPFE_PAIR_CONV2A=0: conv2a single-CTA
   bool pair_stream = true;   // SPFE_PAIR_STREAM=0: conv3a .. convPa|Da single-CTA
   bool pair_conv1 = true;    // SPFE_PAIR_CONV1=0: the fused conv1a+1b kernel single-CTA
+  int nms_smem = 0, nms_list_smem = 0;  // dynamic shared memory of nms_kernel / whether its key list fits in it
   int cov_force = 0;  // SPFE_COV_FORCE (test hook): push floods down the big / sequential fallback paths
   bool pdl = false;  // SPFE_PDL=1: programmatic dependent launch of the tensor-core kernels (measured: no gain, the board is power-capped)
   int conv1_mode = 2;
@@ -427,7 +428,8 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     n.score = s.score; n.argmax = s.argmax; n.hc = hc; n.wc = wc; n.thresh = c->cfg.score_thresh;
     n.radius = c->cfg.nms_radius; n.border = c->cfg.border; n.cap = c->cap;
     n.count = s.count; n.kp_xy = s.kp_xy; n.kp_score = s.kp_score; n.occ = s.occ; n.scratch = s.scratch;
-    nms_kernel<<<B, 1024, c->cells * 7, st>>>(n);
+    n.list_smem = c->nms_list_smem;
+    nms_kernel<<<B, 1024, c->nms_smem, st>>>(n);
     c->launches++;
     CU_OK(c, cudaGetLastError());
     mark("nms", 0, 7.0 * c->cells * B);
@@ -803,9 +805,12 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
     std::lock_guard<std::mutex> lock(mu);
     int &nms_smem_max = nms_granted[c->cfg.device_id & 63];
     if (nms_smem_max == 0) nms_smem_max = 48 * 1024;
-    if (c->cells * 7 > nms_smem_max) {
-      CU_OK(c, cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->cells * 7));
-      nms_smem_max = c->cells * 7;
+    // cell arrays (7 bytes per cell) + the sort-key list (8 bytes per cell) when both fit
+    c->nms_list_smem = ((c->cells * 7 + 7) & ~7) + c->cells * 8 <= 200 * 1024;
+    c->nms_smem = c->nms_list_smem ? ((c->cells * 7 + 7) & ~7) + c->cells * 8 : c->cells * 7;
+    if (c->nms_smem > nms_smem_max) {
+      CU_OK(c, cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->nms_smem));
+      nms_smem_max = c->nms_smem;
     }
     CU_OK(c, cudaFuncSetAttribute(conv1ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1ab::SMEM));
     CU_OK(c, cudaFuncSetAttribute(conv1ab_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c1m::SMEM));
