@@ -77,7 +77,7 @@ struct CovArgs {
 // Claim value: smaller wins (atomicMin).  Later rounds of a batch override earlier ones, and later batches override
 // earlier batches (epoch_tag falls from 508 << 22 to 0 over 509 batches), so the owner map is cleared only every 509
 // batches instead of every batch; a stale claim of an older batch never equals a current one.
-__device__ __forceinline__ int cov_tag(int epoch_tag, int round, int k) { return epoch_tag | ((64 - round) << 16) | k; }
+__device__ __forceinline__ int cov_tag(int epoch_tag, int round, int k) { return epoch_tag + ((63 - round) << 16) + k; }  // (63 << 16) < (1 << 22), k < 65536
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // Moments of a popped-pixel list, in the reference's order of operations (sp_extractor.cpp:316-333); one thread.

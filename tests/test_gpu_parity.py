@@ -387,6 +387,11 @@ def test_covariance_dense_full_size_and_device_only(ex_cache):
         assert np.array_equal(o["kp_response"], resp), t
         assert np.array_equal(o["cov2"], cov2) and np.array_equal(o["cov2_inv"], cov2_inv), t
         assert np.all(qlen[t, :o["n"]] > 0) and np.all(done[t, :o["n"]] == 1)             # every flood completed
+    for _ in range(3):                                    # consecutive batches (odd and even claim epochs): still exact, and the
+        again = ex.extract_batch(list(frames))            # parallel rounds resolve every conflict (nothing left for the sequential replay)
+        assert ex.debug_read(0, "cov_replayed", 3)[:, 0].sum() == 0
+        for o, o2 in zip(outs, again):
+            assert np.array_equal(o["cov2"], o2["cov2"]) and np.array_equal(o["kp_response"], o2["kp_response"])
     dev = ex_cache(H, W, 800, max_batch=3, emit_heat=False, emit_cov=True)
     outs2 = dev.extract_batch(list(frames))
     for o, o2 in zip(outs, outs2):
