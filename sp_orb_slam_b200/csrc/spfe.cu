@@ -47,7 +47,7 @@ std::string fmt(const char *f, ...) {
 //                                                                                     tile pair (HALVES = 2)
 using CfgC64 = ConvCfg<9, 1, 64, EPI_RELU, true, 2, 1, 2>;          // conv2a          slab 54 KB x2 + 72 KB weights
 using CfgC64P = ConvCfg<9, 1, 64, EPI_RELU_POOL, true, 2, 1, 2>;    // conv1b, conv2b
-using CfgC64X = ConvCfg<9, 1, 64, EPI_RELU, true, 3, 1, 2, 1, true>;        // the same as CTA pairs (cta_group::2): default
+using CfgC64X = ConvCfg<9, 1, 64, EPI_RELU, true, 3, 1, 2, 2, true>;        // the same as CTA pairs (cta_group::2): default
 using CfgC64PX = ConvCfg<9, 1, 64, EPI_RELU_POOL, true, 3, 1, 2, 1, true>;
 using CfgC3a = ConvCfg<9, 1, 128, EPI_RELU, true, 2, 1, 1>;         // conv3a          144 KB weights: single tiles
 using CfgC128 = ConvCfg<9, 2, 128, EPI_RELU, false, 2, 6, 2>;       // conv4a, conv4b  slab 54 KB x2 + 6 x 16 KB weights
