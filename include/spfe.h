@@ -184,6 +184,11 @@ typedef struct spfe_guided_search {
 } spfe_guided_search;
 int spfe_search_guided(spfe_ctx *ctx, const spfe_guided_search *g, int32_t *q2kp, float *qdist, uint8_t *kp_taken_out);
 
+/* Changes the detection threshold (spfe_config.score_thresh, 0.007 upstream) for the batches submitted from now on.
+ * The reference has no such knob; it exists for the optional global keypoint budget of a multi-GPU job: every rank
+ * all-reduces a 64-bin score histogram (sp_orb_slam_b200/sharding.py, NCCL) and applies the common cut here. */
+int spfe_set_score_threshold(spfe_ctx *ctx, float score_thresh);
+
 /* SPFE_MATCH_PREV: forget the slot's previous frame (start of a new camera stream). */
 int spfe_reset_stream(spfe_ctx *ctx, int32_t slot);
 

@@ -1186,6 +1186,13 @@ int spfe_search_guided(spfe_ctx *c, const spfe_guided_search *g, int32_t *q2kp, 
   return SPFE_OK;
 }
 
+int spfe_set_score_threshold(spfe_ctx *c, float score_thresh) {
+  if (!c) return SPFE_ERR_INVALID;
+  if (!(score_thresh >= 0.0f && score_thresh <= 1.0f)) return c->fail(SPFE_ERR_INVALID, "spfe_set_score_threshold: threshold outside [0, 1]");
+  c->cfg.score_thresh = score_thresh;  // read by run_pipeline at the next submit
+  return SPFE_OK;
+}
+
 int spfe_reset_stream(spfe_ctx *c, int32_t slot) {
   int rc = check_slot(c, slot);
   if (rc) return rc;

@@ -184,6 +184,10 @@ class SPExtractor:
     def sync(self, slot: int) -> None:
         self._check(self._lib.spfe_slot_sync(self._ctx, slot))
 
+    def set_score_threshold(self, thresh: float) -> None:
+        """Detection threshold for the batches submitted from now on (the common cut of ``sharding.global_keypoint_budget``)."""
+        self._check(self._lib.spfe_set_score_threshold(self._ctx, C.c_float(thresh)))
+
     def reset_stream(self, slot: int) -> None:
         self._check(self._lib.spfe_reset_stream(self._ctx, slot))
 

@@ -447,6 +447,30 @@ def test_tiny_frames(H, W, weights):
     ex.close()
 
 
+def test_global_keypoint_budget_cut():
+    """The optional multi-GPU keypoint budget end to end on one rank: histogram -> common score cut (sharding.py, one
+    all-reduce when a process group exists) -> spfe_set_score_threshold -> fewer keypoints, NMS still exact at the new cut."""
+    from sp_orb_slam_b200 import sharding
+    H, W = 240, 320
+    ex = SPExtractor(800, H, W, WEIGHTS, emit_heat=False, emit_cov=False)
+    frame = synth.make_frame(H, W, seed=5, n_shapes=200)
+    base = ex.extract(frame)
+    score, argmax = ex.debug_read(0, "score", 1)[0], ex.debug_read(0, "argmax", 1)[0]
+    cut = sharding.global_keypoint_budget(score[score >= O.SCORE_THRESH], budget=base["n"] // 3)
+    assert cut > O.SCORE_THRESH
+    ex.set_score_threshold(cut)
+    o = ex.extract(frame)
+    mask = score >= np.float32(cut)
+    cy, cx = np.nonzero(mask)
+    pts = np.stack([cx * 8 + argmax[mask] % 8, cy * 8 + argmax[mask] // 8], 1).astype(np.float32)
+    order = O.sort_desc(score[mask])
+    sel, occ = O.nms(pts[order], 800, W, H)
+    assert 0 < o["n"] < base["n"] and np.array_equal(o["kp_xy"], pts[order][sel]) and np.array_equal(o["occ_grid"], occ)
+    with pytest.raises(SpfeError):
+        ex.set_score_threshold(2.0)
+    ex.close()
+
+
 def test_slots_pipeline(ex_cache):
     H, W = 240, 320
     ex = ex_cache(H, W, 800, max_batch=2, num_slots=3, emit_heat=False, emit_cov=False)
