@@ -82,7 +82,7 @@ struct Slot {
   // compute queue: the persistent kernels of consecutive batches never fight for SMs; copies overlap on their own
   // engines); SPFE_SLOT_STREAMS=1 gives every slot a private stream for all three instead.
   cudaStream_t stream = nullptr, in_stream = nullptr, out_stream = nullptr;
-  cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr, ev_fork = nullptr, ev_join = nullptr;
   int batch = 0;
   bool pending = false, on_host = false;
   // device activations (NHWC fp16)
@@ -157,7 +157,7 @@ struct spfe_ctx {
   std::string error;
   std::mutex match_mu;
   cudaStream_t match_stream = nullptr;
-  cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;
+  cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr, aux = nullptr;  // aux: covariance beside the matcher
   bool slot_streams = false;
   MatchScratch match;  // for spfe_match_mutual_nn (host pointers)
   float *h_match_q = nullptr, *h_match_t = nullptr;
@@ -442,6 +442,16 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     CU_OK(c, cudaGetLastError());
     mark("sample_desc", 0, 3072.0 * c->cap * B);
   }
+  // computeCovariance (with to_heat) and the match to the previous frame both depend only on what is on the stream so
+  // far: outside profiling runs the former goes to the auxiliary queue so that its latency-bound kernels overlap the
+  // matcher's; the two queues join again at the end of the plan
+  const bool fork = tm == nullptr && c->cov && c->match_prev && c->aux != nullptr && !c->slot_streams;
+  cudaStream_t st_main = st;
+  if (fork) {
+    CU_OK(c, cudaEventRecord(s.ev_fork, st_main));
+    CU_OK(c, cudaStreamWaitEvent(c->aux, s.ev_fork, 0));
+    st = c->aux;
+  }
   if (c->heat) {
     dim3 grid(64, B);
     heat_norm_kernel<<<grid, 256, 0, st>>>(s.heat_log, s.heat_mm, c->heat_host ? s.heat : nullptr, s.heat_inv, s.heat_mm_f, H * W);
@@ -483,6 +493,10 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     CU_OK(c, cudaGetLastError());
     mark("cov_replay", 0, 0);
   }
+  if (fork) {
+    CU_OK(c, cudaEventRecord(s.ev_join, c->aux));
+    st = st_main;
+  }
   if (c->match_prev) {
     // frame z vs frame z-1 (frame 0 vs the carry in slot 0): fp16 candidate GEMM on the tensor core for both
     // directions, exact fp32 re-rank of the candidates, cross-check; then the last frame becomes the carry.
@@ -509,6 +523,7 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     CU_OK(c, cudaMemcpyAsync(s.count_all, s.count_all + B, sizeof(int), cudaMemcpyDeviceToDevice, st));
     mark("match_final", 0, 2048.0 * c->cap * B);
   }
+  if (fork) CU_OK(c, cudaStreamWaitEvent(st_main, s.ev_join, 0));
   s.batch = B;
   return SPFE_OK;
 }
@@ -622,6 +637,8 @@ static int create_impl(spfe_ctx *c) {
       CU_OK(c, cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
       CU_OK(c, cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
       CU_OK(c, cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+      const char *ax = getenv("SPFE_AUX_STREAM");
+      if (!(ax && ax[0] == '0')) CU_OK(c, cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
     }
   }
   const size_t px = static_cast<size_t>(H) * W, cells = c->cells, cap = c->cap;
@@ -635,6 +652,8 @@ static int create_impl(spfe_ctx *c) {
     CU_OK(c, cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
     CU_OK(c, cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
     CU_OK(c, cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
+    CU_OK(c, cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
+    CU_OK(c, cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
     if ((rc = dev_alloc(c, &s.d_gray, Bm * px))) return rc;
     if (!c->fused_conv1 && (rc = dev_alloc(c, &s.a1a, Bm * px * 64))) return rc;
     if ((rc = dev_alloc(c, &s.a1b, Bm * px / 4 * 64))) return rc;
@@ -836,13 +855,13 @@ void spfe_destroy(spfe_ctx *c) {
   cudaDeviceSynchronize();
   for (Slot &s : c->slots) {
     if (s.stream && c->slot_streams) cudaStreamDestroy(s.stream);
-    for (cudaEvent_t e : {s.ev_in, s.ev_done, s.ev_out}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {s.ev_in, s.ev_done, s.ev_out, s.ev_fork, s.ev_join}) if (e) cudaEventDestroy(e);
     if (s.ev0) cudaEventDestroy(s.ev0);
     if (s.ev1) cudaEventDestroy(s.ev1);
   }
   if (c->match_stream) cudaStreamDestroy(c->match_stream);
   if (c->guided_buf) cudaFree(c->guided_buf);
-  for (cudaStream_t st : {c->compute, c->copy_in, c->copy_out}) if (st) cudaStreamDestroy(st);
+  for (cudaStream_t st : {c->compute, c->copy_in, c->copy_out, c->aux}) if (st) cudaStreamDestroy(st);
   for (void *p : c->dev_allocs) cudaFree(p);
   for (void *p : c->host_allocs) cudaFreeHost(p);
   delete c;
