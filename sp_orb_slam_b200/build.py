@@ -56,6 +56,18 @@ def build_shim(force: bool = False) -> str:
         return out
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(PKG, "cpp"),
                            "-o", out, src, shim, "-L", LIB_DIR, "-lspfe", "-Wl,-rpath,$ORIGIN"])
+    build_stream_bench(force=True)
+    return out
+
+
+def build_stream_bench(force: bool = False) -> str:
+    """Native throughput harness over the C ABI (cpp/stream_bench.cc)."""
+    out = os.path.join(LIB_DIR, "stream_bench")
+    src = os.path.join(PKG, "cpp", "stream_bench.cc")
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(LIB)):
+        return out
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), "-o", out, src,
+                           "-L", LIB_DIR, "-lspfe", "-Wl,-rpath,$ORIGIN"])
     return out
 
 

@@ -496,6 +496,18 @@ def test_slots_pipeline(ex_cache):
         assert np.array_equal(o["kp_xy"], o2["kp_xy"]) and np.array_equal(o["desc"], o2["desc"])
 
 
+def test_native_stream_bench():
+    """The C++ throughput harness over the C ABI (no Python in the loop): pinned frames in, pipelined slots, full outputs."""
+    import json
+    from sp_orb_slam_b200 import build
+    exe = build.build_stream_bench()
+    r = subprocess.run([exe, WEIGHTS, "240", "320", "4", "3", "12"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["frames"] == 48 and d["frames_per_s"] > 100 and d["keypoints_per_frame"] > 50 and d["matches_per_frame"] > 20
+    assert d["launches"] > 0
+
+
 def test_cpp_shim_selftest(tmp_path, ex_cache):
     """The C++ drop-in classes, driven like Frame::ExtractORB / trackReferenceKeyFrameANN drive the reference."""
     from sp_orb_slam_b200 import build
