@@ -189,6 +189,8 @@ def main():
     from sp_orb_slam_b200 import SPExtractor, sharding
     rank, local_rank, world = sharding.init_distributed()
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = sharding.bind_to_gpu_numa(local_rank)                 # before any pinned allocation (first touch)
     H, W, B, K, S = args.height, args.width, args.batch, args.steps, args.slots
     n_pool = max(4, -(-(140 << 20) // (B * H * W)))             # inputs > 126 MB L2
     pool = make_pool(H, W, B, n_pool, rank)
@@ -313,7 +315,8 @@ def main():
                                   "only heat_inv_ (= 1 - heat_) stays on the device" if full else
                                   "keypoints, scores, descriptors, occ_grid, dust maps, matches (--lean: no computeCovariance, no heat_)",
                        "l2": f"inputs rotate over {n_pool} batches = {n_pool * stride >> 20} MiB > 126 MB L2; activations per step {B * H * W * 128 * 2 >> 20}+ MiB",
-                       "parallelism": f"{world} independent streams, one per GPU, no data-path collective"},
+                       "parallelism": f"{world} independent streams, one per GPU, no data-path collective",
+                       "host_placement": numa},
             "e2e": {"value": e2e_frames / (e2e_ms_all * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "ms_per_step": e2e_ms_all / Ke, "input": "page-locked host frames (spfe_submit_pinned)",
                     "pageable_input_value": pg_frames / (pg_ms_all * 1e-3)},
@@ -323,6 +326,7 @@ def main():
             "roofline": roofline,
         }
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cpus)                    # the CPU baseline gets every host core again
             out["cpu_baseline"] = cpu_baseline(H, W, args.nf)
         print(json.dumps(out), flush=True)
     ex.close()

@@ -63,6 +63,36 @@ def init_distributed(backend: str | None = None):
     return rank, local_rank, world
 
 
+def _parse_cpulist(text: str):
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus += list(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(local_rank: int) -> str:
+    """Pin this process to the CPUs that are local to its GPU (sysfs ``local_cpulist`` of the GPU's PCI function), so
+    that the page-locked frame / result buffers allocated afterwards are first-touched on the GPU's NUMA node and the
+    H2D / D2H DMA of one rank does not cross sockets.  Best effort: returns a description, never raises."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus or len(cpus) == len(allowed):
+            return f"{bdf}: no narrower local CPU list"
+        os.sched_setaffinity(0, cpus)
+        return f"{bdf}: bound to {len(cpus)} local CPUs"
+    except Exception as e:  # noqa: BLE001
+        return f"not bound ({type(e).__name__})"
+
+
 def _device():
     import torch
     import torch.distributed as dist
