@@ -20,6 +20,8 @@
  *                             SPMatcher::SearchByBruteForce             orb_slam2/src/cv/sp_matcher.cpp:1642-1674
  *                                                                       orb_slam2/src/cv/sp_matcher_loop.cpp:334-376
  *   spfe_l2                <- SPMatcher::DescriptorDistance             orb_slam2/src/cv/sp_matcher.cpp:1636-1640
+ *   spfe_dust_pose_optimize <- Optimizer::PoseOptimizationDust          orb_slam2/src/mapping/optimizer_dust.cpp:170-293
+ *                             (EdgeSE3ProjectDustOnlyPose, orb_slam2/src/optimization/types_dust_tracking.cpp:37-141)
  *
  * The reference is one-frame-blocking with batch size 1 (sp_extractor.cpp:70
  * "TODO: batch-size").  spfe_extract keeps that contract; spfe_submit /
@@ -183,6 +185,43 @@ typedef struct spfe_guided_search {
   float best_init, th_le, th_lt, c2_adaptive;
 } spfe_guided_search;
 int spfe_search_guided(spfe_ctx *ctx, const spfe_guided_search *g, int32_t *q2kp, float *qdist, uint8_t *kp_taken_out);
+
+/* Dust-map pose optimisation -- the inner loop of
+ *   Optimizer::PoseOptimizationDust(Frame*, const vector<MapPoint*>&, vector<bool>&)   orb_slam2/src/mapping/optimizer_dust.cpp:170-293
+ * i.e. a g2o graph of one SE3 vertex and one EdgeSE3ProjectDustOnlyPose per map point
+ *   computeError / linearizeOplus / isInImage / getPixelValue                          orb_slam2/src/optimization/types_dust_tracking.cpp:37-141
+ * solved by 40 Levenberg iterations with a Huber kernel, in ONE kernel launch (dustpose.cuh).  The caller hoists the
+ * map points into a flat array; the intrinsics are those the reference hands the edges: fx / 8, fy / 8, (cx - 3.5) / 8,
+ * (cy - 3.5) / 8 (optimizer_dust.cpp:222-225).  pose = Frame::mTcw as (qx, qy, qz, qw, tx, ty, tz), g2o::SE3Quat order.
+ * dust == NULL reads the dense_dust map of frame `frame` of `slot`'s last completed batch where it already lies in
+ * device memory (the map then never crosses PCIe for tracking); otherwise dust = Frame::dust_ on the host.
+ *   spfe_dust_pose_optimize: pose in / out; visible[i] = !(level == 1 || chi2 > chi2_inlier) (:250-265, is_visible /
+ *     MapPoint::in_view); proj_uv[i] = the edge's (u_, v_) (-> MapPoint::dust_proj_u / v, valid where visible);
+ *     *n_inlier = the function's return value; *n_iter = optimizer.optimize()'s.  stats (may be NULL) receives
+ *     {final lambda, robust chi2 of the accepted state, LM trials}.
+ *   spfe_dust_linearize: one computeActiveErrors + buildSystem pass at a fixed pose, for callers that keep g2o in
+ *     charge of the iteration: level[n] in / out (setLevel(1) is sticky), err[n] = _error, proj_uv, J[n][6] =
+ *     _jacobianOplusXi, Hb[43] = H (6 x 6, row-major), b (6), robust chi2.
+ * Both return SPFE_ERR_STATE where linearizeOplus would throw std::runtime_error(" should be omitted") (:114-116; its
+ * projection falls outside the image although computeError's did not); the shim rethrows.  Thread-safe like
+ * spfe_match_mutual_nn. */
+typedef struct spfe_dust_pose {
+  int32_t struct_size;   /* = sizeof(spfe_dust_pose) */
+  int32_t n;             /* map points, in the caller's order */
+  const double *Xw;      /* [n][3] MapPoint::GetWorldPos() */
+  const float *dust;     /* [rows][cols] or NULL (= device-resident dense_dust of slot / frame) */
+  int32_t rows, cols;    /* H / 8, W / 8 */
+  int32_t slot, frame;   /* used when dust == NULL */
+  double fx, fy, cx, cy; /* in dust-map units */
+  double huber_delta;    /* 0.9 (optimizer_dust.cpp:219); <= 0 = no robust kernel */
+  double chi2_inlier;    /* 0.9 (optimizer_dust.cpp:253) */
+  int32_t iterations;    /* 40  (optimizer_dust.cpp:246) */
+  int32_t reserved;
+} spfe_dust_pose;
+int spfe_dust_pose_optimize(spfe_ctx *ctx, const spfe_dust_pose *p, double *pose7, uint8_t *visible, float *proj_uv,
+                            int32_t *n_inlier, int32_t *n_iter, double *stats);
+int spfe_dust_linearize(spfe_ctx *ctx, const spfe_dust_pose *p, const double *pose7, uint8_t *level, double *err,
+                        float *proj_uv, double *J, double *Hb);
 
 /* Changes the detection threshold (spfe_config.score_thresh, 0.007 upstream) for the batches submitted from now on.
  * The reference has no such knob; it exists for the optional global keypoint budget of a multi-GPU job: every rank

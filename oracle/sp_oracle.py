@@ -5,6 +5,9 @@ fp32 restatement of the reference path, function by function:
   frontend_forward   <- orb_slam2/src/cv/sp_extractor.cpp:79-159  (SPFrontend::forward)
   extract            <- orb_slam2/src/cv/sp_extractor.cpp:361-514 (SPExtractor::operator())
   match_mutual_nn    <- orb_slam2/src/cv/sp_matcher.cpp:1642-1674 (SearchByBruteForce core)
+  dust_linearize / dust_pose_optimize
+                     <- orb_slam2/src/optimization/types_dust_tracking.cpp:37-141 (EdgeSE3ProjectDustOnlyPose) and
+                        orb_slam2/src/mapping/optimizer_dust.cpp:170-293 (PoseOptimizationDust); C in oracle/dust_pose.c
 
 The network half runs on torch CPU (the reference runs the same ATen ops
 through libtorch); the post-processing half is the C restatement in
@@ -35,9 +38,9 @@ def build_post(force: bool = False) -> str:
     out_dir = os.path.join(_HERE, "_build")
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "libsporacle.so")
-    src = os.path.join(_HERE, "sp_post.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src, "-lm"])
+    srcs = [os.path.join(_HERE, "sp_post.c"), os.path.join(_HERE, "dust_pose.c")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, *srcs, "-lm"])
     return so
 
 
@@ -286,3 +289,47 @@ def knn2(q: np.ndarray, t: np.ndarray):
     dist = np.empty((max(len(q), 1), 2), np.float32)
     _lib().orc_knn2(_p(q, C.c_float), len(q), _p(t, C.c_float), len(t), 256, _p(idx, C.c_int32), _p(dist, C.c_float))
     return idx[:len(q)], dist[:len(q)]
+
+
+# ----------------------------------------------------------------------------
+# dust-map pose optimisation -- C restatement in oracle/dust_pose.c
+# ----------------------------------------------------------------------------
+class _DustCam(C.Structure):
+    _fields_ = [("dust", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int), ("fx", C.c_double), ("fy", C.c_double),
+                ("cx", C.c_double), ("cy", C.c_double), ("huber", C.c_double)]
+
+
+def _dust_cam(dust, fx, fy, cx, cy, huber):
+    dust = np.ascontiguousarray(dust, np.float32)
+    return dust, _DustCam(dust.ctypes.data, dust.shape[0], dust.shape[1], fx, fy, cx, cy, huber)
+
+
+def dust_linearize(dust, pose7, Xw, fx, fy, cx, cy, *, huber: float = 0.9, level=None):
+    """One computeActiveErrors + buildSystem pass of the PoseOptimizationDust graph at ``pose7`` = (qx, qy, qz, qw, tx,
+    ty, tz).  -> dict(level, err, uv, J, H, b, chi2, thrown)."""
+    dust, cam = _dust_cam(dust, fx, fy, cx, cy, huber)
+    Xw = np.ascontiguousarray(Xw, np.float64).reshape(-1, 3)
+    n = len(Xw)
+    pose7 = np.ascontiguousarray(pose7, np.float64)
+    level = np.zeros(n, np.uint8) if level is None else np.ascontiguousarray(level, np.uint8).copy()
+    err, uv, J, Hb = np.zeros(n), np.zeros((n, 2), np.float32), np.zeros((n, 6)), np.zeros(43)
+    vp = C.c_void_p
+    rc = _lib().orc_dust_linearize(C.byref(cam), vp(pose7.ctypes.data), vp(Xw.ctypes.data), n, vp(level.ctypes.data),
+                                   vp(err.ctypes.data), vp(uv.ctypes.data), vp(J.ctypes.data), vp(Hb.ctypes.data))
+    return dict(level=level, err=err, uv=uv, J=J, H=Hb[:36].reshape(6, 6).copy(), b=Hb[36:42].copy(), chi2=float(Hb[42]), thrown=rc != 0)
+
+
+def dust_pose_optimize(dust, pose7, Xw, fx, fy, cx, cy, *, huber: float = 0.9, iterations: int = 40, chi2_inlier: float = 0.9):
+    """optimizer.optimize(40) on the PoseOptimizationDust graph + its inlier read-out.
+    -> dict(pose, visible, uv, n_inlier, n_iter (-1: linearizeOplus threw), err, level, stats=(lambda, chi2, trials))."""
+    dust, cam = _dust_cam(dust, fx, fy, cx, cy, huber)
+    Xw = np.ascontiguousarray(Xw, np.float64).reshape(-1, 3)
+    n = len(Xw)
+    pose = np.ascontiguousarray(pose7, np.float64).copy()
+    level, err, uv, vis = np.zeros(n, np.uint8), np.zeros(n), np.zeros((n, 2), np.float32), np.zeros(n, np.uint8)
+    ninl, stats = C.c_int(0), np.zeros(3)
+    vp = C.c_void_p
+    it = _lib().orc_dust_optimize(C.byref(cam), vp(pose.ctypes.data), vp(Xw.ctypes.data), n, int(iterations), C.c_double(chi2_inlier),
+                                  vp(level.ctypes.data), vp(err.ctypes.data), vp(uv.ctypes.data), vp(vis.ctypes.data),
+                                  C.byref(ninl), vp(stats.ctypes.data))
+    return dict(pose=pose, visible=vis, uv=uv, n_inlier=ninl.value, n_iter=int(it), err=err, level=level, stats=stats)

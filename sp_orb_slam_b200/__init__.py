@@ -5,6 +5,6 @@ The product is the C-ABI library ``lib/libspfe.so`` (hand-written sm_100a CUDA,
 ``orbslam::SPExtractor`` / ``orbslam::SPMatcher``.  This Python package is the
 host-side mirror used by the tests and the benchmark.
 """
-from .extractor import SPExtractor, SPMatcher, SpfeError  # noqa: F401
+from .extractor import Optimizer, SPExtractor, SPMatcher, SpfeError  # noqa: F401
 
-__all__ = ["SPExtractor", "SPMatcher", "SpfeError"]
+__all__ = ["Optimizer", "SPExtractor", "SPMatcher", "SpfeError"]

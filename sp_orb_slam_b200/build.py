@@ -51,11 +51,15 @@ def build_shim(force: bool = False) -> str:
     src = os.path.join(PKG, "cpp", "shim_selftest.cc")
     shim = os.path.join(PKG, "cpp", "sp_shim.cc")
     deps = [src, shim, os.path.join(PKG, "cpp", "sp_extractor.h"), os.path.join(PKG, "cpp", "sp_matcher.h"),
-            os.path.join(PKG, "cpp", "mini_cv.h"), LIB]
+            os.path.join(PKG, "cpp", "mini_cv.h"), os.path.join(PKG, "cpp", "optimizer_dust.h"),
+            os.path.join(PKG, "cpp", "dust_pose_selftest.cc"), LIB]
     if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
         return out
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(PKG, "cpp"),
                            "-o", out, src, shim, "-L", LIB_DIR, "-lspfe", "-Wl,-rpath,$ORIGIN"])
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(PKG, "cpp"),
+                           "-o", os.path.join(LIB_DIR, "dust_pose_selftest"), os.path.join(PKG, "cpp", "dust_pose_selftest.cc"), shim,
+                           "-L", LIB_DIR, "-lspfe", "-Wl,-rpath,$ORIGIN"])
     build_stream_bench(force=True)
     return out
 

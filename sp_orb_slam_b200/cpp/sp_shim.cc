@@ -5,6 +5,7 @@
 
 #include "sp_extractor.h"
 #include "sp_matcher.h"
+#include "optimizer_dust.h"
 
 namespace orbslam {
 
@@ -53,6 +54,7 @@ SPExtractor::SPExtractor(int nfeatures_) : BaseExtractor(nfeatures_, 1.0f, 1, 1,
   cfg.weights_path = common::model_path.c_str();
   if (spfe_create(&cfg, &ctx_) != SPFE_OK) throw std::runtime_error(std::string("SPExtractor: ") + spfe_last_error(nullptr));
   SPMatcher::SetBackend(ctx_);
+  Optimizer::SetBackend(ctx_);
 }
 
 SPExtractor::~SPExtractor() { spfe_destroy(ctx_); }

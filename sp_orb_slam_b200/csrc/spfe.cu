@@ -21,12 +21,15 @@
 #include "conv1ab_mma.cuh"
 #include "conv_tc.cuh"
 #include "cov.cuh"
+#include "dustpose.cuh"
 #include "guided.cuh"
 #include "kernels_misc.cuh"
 #include "match.cuh"
 #include "weights.h"
 
 using namespace spfe;
+
+static constexpr int DUST_SMEM_MAX = 200 * 1024;  // dust_pose_kernel stages the dust map in shared memory up to this size
 
 namespace {
 
@@ -831,6 +834,7 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
       CU_OK(c, cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->nms_smem));
       nms_smem_max = c->nms_smem;
     }
+    CU_OK(c, cudaFuncSetAttribute(dust_pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DUST_SMEM_MAX));
     CU_OK(c, cudaFuncSetAttribute(conv1ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1ab::SMEM));
     CU_OK(c, cudaFuncSetAttribute(conv1ab_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c1m::SMEM));
     CU_OK(c, cudaFuncSetAttribute(conv1ab_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c1m::SMEM));
@@ -1203,6 +1207,98 @@ int spfe_search_guided(spfe_ctx *c, const spfe_guided_search *g, int32_t *q2kp, 
   CU_OK(c, cudaStreamSynchronize(st));
   if (over) return c->fail(SPFE_ERR_INVALID, fmt("spfe_search_guided: a query has more than %d candidate keypoints (radius too large)", GUIDED_CAND));
   return SPFE_OK;
+}
+
+// spfe_dust_pose_optimize (mode 1) / spfe_dust_linearize (mode 0): one launch of dust_pose_kernel on the matcher stream
+static int dust_pose_run(spfe_ctx *c, const spfe_dust_pose *p, int mode, double *pose7, uint8_t *level, double *err, float *uv,
+                         double *J, double *Hb, uint8_t *visible, int32_t *n_inlier, int32_t *n_iter) {
+  const char *fn = mode ? "spfe_dust_pose_optimize" : "spfe_dust_linearize";
+  if (!c) return SPFE_ERR_INVALID;
+  if (!p || p->struct_size != (int32_t)sizeof(spfe_dust_pose)) return c->fail(SPFE_ERR_INVALID, fmt("%s: bad struct pointer / struct_size", fn));
+  const int n = p->n;
+  if (n < 0 || n >= (1 << 20) || !pose7 || (n > 0 && !p->Xw) || (mode == 1 && p->iterations < 0))
+    return c->fail(SPFE_ERR_INVALID, fmt("%s: bad n / iterations / NULL pose or Xw", fn));
+  if (mode == 0 && (!Hb || (n > 0 && (!level || !err || !uv || !J)))) return c->fail(SPFE_ERR_INVALID, fmt("%s: NULL output pointer", fn));
+  int rows = p->rows, cols = p->cols;
+  const float *d_dust = nullptr;
+  cudaEvent_t wait_ev = nullptr;
+  if (p->dust == nullptr) {
+    if (p->slot < 0 || p->slot >= (int)c->slots.size()) return c->fail(SPFE_ERR_INVALID, fmt("%s: bad slot", fn));
+    Slot &s = c->slots[p->slot];
+    if (s.pending) return c->fail(SPFE_ERR_STATE, fmt("%s: slot still has an un-waited batch", fn));
+    if (p->frame < 0 || p->frame >= s.batch) return c->fail(SPFE_ERR_STATE, fmt("%s: frame %d is not part of the slot's last batch (%d frames)", fn, p->frame, s.batch));
+    if ((rows && rows != c->hc) || (cols && cols != c->wc)) return c->fail(SPFE_ERR_INVALID, fmt("%s: rows / cols differ from the extractor's H/8 x W/8", fn));
+    rows = c->hc; cols = c->wc;
+    d_dust = s.dense_dust + (size_t)p->frame * c->cells;
+    wait_ev = s.ev_done;
+  }
+  if (rows < 4 || cols < 4 || (size_t)rows * cols >= (1u << 26)) return c->fail(SPFE_ERR_INVALID, fmt("%s: bad dust map size", fn));
+  std::lock_guard<std::mutex> lock(c->match_mu);
+  CU_OK(c, cudaSetDevice(c->cfg.device_id));
+  cudaStream_t st = c->match_stream;
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const size_t nn = n > 0 ? n : 1, map_bytes = (size_t)rows * cols * sizeof(float);
+  const size_t o_dust = carve(p->dust ? map_bytes : 0), o_xw = carve(nn * 24), o_pose = carve(7 * 8), o_level = carve(nn), o_err = carve(nn * 8),
+               o_uv = carve(nn * 8), o_J = carve(mode == 0 ? nn * 48 : 0), o_Hb = carve(43 * 8), o_vis = carve(nn), o_res = carve(8);
+  if (off > c->guided_bytes) {
+    if (c->guided_buf) cudaFree(c->guided_buf);
+    c->guided_buf = nullptr;
+    c->guided_bytes = 0;
+    CU_OK(c, cudaMalloc(&c->guided_buf, off + off / 2));
+    c->guided_bytes = off + off / 2;
+  }
+  uint8_t *base = static_cast<uint8_t *>(c->guided_buf);
+  if (p->dust) {
+    CU_OK(c, cudaMemcpyAsync(base + o_dust, p->dust, map_bytes, cudaMemcpyHostToDevice, st));
+    d_dust = reinterpret_cast<const float *>(base + o_dust);
+  } else {
+    CU_OK(c, cudaStreamWaitEvent(st, wait_ev, 0));
+  }
+  if (n > 0) CU_OK(c, cudaMemcpyAsync(base + o_xw, p->Xw, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+  CU_OK(c, cudaMemcpyAsync(base + o_pose, pose7, 7 * 8, cudaMemcpyHostToDevice, st));
+  if (mode == 0 && n > 0) {
+    CU_OK(c, cudaMemcpyAsync(base + o_level, level, n, cudaMemcpyHostToDevice, st));
+    CU_OK(c, cudaMemsetAsync(base + o_uv, 0, (size_t)n * 8, st));
+  }
+  DustPoseArgs a;
+  a.dust = d_dust; a.rows = rows; a.cols = cols; a.dust_in_smem = map_bytes <= (size_t)DUST_SMEM_MAX;
+  a.Xw = reinterpret_cast<const double *>(base + o_xw); a.n = n; a.mode = mode; a.iterations = p->iterations;
+  a.fx = p->fx; a.fy = p->fy; a.cx = p->cx; a.cy = p->cy; a.huber = p->huber_delta; a.chi2_inlier = p->chi2_inlier;
+  a.pose = reinterpret_cast<double *>(base + o_pose); a.level = base + o_level; a.err = reinterpret_cast<double *>(base + o_err);
+  a.uv = reinterpret_cast<float *>(base + o_uv); a.J = reinterpret_cast<double *>(base + o_J); a.Hb = reinterpret_cast<double *>(base + o_Hb);
+  a.visible = base + o_vis; a.result = reinterpret_cast<int *>(base + o_res);
+  dust_pose_kernel<<<1, DP_THREADS, a.dust_in_smem ? map_bytes : 0, st>>>(a);
+  c->launches += 1;
+  CU_OK(c, cudaGetLastError());
+  int res[2] = {0, 0};
+  double hb[43];
+  CU_OK(c, cudaMemcpyAsync(res, base + o_res, 8, cudaMemcpyDeviceToHost, st));
+  CU_OK(c, cudaMemcpyAsync(hb, base + o_Hb, 43 * 8, cudaMemcpyDeviceToHost, st));
+  if (mode == 1) CU_OK(c, cudaMemcpyAsync(pose7, base + o_pose, 7 * 8, cudaMemcpyDeviceToHost, st));
+  if (n > 0) {
+    if (uv) CU_OK(c, cudaMemcpyAsync(uv, base + o_uv, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    if (level) CU_OK(c, cudaMemcpyAsync(level, base + o_level, n, cudaMemcpyDeviceToHost, st));
+    if (err) CU_OK(c, cudaMemcpyAsync(err, base + o_err, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    if (J) CU_OK(c, cudaMemcpyAsync(J, base + o_J, (size_t)n * 48, cudaMemcpyDeviceToHost, st));
+    if (visible) CU_OK(c, cudaMemcpyAsync(visible, base + o_vis, n, cudaMemcpyDeviceToHost, st));
+  }
+  CU_OK(c, cudaStreamSynchronize(st));
+  if (Hb) memcpy(Hb, hb, (mode == 0 ? 43 : 3) * sizeof(double));
+  if (n_inlier) *n_inlier = res[1];
+  if (n_iter) *n_iter = res[0];
+  if (res[0] < 0) return c->fail(SPFE_ERR_STATE, fmt("%s: an edge's linearizeOplus projection left the image ( should be omitted)", fn));
+  return SPFE_OK;
+}
+
+int spfe_dust_pose_optimize(spfe_ctx *c, const spfe_dust_pose *p, double *pose7, uint8_t *visible, float *proj_uv,
+                            int32_t *n_inlier, int32_t *n_iter, double *stats) {
+  return dust_pose_run(c, p, 1, pose7, nullptr, nullptr, proj_uv, nullptr, stats, visible, n_inlier, n_iter);
+}
+
+int spfe_dust_linearize(spfe_ctx *c, const spfe_dust_pose *p, const double *pose7, uint8_t *level, double *err,
+                        float *proj_uv, double *J, double *Hb) {
+  return dust_pose_run(c, p, 0, const_cast<double *>(pose7), level, err, proj_uv, J, Hb, nullptr, nullptr, nullptr);
 }
 
 int spfe_set_score_threshold(spfe_ctx *c, float score_thresh) {

@@ -246,6 +246,45 @@ class SPExtractor:
                                                  qdist.ctypes.data_as(C.c_void_p), taken.ctypes.data_as(C.c_void_p)))
         return q2kp[:m], qdist[:m], taken[:n]
 
+    def _dust_struct(self, Xw, dust, fx, fy, cx, cy, huber, chi2_inlier, iterations, slot, frame):
+        Xw = np.ascontiguousarray(Xw, np.float64).reshape(-1, 3)
+        d = capi.DustPose()
+        d.struct_size, d.n = C.sizeof(capi.DustPose), len(Xw)
+        d.Xw = Xw.ctypes.data if len(Xw) else None
+        if dust is not None:
+            dust = np.ascontiguousarray(dust, np.float32)
+            d.dust, d.rows, d.cols = dust.ctypes.data, dust.shape[0], dust.shape[1]
+        else:
+            d.dust, d.rows, d.cols, d.slot, d.frame = None, 0, 0, slot, frame
+        d.fx, d.fy, d.cx, d.cy, d.huber_delta, d.chi2_inlier, d.iterations = fx, fy, cx, cy, huber, chi2_inlier, iterations
+        return d, Xw, dust
+
+    def dust_pose_optimize(self, pose7, Xw, fx, fy, cx, cy, *, dust=None, slot: int = 0, frame: int = 0, huber: float = 0.9,
+                           chi2_inlier: float = 0.9, iterations: int = 40):
+        """spfe_dust_pose_optimize on plain arrays.  ``dust=None`` uses the dense_dust map of ``frame`` of ``slot``'s last
+        batch where it lies on the device.  -> dict(pose, visible, uv, n_inlier, n_iter, stats)."""
+        d, Xw, dust = self._dust_struct(Xw, dust, fx, fy, cx, cy, huber, chi2_inlier, iterations, slot, frame)
+        n = len(Xw)
+        pose = np.ascontiguousarray(pose7, np.float64).copy()
+        vis, uv, stats = np.zeros(max(n, 1), np.uint8), np.zeros((max(n, 1), 2), np.float32), np.zeros(3)
+        ninl, nit = C.c_int32(0), C.c_int32(0)
+        vp = C.c_void_p
+        self._check(self._lib.spfe_dust_pose_optimize(self._ctx, C.byref(d), vp(pose.ctypes.data), vp(vis.ctypes.data),
+                                                      vp(uv.ctypes.data), C.byref(ninl), C.byref(nit), vp(stats.ctypes.data)))
+        return dict(pose=pose, visible=vis[:n], uv=uv[:n], n_inlier=ninl.value, n_iter=nit.value, stats=stats)
+
+    def dust_linearize(self, pose7, Xw, fx, fy, cx, cy, *, dust=None, slot: int = 0, frame: int = 0, huber: float = 0.9, level=None):
+        """spfe_dust_linearize on plain arrays -> dict(level, err, uv, J, H, b, chi2)."""
+        d, Xw, dust = self._dust_struct(Xw, dust, fx, fy, cx, cy, huber, 0.9, 0, slot, frame)
+        n = len(Xw)
+        pose = np.ascontiguousarray(pose7, np.float64)
+        level = np.zeros(max(n, 1), np.uint8) if level is None else np.ascontiguousarray(level, np.uint8).copy()
+        err, uv, J, Hb = np.zeros(max(n, 1)), np.zeros((max(n, 1), 2), np.float32), np.zeros((max(n, 1), 6)), np.zeros(43)
+        vp = C.c_void_p
+        self._check(self._lib.spfe_dust_linearize(self._ctx, C.byref(d), vp(pose.ctypes.data), vp(level.ctypes.data), vp(err.ctypes.data),
+                                                  vp(uv.ctypes.data), vp(J.ctypes.data), vp(Hb.ctypes.data)))
+        return dict(level=level[:n], err=err[:n], uv=uv[:n], J=J[:n], H=Hb[:36].reshape(6, 6).copy(), b=Hb[36:42].copy(), chi2=float(Hb[42]))
+
     # -- introspection
     _DEBUG = {"conv1a": (lambda s: (s.height, s.width, 64), np.float16), "conv1b": (lambda s: (s.height // 2, s.width // 2, 64), np.float16),
               "conv2a": (lambda s: (s.height // 2, s.width // 2, 64), np.float16), "conv2b": (lambda s: (s.height // 4, s.width // 4, 64), np.float16),
@@ -358,3 +397,23 @@ class SPMatcher:
         hit = np.flatnonzero(q2t >= 0)
         out[idx_t[q2t[hit]]] = idx_q[hit]
         return out, int(len(hit))
+
+
+class Optimizer:
+    """Mirror of the one ``orbslam::Optimizer`` entry that sits on the dust-tracking path
+    (orb_slam2/src/mapping/optimizer_dust.cpp:170-293), on plain arrays."""
+
+    HUBER_DELTA, CHI2_INLIER, ITERATIONS = 0.9, 0.9, 40    # optimizer_dust.cpp:219, :253, :246
+
+    def __init__(self, extractor: SPExtractor):
+        self._ex = extractor
+
+    def PoseOptimizationDust(self, Tcw_pose7, map_points_xyz, fx: float, fy: float, cx: float, cy: float, *, dust=None,
+                             slot: int = 0, frame: int = 0):
+        """``PoseOptimizationDust(Frame*, mps, is_visible)``: ``fx .. cy`` are the FRAME's intrinsics in pixels (the /8 and
+        -3.5 of optimizer_dust.cpp:222-225 are applied here); ``Tcw_pose7`` = (qx, qy, qz, qw, tx, ty, tz).
+        Returns (n_inlier, pose7, is_visible[n], dust_proj_uv[n, 2])."""
+        r = self._ex.dust_pose_optimize(Tcw_pose7, map_points_xyz, fx / 8.0, fy / 8.0, (cx - 3.5) / 8.0, (cy - 3.5) / 8.0,
+                                        dust=dust, slot=slot, frame=frame, huber=self.HUBER_DELTA,
+                                        chi2_inlier=self.CHI2_INLIER, iterations=self.ITERATIONS)
+        return r["n_inlier"], r["pose"], r["visible"].astype(bool), r["uv"]

@@ -1,0 +1,254 @@
+"""Dust-map pose optimisation, SURVEY.md section 8(f) rank 4: the oracle's restatement of EdgeSE3ProjectDustOnlyPose
+(types_dust_tracking.cpp:37-141) and of the Levenberg loop of Optimizer::PoseOptimizationDust (optimizer_dust.cpp:170-293)
+(CPU tests), and the one-launch device solve against it through the C ABI (GPU tests).
+
+Tolerances: per-edge results (error, level, u_/v_, Jacobian) are compared BIT-EXACTLY (same IEEE operations in the same
+order); the 6 x 6 normal equations and the robust chi2 within 1e-12 relative (the device sums the edges in a fixed tree,
+the oracle one after the other, as g2o does); the optimised pose within 1e-9 absolute, with identical iteration counts
+and inlier sets."""
+import numpy as np
+import pytest
+
+from conftest import WEIGHTS
+from oracle import sp_oracle as O
+from sp_orb_slam_b200 import Optimizer, SPExtractor, synth
+
+FX, FY, CX, CY = 458.654, 457.296, 367.215, 248.375          # EuRoC cam0 (orb_ros/cfg/euroc_mono.yaml)
+CAM = (FX / 8.0, FY / 8.0, (CX - 3.5) / 8.0, (CY - 3.5) / 8.0)  # optimizer_dust.cpp:222-225
+
+
+def quat_mul(a, b):
+    ax, ay, az, aw = a
+    bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by + ay * bw + az * bx - ax * bz,
+                     aw * bz + az * bw + ax * by - ay * bx, aw * bw - ax * bx - ay * by - az * bz])
+
+
+def rot(q, v):
+    x, y, z, w = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    return v @ R.T
+
+
+def make_scene(seed, n=300, rows=60, cols=94, outliers=0.15, behind=0.02):
+    """A dust map that is ~0.97 everywhere except smooth dips (dustbin probability is low at features) at the projections
+    of n map points under a true pose; a start pose a few hundredths off; some points placed to project outside / behind."""
+    rng = np.random.RandomState(seed)
+    ang = rng.uniform(-0.2, 0.2, 3)
+    q = np.array([*(np.sin(ang / 2)), 1.0])
+    q /= np.linalg.norm(q)
+    t = rng.uniform(-0.5, 0.5, 3)
+    true = np.concatenate([q, t])
+    fx, fy, cx, cy = CAM
+    u = rng.uniform(3, cols - 4, n)
+    v = rng.uniform(3, rows - 4, n)
+    z = rng.uniform(1.0, 8.0, n)
+    Xc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)
+    qi = np.array([-q[0], -q[1], -q[2], q[3]])
+    Xw = rot(qi, Xc - t)
+    yy, xx = np.mgrid[0:rows, 0:cols]
+    dust = np.full((rows, cols), 0.97)
+    keep = rng.rand(n) > outliers
+    for ui, vi in zip(u[keep], v[keep]):
+        dust -= 0.9 * np.exp(-((xx - ui) ** 2 + (yy - vi) ** 2) / (2 * 1.2 ** 2)) * (dust / 0.97)
+    dust = np.clip(dust + rng.normal(0, 0.004, dust.shape), 0.001, 0.999).astype(np.float32)
+    nb = int(behind * n)
+    if nb:
+        Xw[:nb] = rot(qi, np.stack([rng.uniform(-1, 1, nb), rng.uniform(-1, 1, nb), -rng.uniform(0.5, 3, nb)], 1) - t)
+    dq = np.array([*rng.normal(0, 0.004, 3), 1.0])
+    start = np.concatenate([quat_mul(dq / np.linalg.norm(dq), q), t + rng.normal(0, 0.01, 3)])
+    return dict(dust=dust, Xw=np.ascontiguousarray(Xw), true=true, start=start)
+
+
+# ---------------------------------------------------------------- oracle (CPU)
+def test_oracle_edge_error_and_jacobian_semantics():
+    s = make_scene(1, n=120)
+    r = O.dust_linearize(s["dust"], s["start"], s["Xw"], *CAM)
+    assert not r["thrown"]
+    xc = rot(s["start"][:4], s["Xw"]) + s["start"][4:]
+    u = xc[:, 0] * CAM[0] / xc[:, 2] + CAM[2]
+    v = xc[:, 1] * CAM[1] / xc[:, 2] + CAM[3]
+    inside = (xc[:, 2] >= 0) & (u >= 1) & (u + 2 < 94) & (v >= 1) & (v + 2 < 60)     # isInImage, border 1 (:37-42)
+    assert np.array_equal(r["level"] == 0, inside)
+    assert np.all(r["err"][~inside] == 0) and np.all(r["J"][~inside] == 0)
+    assert np.allclose(r["uv"][inside], np.stack([u, v], 1)[inside], atol=1e-4)
+    # the error is the bilinear sample of the map (getPixelValue :44-58)
+    i = np.flatnonzero(inside)[:40]
+    x0, y0 = np.floor(r["uv"][i, 0]).astype(int), np.floor(r["uv"][i, 1]).astype(int)
+    ax, ay = r["uv"][i, 0] - x0, r["uv"][i, 1] - y0
+    d = s["dust"].astype(np.float64)
+    bil = (1 - ax) * (1 - ay) * d[y0, x0] + ax * (1 - ay) * d[y0, x0 + 1] + (1 - ax) * ay * d[y0 + 1, x0] + ax * ay * d[y0 + 1, x0 + 1]
+    assert np.allclose(r["err"][i], bil, atol=1e-6)
+    # Jacobian = central-difference map gradient x the SE3 projection Jacobian (left-multiplied exp).  On a planar map the
+    # bilinear sample and the central difference are exact, so a finite difference of the error along each twist axis
+    # must reproduce the column.
+    yy, xx = np.mgrid[0:60, 0:94]
+    ramp = (0.2 + 0.004 * xx + 0.006 * yy).astype(np.float32)
+    ra = O.dust_linearize(ramp, s["start"], s["Xw"], *CAM)
+    q, t = s["start"][:4], s["start"][4:]
+    for k in range(6):
+        eps = 1e-5
+        if k < 3:        # rotation about axis k: exp(eps e_k) * T
+            dq = np.zeros(4); dq[k] = np.sin(eps / 2); dq[3] = np.cos(eps / 2)
+            e = np.zeros(3); e[k] = 1.0
+            p2 = np.concatenate([quat_mul(dq, q), t + eps * np.cross(e, t)])
+        else:
+            p2 = s["start"].copy(); p2[4 + k - 3] += eps
+        r2 = O.dust_linearize(ramp, p2, s["Xw"], *CAM)
+        both = (ra["level"] == 0) & (r2["level"] == 0)
+        fd = (r2["err"] - ra["err"]) / eps
+        assert np.abs(fd[both] - ra["J"][both, k]).max() < 0.02 * np.abs(ra["J"][both, k]).max() + 0.02, k
+    # H, b are the (Huber-weighted) sums over the edges
+    e2 = r["err"] ** 2
+    w = np.where(e2 <= 0.81, 1.0, 0.9 / np.sqrt(np.maximum(e2, 1e-300)))
+    assert np.allclose(r["H"], (r["J"] * w[:, None]).T @ r["J"], rtol=1e-12, atol=1e-15)
+    assert np.allclose(r["b"], -(r["J"] * (w * r["err"])[:, None]).sum(0), rtol=1e-12, atol=1e-15)
+    rho0 = np.where(e2 <= 0.81, e2, 2 * np.sqrt(e2) * 0.9 - 0.81)
+    assert np.isclose(r["chi2"], rho0.sum(), rtol=1e-13)
+
+
+def test_oracle_level_is_sticky():
+    s = make_scene(2, n=50)
+    lvl = np.ones(50, np.uint8)
+    r = O.dust_linearize(s["dust"], s["start"], s["Xw"], *CAM, level=lvl)
+    assert np.all(r["level"] == 1) and np.all(r["J"] == 0)
+    assert np.count_nonzero(r["err"]) > 30                      # computeError still samples the map (:85-92)
+    assert np.allclose(r["H"], 0) and r["chi2"] > 0
+
+
+@pytest.mark.parametrize("seed", [3, 4, 5])
+def test_oracle_lm_converges(seed):
+    s = make_scene(seed)
+    r0 = O.dust_linearize(s["dust"], s["start"], s["Xw"], *CAM)
+    r = O.dust_pose_optimize(s["dust"], s["start"], s["Xw"], *CAM)
+    assert 1 <= r["n_iter"] <= 40
+    rt = O.dust_linearize(s["dust"], s["true"], s["Xw"], *CAM)
+    assert r["stats"][1] < r0["chi2"]                           # robust chi2 went down ...
+    assert r["stats"][1] <= 1.02 * rt["chi2"]                   # ... to (at least) the level of the pose the map was drawn from
+    assert np.abs(r["pose"] - s["true"]).max() < 0.03           # and stayed in its neighbourhood (the map is noisy)
+    rf = O.dust_linearize(s["dust"], r["pose"], s["Xw"], *CAM)
+    assert np.isclose(rf["chi2"], r["stats"][1], rtol=1e-9)     # stats[1] is the chi2 of the returned pose
+    assert abs(np.linalg.norm(r["pose"][:4]) - 1) < 1e-12 and r["pose"][3] >= 0    # normalizeRotation
+    assert r["n_inlier"] == int(r["visible"].sum()) and r["n_inlier"] > 150
+    bad = (r["level"] == 1) | (r["err"] ** 2 > 0.9)
+    assert np.array_equal(r["visible"] == 0, bad)
+
+
+def test_oracle_empty_and_zero_iterations():
+    s = make_scene(6, n=10)
+    r = O.dust_pose_optimize(s["dust"], s["start"], s["Xw"], *CAM, iterations=0)
+    assert r["n_iter"] == 0 and np.array_equal(r["pose"], s["start"]) and r["n_inlier"] == 10   # nothing evaluated: all level 0, chi2 0
+    r = O.dust_pose_optimize(s["dust"], s["start"], np.zeros((0, 3)), *CAM)
+    assert r["n_inlier"] == 0 and np.array_equal(r["pose"], s["start"])
+
+
+# ---------------------------------------------------------------- device (GPU), through the C ABI
+@pytest.fixture(scope="module")
+def ex():
+    e = SPExtractor(800, 480, 752, WEIGHTS, emit_heat=False, emit_cov=False, max_batch=2)
+    yield e
+    e.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,n", [(11, 300), (12, 37), (13, 1000), (14, 1)])
+def test_gpu_linearize_matches_oracle(ex, seed, n):
+    s = make_scene(seed, n=n, behind=0.05)
+    for level in (None, (np.arange(n) % 5 == 0).astype(np.uint8)):
+        ref = O.dust_linearize(s["dust"], s["start"], s["Xw"], *CAM, level=level)
+        got = ex.dust_linearize(s["start"], s["Xw"], *CAM, dust=s["dust"], level=level)
+        assert np.array_equal(got["level"], ref["level"])
+        assert np.array_equal(got["err"], ref["err"])           # bit-exact
+        assert np.array_equal(got["uv"], ref["uv"])
+        assert np.array_equal(got["J"], ref["J"])
+        scale = np.abs(ref["H"]).max() + 1e-300
+        assert np.abs(got["H"] - ref["H"]).max() <= 1e-12 * scale
+        assert np.abs(got["b"] - ref["b"]).max() <= 1e-12 * (np.abs(ref["b"]).max() + 1e-300)
+        assert abs(got["chi2"] - ref["chi2"]) <= 1e-12 * max(ref["chi2"], 1e-300)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,n,shape", [(21, 300, (60, 94)), (22, 120, (60, 80)), (23, 800, (135, 240)), (24, 2, (60, 94))])
+def test_gpu_pose_optimize_matches_oracle(ex, seed, n, shape):
+    s = make_scene(seed, n=n, rows=shape[0], cols=shape[1])
+    ref = O.dust_pose_optimize(s["dust"], s["start"], s["Xw"], *CAM)
+    got = ex.dust_pose_optimize(s["start"], s["Xw"], *CAM, dust=s["dust"])
+    print(f"dust pose n={n}: iters {got['n_iter']}/{ref['n_iter']} inliers {got['n_inlier']}/{ref['n_inlier']} "
+          f"pose diff {np.abs(got['pose'] - ref['pose']).max():.2e} chi2 {got['stats'][1]:.9f}/{ref['stats'][1]:.9f} trials {got['stats'][2]}/{ref['stats'][2]}")
+    assert got["n_iter"] == ref["n_iter"] and got["stats"][2] == ref["stats"][2]
+    assert np.abs(got["pose"] - ref["pose"]).max() < 1e-9
+    assert np.array_equal(got["visible"], ref["visible"]) and got["n_inlier"] == ref["n_inlier"]
+    vis = ref["visible"] == 1
+    assert np.allclose(got["uv"][vis], ref["uv"][vis], atol=1e-4)
+    assert abs(got["stats"][1] - ref["stats"][1]) <= 1e-9 * max(ref["stats"][1], 1.0)
+
+
+@pytest.mark.gpu
+def test_gpu_pose_optimize_on_device_resident_dust(ex):
+    """dust == NULL: the solve reads the dense_dust map of an extracted frame where it lies in device memory; the result
+    equals the solve on the host copy of the same map (Frame::dust_)."""
+    frames = synth.make_stream(480, 752, 2, seed=5)
+    outs = ex.extract_batch(list(frames))
+    s = make_scene(31, n=250)
+    opt = Optimizer(ex)
+    for f in (0, 1):
+        dust = np.array(outs[f]["dense_dust"], np.float32).reshape(60, 94)
+        n_a, pose_a, vis_a, uv_a = opt.PoseOptimizationDust(s["start"], s["Xw"], FX, FY, CX, CY, slot=0, frame=f)
+        n_b, pose_b, vis_b, uv_b = opt.PoseOptimizationDust(s["start"], s["Xw"], FX, FY, CX, CY, dust=dust)
+        assert n_a == n_b and np.array_equal(pose_a, pose_b) and np.array_equal(vis_a, vis_b) and np.array_equal(uv_a, uv_b)
+        ref = O.dust_pose_optimize(dust, s["start"], s["Xw"], *CAM)
+        assert np.abs(pose_a - ref["pose"]).max() < 1e-9 and n_a == ref["n_inlier"]
+    with pytest.raises(Exception):
+        opt.PoseOptimizationDust(s["start"], s["Xw"], FX, FY, CX, CY, slot=0, frame=2)     # not part of the last batch
+
+
+@pytest.mark.gpu
+def test_gpu_dust_pose_bad_arguments(ex):
+    s = make_scene(41, n=5)
+    with pytest.raises(Exception):
+        ex.dust_pose_optimize(s["start"], s["Xw"], *CAM, dust=np.zeros((2, 2), np.float32))
+    r = ex.dust_pose_optimize(s["start"], np.zeros((0, 3)), *CAM, dust=s["dust"])
+    assert r["n_inlier"] == 0 and np.array_equal(r["pose"], s["start"])
+    r = ex.dust_pose_optimize(s["start"], s["Xw"], *CAM, dust=s["dust"], iterations=0)
+    assert r["n_iter"] == 0 and np.array_equal(r["pose"], s["start"]) and r["n_inlier"] == 5
+
+
+def rot_matrix(q):
+    return rot(q, np.eye(3)).T
+
+
+@pytest.mark.gpu
+def test_gpu_cpp_shim_pose_optimization_dust(tmp_path):
+    """orbslam::Optimizer::PoseOptimizationDust of the C++ shim (cpp/optimizer_dust.h) on a Frame / MapPoint pair shaped
+    like the reference's, against the oracle started from the pose the shim derived from the float Tcw."""
+    import subprocess
+    from sp_orb_slam_b200 import build
+    build.build_shim()
+    exe = build.LIB_DIR + "/dust_pose_selftest"
+    s = make_scene(51, n=280)
+    T = np.eye(4, dtype=np.float32)
+    T[:3, :3] = rot_matrix(s["start"][:4]).astype(np.float32)
+    T[:3, 3] = s["start"][4:].astype(np.float32)
+    Xw32 = s["Xw"].astype(np.float32)
+    k = np.array([FX, FY, CX, CY], np.float32)
+    with open(tmp_path / "scene.bin", "wb") as f:
+        np.array([60, 94, len(Xw32)], np.int32).tofile(f)
+        k.tofile(f); T.tofile(f); s["dust"].tofile(f); Xw32.tofile(f)
+    r = subprocess.run([exe, WEIGHTS, str(tmp_path / "scene.bin"), str(tmp_path / "out.txt")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = open(tmp_path / "out.txt").read().splitlines()
+    n_inlier, start = int(lines[0]), np.array(lines[1].split(), np.float64)
+    Tout = np.array(lines[2].split(), np.float32).reshape(4, 4)
+    rows = np.array([l.split() for l in lines[3:]], np.float64)
+    assert np.abs(rot_matrix(start[:4]) - T[:3, :3]).max() < 1e-6 and np.allclose(start[4:], T[:3, 3])   # Converter::toSE3Quat
+    cam = (float(k[0] / np.float32(8)), float(k[1] / np.float32(8)), (float(k[2]) - 3.5) / 8.0, (float(k[3]) - 3.5) / 8.0)
+    ref = O.dust_pose_optimize(s["dust"], start, Xw32.astype(np.float64), *cam)
+    assert n_inlier == ref["n_inlier"] and np.array_equal(rows[:, 0].astype(np.uint8), ref["visible"])
+    assert np.array_equal(rows[:, 0], rows[:, 1])                                    # in_view set with is_visible
+    vis = ref["visible"] == 1
+    assert np.allclose(rows[vis, 2:], ref["uv"][vis], atol=1e-4)
+    Tref = np.eye(4)
+    Tref[:3, :3], Tref[:3, 3] = rot_matrix(ref["pose"][:4]), ref["pose"][4:]
+    assert np.abs(Tout - Tref).max() < 1e-6                                          # Frame::SetPose(Converter::toCvMat(...))
