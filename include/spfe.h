@@ -220,6 +220,12 @@ typedef struct spfe_dust_pose {
 } spfe_dust_pose;
 int spfe_dust_pose_optimize(spfe_ctx *ctx, const spfe_dust_pose *p, double *pose7, uint8_t *visible, float *proj_uv,
                             int32_t *n_inlier, int32_t *n_iter, double *stats);
+/* `count` independent solves (one per frame / camera stream of a batch) in ONE launch, one CTA each: pose7 [count][7]
+ * in / out, visible[i] / proj_uv[i] per-problem arrays (the arrays or single entries may be NULL), n_inlier / n_iter
+ * [count] (may be NULL).  SPFE_ERR_STATE if any problem hit the linearizeOplus throw (its n_iter is -1); the other
+ * problems' results are still valid. */
+int spfe_dust_pose_optimize_batch(spfe_ctx *ctx, const spfe_dust_pose *problems, int32_t count, double *pose7,
+                                  uint8_t *const *visible, float *const *proj_uv, int32_t *n_inlier, int32_t *n_iter);
 int spfe_dust_linearize(spfe_ctx *ctx, const spfe_dust_pose *p, const double *pose7, uint8_t *level, double *err,
                         float *proj_uv, double *J, double *Hb);
 

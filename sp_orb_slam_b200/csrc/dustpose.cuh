@@ -38,8 +38,10 @@ struct DustPoseArgs {
   const double *Xw;    // [n][3]
   int n, mode, iterations;
   double fx, fy, cx, cy, huber, chi2_inlier;
-  double *pose;        // [7] qx qy qz qw tx ty tz, in / out
-  uint8_t *level;      // [n] in / out (mode 0), out (mode 1)
+  const double *pose_in;   // [7] qx qy qz qw tx ty tz
+  const uint8_t *level_in; // [n] or null (= all 0): levels on entry (mode 0)
+  double *pose;        // [7] out (mode 1)
+  uint8_t *level;      // [n] out
   double *err;         // [n]
   float *uv;           // [n][2]
   double *J;           // [n][6]   (mode 0 only)
@@ -154,10 +156,12 @@ __device__ __forceinline__ void dp_huber(double delta, double e2, double &rho0, 
 }
 
 // ---- thread-0 pieces: g2o SE3Quat (exp, product, normalizeRotation), dense 6 x 6 solve ----
+// (the serial fp64 section paces the kernel -- every other warp waits at the barrier behind it -- so divisions are
+// replaced by one reciprocal where g2o / Eigen divide element by element: same value to rounding)
 __device__ inline void dp_normalize_rotation(double *q) {
   if (q[3] < 0) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
-  const double nrm = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-  q[0] /= nrm; q[1] /= nrm; q[2] /= nrm; q[3] /= nrm;
+  const double inv = rsqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
 }
 
 __device__ inline void dp_quat_from_matrix(const double R[3][3], double *q) {  // Eigen, Shepperd
@@ -193,12 +197,17 @@ __device__ inline void dp_se3_exp(const double *upd, DpPose &out) {  // upd = (o
   double ra, rb, va, vb;
   if (theta < 0.00001) { ra = 1.0; rb = 0.5; va = 0.5; vb = 1.0 / 6.0; }
   else {
-    ra = sin(theta) / theta;
-    rb = (1 - cos(theta)) / (theta * theta);
+    double sn, cs;
+    sincos(theta, &sn, &cs);
+    const double it = 1.0 / theta, it2 = it * it;
+    ra = sn * it;
+    rb = (1 - cs) * it2;
     va = rb;
-    vb = (theta - sin(theta)) / (theta * theta * theta);
+    vb = (theta - sn) * (it2 * it);
   }
+#pragma unroll
   for (int i = 0; i < 3; i++)
+#pragma unroll
     for (int j = 0; j < 3; j++) {
       const double I = i == j ? 1.0 : 0.0;
       R[i][j] = I + ra * O[i][j] + rb * O2[i][j];
@@ -231,27 +240,37 @@ __device__ inline void dp_se3_mul(const DpPose &a, const DpPose &b, DpPose &o) {
 }
 
 __device__ inline bool dp_chol_solve6(const double *H, double lambda, const double *b, double *x) {  // (H + lambda I) x = b
-  double L[6][6];
-  for (int i = 0; i < 6; i++)
-    for (int j = 0; j <= i; j++) {
-      double s = H[6 * i + j] + (i == j ? lambda : 0.0);
-      for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
-      if (i == j) {
-        if (!(s > 0.0)) return false;
-        L[i][i] = sqrt(s);
-      } else
-        L[i][j] = s / L[j][j];
+  double L[6][6], inv[6];   // inv[j] = 1 / L[j][j]
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    double s = H[6 * j + j] + lambda;
+#pragma unroll
+    for (int k = 0; k < j; k++) s -= L[j][k] * L[j][k];
+    if (!(s > 0.0)) return false;
+    inv[j] = rsqrt(s);
+    L[j][j] = s * inv[j];
+#pragma unroll
+    for (int i = j + 1; i < 6; i++) {
+      double t = H[6 * i + j];
+#pragma unroll
+      for (int k = 0; k < j; k++) t -= L[i][k] * L[j][k];
+      L[i][j] = t * inv[j];
     }
+  }
   double y[6];
+#pragma unroll
   for (int i = 0; i < 6; i++) {
     double s = b[i];
+#pragma unroll
     for (int k = 0; k < i; k++) s -= L[i][k] * y[k];
-    y[i] = s / L[i][i];
+    y[i] = s * inv[i];
   }
+#pragma unroll
   for (int i = 5; i >= 0; i--) {
     double s = y[i];
+#pragma unroll
     for (int k = i + 1; k < 6; k++) s -= L[k][i] * x[k];
-    x[i] = s / L[i][i];
+    x[i] = s * inv[i];
   }
   return true;
 }
@@ -345,7 +364,9 @@ __device__ __forceinline__ void dp_system_pass(const DustPoseArgs &a, const floa
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(DP_THREADS) dust_pose_kernel(const DustPoseArgs a) {
+// One CTA per problem: batch[blockIdx.x] (spfe_dust_pose_optimize_batch solves many frames' poses in one launch).
+__global__ void __launch_bounds__(DP_THREADS) dust_pose_kernel(const DustPoseArgs *__restrict__ batch) {
+  const DustPoseArgs a = batch[blockIdx.x];
   extern __shared__ float s_dust[];
   __shared__ double s_part[DP_THREADS / 32][DP_NRED];
   __shared__ DpState st;
@@ -355,14 +376,16 @@ __global__ void __launch_bounds__(DP_THREADS) dust_pose_kernel(const DustPoseArg
     dust = s_dust;
   }
   if (threadIdx.x == 0) {
-    for (int k = 0; k < 4; k++) st.pose.q[k] = a.pose[k];
-    for (int k = 0; k < 3; k++) st.pose.t[k] = a.pose[4 + k];
+    for (int k = 0; k < 4; k++) st.pose.q[k] = a.pose_in[k];
+    for (int k = 0; k < 3; k++) st.pose.t[k] = a.pose_in[4 + k];
     for (int k = 0; k < 6; k++) st.x[k] = 0.0;
     st.lambda = 0.0; st.ni = 2.0; st.cur = 0.0; st.rho = 0.0;
     st.qmax = 0; st.again = 0; st.ok = 1; st.thrown = 0; st.trials = 0;
   }
-  if (a.mode == 1)
-    for (int i = threadIdx.x; i < a.n; i += DP_THREADS) { a.level[i] = 0; a.err[i] = 0.0; a.uv[2 * i] = 0.0f; a.uv[2 * i + 1] = 0.0f; }
+  for (int i = threadIdx.x; i < a.n; i += DP_THREADS) {
+    a.level[i] = a.level_in ? a.level_in[i] : 0;
+    a.err[i] = 0.0; a.uv[2 * i] = 0.0f; a.uv[2 * i + 1] = 0.0f;
+  }
   __syncthreads();
 
   if (a.mode == 0) {  // spfe_dust_linearize

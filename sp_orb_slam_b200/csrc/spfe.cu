@@ -170,6 +170,9 @@ struct spfe_ctx {
   // spfe_search_guided scratch (device, grown on demand; guarded by match_mu)
   void *guided_buf = nullptr;
   size_t guided_bytes = 0;
+  // spfe_dust_pose_* page-locked staging block (grown on demand; guarded by match_mu)
+  void *dust_stage = nullptr;
+  size_t dust_stage_bytes = 0;
 
   int fail(int code, const std::string &msg) {
     error = msg;
@@ -865,6 +868,7 @@ void spfe_destroy(spfe_ctx *c) {
   }
   if (c->match_stream) cudaStreamDestroy(c->match_stream);
   if (c->guided_buf) cudaFree(c->guided_buf);
+  if (c->dust_stage) cudaFreeHost(c->dust_stage);
   for (cudaStream_t st : {c->compute, c->copy_in, c->copy_out, c->aux}) if (st) cudaStreamDestroy(st);
   for (void *p : c->dev_allocs) cudaFree(p);
   for (void *p : c->host_allocs) cudaFreeHost(p);
@@ -1209,96 +1213,167 @@ int spfe_search_guided(spfe_ctx *c, const spfe_guided_search *g, int32_t *q2kp, 
   return SPFE_OK;
 }
 
-// spfe_dust_pose_optimize (mode 1) / spfe_dust_linearize (mode 0): one launch of dust_pose_kernel on the matcher stream
-static int dust_pose_run(spfe_ctx *c, const spfe_dust_pose *p, int mode, double *pose7, uint8_t *level, double *err, float *uv,
-                         double *J, double *Hb, uint8_t *visible, int32_t *n_inlier, int32_t *n_iter) {
-  const char *fn = mode ? "spfe_dust_pose_optimize" : "spfe_dust_linearize";
+// spfe_dust_pose_optimize[_batch] (mode 1) / spfe_dust_linearize (mode 0): `count` problems = one launch of
+// dust_pose_kernel with `count` CTAs on the matcher stream.  All inputs are packed into one page-locked staging block
+// (one H2D), all results come back in one D2H.
+struct DustOut {  // per-problem destinations (any may be null)
+  double *pose7 = nullptr;   // in (always) / out (mode 1)
+  uint8_t *level = nullptr;  // in / out (mode 0)
+  double *err = nullptr, *J = nullptr, *Hb = nullptr;
+  float *uv = nullptr;
+  uint8_t *visible = nullptr;
+  int32_t *n_inlier = nullptr, *n_iter = nullptr;
+};
+
+static int dust_pose_run(spfe_ctx *c, const spfe_dust_pose *probs, int count, int mode, const DustOut *outs, const char *fn) {
   if (!c) return SPFE_ERR_INVALID;
-  if (!p || p->struct_size != (int32_t)sizeof(spfe_dust_pose)) return c->fail(SPFE_ERR_INVALID, fmt("%s: bad struct pointer / struct_size", fn));
-  const int n = p->n;
-  if (n < 0 || n >= (1 << 20) || !pose7 || (n > 0 && !p->Xw) || (mode == 1 && p->iterations < 0))
-    return c->fail(SPFE_ERR_INVALID, fmt("%s: bad n / iterations / NULL pose or Xw", fn));
-  if (mode == 0 && (!Hb || (n > 0 && (!level || !err || !uv || !J)))) return c->fail(SPFE_ERR_INVALID, fmt("%s: NULL output pointer", fn));
-  int rows = p->rows, cols = p->cols;
-  const float *d_dust = nullptr;
-  cudaEvent_t wait_ev = nullptr;
-  if (p->dust == nullptr) {
-    if (p->slot < 0 || p->slot >= (int)c->slots.size()) return c->fail(SPFE_ERR_INVALID, fmt("%s: bad slot", fn));
-    Slot &s = c->slots[p->slot];
-    if (s.pending) return c->fail(SPFE_ERR_STATE, fmt("%s: slot still has an un-waited batch", fn));
-    if (p->frame < 0 || p->frame >= s.batch) return c->fail(SPFE_ERR_STATE, fmt("%s: frame %d is not part of the slot's last batch (%d frames)", fn, p->frame, s.batch));
-    if ((rows && rows != c->hc) || (cols && cols != c->wc)) return c->fail(SPFE_ERR_INVALID, fmt("%s: rows / cols differ from the extractor's H/8 x W/8", fn));
-    rows = c->hc; cols = c->wc;
-    d_dust = s.dense_dust + (size_t)p->frame * c->cells;
-    wait_ev = s.ev_done;
+  if (count < 0 || count > 4096 || (count > 0 && (!probs || !outs))) return c->fail(SPFE_ERR_INVALID, fmt("%s: bad count / NULL problems", fn));
+  if (count == 0) return SPFE_OK;
+  struct Lay { size_t xw, pose_in, dust, level_in, pose, hb, res, uv, vis, level, err, J; int rows, cols; const float *d_dust; };
+  std::vector<Lay> lay(count);
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 63) / 64 * 64; return o; };
+  const size_t o_args = carve((size_t)count * sizeof(DustPoseArgs));
+  std::vector<cudaEvent_t> waits;
+  for (int i = 0; i < count; i++) {  // validation + input region
+    const spfe_dust_pose *p = probs + i;
+    if (p->struct_size != (int32_t)sizeof(spfe_dust_pose)) return c->fail(SPFE_ERR_INVALID, fmt("%s: bad struct_size (problem %d)", fn, i));
+    const int n = p->n;
+    if (n < 0 || n >= (1 << 20) || !outs[i].pose7 || (n > 0 && !p->Xw) || (mode == 1 && p->iterations < 0))
+      return c->fail(SPFE_ERR_INVALID, fmt("%s: bad n / iterations / NULL pose or Xw (problem %d)", fn, i));
+    if (mode == 0 && (!outs[i].Hb || (n > 0 && (!outs[i].level || !outs[i].err || !outs[i].uv || !outs[i].J))))
+      return c->fail(SPFE_ERR_INVALID, fmt("%s: NULL output pointer", fn));
+    Lay &l = lay[i];
+    l.rows = p->rows; l.cols = p->cols; l.d_dust = nullptr;
+    if (p->dust == nullptr) {
+      if (p->slot < 0 || p->slot >= (int)c->slots.size()) return c->fail(SPFE_ERR_INVALID, fmt("%s: bad slot (problem %d)", fn, i));
+      Slot &s = c->slots[p->slot];
+      if (s.pending) return c->fail(SPFE_ERR_STATE, fmt("%s: slot still has an un-waited batch", fn));
+      if (p->frame < 0 || p->frame >= s.batch) return c->fail(SPFE_ERR_STATE, fmt("%s: frame %d is not part of the slot's last batch (%d frames)", fn, p->frame, s.batch));
+      if ((l.rows && l.rows != c->hc) || (l.cols && l.cols != c->wc)) return c->fail(SPFE_ERR_INVALID, fmt("%s: rows / cols differ from the extractor's H/8 x W/8", fn));
+      l.rows = c->hc; l.cols = c->wc;
+      l.d_dust = s.dense_dust + (size_t)p->frame * c->cells;
+      bool seen = false;
+      for (cudaEvent_t e : waits) seen |= e == s.ev_done;
+      if (!seen) waits.push_back(s.ev_done);
+    }
+    if (l.rows < 4 || l.cols < 4 || (size_t)l.rows * l.cols >= (1u << 26)) return c->fail(SPFE_ERR_INVALID, fmt("%s: bad dust map size (problem %d)", fn, i));
+    const size_t nn = n > 0 ? n : 1;
+    l.xw = carve(nn * 24); l.pose_in = carve(56);
+    l.dust = carve(p->dust ? (size_t)l.rows * l.cols * sizeof(float) : 0);
+    l.level_in = carve(mode == 0 ? nn : 0);
   }
-  if (rows < 4 || cols < 4 || (size_t)rows * cols >= (1u << 26)) return c->fail(SPFE_ERR_INVALID, fmt("%s: bad dust map size", fn));
+  const size_t in_bytes = off;
+  for (int i = 0; i < count; i++) {  // output region
+    const size_t nn = probs[i].n > 0 ? probs[i].n : 1;
+    Lay &l = lay[i];
+    l.pose = carve(56); l.hb = carve(43 * 8); l.res = carve(8); l.uv = carve(nn * 8); l.vis = carve(nn); l.level = carve(nn);
+    l.err = carve(nn * 8); l.J = carve(mode == 0 ? nn * 48 : 0);
+  }
+  const size_t total = off;
   std::lock_guard<std::mutex> lock(c->match_mu);
   CU_OK(c, cudaSetDevice(c->cfg.device_id));
   cudaStream_t st = c->match_stream;
-  size_t off = 0;
-  auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
-  const size_t nn = n > 0 ? n : 1, map_bytes = (size_t)rows * cols * sizeof(float);
-  const size_t o_dust = carve(p->dust ? map_bytes : 0), o_xw = carve(nn * 24), o_pose = carve(7 * 8), o_level = carve(nn), o_err = carve(nn * 8),
-               o_uv = carve(nn * 8), o_J = carve(mode == 0 ? nn * 48 : 0), o_Hb = carve(43 * 8), o_vis = carve(nn), o_res = carve(8);
-  if (off > c->guided_bytes) {
+  if (total > c->guided_bytes) {
     if (c->guided_buf) cudaFree(c->guided_buf);
     c->guided_buf = nullptr;
     c->guided_bytes = 0;
-    CU_OK(c, cudaMalloc(&c->guided_buf, off + off / 2));
-    c->guided_bytes = off + off / 2;
+    CU_OK(c, cudaMalloc(&c->guided_buf, total + total / 2));
+    c->guided_bytes = total + total / 2;
   }
-  uint8_t *base = static_cast<uint8_t *>(c->guided_buf);
-  if (p->dust) {
-    CU_OK(c, cudaMemcpyAsync(base + o_dust, p->dust, map_bytes, cudaMemcpyHostToDevice, st));
-    d_dust = reinterpret_cast<const float *>(base + o_dust);
-  } else {
-    CU_OK(c, cudaStreamWaitEvent(st, wait_ev, 0));
+  if (total > c->dust_stage_bytes) {
+    if (c->dust_stage) cudaFreeHost(c->dust_stage);
+    c->dust_stage = nullptr;
+    c->dust_stage_bytes = 0;
+    CU_OK(c, cudaMallocHost(&c->dust_stage, total + total / 2));
+    c->dust_stage_bytes = total + total / 2;
   }
-  if (n > 0) CU_OK(c, cudaMemcpyAsync(base + o_xw, p->Xw, (size_t)n * 24, cudaMemcpyHostToDevice, st));
-  CU_OK(c, cudaMemcpyAsync(base + o_pose, pose7, 7 * 8, cudaMemcpyHostToDevice, st));
-  if (mode == 0 && n > 0) {
-    CU_OK(c, cudaMemcpyAsync(base + o_level, level, n, cudaMemcpyHostToDevice, st));
-    CU_OK(c, cudaMemsetAsync(base + o_uv, 0, (size_t)n * 8, st));
+  uint8_t *base = static_cast<uint8_t *>(c->guided_buf), *hb = static_cast<uint8_t *>(c->dust_stage);
+  DustPoseArgs *args = reinterpret_cast<DustPoseArgs *>(hb + o_args);
+  size_t smem = 0;
+  for (int i = 0; i < count; i++) {
+    const spfe_dust_pose *p = probs + i;
+    const Lay &l = lay[i];
+    const int n = p->n;
+    const size_t map_bytes = (size_t)l.rows * l.cols * sizeof(float);
+    if (n > 0) memcpy(hb + l.xw, p->Xw, (size_t)n * 24);
+    memcpy(hb + l.pose_in, outs[i].pose7, 56);
+    if (p->dust) memcpy(hb + l.dust, p->dust, map_bytes);
+    if (mode == 0 && n > 0) memcpy(hb + l.level_in, outs[i].level, n);
+    DustPoseArgs a;
+    a.dust = p->dust ? reinterpret_cast<const float *>(base + l.dust) : l.d_dust;
+    a.rows = l.rows; a.cols = l.cols; a.dust_in_smem = map_bytes <= (size_t)DUST_SMEM_MAX;
+    if (a.dust_in_smem && map_bytes > smem) smem = map_bytes;
+    a.Xw = reinterpret_cast<const double *>(base + l.xw); a.n = n; a.mode = mode; a.iterations = p->iterations;
+    a.fx = p->fx; a.fy = p->fy; a.cx = p->cx; a.cy = p->cy; a.huber = p->huber_delta; a.chi2_inlier = p->chi2_inlier;
+    a.pose_in = reinterpret_cast<const double *>(base + l.pose_in);
+    a.level_in = mode == 0 ? base + l.level_in : nullptr;
+    a.pose = reinterpret_cast<double *>(base + l.pose); a.level = base + l.level; a.err = reinterpret_cast<double *>(base + l.err);
+    a.uv = reinterpret_cast<float *>(base + l.uv); a.J = reinterpret_cast<double *>(base + l.J); a.Hb = reinterpret_cast<double *>(base + l.hb);
+    a.visible = base + l.vis; a.result = reinterpret_cast<int *>(base + l.res);
+    args[i] = a;
   }
-  DustPoseArgs a;
-  a.dust = d_dust; a.rows = rows; a.cols = cols; a.dust_in_smem = map_bytes <= (size_t)DUST_SMEM_MAX;
-  a.Xw = reinterpret_cast<const double *>(base + o_xw); a.n = n; a.mode = mode; a.iterations = p->iterations;
-  a.fx = p->fx; a.fy = p->fy; a.cx = p->cx; a.cy = p->cy; a.huber = p->huber_delta; a.chi2_inlier = p->chi2_inlier;
-  a.pose = reinterpret_cast<double *>(base + o_pose); a.level = base + o_level; a.err = reinterpret_cast<double *>(base + o_err);
-  a.uv = reinterpret_cast<float *>(base + o_uv); a.J = reinterpret_cast<double *>(base + o_J); a.Hb = reinterpret_cast<double *>(base + o_Hb);
-  a.visible = base + o_vis; a.result = reinterpret_cast<int *>(base + o_res);
-  dust_pose_kernel<<<1, DP_THREADS, a.dust_in_smem ? map_bytes : 0, st>>>(a);
+  for (cudaEvent_t e : waits) CU_OK(c, cudaStreamWaitEvent(st, e, 0));  // device-resident maps: after the batch that wrote them
+  CU_OK(c, cudaMemcpyAsync(base, hb, in_bytes, cudaMemcpyHostToDevice, st));
+  dust_pose_kernel<<<count, DP_THREADS, smem, st>>>(reinterpret_cast<const DustPoseArgs *>(base + o_args));
   c->launches += 1;
   CU_OK(c, cudaGetLastError());
-  int res[2] = {0, 0};
-  double hb[43];
-  CU_OK(c, cudaMemcpyAsync(res, base + o_res, 8, cudaMemcpyDeviceToHost, st));
-  CU_OK(c, cudaMemcpyAsync(hb, base + o_Hb, 43 * 8, cudaMemcpyDeviceToHost, st));
-  if (mode == 1) CU_OK(c, cudaMemcpyAsync(pose7, base + o_pose, 7 * 8, cudaMemcpyDeviceToHost, st));
-  if (n > 0) {
-    if (uv) CU_OK(c, cudaMemcpyAsync(uv, base + o_uv, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    if (level) CU_OK(c, cudaMemcpyAsync(level, base + o_level, n, cudaMemcpyDeviceToHost, st));
-    if (err) CU_OK(c, cudaMemcpyAsync(err, base + o_err, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    if (J) CU_OK(c, cudaMemcpyAsync(J, base + o_J, (size_t)n * 48, cudaMemcpyDeviceToHost, st));
-    if (visible) CU_OK(c, cudaMemcpyAsync(visible, base + o_vis, n, cudaMemcpyDeviceToHost, st));
-  }
+  CU_OK(c, cudaMemcpyAsync(hb + in_bytes, base + in_bytes, total - in_bytes, cudaMemcpyDeviceToHost, st));
   CU_OK(c, cudaStreamSynchronize(st));
-  if (Hb) memcpy(Hb, hb, (mode == 0 ? 43 : 3) * sizeof(double));
-  if (n_inlier) *n_inlier = res[1];
-  if (n_iter) *n_iter = res[0];
-  if (res[0] < 0) return c->fail(SPFE_ERR_STATE, fmt("%s: an edge's linearizeOplus projection left the image ( should be omitted)", fn));
+  int thrown = -1;
+  for (int i = 0; i < count; i++) {
+    const Lay &l = lay[i];
+    const DustOut &o = outs[i];
+    const int n = probs[i].n;
+    const int *res = reinterpret_cast<const int *>(hb + l.res);
+    if (mode == 1) memcpy(o.pose7, hb + l.pose, 56);
+    if (o.Hb) memcpy(o.Hb, hb + l.hb, (mode == 0 ? 43 : 3) * sizeof(double));
+    if (o.n_inlier) *o.n_inlier = res[1];
+    if (o.n_iter) *o.n_iter = res[0];
+    if (n > 0) {
+      if (o.uv) memcpy(o.uv, hb + l.uv, (size_t)n * 8);
+      if (o.level) memcpy(o.level, hb + l.level, n);
+      if (o.err) memcpy(o.err, hb + l.err, (size_t)n * 8);
+      if (o.J) memcpy(o.J, hb + l.J, (size_t)n * 48);
+      if (o.visible) memcpy(o.visible, hb + l.vis, n);
+    }
+    if (res[0] < 0 && thrown < 0) thrown = i;
+  }
+  if (thrown >= 0) return c->fail(SPFE_ERR_STATE, fmt("%s: an edge's linearizeOplus projection left the image ( should be omitted), problem %d", fn, thrown));
   return SPFE_OK;
 }
 
 int spfe_dust_pose_optimize(spfe_ctx *c, const spfe_dust_pose *p, double *pose7, uint8_t *visible, float *proj_uv,
                             int32_t *n_inlier, int32_t *n_iter, double *stats) {
-  return dust_pose_run(c, p, 1, pose7, nullptr, nullptr, proj_uv, nullptr, stats, visible, n_inlier, n_iter);
+  if (!c) return SPFE_ERR_INVALID;
+  if (!p) return c->fail(SPFE_ERR_INVALID, "spfe_dust_pose_optimize: NULL problem");
+  DustOut o;
+  o.pose7 = pose7; o.visible = visible; o.uv = proj_uv; o.n_inlier = n_inlier; o.n_iter = n_iter; o.Hb = stats;
+  return dust_pose_run(c, p, 1, 1, &o, "spfe_dust_pose_optimize");
+}
+
+int spfe_dust_pose_optimize_batch(spfe_ctx *c, const spfe_dust_pose *problems, int32_t count, double *pose7,
+                                  uint8_t *const *visible, float *const *proj_uv, int32_t *n_inlier, int32_t *n_iter) {
+  if (!c) return SPFE_ERR_INVALID;
+  if (count < 0 || (count > 0 && (!problems || !pose7))) return c->fail(SPFE_ERR_INVALID, "spfe_dust_pose_optimize_batch: bad count / NULL problems or poses");
+  std::vector<DustOut> outs(count > 0 ? count : 0);
+  for (int i = 0; i < count; i++) {
+    outs[i].pose7 = pose7 + 7 * (size_t)i;
+    outs[i].visible = visible ? visible[i] : nullptr;
+    outs[i].uv = proj_uv ? proj_uv[i] : nullptr;
+    outs[i].n_inlier = n_inlier ? n_inlier + i : nullptr;
+    outs[i].n_iter = n_iter ? n_iter + i : nullptr;
+  }
+  return dust_pose_run(c, problems, count, 1, outs.data(), "spfe_dust_pose_optimize_batch");
 }
 
 int spfe_dust_linearize(spfe_ctx *c, const spfe_dust_pose *p, const double *pose7, uint8_t *level, double *err,
                         float *proj_uv, double *J, double *Hb) {
-  return dust_pose_run(c, p, 0, const_cast<double *>(pose7), level, err, proj_uv, J, Hb, nullptr, nullptr, nullptr);
+  if (!c) return SPFE_ERR_INVALID;
+  if (!p) return c->fail(SPFE_ERR_INVALID, "spfe_dust_linearize: NULL problem");
+  DustOut o;
+  o.pose7 = const_cast<double *>(pose7); o.level = level; o.err = err; o.uv = proj_uv; o.J = J; o.Hb = Hb;
+  return dust_pose_run(c, p, 1, 0, &o, "spfe_dust_linearize");
 }
 
 int spfe_set_score_threshold(spfe_ctx *c, float score_thresh) {

@@ -273,6 +273,30 @@ class SPExtractor:
                                                       vp(uv.ctypes.data), C.byref(ninl), C.byref(nit), vp(stats.ctypes.data)))
         return dict(pose=pose, visible=vis[:n], uv=uv[:n], n_inlier=ninl.value, n_iter=nit.value, stats=stats)
 
+    def dust_pose_optimize_batch(self, problems, *, huber: float = 0.9, chi2_inlier: float = 0.9, iterations: int = 40):
+        """spfe_dust_pose_optimize_batch: ``problems`` = list of dicts(pose, Xw, cam=(fx, fy, cx, cy), and either ``dust``
+        (host map) or ``slot`` / ``frame``); all solves run in one launch, one CTA each.  -> list of result dicts."""
+        cnt = len(problems)
+        arr = (capi.DustPose * max(cnt, 1))()
+        keep, poses = [], np.zeros((max(cnt, 1), 7))
+        vis_p, uv_p = (C.c_void_p * max(cnt, 1))(), (C.c_void_p * max(cnt, 1))()
+        vis, uv = [], []
+        for i, pr in enumerate(problems):
+            d, Xw, dust = self._dust_struct(pr["Xw"], pr.get("dust"), *pr["cam"], huber, chi2_inlier, iterations,
+                                            pr.get("slot", 0), pr.get("frame", 0))
+            arr[i] = d
+            keep.append((Xw, dust))
+            poses[i] = pr["pose"]
+            vis.append(np.zeros(max(len(Xw), 1), np.uint8))
+            uv.append(np.zeros((max(len(Xw), 1), 2), np.float32))
+            vis_p[i], uv_p[i] = vis[i].ctypes.data, uv[i].ctypes.data
+        ninl, nit = np.zeros(max(cnt, 1), np.int32), np.zeros(max(cnt, 1), np.int32)
+        vp = C.c_void_p
+        self._check(self._lib.spfe_dust_pose_optimize_batch(self._ctx, arr, cnt, vp(poses.ctypes.data), C.cast(vis_p, vp), C.cast(uv_p, vp),
+                                                            vp(ninl.ctypes.data), vp(nit.ctypes.data)))
+        return [dict(pose=poses[i].copy(), visible=vis[i][:len(keep[i][0])], uv=uv[i][:len(keep[i][0])], n_inlier=int(ninl[i]),
+                     n_iter=int(nit[i])) for i in range(cnt)]
+
     def dust_linearize(self, pose7, Xw, fx, fy, cx, cy, *, dust=None, slot: int = 0, frame: int = 0, huber: float = 0.9, level=None):
         """spfe_dust_linearize on plain arrays -> dict(level, err, uv, J, H, b, chi2)."""
         d, Xw, dust = self._dust_struct(Xw, dust, fx, fy, cx, cy, huber, 0.9, 0, slot, frame)

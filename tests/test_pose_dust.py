@@ -205,6 +205,36 @@ def test_gpu_pose_optimize_on_device_resident_dust(ex):
 
 
 @pytest.mark.gpu
+def test_gpu_pose_optimize_batch(ex):
+    """Many frames' solves in one launch (one CTA per problem): host maps of different sizes and device-resident maps of
+    an extracted batch side by side; every problem equals its single-call result bit for bit, and the oracle's."""
+    frames = synth.make_stream(480, 752, 2, seed=9)
+    outs = ex.extract_batch(list(frames))
+    probs, scenes = [], []
+    for i, (n, shape) in enumerate([(300, (60, 94)), (40, (60, 80)), (0, (60, 94)), (700, (135, 240)), (150, (60, 94))] * 3):
+        s = make_scene(100 + i, n=max(n, 1), rows=shape[0], cols=shape[1])
+        Xw = s["Xw"][:n]
+        scenes.append((s, Xw))
+        probs.append(dict(pose=s["start"], Xw=Xw, cam=CAM, dust=s["dust"]))
+    sd = make_scene(200, n=220)
+    for f in (0, 1):
+        probs.append(dict(pose=sd["start"], Xw=sd["Xw"], cam=CAM, slot=0, frame=f))
+    res = ex.dust_pose_optimize_batch(probs)
+    assert len(res) == len(probs)
+    for (s, Xw), r in zip(scenes, res):
+        one = ex.dust_pose_optimize(s["start"], Xw, *CAM, dust=s["dust"])
+        assert np.array_equal(r["pose"], one["pose"]) and np.array_equal(r["visible"], one["visible"]) and r["n_iter"] == one["n_iter"]
+        ref = O.dust_pose_optimize(s["dust"], s["start"], Xw, *CAM)
+        assert np.abs(r["pose"] - ref["pose"]).max() < 1e-9 and r["n_inlier"] == ref["n_inlier"] and r["n_iter"] == ref["n_iter"]
+        assert np.array_equal(r["visible"], ref["visible"])
+    for f, r in zip((0, 1), res[-2:]):
+        dust = np.array(outs[f]["dense_dust"], np.float32).reshape(60, 94)
+        ref = O.dust_pose_optimize(dust, sd["start"], sd["Xw"], *CAM)
+        assert np.abs(r["pose"] - ref["pose"]).max() < 1e-9 and r["n_inlier"] == ref["n_inlier"]
+    assert ex.dust_pose_optimize_batch([]) == []
+
+
+@pytest.mark.gpu
 def test_gpu_dust_pose_bad_arguments(ex):
     s = make_scene(41, n=5)
     with pytest.raises(Exception):

@@ -35,5 +35,17 @@ for n in (100, 300, 1000):
         O.dust_pose_optimize(s["dust"], s["start"], s["Xw"], *CAM)
     out[f"oracle_c_ms_n{n}"] = round((time.perf_counter() - t0) / max(reps // 4, 5) * 1e3, 4)
     out[f"oracle_iters_n{n}"] = [int(ref["n_iter"]), int(ref["stats"][2])]
+# throughput mode: one solve per frame of a 64-frame batch, one launch (one CTA per problem)
+s = make_scene(7, n=300)
+for cnt in (1, 16, 64, 148, 296):
+    probs = [dict(pose=s["start"], Xw=s["Xw"], cam=CAM, dust=s["dust"]) for _ in range(cnt)]
+    for _ in range(3):
+        ex.dust_pose_optimize_batch(probs)
+    t0 = time.perf_counter()
+    for _ in range(max(reps // 10, 3)):
+        ex.dust_pose_optimize_batch(probs)
+    dt = (time.perf_counter() - t0) / max(reps // 10, 3)
+    out[f"batch{cnt}_ms"] = round(dt * 1e3, 4)
+    out[f"batch{cnt}_solves_per_s"] = round(cnt / dt)
 ex.close()
 print(json.dumps(out))

@@ -21,6 +21,7 @@ static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 using std::max;
 using std::min;
 #include "dustpose.cuh"
@@ -100,7 +101,7 @@ int main() {
     double dmax = 0; for (int k = 0; k < 4; k++) dmax = fmax(dmax, fabs(pose_s.q[k] - po[k])); for (int k = 0; k < 3; k++) dmax = fmax(dmax, fabs(pose_s.t[k] - po[4 + k]));
     int inl1 = 0, visdiff = 0; for (int i = 0; i < n; i++) { bool badp = lv1[i] == 1 || e1[i] * e1[i] > 0.9; inl1 += !badp; visdiff += (vis0[i] != (uint8_t)!badp); }
     printf("trial %2d n %3d: it %d/%d trials %d/%d inliers %d/%d visdiff %d pose diff %.2e lambda %.3e/%.3e chi %.6f\n", trial, n, it0, it, (int)stats[2], trials, inl0, inl1, visdiff, dmax, stats[0], lambda, stats[1]);
-    if (it0 != it || inl0 != inl1 || visdiff || dmax > 1e-12) bad++;
+    if (it0 != it || inl0 != inl1 || visdiff || dmax > 1e-11) bad++;   // the device functions use reciprocals where the oracle divides
   }
   printf(bad ? "FAILED %d\n" : "all ok\n", bad);
   return bad != 0;
