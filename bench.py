@@ -235,14 +235,15 @@ def main():
         lean.close()
 
     # ---------------- per-kernel device times (roofline), CUDA events between stages on the library's stream
-    stages = {}
-    for rep in range(4):
+    # (median of 8 passes after one warm-up pass: the board is power-capped and a single pass can land in a clock dip)
+    stages, samples = {}, {}
+    for rep in range(9):
         for s in ex.profile_device(0, d_pool.data_ptr() + (rep % n_pool) * stride, B):
             if rep:                                               # first repetition is warm-up
-                d = stages.setdefault(s["name"], dict(ms=0.0, flop=s["flop"], bytes=s["bytes"], n=0))
-                d["ms"] += s["ms"]; d["n"] += 1
-    for d in stages.values():
-        d["ms"] /= max(d["n"], 1)
+                stages.setdefault(s["name"], dict(ms=0.0, flop=s["flop"], bytes=s["bytes"]))
+                samples.setdefault(s["name"], []).append(s["ms"])
+    for n, d in stages.items():
+        d["ms"] = float(np.median(samples[n]))
     peaks = measured_peaks()
     conv_names = [n for n in stages if n.startswith("conv")]
     dom = max(conv_names, key=lambda n: stages[n]["ms"])
