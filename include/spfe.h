@@ -21,7 +21,7 @@
  *                                                                       orb_slam2/src/cv/sp_matcher_loop.cpp:334-376
  *   spfe_l2                <- SPMatcher::DescriptorDistance             orb_slam2/src/cv/sp_matcher.cpp:1636-1640
  *   spfe_dust_pose_optimize <- Optimizer::PoseOptimizationDust          orb_slam2/src/mapping/optimizer_dust.cpp:170-293
- *                             (EdgeSE3ProjectDustOnlyPose, orb_slam2/src/optimization/types_dust_tracking.cpp:37-141)
+ *                             (EdgeSE3ProjectDustOnlyPose, orb_slam2/src/optimization/types_dust_tracking.cpp:36-141)
  *
  * The reference is one-frame-blocking with batch size 1 (sp_extractor.cpp:70
  * "TODO: batch-size").  spfe_extract keeps that contract; spfe_submit /
@@ -189,7 +189,7 @@ int spfe_search_guided(spfe_ctx *ctx, const spfe_guided_search *g, int32_t *q2kp
 /* Dust-map pose optimisation -- the inner loop of
  *   Optimizer::PoseOptimizationDust(Frame*, const vector<MapPoint*>&, vector<bool>&)   orb_slam2/src/mapping/optimizer_dust.cpp:170-293
  * i.e. a g2o graph of one SE3 vertex and one EdgeSE3ProjectDustOnlyPose per map point
- *   computeError / linearizeOplus / isInImage / getPixelValue                          orb_slam2/src/optimization/types_dust_tracking.cpp:37-141
+ *   computeError / linearizeOplus / isInImage / getPixelValue                          orb_slam2/src/optimization/types_dust_tracking.cpp:36-141
  * solved by 40 Levenberg iterations with a Huber kernel, in ONE kernel launch (dustpose.cuh).  The caller hoists the
  * map points into a flat array; the intrinsics are those the reference hands the edges: fx / 8, fy / 8, (cx - 3.5) / 8,
  * (cy - 3.5) / 8 (optimizer_dust.cpp:222-225).  pose = Frame::mTcw as (qx, qy, qz, qw, tx, ty, tz), g2o::SE3Quat order.

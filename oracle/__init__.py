@@ -7,9 +7,12 @@ the checker or the timed CPU baseline -- never as a fallback for the CUDA path.
 
 Parity status: **parity unpinned by the reference** -- the reference ships no
 tests, golden vectors or fixtures for this path.  The
-oracle is instead pinned against (i) the reference's own ``SPFrontend`` C++
-compiled against libtorch in this container (``oracle/ref_build.sh`` ->
-``oracle/_ref/``) and (ii) OpenCV (``cv2.BFMatcher``, ``cv2.sortIdx``,
+oracle is instead pinned against (i) the reference's own code compiled in this
+container by ``oracle/ref_build.sh`` into ``oracle/_ref/``: its ``SPFrontend``
+against libtorch (network half), its ``nms`` / ``computeCovariance`` verbatim
+against a cv / Eigen stand-in (``ref_cv_stub.h``) and its
+``EdgeSE3ProjectDustOnlyPose`` verbatim against a g2o stand-in
+(``ref_g2o_stub.h``), and (ii) OpenCV (``cv2.BFMatcher``, ``cv2.sortIdx``,
 ``cv2.minMaxLoc``) for the third-party arithmetic the reference calls; the
 resulting vectors are committed under ``tests/golden/``.
 """

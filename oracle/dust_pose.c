@@ -2,8 +2,8 @@
  * CPU oracle, dust-map pose optimisation -- TEST INFRASTRUCTURE ONLY
  * (see oracle/__init__.py).  Plain-C, double-precision restatement of
  *
- *   orc_dust_error      <- EdgeSE3ProjectDustOnlyPose::computeError     orb_slam2/src/optimization/types_dust_tracking.cpp:64-94
- *                          (isInImage :37-42, getPixelValue :44-58)
+ *   orc_dust_error      <- EdgeSE3ProjectDustOnlyPose::computeError     orb_slam2/src/optimization/types_dust_tracking.cpp:62-94
+ *                          (isInImage :36-41, getPixelValue :43-56)
  *   orc_dust_jacobian   <- EdgeSE3ProjectDustOnlyPose::linearizeOplus   :96-141
  *   orc_dust_linearize  <- one computeActiveErrors + buildSystem pass of the graph that
  *                          Optimizer::PoseOptimizationDust(Frame*, mps, is_visible) builds
@@ -24,7 +24,12 @@
  *          [1/3, 2/3], ni doubling, 10 trials, rho==0 terminates), SparseOptimizer::optimize, push / pop of the vertex
  *          estimate, LinearSolverDense (here: Cholesky of H + lambda I; g2o uses Eigen::LDLT -- same solution to
  *          rounding).
- * PARITY UNPINNED for this file: the reference ships no test or golden vector for it and g2o cannot be built here.
+ * Parity status: the reference ships no test or golden vector for this path.  The per-edge half (orc_dust_error,
+ * orc_dust_jacobian) IS pinned: oracle/ref_build.sh compiles the reference's own EdgeSE3ProjectDustOnlyPose verbatim
+ * (types_dust_tracking.h:22-65, types_dust_tracking.cpp:36-141) against a g2o / Eigen stand-in (oracle/ref_g2o_stub.h)
+ * into oracle/_ref/libspdust_ref.so, and tests/test_pose_dust.py::test_reference_edge_pins_oracle finds error, level,
+ * (u_, v_) and Jacobian bit-identical.  The Levenberg loop (orc_dust_optimize) is PARITY UNPINNED: g2o cannot be built
+ * here.
  *
  * Behaviour kept on purpose: setLevel(1) is sticky (an edge that left the image once keeps a zero Jacobian but its
  * error still enters chi2 when it projects inside again); u_ / v_ and _error are those of the LAST computeError call,

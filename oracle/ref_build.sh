@@ -1,5 +1,5 @@
 #!/bin/bash
-# Compile the reference's own SPFrontend (network half of the hot path) from the
+# Compile the reference's own SPFrontend (network half of the hot path) and its own nms / computeCovariance from the
 # sources where they lie under $SPFE_REFERENCE (default /root/reference) against
 # this image's libtorch (CPU).  Outputs ONLY into oracle/_ref/ (git-ignored).
 # The rest of the reference (OpenCV / Eigen / ROS / g2o / Pangolin) is
@@ -20,3 +20,13 @@ g++ -O2 -std=c++17 -fPIC -shared -D_GLIBCXX_USE_CXX11_ABI=1 -w \
   "$HERE/ref_driver.cc" -o "$OUT/libspref.so" \
   -L"$TORCH/lib" -ltorch -ltorch_cpu -lc10 -Wl,-rpath,"$TORCH/lib"
 echo "built $OUT/libspref.so"
+# the reference's own nms + computeCovariance (sp_extractor.cpp:161-340), verbatim, against oracle/ref_cv_stub.h
+sed -n '161,340p' "$REF/orb_slam2/src/cv/sp_extractor.cpp" > "$OUT/gen/sppost_impl.inc"
+g++ -O2 -std=c++17 -ffp-contract=off -fPIC -shared -w -I"$OUT/gen" -I"$HERE" "$HERE/ref_post_driver.cc" -o "$OUT/libsppost_ref.so"
+echo "built $OUT/libsppost_ref.so"
+# the reference's own EdgeSE3ProjectDustOnlyPose (class + computeError / linearizeOplus / isInImage / getPixelValue),
+# verbatim, against oracle/ref_g2o_stub.h
+sed -n '22,65p' "$REF/orb_slam2/include/orb_slam/optimization/types_dust_tracking.h" > "$OUT/gen/dust_edge_decl.inc"
+sed -n '36,141p' "$REF/orb_slam2/src/optimization/types_dust_tracking.cpp" > "$OUT/gen/dust_edge_impl.inc"
+g++ -O2 -std=c++17 -ffp-contract=off -fPIC -shared -w -I"$OUT/gen" -I"$HERE" "$HERE/ref_dust_driver.cc" -o "$OUT/libspdust_ref.so"
+echo "built $OUT/libspdust_ref.so"

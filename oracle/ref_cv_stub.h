@@ -1,0 +1,107 @@
+// Minimal stand-ins for the handful of OpenCV / Eigen facilities that the reference's own `nms` and
+// `computeCovariance` (orb_slam2/src/cv/sp_extractor.cpp:161-340) touch, so that those two functions can be compiled
+// VERBATIM from /root/reference in a container without OpenCV / Eigen (oracle/ref_build.sh).  TEST INFRASTRUCTURE ONLY.
+// Written for this purpose, not taken from either library; only the semantics the two functions rely on are
+// provided: cv::Mat as a typed 2-D array with shared row headers, copyMakeBorder(BORDER_CONSTANT), element-wise float
+// Vector2f arithmetic (IEEE single precision, no reassociation).
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#define CV_8UC1 0
+#define CV_16UC1 2
+#define CV_16SC1 3
+#define CV_32FC1 5
+#define CV_8UC3 16
+
+namespace cv {
+typedef unsigned char uchar;
+enum { BORDER_CONSTANT = 0 };
+struct Size { int width, height; Size(int w, int h) : width(w), height(h) {} };
+struct Scalar {
+  double v[4];
+  Scalar(double a = 0, double b = 0, double c = 0, double d = 0) : v{a, b, c, d} {}
+  static Scalar all(double a) { return Scalar(a, a, a, a); }
+};
+struct Point2f { float x, y; Point2f() : x(0), y(0) {} Point2f(float x_, float y_) : x(x_), y(y_) {} };
+struct KeyPoint {
+  Point2f pt; float size, angle, response; int octave, class_id;
+  KeyPoint() : size(0), angle(-1), response(0), octave(0), class_id(-1) {}
+  KeyPoint(float x, float y, float size_, float angle_ = -1, float response_ = 0, int octave_ = 0, int class_id_ = -1)
+      : pt(x, y), size(size_), angle(angle_), response(response_), octave(octave_), class_id(class_id_) {}
+};
+class Mat {
+ public:
+  int rows = 0, cols = 0;
+  size_t step = 0;
+  uint8_t *data = nullptr;
+  Mat() {}
+  Mat(int r, int c, int type) { create(r, c, type); }
+  Mat(Size s, int type) { create(s.height, s.width, type); }
+  Mat(int r, int c, int type, const Scalar &s) { create(r, c, type); fill(s); }
+  Mat(Size sz, int type, const Scalar &s) { create(sz.height, sz.width, type); fill(s); }
+  Mat(int r, int c, int type, void *ext) : rows(r), cols(c), data(static_cast<uint8_t *>(ext)), type_(type) { step = c * elemSize(); }  // external memory (driver only)
+  void create(int r, int c, int type) {
+    rows = r; cols = c; type_ = type; step = c * elemSize();
+    store_ = std::make_shared<std::vector<uint8_t>>(static_cast<size_t>(r) * step + 8, 0xCD);  // "uninitialised"
+    data = store_->data();
+  }
+  size_t elemSize() const { return type_ == CV_8UC1 ? 1 : type_ == CV_8UC3 ? 3 : (type_ == CV_16UC1 || type_ == CV_16SC1) ? 2 : 4; }
+  int type() const { return type_; }
+  template <class T> T &at(int r, int c) { return *reinterpret_cast<T *>(data + r * step + c * sizeof(T)); }
+  template <class T> const T &at(int r, int c) const { return *reinterpret_cast<const T *>(data + r * step + c * sizeof(T)); }
+  Mat &setTo(const Scalar &s) { fill(s); return *this; }
+  Mat row(int r) const { Mat m = *this; m.rows = 1; m.data = data + r * step; return m; }  // header sharing the storage
+  void copyTo(Mat dst) const {  // dst is a header onto existing storage of the same shape (descriptors.row(i))
+    for (int r = 0; r < rows; r++) memcpy(dst.data + r * dst.step, data + r * step, cols * elemSize());
+  }
+ private:
+  void fill(const Scalar &s) {
+    for (int r = 0; r < rows; r++)
+      for (int c = 0; c < cols; c++) {
+        uint8_t *p = data + r * step + c * elemSize();
+        switch (type_) {
+          case CV_8UC1: *p = static_cast<uint8_t>(s.v[0]); break;
+          case CV_8UC3: p[0] = static_cast<uint8_t>(s.v[0]); p[1] = static_cast<uint8_t>(s.v[1]); p[2] = static_cast<uint8_t>(s.v[2]); break;
+          case CV_16UC1: *reinterpret_cast<uint16_t *>(p) = static_cast<uint16_t>(s.v[0]); break;
+          case CV_16SC1: *reinterpret_cast<int16_t *>(p) = static_cast<int16_t>(s.v[0]); break;
+          default: *reinterpret_cast<float *>(p) = static_cast<float>(s.v[0]);
+        }
+      }
+  }
+  int type_ = CV_8UC1;
+  std::shared_ptr<std::vector<uint8_t>> store_;
+};
+inline void copyMakeBorder(const Mat &src, Mat &dst, int top, int bottom, int left, int right, int /*BORDER_CONSTANT*/, const Scalar &value) {
+  Mat out(src.rows + top + bottom, src.cols + left + right, src.type(), value);
+  for (int r = 0; r < src.rows; r++) memcpy(out.data + (r + top) * out.step + left * src.elemSize(), src.data + r * src.step, src.cols * src.elemSize());
+  dst = out;
+}
+}  // namespace cv
+
+namespace Eigen {
+struct Array2f {
+  float v[2];
+  Array2f square() const { return Array2f{{v[0] * v[0], v[1] * v[1]}}; }
+};
+struct Vector2f {
+  float v[2];
+  Vector2f() : v{0, 0} {}
+  Vector2f(float a, float b) : v{a, b} {}
+  Vector2f(const Array2f &a) : v{a.v[0], a.v[1]} {}
+  static Vector2f Zero() { return Vector2f(0, 0); }
+  float &x() { return v[0]; }
+  float &y() { return v[1]; }
+  float x() const { return v[0]; }
+  float y() const { return v[1]; }
+  Array2f array() const { return Array2f{{v[0], v[1]}}; }
+  Vector2f operator-(const Vector2f &o) const { return Vector2f(v[0] - o.v[0], v[1] - o.v[1]); }
+  Vector2f &operator+=(const Vector2f &o) { v[0] += o.v[0]; v[1] += o.v[1]; return *this; }
+  struct Comma { Vector2f *t; int i; Comma operator,(float a) { t->v[i] = a; return Comma{t, i + 1}; } };
+  Comma operator<<(float a) { v[0] = a; return Comma{this, 1}; }
+};
+inline Vector2f operator*(float s, const Vector2f &a) { return Vector2f(s * a.v[0], s * a.v[1]); }
+struct Matrix2f { float m[4]; };
+}  // namespace Eigen

@@ -6,7 +6,7 @@ fp32 restatement of the reference path, function by function:
   extract            <- orb_slam2/src/cv/sp_extractor.cpp:361-514 (SPExtractor::operator())
   match_mutual_nn    <- orb_slam2/src/cv/sp_matcher.cpp:1642-1674 (SearchByBruteForce core)
   dust_linearize / dust_pose_optimize
-                     <- orb_slam2/src/optimization/types_dust_tracking.cpp:37-141 (EdgeSE3ProjectDustOnlyPose) and
+                     <- orb_slam2/src/optimization/types_dust_tracking.cpp:36-141 (EdgeSE3ProjectDustOnlyPose) and
                         orb_slam2/src/mapping/optimizer_dust.cpp:170-293 (PoseOptimizationDust); C in oracle/dust_pose.c
 
 The network half runs on torch CPU (the reference runs the same ATen ops

@@ -2,8 +2,11 @@
  * CPU oracle, post-processing half -- TEST INFRASTRUCTURE ONLY (see
  * oracle/__init__.py).  Plain-C restatement of the reference's host-side
  * algorithms with cv::Mat / Eigen replaced by flat arrays.  Parity status:
- * unpinned by the reference (it ships no tests); pinned here against OpenCV
- * (cv2.BFMatcher / sortIdx) in tests/test_oracle.py.
+ * unpinned by the reference (it ships no tests); pinned here against the
+ * reference's OWN nms() / computeCovariance() compiled verbatim into
+ * oracle/_ref/libsppost_ref.so (oracle/ref_build.sh, oracle/ref_cv_stub.h;
+ * bit-identical in tests/test_oracle.py::test_reference_*_pins_oracle) and
+ * against OpenCV (cv2.BFMatcher / sortIdx) for the third-party calls.
  *
  *   orc_to_heat       <- orb_slam2/src/cv/sp_extractor.cpp:461-474 (to_heat lambda)
  *   orc_sort_desc     <- :489-498 (cv::sortIdx, SORT_DESCENDING; ties: lower index first)

@@ -2,7 +2,7 @@
 //
 // Replaces the inner loop of Optimizer::PoseOptimizationDust(Frame*, mps, is_visible)
 // (orb_slam2/src/mapping/optimizer_dust.cpp:170-293): a g2o graph with one SE3 vertex and one unary edge per map point,
-// EdgeSE3ProjectDustOnlyPose (orb_slam2/src/optimization/types_dust_tracking.cpp:37-141), whose error is the bilinear
+// EdgeSE3ProjectDustOnlyPose (orb_slam2/src/optimization/types_dust_tracking.cpp:36-141), whose error is the bilinear
 // sample of the dustbin probability map (hc x wc, Frame::dust_ = SPExtractor::dense_dust_) at the projection of the
 // point, run for 40 Levenberg-Marquardt iterations with a Huber kernel (delta 0.9).
 //
@@ -75,7 +75,7 @@ __device__ __forceinline__ void dp_map(const DpPose &p, const double *v, double 
   o[2] = DP_ADD(DP_ADD(DP_ADD(v[2], DP_MUL(qw, uv2)), c2), p.t[2]);
 }
 
-// isInImage, border = 1.0 (types_dust_tracking.cpp:37-42); w_, h_ are floats there
+// isInImage, border = 1.0 (types_dust_tracking.cpp:36-41); w_, h_ are floats there
 __device__ __forceinline__ bool dp_in_image(const DustPoseArgs &a, double u, double v) {
   const double w = (double)(float)a.cols, h = (double)(float)a.rows;
   return u >= 1.0 && DP_ADD(DP_ADD(u, 1.0), 1.0) < w && v >= 1.0 && DP_ADD(DP_ADD(v, 1.0), 1.0) < h;
@@ -87,7 +87,7 @@ __device__ __forceinline__ float dp_at(const DustPoseArgs &a, const float *dust,
   return dust[y * a.cols + x];
 }
 
-// getPixelValue (types_dust_tracking.cpp:44-58), all float, left to right
+// getPixelValue (types_dust_tracking.cpp:43-56), all float, left to right
 __device__ __forceinline__ float dp_pixel(const DustPoseArgs &a, const float *dust, float x, float y) {
   const int x_f = (int)floorf(x), y_f = (int)floorf(y);
   const float xx = DP_FSUB(x, (float)x_f), yy = DP_FSUB(y, (float)y_f);
@@ -99,7 +99,7 @@ __device__ __forceinline__ float dp_pixel(const DustPoseArgs &a, const float *du
   return DP_FADD(DP_FADD(DP_FADD(t0, t1), t2), t3);
 }
 
-// computeError (types_dust_tracking.cpp:64-94)
+// computeError (types_dust_tracking.cpp:62-94)
 __device__ __forceinline__ double dp_error(const DustPoseArgs &a, const float *dust, const DpPose &p, const double *Xw,
                                            uint8_t &level, float *uv) {
   double xl[3];

@@ -168,3 +168,80 @@ def test_golden_fixture_self_consistency(name, golden):
         d = np.abs(kp[:, None, :] - kp[None, :, :]).max(-1) + 100 * np.eye(len(kp), dtype=int)
         assert d.min() > 4                                                # NMS radius
     assert WEIGHTS.endswith(".spw")
+
+
+def _ref_post():
+    from oracle import ref_post as RP
+    if not RP.available():
+        pytest.skip("oracle/_ref/libsppost_ref.so not built (run oracle/ref_build.sh where /root/reference exists)")
+    return RP
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_reference_nms_pins_oracle(seed):
+    """The reference's OWN nms() (sp_extractor.cpp:161-250, compiled verbatim into oracle/_ref) against the C
+    restatement: identical keypoints, raster order, occ_grid and gathered descriptor rows -- dense and sparse
+    candidate sets, the nfeatures cap (kept count > nf stops the loop), points inside the border band, tiny images."""
+    RP = _ref_post()
+    rng = np.random.RandomState(seed)
+    H, W = [(96, 128), (480, 752), (64, 64), (240, 320)][seed % 4]
+    hc, wc = H // 8, W // 8
+    cells = np.flatnonzero(rng.rand(hc * wc) < [0.9, 0.35, 1.0, 0.6][seed % 4])
+    pos = rng.randint(0, 64, len(cells))
+    pts = np.stack([(cells % wc) * 8 + pos % 8, (cells // wc) * 8 + pos // 8], 1).astype(np.float32)
+    order = O.sort_desc(rng.permutation(len(cells)).astype(np.float32))
+    pts = pts[order]
+    desc = rng.randn(len(pts), 256).astype(np.float32)
+    for nf in (800, 25, 3):
+        sel, occ = O.nms(pts, nf, W, H)
+        kps_ref, occ_ref, desc_ref = RP.nms(pts, desc, nf, W, H)
+        assert np.array_equal(pts[sel], kps_ref)
+        assert np.array_equal(occ, occ_ref)
+        assert np.array_equal(desc[sel], desc_ref)
+    k0, o0, _ = RP.nms(np.zeros((0, 2), np.float32), None, 800, W, H)          # no candidates at all
+    s0, oc0 = O.nms(np.zeros((0, 2), np.float32), 800, W, H)
+    assert len(k0) == 0 and len(s0) == 0 and np.array_equal(o0, oc0) and np.all(o0 == -1)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_reference_covariance_pins_oracle(seed):
+    """The reference's OWN computeCovariance() (sp_extractor.cpp:252-340) against the C restatement, bit for bit:
+    smooth maps with overlapping basins (the visited map is shared between keypoints, so the keypoint ORDER matters),
+    plateaus and exact zeros (the `0 < heat < parent` test), keypoints on the image edge (the `xx > 0` / `yy > 0`
+    boundary tests never visit row / column 0)."""
+    RP = _ref_post()
+    rng = np.random.RandomState(100 + seed)
+    H, W = [(64, 96), (120, 160), (48, 48)][seed % 3]
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    heat = np.zeros((H, W), np.float32)
+    n = [12, 60, 5][seed % 3]
+    cx, cy = rng.randint(0, W, n), rng.randint(0, H, n)
+    for x, y in zip(cx, cy):
+        s = rng.uniform(0.8, 1.6)      # narrow peaks, cut to 0 below 5 %: the flood re-pushes a pixel once per uphill path
+        blob = np.exp(-((xx - x) ** 2 + (yy - y) ** 2) / (2 * s * s))           # (duplicates, :296-300), wide smooth basins blow up
+        heat = np.maximum(heat, (rng.uniform(0.3, 1.0) * np.where(blob > 0.05, blob, 0.0)).astype(np.float32))
+    if seed % 2:
+        heat = np.round(heat * 16) / 16                                       # plateaus and exact zeros
+    heat = heat.astype(np.float32)
+    kps = np.stack([cx, cy], 1).astype(np.float32)
+    kps = kps[np.lexsort((kps[:, 0], kps[:, 1]))]                              # raster order, as nms() emits them
+    for k in (kps, kps[::-1].copy()):                                          # and a different order: results change, parity must not
+        r0, c0, i0 = O.covariance(heat, k)
+        r1, c1, i1 = RP.covariance(heat, k)
+        assert np.array_equal(r0, r1) and np.array_equal(c0, c1) and np.array_equal(i0, i1)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_reference_post_pins_golden(name, golden):
+    """The committed golden fixtures re-derived with the reference's own nms(): the golden candidate lists, sorted as
+    SPExtractor::operator() sorts them (:489-498), give the golden keypoints and occ_grid -- including the cap case."""
+    RP = _ref_post()
+    g = golden(name)
+    H, W = g["frames"].shape[1:]
+    nf = int(g["nfeatures"])
+    for t in range(2):
+        pts = g[f"f{t}_cand_pixels"].astype(np.float32).T.reshape(-1, 2) if g[f"f{t}_cand_pixels"].shape[0] == 2 else g[f"f{t}_cand_pixels"].astype(np.float32)
+        order = O.sort_desc(g[f"f{t}_cand_score"])
+        kps, occ, _ = RP.nms(pts[order], None, nf, W, H)
+        assert np.array_equal(kps.astype(np.int16), g[f"f{t}_kp_xy"])
+        assert np.array_equal(occ, g[f"f{t}_occ_grid"])

@@ -1,5 +1,5 @@
 """Dust-map pose optimisation, SURVEY.md section 8(f) rank 4: the oracle's restatement of EdgeSE3ProjectDustOnlyPose
-(types_dust_tracking.cpp:37-141) and of the Levenberg loop of Optimizer::PoseOptimizationDust (optimizer_dust.cpp:170-293)
+(types_dust_tracking.cpp:36-141) and of the Levenberg loop of Optimizer::PoseOptimizationDust (optimizer_dust.cpp:170-293)
 (CPU tests), and the one-launch device solve against it through the C ABI (GPU tests).
 
 Tolerances: per-edge results (error, level, u_/v_, Jacobian) are compared BIT-EXACTLY (same IEEE operations in the same
@@ -107,6 +107,27 @@ def test_oracle_edge_error_and_jacobian_semantics():
     assert np.allclose(r["b"], -(r["J"] * (w * r["err"])[:, None]).sum(0), rtol=1e-12, atol=1e-15)
     rho0 = np.where(e2 <= 0.81, e2, 2 * np.sqrt(e2) * 0.9 - 0.81)
     assert np.isclose(r["chi2"], rho0.sum(), rtol=1e-13)
+
+
+@pytest.mark.parametrize("seed,n,shape", [(61, 300, (60, 94)), (62, 1000, (60, 80)), (63, 500, (135, 240)), (64, 3, (60, 94))])
+def test_reference_edge_pins_oracle(seed, n, shape):
+    """The reference's OWN EdgeSE3ProjectDustOnlyPose (class + computeError / linearizeOplus / isInImage / getPixelValue,
+    compiled verbatim from /root/reference into oracle/_ref against a g2o / Eigen stand-in) against the C restatement:
+    error, level, (u_, v_) and Jacobian bit for bit -- fresh and sticky levels, points behind the camera and outside."""
+    from oracle import ref_post as RP
+    if not RP.dust_available():
+        pytest.skip("oracle/_ref/libspdust_ref.so not built (run oracle/ref_build.sh where /root/reference exists)")
+    s = make_scene(seed, n=n, rows=shape[0], cols=shape[1], behind=0.05)
+    rng = np.random.RandomState(seed)
+    Xw = s["Xw"] * rng.uniform(0.7, 1.4, (n, 1))                  # push a share of the points out of the image
+    for level in (None, (np.arange(n) % 3 == 0).astype(np.uint8)):
+        a = O.dust_linearize(s["dust"], s["start"], Xw, *CAM, level=level)
+        b = RP.dust_edges(s["dust"], s["start"], Xw, *CAM, level=level)
+        assert not b["thrown"] and not a["thrown"]
+        assert np.array_equal(a["level"], b["level"]) and (n < 100 or 0 < int(a["level"].sum()) < n)
+        assert np.array_equal(a["err"], b["err"])
+        assert np.array_equal(a["uv"], b["uv"])
+        assert np.array_equal(a["J"], b["J"])
 
 
 def test_oracle_level_is_sticky():
