@@ -1,5 +1,5 @@
 // Minimal stand-ins for the handful of OpenCV / Eigen facilities that the reference's own `nms` and
-// `computeCovariance` (orb_slam2/src/cv/sp_extractor.cpp:161-340) touch, so that those two functions can be compiled
+// `computeCovariance` (orb_slam2/src/cv/sp_extractor.cpp:161-340) (and the guided-search loops, oracle/ref_guided_driver.cc) touch, so that those functions can be compiled
 // VERBATIM from /root/reference in a container without OpenCV / Eigen (oracle/ref_build.sh).  TEST INFRASTRUCTURE ONLY.
 // Written for this purpose, not taken from either library; only the semantics the two functions rely on are
 // provided: cv::Mat as a typed 2-D array with shared row headers, copyMakeBorder(BORDER_CONSTANT), element-wise float
@@ -54,6 +54,11 @@ class Mat {
   template <class T> const T &at(int r, int c) const { return *reinterpret_cast<const T *>(data + r * step + c * sizeof(T)); }
   Mat &setTo(const Scalar &s) { fill(s); return *this; }
   Mat row(int r) const { Mat m = *this; m.rows = 1; m.data = data + r * step; return m; }  // header sharing the storage
+  Mat clone() const {
+    Mat m(rows, cols, type_);
+    for (int r = 0; r < rows; r++) memcpy(m.data + r * m.step, data + r * step, cols * elemSize());
+    return m;
+  }
   void copyTo(Mat dst) const {  // dst is a header onto existing storage of the same shape (descriptors.row(i))
     for (int r = 0; r < rows; r++) memcpy(dst.data + r * dst.step, data + r * step, cols * elemSize());
   }
@@ -78,6 +83,15 @@ inline void copyMakeBorder(const Mat &src, Mat &dst, int top, int bottom, int le
   Mat out(src.rows + top + bottom, src.cols + left + right, src.type(), value);
   for (int r = 0; r < src.rows; r++) memcpy(out.data + (r + top) * out.step + left * src.elemSize(), src.data + r * src.step, src.cols * src.elemSize());
   dst = out;
+}
+enum { NORM_L2 = 4 };
+// cv::norm(a, b, NORM_L2) on two CV_32F rows: sqrt of the sum of squared differences, accumulated like the oracle's
+// orc_l2 (the arithmetic is OpenCV's, third-party; the pin is about the callers' control flow)
+inline double norm(const Mat &a, const Mat &b, int /*NORM_L2*/) {
+  float s = 0.0f;
+  const float *pa = reinterpret_cast<const float *>(a.data), *pb = reinterpret_cast<const float *>(b.data);
+  for (int i = 0; i < a.cols; i++) { const float t = pa[i] - pb[i]; s += t * t; }
+  return (double)__builtin_sqrtf(s);
 }
 }  // namespace cv
 

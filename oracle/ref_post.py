@@ -79,3 +79,69 @@ def dust_edges(dust, pose7, Xw, fx, fy, cx, cy, level=None):
                                     dbl(fx), dbl(fy), dbl(cx), dbl(cy), vp(level.ctypes.data), vp(err.ctypes.data), vp(uv.ctypes.data),
                                     vp(J.ctypes.data))
     return dict(level=level[:n], err=err[:n], uv=uv[:n], J=J[:n], thrown=rc != 0)
+
+
+# ---- the reference's own guided-search loops (frame.cpp:382-474, sp_matcher.cpp:344-439, tracker_dust.cpp:105-172),
+# ---- oracle/_ref/libspguided_ref.so
+GUIDED_LIB = os.path.join(_HERE, "_ref", "libspguided_ref.so")
+_guided_lib = None
+
+
+def guided_available() -> bool:
+    return os.path.exists(GUIDED_LIB)
+
+
+def _guided():
+    global _guided_lib
+    if _guided_lib is None:
+        _guided_lib = C.CDLL(GUIDED_LIB)
+    return _guided_lib
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, np.float32)
+    return a if shape is None else a.reshape(shape)
+
+
+def features_in_area(occ, kp_un, x, y, r, min_x=0.0, min_y=0.0):
+    occ = np.ascontiguousarray(occ, np.int16)
+    kp_un = _f32(kp_un, (-1, 2))
+    out = np.zeros(occ.size + 4, np.int32)
+    vp, f = C.c_void_p, C.c_float
+    n = _guided().spref_features_in_area(vp(occ.ctypes.data), occ.shape[0], occ.shape[1], vp(kp_un.ctypes.data), len(kp_un), f(x), f(y), f(r),
+                                         f(min_x), f(min_y), vp(out.ctypes.data))
+    return out[:n].copy()
+
+
+def search_by_projection(qdesc, qxy, view_cos, occ, kp_un, kdesc, *, th, th_dist, in_view=None, bad=None, nobs=None, kp_taken=None,
+                         c2_adaptive=0.0, min_x=0.0, min_y=0.0):
+    """The reference's SPMatcher::SearchByProjection(Frame&, MapPoints, th, th_dist) -> (kp2mp [n], nmatches)."""
+    qdesc, kdesc = _f32(qdesc, (-1, 256)), _f32(kdesc, (-1, 256))
+    m, n = len(qdesc), len(kdesc)
+    qxy, kp_un, view_cos = _f32(qxy, (m, 2)), _f32(kp_un, (n, 2)), _f32(view_cos, (m,))
+    occ = np.ascontiguousarray(occ, np.int16)
+    u8 = lambda a: None if a is None else np.ascontiguousarray(a, np.uint8)
+    in_view, bad, kp_taken = u8(in_view), u8(bad), u8(kp_taken)
+    nobs = None if nobs is None else np.ascontiguousarray(nobs, np.int32)
+    kp2mp = np.full(max(n, 1), -1, np.int32)
+    vp, f = C.c_void_p, C.c_float
+    p = lambda a: None if a is None else vp(a.ctypes.data)
+    nm = _guided().spref_search_by_projection(m, p(qdesc), p(qxy), p(view_cos), p(in_view), p(bad), p(nobs), p(kdesc), p(kp_un), n, p(occ),
+                                              occ.shape[0], occ.shape[1], p(kp_taken), f(min_x), f(min_y), f(th), f(th_dist), f(c2_adaptive),
+                                              p(kp2mp))
+    return kp2mp[:n], nm
+
+
+def dust_associate(qdesc, quv, occ, kdesc, *, in_view=None, bad=None):
+    """The reference's dust-track association block -> (kp2mp [n], n_matches, dust_match [m])."""
+    qdesc, kdesc = _f32(qdesc, (-1, 256)), _f32(kdesc, (-1, 256))
+    m, n = len(qdesc), len(kdesc)
+    quv = _f32(quv, (m, 2))
+    occ = np.ascontiguousarray(occ, np.int16)
+    u8 = lambda a: None if a is None else np.ascontiguousarray(a, np.uint8)
+    in_view, bad = u8(in_view), u8(bad)
+    kp2mp, dm = np.full(max(n, 1), -1, np.int32), np.zeros(max(m, 1), np.uint8)
+    vp = C.c_void_p
+    p = lambda a: None if a is None else vp(a.ctypes.data)
+    nm = _guided().spref_dust_associate(m, p(qdesc), p(quv), p(in_view), p(bad), p(kdesc), n, p(occ), occ.shape[0], occ.shape[1], p(kp2mp), p(dm))
+    return kp2mp[:n], nm, dm[:m]

@@ -204,6 +204,8 @@ void orc_match_mutual(const float *q, int nq, const float *t, int nt, int d,
  *   the matched keypoint becomes unavailable to later queries (pMP->Observations() > 0; always for mode 1, which
  *   clears the occ_grid cell), kp_taken[idx] = the keypoint already carries an observed map point on entry.
  *   Acceptance: best <= th_le  ||  best < (c2 > 0 ? 1.2f * c2 / (c2 + duv) : th_lt).
+ *   Pinned against the reference's own GetFeaturesInArea / SearchByProjection(Frame&, MapPoints) / association block,
+ *   compiled verbatim into oracle/_ref/libspguided_ref.so (tests/test_guided.py::test_reference_*_pins_oracle).
  *   The reference dereferences mvKeysUn[-1] when every candidate of a map point is skipped (sp_matcher.cpp:416-417,
  *   undefined behaviour); here that is "no match".  Mode 1 reads occ_grid without a bounds check upstream; here
  *   out-of-range cells are skipped.

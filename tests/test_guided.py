@@ -77,6 +77,80 @@ def test_greedy_order_semantics():
     assert got[0] == k0 and got[1] == -1 and taken[k0] == 1
 
 
+def _ref_guided():
+    from oracle import ref_post as RP
+    if not RP.guided_available():
+        pytest.skip("oracle/_ref/libspguided_ref.so not built (run oracle/ref_build.sh where /root/reference exists)")
+    return RP
+
+
+def test_reference_features_in_area_pins_oracle():
+    """The reference's OWN Frame::GetFeaturesInArea (frame.cpp:382-474, compiled verbatim into oracle/_ref)."""
+    RP = _ref_guided()
+    rng = np.random.RandomState(13)
+    f = random_frame(rng)
+    H, W = f["occ_grid"].shape[0] * 8, f["occ_grid"].shape[1] * 8
+    for k in range(400):
+        x, y = rng.uniform(-40, W + 40), rng.uniform(-40, H + 40)
+        r = float(rng.choice([2.5, 4.0, 7.5, 12.0, 15.0]))
+        mx, my = (0.0, 0.0) if k % 3 else (float(rng.uniform(-5, 5)), float(rng.uniform(-5, 5)))
+        a = O.features_in_area(f["occ_grid"], f["kp_un"], x, y, r, mx, my)
+        b = RP.features_in_area(f["occ_grid"], f["kp_un"], x, y, r, mx, my)
+        assert list(a) == list(b)
+
+
+@pytest.mark.parametrize("seed,m,th,c2", [(1, 300, 1.0, 0.0), (2, 800, 3.0, 0.0), (3, 500, 3.0, 50.0), (4, 40, 1.0, 20.0), (5, 1500, 2.0, 0.0)])
+def test_reference_search_by_projection_pins_oracle(seed, m, th, c2):
+    """The reference's OWN SPMatcher::SearchByProjection(Frame&, MapPoints, th, th_dist) + RadiusByViewingCos +
+    DescriptorDistance (sp_matcher.cpp:344-439, :1636-1640), compiled verbatim into oracle/_ref against class skeletons,
+    on the same frame and map points as the flat-array restatement: identical final Frame::mvpMapPoints and match count
+    (duplicates competing for a keypoint, bad / out-of-view / unobserved map points, pre-taken keypoints, adaptive rule)."""
+    RP = _ref_guided()
+    rng = np.random.RandomState(seed)
+    f = random_frame(rng)
+    fr = dict(desc=f["desc"], kp_xy=f["kp_un"])
+    qdesc, qxy, in_view, observed = _scenario(rng, fr, m, jitter=3.0, noise=0.035)
+    bad = (rng.rand(m) < 0.1).astype(np.uint8)
+    cos = np.where(rng.rand(m) < 0.5, 0.9995, 0.99).astype(np.float32)
+    taken = (rng.rand(len(f["desc"])) < 0.15).astype(np.uint8)
+    th_dist = 0.55
+    r = np.where(cos > np.float32(0.998), np.float32(2.5), np.float32(4.0))
+    if th != 1.0:
+        r = r * np.float32(th)
+    q2kp, _, _ = O.search_by_projection_map_points(qdesc, qxy, r, f["occ_grid"], f["kp_un"], f["desc"], th_dist=th_dist,
+                                                   in_view=(in_view & (1 - bad)).astype(np.uint8), observed=observed, kp_taken=taken, c2_adaptive=c2)
+    exp = -np.ones(len(f["desc"]), np.int32)
+    for i, k in enumerate(q2kp):            # F.mvpMapPoints[bestIdx] = pMP, in map-point order (an unobserved one can be overwritten)
+        if k >= 0:
+            exp[k] = i
+    kp2mp, nm = RP.search_by_projection(qdesc, qxy, cos, f["occ_grid"], f["kp_un"], f["desc"], th=th, th_dist=th_dist, in_view=in_view,
+                                        bad=bad, nobs=observed.astype(np.int32) * 2, kp_taken=taken, c2_adaptive=c2)
+    assert nm == int((q2kp >= 0).sum()) and nm > m // 10
+    assert np.array_equal(kp2mp, exp)
+
+
+@pytest.mark.parametrize("seed,m", [(1, 300), (2, 1200), (3, 25)])
+def test_reference_dust_association_pins_oracle(seed, m):
+    """The reference's OWN patch-wise association block of Tracking::trackFrameDustKFLocal (tracker_dust.cpp:105-172)."""
+    RP = _ref_guided()
+    rng = np.random.RandomState(40 + seed)
+    f = random_frame(rng, fill=0.6)
+    fr = dict(desc=f["desc"], kp_xy=f["kp_un"])
+    qdesc, qxy, in_view, _ = _scenario(rng, fr, m, jitter=6.0, noise=0.04)
+    hc, wc = f["occ_grid"].shape
+    quv = np.clip((qxy - 3.5) / 8.0, 0.0, [wc - 2.001, hc - 2.001]).astype(np.float32)   # upstream reads the 2x2 cells unchecked
+    bad = (rng.rand(m) < 0.1).astype(np.uint8)
+    q2kp, _, _ = O.dust_associate(qdesc, quv, f["occ_grid"], f["desc"], in_view=(in_view & (1 - bad)).astype(np.uint8))
+    exp = -np.ones(len(f["desc"]), np.int32)
+    for i, k in enumerate(q2kp):
+        if k >= 0:
+            assert exp[k] == -1             # the matched cell is cleared: one map point per keypoint
+            exp[k] = i
+    kp2mp, nm, dm = RP.dust_associate(qdesc, quv, f["occ_grid"], f["desc"], in_view=in_view, bad=bad)
+    assert nm == int((q2kp >= 0).sum()) and nm > m // 20
+    assert np.array_equal(kp2mp, exp) and np.array_equal(dm, (q2kp >= 0).astype(np.uint8))
+
+
 def test_guided_struct_matches_header():
     import re
     import os
