@@ -31,10 +31,13 @@ sed -n '36,141p' "$REF/orb_slam2/src/optimization/types_dust_tracking.cpp" > "$O
 g++ -O2 -std=c++17 -ffp-contract=off -fPIC -shared -w -I"$OUT/gen" -I"$HERE" "$HERE/ref_dust_driver.cc" -o "$OUT/libspdust_ref.so"
 echo "built $OUT/libspdust_ref.so"
 # the reference's own guided-search loops: Frame::GetFeaturesInArea, SPMatcher::SearchByProjection(Frame&, MapPoints),
-# RadiusByViewingCos, DescriptorDistance and the dust-track association block, verbatim, against class skeletons
+# SearchByProjection(Cur, Last), RadiusByViewingCos, DescriptorDistance and the dust-track association block, verbatim,
+# against class skeletons
 sed -n '382,474p' "$REF/orb_slam2/src/type/frame.cpp" > "$OUT/gen/frame_area.inc"
 sed -n '344,439p' "$REF/orb_slam2/src/cv/sp_matcher.cpp" > "$OUT/gen/matcher_proj.inc"
 sed -n '1636,1640p' "$REF/orb_slam2/src/cv/sp_matcher.cpp" > "$OUT/gen/matcher_dist.inc"
 sed -n '105,172p' "$REF/orb_slam2/src/tracking/tracker_dust.cpp" > "$OUT/gen/dust_assoc.inc"
+sed -n '18,20p' "$REF/orb_slam2/src/cv/sp_matcher.cpp" > "$OUT/gen/matcher_const.inc"
+sed -n '1439,1543p' "$REF/orb_slam2/src/cv/sp_matcher.cpp" > "$OUT/gen/matcher_last.inc"
 g++ -O2 -std=c++17 -ffp-contract=off -fPIC -shared -w -I"$OUT/gen" -I"$HERE" "$HERE/ref_guided_driver.cc" -o "$OUT/libspguided_ref.so"
 echo "built $OUT/libspguided_ref.so"

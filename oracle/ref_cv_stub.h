@@ -54,6 +54,22 @@ class Mat {
   template <class T> const T &at(int r, int c) const { return *reinterpret_cast<const T *>(data + r * step + c * sizeof(T)); }
   Mat &setTo(const Scalar &s) { fill(s); return *this; }
   Mat row(int r) const { Mat m = *this; m.rows = 1; m.data = data + r * step; return m; }  // header sharing the storage
+  // sub-matrix headers and the small CV_32F algebra SearchByProjection(Cur, Last) uses on 3x3 / 3x1 blocks of mTcw
+  Mat rowRange(int a, int b) const { Mat m = *this; m.rows = b - a; m.data = data + a * step; return m; }
+  Mat colRange(int a, int b) const { Mat m = *this; m.cols = b - a; m.data = data + a * elemSize(); return m; }
+  Mat col(int c) const { return colRange(c, c + 1); }
+  template <class T> T &at(int i) { return cols == 1 ? at<T>(i, 0) : at<T>(0, i); }
+  template <class T> const T &at(int i) const { return cols == 1 ? at<T>(i, 0) : at<T>(0, i); }
+  Mat t() const {
+    Mat m(cols, rows, type_);
+    for (int r = 0; r < rows; r++) for (int c = 0; c < cols; c++) m.at<float>(c, r) = at<float>(r, c);
+    return m;
+  }
+  Mat operator-() const {
+    Mat m(rows, cols, type_);
+    for (int r = 0; r < rows; r++) for (int c = 0; c < cols; c++) m.at<float>(r, c) = -at<float>(r, c);
+    return m;
+  }
   Mat clone() const {
     Mat m(rows, cols, type_);
     for (int r = 0; r < rows; r++) memcpy(m.data + r * m.step, data + r * step, cols * elemSize());
@@ -83,6 +99,21 @@ inline void copyMakeBorder(const Mat &src, Mat &dst, int top, int bottom, int le
   Mat out(src.rows + top + bottom, src.cols + left + right, src.type(), value);
   for (int r = 0; r < src.rows; r++) memcpy(out.data + (r + top) * out.step + left * src.elemSize(), src.data + r * src.step, src.cols * src.elemSize());
   dst = out;
+}
+inline Mat operator*(const Mat &a, const Mat &b) {  // CV_32F gemm, double accumulator like OpenCV's small-matrix path
+  Mat m(a.rows, b.cols, CV_32FC1);
+  for (int r = 0; r < a.rows; r++)
+    for (int c = 0; c < b.cols; c++) {
+      double s = 0;
+      for (int k = 0; k < a.cols; k++) s += (double)a.at<float>(r, k) * b.at<float>(k, c);
+      m.at<float>(r, c) = (float)s;
+    }
+  return m;
+}
+inline Mat operator+(const Mat &a, const Mat &b) {
+  Mat m(a.rows, a.cols, CV_32FC1);
+  for (int r = 0; r < a.rows; r++) for (int c = 0; c < a.cols; c++) m.at<float>(r, c) = a.at<float>(r, c) + b.at<float>(r, c);
+  return m;
 }
 enum { NORM_L2 = 4 };
 // cv::norm(a, b, NORM_L2) on two CV_32F rows: sqrt of the sum of squared differences, accumulated like the oracle's

@@ -3,11 +3,14 @@
 //   frame_area.inc      orb_slam2/src/type/frame.cpp:382-474             Frame::GetFeaturesInArea
 //   matcher_proj.inc    orb_slam2/src/cv/sp_matcher.cpp:344-439          SPMatcher::SearchByProjection(Frame&, MapPoints, th, th_dist), RadiusByViewingCos
 //   matcher_dist.inc    orb_slam2/src/cv/sp_matcher.cpp:1636-1640        SPMatcher::DescriptorDistance
+//   matcher_const.inc   orb_slam2/src/cv/sp_matcher.cpp:18-20            TH_HIGH / TH_LOW / HISTO_LENGTH
+//   matcher_last.inc    orb_slam2/src/cv/sp_matcher.cpp:1439-1543        SPMatcher::SearchByProjection(Frame &Cur, const Frame &Last, th, bMono)
 //   dust_assoc.inc      orb_slam2/src/tracking/tracker_dust.cpp:105-172  the patch-wise association block of Tracking::trackFrameDustKFLocal
 // and compiles them against the class skeletons below (only the members those bodies touch; the real classes need
 // ROS / g2o / OpenCV) and oracle/ref_cv_stub.h.
 #include <cmath>
 #include <cstdint>
+#include <limits>
 #include <vector>
 
 #include "ref_cv_stub.h"
@@ -32,6 +35,8 @@ class MapPoint {
   bool isBad() const { return bad; }
   int Observations() const { return nobs; }
   cv::Mat getDescTrack() const { return desc; }
+  cv::Mat Xw;  // 3x1 CV_32F
+  cv::Mat GetWorldPos() const { return Xw.clone(); }
 };
 
 class Frame {
@@ -43,11 +48,20 @@ class Frame {
   vector<cv::KeyPoint> mvKeysUn;
   vector<MapPoint *> mvpMapPoints;
   vector<float> mvScaleFactors{1.0f};
+  // SearchByProjection(Cur, Last) also reads:
+  cv::Mat mTcw;
+  float fx = 1, fy = 1, cx = 0, cy = 0, mb = 0, mbf = 0, mnMaxX = 0, mnMaxY = 0;
+  vector<bool> mvbOutlier;
+  vector<cv::KeyPoint> mvKeys;
+  vector<float> mvuRight;
 };
 
 class SPMatcher {
  public:
   int SearchByProjection(Frame &F, const vector<MapPoint *> &vpMapPoints, const float th, const float th_dist);
+  int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono);
+  static const float TH_LOW, TH_HIGH;
+  static const int HISTO_LENGTH;
   static float DescriptorDistance(const cv::Mat &a, const cv::Mat &b);
   float RadiusByViewingCos(const float &viewCos);
 };
@@ -55,6 +69,8 @@ class SPMatcher {
 #include "frame_area.inc"
 #include "matcher_proj.inc"
 #include "matcher_dist.inc"
+#include "matcher_const.inc"
+#include "matcher_last.inc"
 
 // tracker_dust.cpp:105-172 lives inside Tracking::trackFrameDustKFLocal; the block reads `mCurrentFrame` and
 // `mps_for_track` and leaves its count in `n_matches`
@@ -119,6 +135,41 @@ int spref_search_by_projection(int m, const float *qdesc, const float *qxy, cons
   SPMatcher matcher;
   const int nm = matcher.SearchByProjection(F, vp, th, th_dist);
   for (int k = 0; k < n; k++) kp2mp[k] = (F.mvpMapPoints[k] && F.mvpMapPoints[k] != &holder) ? (int32_t)(F.mvpMapPoints[k] - mps.data()) : -1;
+  return nm;
+}
+
+// SearchByProjection(Cur, Last, th, bMono = true).  The last frame's map points (one per last-frame keypoint, or none:
+// has_mp[i] = 0) carry world positions Xw; Tcw_cur / Tcw_last are 4x4 row-major; K = fx, fy, cx, cy; bounds = mnMinX,
+// mnMaxX, mnMinY, mnMaxY of the current frame.  kp2mp[k] = last-frame index whose map point landed on keypoint k.
+int spref_search_by_projection_last(int m, const float *qdesc, const float *Xw, const uint8_t *has_mp, const uint8_t *outlier, const int32_t *nobs,
+                                    const float *Tcw_cur, const float *Tcw_last, const float *K, const float *bounds, const float *kdesc,
+                                    const float *kp_un, int n, const int16_t *occ, int grid_rows, int grid_cols, const uint8_t *kp_taken,
+                                    float th, int32_t *kp2mp) {
+  Frame Cur, Last;
+  fill_frame(Cur, kdesc, kp_un, n, occ, grid_rows, grid_cols, bounds[0], bounds[2]);
+  Cur.mnMaxX = bounds[1]; Cur.mnMaxY = bounds[3];
+  Cur.fx = K[0]; Cur.fy = K[1]; Cur.cx = K[2]; Cur.cy = K[3];
+  Cur.mTcw = cv::Mat(4, 4, CV_32FC1); memcpy(Cur.mTcw.data, Tcw_cur, 64);
+  Last.mTcw = cv::Mat(4, 4, CV_32FC1); memcpy(Last.mTcw.data, Tcw_last, 64);
+  Cur.mvuRight.assign(n, -1.0f);  // monocular
+  MapPoint holder;
+  holder.nobs = 1;
+  for (int k = 0; k < n; k++) if (kp_taken && kp_taken[k]) Cur.mvpMapPoints[k] = &holder;
+  std::vector<MapPoint> mps(m);
+  Last.N = m;
+  for (int i = 0; i < m; i++) {
+    mps[i].desc = cv::Mat(1, 256, CV_32FC1);
+    memcpy(mps[i].desc.data, qdesc + 256 * (size_t)i, 1024);
+    mps[i].Xw = cv::Mat(3, 1, CV_32FC1);
+    for (int k = 0; k < 3; k++) mps[i].Xw.at<float>(k, 0) = Xw[3 * i + k];
+    mps[i].nobs = nobs ? nobs[i] : 1;
+    Last.mvpMapPoints.push_back(has_mp && !has_mp[i] ? nullptr : &mps[i]);
+    Last.mvbOutlier.push_back(outlier && outlier[i]);
+    Last.mvKeys.push_back(cv::KeyPoint(0.f, 0.f, 1.0f));  // octave 0
+  }
+  SPMatcher matcher;
+  const int nm = matcher.SearchByProjection(Cur, Last, th, true);
+  for (int k = 0; k < n; k++) kp2mp[k] = (Cur.mvpMapPoints[k] && Cur.mvpMapPoints[k] != &holder) ? (int32_t)(Cur.mvpMapPoints[k] - mps.data()) : -1;
   return nm;
 }
 

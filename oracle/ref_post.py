@@ -145,3 +145,22 @@ def dust_associate(qdesc, quv, occ, kdesc, *, in_view=None, bad=None):
     p = lambda a: None if a is None else vp(a.ctypes.data)
     nm = _guided().spref_dust_associate(m, p(qdesc), p(quv), p(in_view), p(bad), p(kdesc), n, p(occ), occ.shape[0], occ.shape[1], p(kp2mp), p(dm))
     return kp2mp[:n], nm, dm[:m]
+
+
+def search_by_projection_last(qdesc, Xw, occ, kp_un, kdesc, *, th, Tcw_cur, Tcw_last, K, bounds, has_mp=None, outlier=None, nobs=None,
+                              kp_taken=None):
+    """The reference's SPMatcher::SearchByProjection(Frame &Cur, const Frame &Last, th, bMono=true) -> (kp2mp [n], nmatches)."""
+    qdesc, kdesc = _f32(qdesc, (-1, 256)), _f32(kdesc, (-1, 256))
+    m, n = len(qdesc), len(kdesc)
+    Xw, kp_un = _f32(Xw, (m, 3)), _f32(kp_un, (n, 2))
+    occ = np.ascontiguousarray(occ, np.int16)
+    u8 = lambda a: None if a is None else np.ascontiguousarray(a, np.uint8)
+    has_mp, outlier, kp_taken = u8(has_mp), u8(outlier), u8(kp_taken)
+    nobs = None if nobs is None else np.ascontiguousarray(nobs, np.int32)
+    Tc, Tl, K, bounds = _f32(Tcw_cur, (4, 4)), _f32(Tcw_last, (4, 4)), _f32(K, (4,)), _f32(bounds, (4,))
+    kp2mp = np.full(max(n, 1), -1, np.int32)
+    vp = C.c_void_p
+    p = lambda a: None if a is None else vp(a.ctypes.data)
+    nm = _guided().spref_search_by_projection_last(m, p(qdesc), p(Xw), p(has_mp), p(outlier), p(nobs), p(Tc), p(Tl), p(K), p(bounds), p(kdesc),
+                                                   p(kp_un), n, p(occ), occ.shape[0], occ.shape[1], p(kp_taken), C.c_float(th), p(kp2mp))
+    return kp2mp[:n], nm

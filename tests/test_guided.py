@@ -129,6 +129,42 @@ def test_reference_search_by_projection_pins_oracle(seed, m, th, c2):
     assert np.array_equal(kp2mp, exp)
 
 
+@pytest.mark.parametrize("seed,m,th", [(1, 400, 7.0), (2, 1200, 15.0), (3, 30, 7.0)])
+def test_reference_search_by_projection_last_frame_pins_oracle(seed, m, th):
+    """The reference's OWN SPMatcher::SearchByProjection(Frame &Cur, const Frame &Last, th, bMono) (sp_matcher.cpp:1439-1543),
+    compiled verbatim.  The camera is chosen so that its projection code is exact in any arithmetic (identity pose, unit
+    intrinsics, depths +-1 / +-2): what is compared is the loop -- its `continue` tests (no map point, outlier, behind the
+    camera, outside the image bounds), the candidate search and the greedy assignment under TH_HIGH."""
+    RP = _ref_guided()
+    rng = np.random.RandomState(70 + seed)
+    f = random_frame(rng)
+    fr = dict(desc=f["desc"], kp_xy=f["kp_un"])
+    qdesc, qxy, _, observed = _scenario(rng, fr, m, jitter=th * 0.6, noise=0.04)
+    qxy = (np.round(qxy * 4) / 4).astype(np.float32)                     # quarter pixels: exact under * 2 and / 2
+    hc, wc = f["occ_grid"].shape
+    bounds = np.array([0.0, wc * 8.0 - 12, 0.0, hc * 8.0 - 12], np.float32)  # mnMinX, mnMaxX, mnMinY, mnMaxY
+    z = rng.choice([1.0, 2.0, -1.0, -2.0], m, p=[0.45, 0.45, 0.05, 0.05]).astype(np.float32)
+    Xw = np.stack([qxy[:, 0] * z, qxy[:, 1] * z, z], 1).astype(np.float32)
+    has_mp = (rng.rand(m) < 0.85).astype(np.uint8)
+    outlier = (rng.rand(m) < 0.1).astype(np.uint8)
+    taken = (rng.rand(len(f["desc"])) < 0.15).astype(np.uint8)
+    inside = (qxy[:, 0] >= bounds[0]) & (qxy[:, 0] <= bounds[1]) & (qxy[:, 1] >= bounds[2]) & (qxy[:, 1] <= bounds[3])
+    valid = (has_mp == 1) & (outlier == 0) & (z > 0) & inside
+    assert m < 100 or (0 < (~inside).sum() and 0 < (z < 0).sum())
+    q2kp, _, _ = O.search_by_projection_last_frame(qdesc, qxy, np.float32(th), f["occ_grid"], f["kp_un"], f["desc"],
+                                                   valid=valid.astype(np.uint8), observed=observed, kp_taken=taken)
+    exp = -np.ones(len(f["desc"]), np.int32)
+    for i, k in enumerate(q2kp):
+        if k >= 0:
+            exp[k] = i
+    eye = np.eye(4, dtype=np.float32)
+    kp2mp, nm = RP.search_by_projection_last(qdesc, Xw, f["occ_grid"], f["kp_un"], f["desc"], th=th, Tcw_cur=eye, Tcw_last=eye,
+                                             K=[1, 1, 0, 0], bounds=bounds, has_mp=has_mp, outlier=outlier,
+                                             nobs=observed.astype(np.int32) * 3, kp_taken=taken)
+    assert nm == int((q2kp >= 0).sum()) and nm > m // 10
+    assert np.array_equal(kp2mp, exp)
+
+
 @pytest.mark.parametrize("seed,m", [(1, 300), (2, 1200), (3, 25)])
 def test_reference_dust_association_pins_oracle(seed, m):
     """The reference's OWN patch-wise association block of Tracking::trackFrameDustKFLocal (tracker_dust.cpp:105-172)."""
