@@ -165,6 +165,24 @@ def test_oracle_empty_and_zero_iterations():
     assert r["n_inlier"] == 0 and np.array_equal(r["pose"], s["start"])
 
 
+def test_device_functions_compiled_for_the_host_match_oracle(tmp_path):
+    """tools/dustpose_hostcheck.cc: the __device__ per-edge and Levenberg-step functions of csrc/dustpose.cuh, compiled for
+    the host (round-to-nearest intrinsics mapped to plain IEEE operations) and driven by a sequential re-enactment of the
+    kernel's control flow, against oracle/dust_pose.c on 40 random problems: per-edge results bit-identical, iteration /
+    trial counts and inlier sets identical, pose within 1e-11.  A logic check of the CUDA header where no GPU exists;
+    the kernel itself is covered by the -m gpu tests below."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = str(tmp_path / "dp_check")
+    flags = ["-O2", "-ffp-contract=off"]
+    subprocess.check_call(["gcc", *flags, "-c", os.path.join(ROOT, "oracle", "dust_pose.c"), "-o", str(tmp_path / "o.o")])
+    subprocess.check_call(["g++", *flags, "-std=c++17", "-I", os.path.join(ROOT, "sp_orb_slam_b200", "csrc"),
+                           os.path.join(ROOT, "tools", "dustpose_hostcheck.cc"), str(tmp_path / "o.o"), "-o", exe, "-lm"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("all ok"), r.stdout[-2000:]
+
+
 # ---------------------------------------------------------------- device (GPU), through the C ABI
 @pytest.fixture(scope="module")
 def ex():
