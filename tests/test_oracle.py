@@ -102,6 +102,28 @@ def test_to_heat_properties():
     np.testing.assert_allclose(heat, (-x - mn) / (mx - mn), atol=1e-6)
 
 
+def test_to_heat_vs_opencv_convert_scale():
+    """to_heat (sp_extractor.cpp:461-474) is OpenCV arithmetic: a MatExpr folded into one convertTo(alpha, beta) with
+    alpha = 1 / (max - min), beta = -min * alpha computed in double and narrowed to float.  cv2.normalize(NORM_MINMAX)
+    runs the same convertTo with the same alpha / beta, so it pins that derivation.  This cv2 build (4.x, AVX2) fuses
+    x * alpha + beta into one FMA; OpenCV 3.2 (the reference's, SSE2) rounds the product first, which is what the oracle
+    and the device do -- the two differ by at most one ulp, and the oracle's alpha / beta under an emulated FMA reproduce
+    cv2 exactly (up to the emulation's own double rounding)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.RandomState(0)
+    for _ in range(3):
+        x = np.log(np.clip(rng.rand(120, 160).astype(np.float32) ** 3, 1e-3, None)).astype(np.float32)
+        heat, _, mn, mx = O.to_heat(x)
+        img = (-x).astype(np.float32)
+        ref = cv2.normalize(img, None, alpha=0, beta=1, norm_type=cv2.NORM_MINMAX, dtype=cv2.CV_32F)
+        assert (mn, mx) == cv2.minMaxLoc(img)[:2]
+        assert np.abs(heat - ref).max() <= 2.0 ** -23                       # one ulp below 1.0
+        a, b = np.float32(1.0 / (mx - mn)), np.float32(-mn * (1.0 / (mx - mn)))
+        assert np.array_equal(heat, img * a + b)                            # the oracle = separate multiply and add
+        fma = (img.astype(np.float64) * np.float64(a) + np.float64(b)).astype(np.float32)
+        assert (fma != ref).mean() < 1e-3
+
+
 def test_covariance_simple_peak():
     h = np.zeros((16, 16), np.float32)
     h[8, 8], h[8, 7], h[8, 9], h[7, 8], h[9, 8] = 1.0, 0.5, 0.5, 0.25, 0.25
