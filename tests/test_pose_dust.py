@@ -274,6 +274,32 @@ def test_gpu_pose_optimize_batch(ex):
 
 
 @pytest.mark.gpu
+def test_gpu_pose_optimization_heat_sized_map(ex):
+    """Optimizer::PoseOptimizationHeat (optimizer_dust.cpp:415-522) = the same edges on the full-resolution heat_ map with
+    pixel intrinsics and chi2 > 0.02: a 480 x 752 map (1.4 MB) does not fit in shared memory, so the kernel samples it
+    from global memory.  Same parity bar as the dust-sized maps."""
+    rng = np.random.RandomState(77)
+    H, W, n = 480, 752, 200
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    heat = (0.9 * (0.5 + 0.5 * np.sin(xx / 7.0) * np.cos(yy / 9.0)) ** 2 + 0.02 * rng.rand(H, W)).astype(np.float32)
+    q = np.array([0.01, -0.02, 0.015, 1.0]); q /= np.linalg.norm(q)
+    pose = np.concatenate([q, [0.05, -0.03, 0.02]])
+    u, v, z = rng.uniform(-20, W + 20, n), rng.uniform(-20, H + 20, n), rng.uniform(1.0, 8.0, n)
+    Xc = np.stack([(u - CX) / FX * z, (v - CY) / FY * z, z], 1)
+    Xw = rot(np.array([-q[0], -q[1], -q[2], q[3]]), Xc - pose[4:])
+    cam = (FX, FY, CX, CY)
+    a = O.dust_linearize(heat, pose, Xw, *cam)
+    b = ex.dust_linearize(pose, Xw, *cam, dust=heat)
+    assert 0 < int(a["level"].sum()) < n
+    assert np.array_equal(a["level"], b["level"]) and np.array_equal(a["err"], b["err"]) and np.array_equal(a["J"], b["J"])
+    ref = O.dust_pose_optimize(heat, pose, Xw, *cam, chi2_inlier=0.02)
+    got = ex.dust_pose_optimize(pose, Xw, *cam, dust=heat, chi2_inlier=0.02)
+    assert 0 < ref["n_inlier"] < n
+    assert got["n_iter"] == ref["n_iter"] and got["n_inlier"] == ref["n_inlier"] and np.array_equal(got["visible"], ref["visible"])
+    assert np.abs(got["pose"] - ref["pose"]).max() < 1e-9
+
+
+@pytest.mark.gpu
 def test_gpu_dust_pose_bad_arguments(ex):
     s = make_scene(41, n=5)
     with pytest.raises(Exception):
