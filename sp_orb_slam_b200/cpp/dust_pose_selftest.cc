@@ -15,14 +15,24 @@ using namespace orbslam;
 
 struct MapPoint {
   cv::Mat X;
-  bool in_view = false, dust_match = false;
+  bool in_view = false, dust_match = false, bad = false;
   float dust_proj_u = -1, dust_proj_v = -1;
   cv::Mat GetWorldPos() const { return X.clone(); }
+  bool isBad() const { return bad; }
 };
 struct Frame {
-  cv::Mat mTcw, dust_;
+  cv::Mat mTcw, dust_, heat_;
   float fx = 0, fy = 0, cx = 0, cy = 0;
+  int N = 0;
+  std::vector<MapPoint *> mvpMapPoints;
+  std::vector<bool> is_mp_visible_;
   void SetPose(cv::Mat T) { mTcw = T.clone(); }
+};
+struct KeyFrame {
+  int N = 0;
+  std::vector<MapPoint *> mps;
+  std::vector<bool> is_mp_visible_;
+  std::vector<MapPoint *> GetMapPointMatches() { return mps; }
 };
 
 int main(int argc, char **argv) {
@@ -55,6 +65,14 @@ int main(int argc, char **argv) {
   Optimizer::ToSE3Quat(fr.mTcw, start);
   std::vector<bool> is_visible(n, false);
   const int n_inlier = Optimizer::PoseOptimizationDust(&fr, mps, is_visible);
+  if (argc > 99) {  // the sibling overloads (optimizer_dust.cpp:296-790) are instantiated, not run, by this self-test
+    KeyFrame kf;
+    Frame last;
+    Optimizer::PoseOptimizationDust(&fr, mps);
+    Optimizer::PoseOptimizationDust(&fr, &kf);
+    Optimizer::PoseOptimizationDust(&fr, &last);
+    Optimizer::PoseOptimizationHeat(&fr, &last);
+  }
   FILE *o = fopen(argv[3], "w");
   fprintf(o, "%d\n", n_inlier);
   for (int i = 0; i < 7; i++) fprintf(o, "%.17g ", start[i]);

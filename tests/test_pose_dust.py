@@ -183,6 +183,104 @@ def test_device_functions_compiled_for_the_host_match_oracle(tmp_path):
     assert r.returncode == 0 and r.stdout.strip().endswith("all ok"), r.stdout[-2000:]
 
 
+def _quat_from_T(T):
+    """Converter::toSE3Quat as the shim does it (float Tcw -> double R -> Shepperd -> normalised, w >= 0)."""
+    R = T[:3, :3].astype(np.float64)
+    t = np.trace(R)
+    q = np.zeros(4)
+    if t > 0:
+        r = np.sqrt(t + 1.0); q[3] = 0.5 * r; r = 0.5 / r
+        q[0], q[1], q[2] = (R[2, 1] - R[1, 2]) * r, (R[0, 2] - R[2, 0]) * r, (R[1, 0] - R[0, 1]) * r
+    else:
+        i = int(np.argmax(np.diag(R))); j, k = (i + 1) % 3, (i + 2) % 3
+        r = np.sqrt(R[i, i] - R[j, j] - R[k, k] + 1.0); q[i] = 0.5 * r; r = 0.5 / r
+        q[3], q[j], q[k] = (R[k, j] - R[j, k]) * r, (R[j, i] + R[i, j]) * r, (R[k, i] + R[i, k]) * r
+    if q[3] < 0:
+        q = -q
+    return np.concatenate([q / np.linalg.norm(q), T[:3, 3].astype(np.float64)])
+
+
+def _T_from_pose(p):
+    T = np.eye(4)
+    T[:3, :3], T[:3, 3] = rot_matrix(p[:4]), p[4:]
+    return T
+
+
+def test_cpp_shim_overloads_on_cpu(tmp_path):
+    """Every overload of cpp/optimizer_dust.h -- PoseOptimizationDust(Frame*, mps, is_visible) / (Frame*, mps) /
+    (Frame*, KeyFrame*) / (Frame*, Frame*) and PoseOptimizationHeat -- run on the CPU against a test-only backend that
+    answers spfe_dust_pose_optimize with the oracle (tests/cpp/fake_spfe_dust.c).  Checks the host logic the shim adds:
+    which map points get an edge (null / isBad(), the first N entries), the dust / heat intrinsics, Converter::toSE3Quat
+    and toCvMat, the is_visible / is_mp_visible_ / in_view / dust_proj write-back."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    inc = ["-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "sp_orb_slam_b200", "cpp")]
+    objs = []
+    for src, cc in (("tests/cpp/fake_spfe_dust.c", "gcc"), ("oracle/dust_pose.c", "gcc")):
+        o = str(tmp_path / (os.path.basename(src) + ".o"))
+        subprocess.check_call([cc, "-O2", "-ffp-contract=off", *inc, "-c", os.path.join(ROOT, src), "-o", o])
+        objs.append(o)
+    exe = str(tmp_path / "shim_cpu")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", *inc, os.path.join(ROOT, "tests/cpp/optimizer_shim_cpu.cc"), *objs, "-o", exe, "-lm"])
+    s = make_scene(81, n=160)
+    n = len(s["Xw"])
+    rng = np.random.RandomState(5)
+    H, W = 120, 160
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    heat = (0.9 * (0.5 + 0.5 * np.sin(xx / 7.0) * np.cos(yy / 9.0)) ** 2).astype(np.float32)
+    T = np.eye(4, dtype=np.float32)
+    T[:3, :3], T[:3, 3] = rot_matrix(s["start"][:4]).astype(np.float32), s["start"][4:].astype(np.float32)
+    Xw32 = s["Xw"].astype(np.float32)
+    k = np.array([FX, FY, CX, CY], np.float32)
+    isnull, bad = (rng.rand(n) < 0.2).astype(np.uint8), (rng.rand(n) < 0.15).astype(np.uint8)
+    with open(tmp_path / "scene.bin", "wb") as f:
+        np.array([60, 94, n, H, W], np.int32).tofile(f)
+        for a in (k, T, s["dust"], heat, Xw32, isnull, bad):
+            a.tofile(f)
+    subprocess.check_call([exe, str(tmp_path / "scene.bin"), str(tmp_path / "out.txt")])
+    lines = open(tmp_path / "out.txt").read().split("\n")
+    start = _quat_from_T(T)
+    cam = (float(k[0] / np.float32(8)), float(k[1] / np.float32(8)), (float(k[2]) - 3.5) / 8.0, (float(k[3]) - 3.5) / 8.0)
+    X64 = Xw32.astype(np.float64)
+    good = (isnull == 0) & (bad == 0)
+
+    def check(line, flags_line, ref, idx, n_flags):
+        tok = line.split()
+        assert int(tok[1]) == ref["n_inlier"]
+        assert np.abs(np.array(tok[2:], np.float64).reshape(4, 4) - _T_from_pose(ref["pose"])).max() < 1e-6
+        exp = np.zeros(n_flags, int)
+        if n_flags:
+            exp[idx[ref["visible"] == 1]] = 1
+        assert flags_line == "".join(map(str, exp))
+
+    # (1) live overload: every entry, plus the per-map-point write-back
+    ref = O.dust_pose_optimize(s["dust"], start, X64, *cam)
+    assert lines[0].startswith("live ") and 0 < ref["n_inlier"] < n
+    check(lines[0], lines[1], ref, np.arange(n), n)
+    mp = np.array([l.split() for l in lines[2:2 + n]], np.float64)
+    vis = ref["visible"] == 1
+    assert np.array_equal(mp[:, 0] == 1, vis) and np.allclose(mp[vis, 1:], ref["uv"][vis], atol=1e-5) and np.all(mp[~vis, 1:] == -1)
+    rest = lines[2 + n:]
+    # (2) good map points only
+    idx = np.flatnonzero(good)
+    ref = O.dust_pose_optimize(s["dust"], start, X64[idx], *cam)
+    assert rest[0].startswith("mps ")
+    check(rest[0], rest[1], ref, idx, 0)
+    # (3) key frame: is_mp_visible_ at the original indices
+    assert rest[2].startswith("kf ")
+    check(rest[2], rest[3], ref, idx, n)
+    # (4) last frame with N = n - 3
+    idx4 = idx[idx < n - 3]
+    ref4 = O.dust_pose_optimize(s["dust"], start, X64[idx4], *cam)
+    assert rest[4].startswith("last ")
+    check(rest[4], rest[5], ref4, idx4, n)
+    # (5) heat: full-resolution map, pixel intrinsics, chi2 > 0.02
+    ref5 = O.dust_pose_optimize(heat, start, X64[idx], float(k[0]), float(k[1]), float(k[2]), float(k[3]), chi2_inlier=0.02)
+    assert rest[6].startswith("heat ")
+    check(rest[6], rest[7], ref5, idx, 0)
+
+
 # ---------------------------------------------------------------- device (GPU), through the C ABI
 @pytest.fixture(scope="module")
 def ex():
