@@ -187,6 +187,54 @@ def test_reference_dust_association_pins_oracle(seed, m):
     assert np.array_equal(kp2mp, exp) and np.array_equal(dm, (q2kp >= 0).astype(np.uint8))
 
 
+@pytest.mark.parametrize("seed,m,th,c2", [(1, 500, 3.0, 0.0), (2, 900, 1.0, 40.0)])
+def test_cpp_shim_guided_templates_match_reference_on_cpu(tmp_path, seed, m, th, c2):
+    """The drop-in templates of cpp/sp_matcher.h (SearchByProjection(Frame&, MapPoints), DustAssociate) on Frame / MapPoint
+    objects shaped like the reference's, run on the CPU with a test-only backend that answers spfe_search_guided with the
+    oracle (tests/cpp/fake_spfe_guided.c), against the REFERENCE's own functions compiled verbatim (oracle/_ref): the
+    same Frame::mvpMapPoints, match counts and dust_match flags.  Covers what the shim adds on the host: hoisting
+    mbTrackInView / isBad() / Observations() / RadiusByViewingCos into flat arrays and applying the result in order."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    RP = _ref_guided()
+    inc = ["-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "sp_orb_slam_b200", "cpp")]
+    objs = []
+    for src in ("tests/cpp/fake_spfe_guided.c", "oracle/sp_post.c"):
+        o = str(tmp_path / (os.path.basename(src) + ".o"))
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", *inc, "-c", os.path.join(ROOT, src), "-o", o])
+        objs.append(o)
+    exe = str(tmp_path / "matcher_cpu")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", *inc, os.path.join(ROOT, "tests/cpp/matcher_shim_cpu.cc"), *objs, "-o", exe, "-lm"])
+    rng = np.random.RandomState(90 + seed)
+    f = random_frame(rng, fill=0.55)
+    fr = dict(desc=f["desc"], kp_xy=f["kp_un"])
+    n = len(f["desc"])
+    qdesc, qxy, in_view, observed = _scenario(rng, fr, m, jitter=4.0, noise=0.04)
+    bad = (rng.rand(m) < 0.1).astype(np.uint8)
+    cos = np.where(rng.rand(m) < 0.5, 0.9995, 0.99).astype(np.float32)
+    nobs = (observed.astype(np.int32) * 2)
+    taken = (rng.rand(n) < 0.15).astype(np.uint8)
+    hc, wc = f["occ_grid"].shape
+    quv = np.clip((qxy - 3.5) / 8.0, 0.0, [wc - 2.001, hc - 2.001]).astype(np.float32)
+    th_dist = 0.55
+    with open(tmp_path / "scene.bin", "wb") as fh:
+        np.array([m, n, hc, wc], np.int32).tofile(fh)
+        np.array([th, th_dist, c2], np.float32).tofile(fh)
+        for a in (qdesc, qxy, quv, cos, in_view, bad, nobs, f["desc"], f["kp_un"], f["occ_grid"], taken):
+            np.ascontiguousarray(a).tofile(fh)
+    subprocess.check_call([exe, str(tmp_path / "scene.bin"), str(tmp_path / "out.txt")])
+    L = open(tmp_path / "out.txt").read().split("\n")
+    kp2mp, nm = RP.search_by_projection(qdesc, qxy, cos, f["occ_grid"], f["kp_un"], f["desc"], th=th, th_dist=th_dist, in_view=in_view,
+                                        bad=bad, nobs=nobs, kp_taken=taken, c2_adaptive=c2)
+    assert int(L[0]) == nm and nm > m // 10
+    assert np.array_equal(np.array(L[1].split(), np.int64), kp2mp)
+    kp2mp_d, nm_d, dm = RP.dust_associate(qdesc, quv, f["occ_grid"], f["desc"], in_view=in_view, bad=bad)
+    assert int(L[2]) == nm_d and nm_d > m // 20
+    assert np.array_equal(np.array(L[3].split(), np.int64), kp2mp_d)
+    assert L[4] == "".join(map(str, dm))
+
+
 def test_guided_struct_matches_header():
     import re
     import os
