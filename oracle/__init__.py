@@ -14,7 +14,8 @@ against a cv / Eigen stand-in (``ref_cv_stub.h``) and its
 ``EdgeSE3ProjectDustOnlyPose`` verbatim against a g2o stand-in
 (``ref_g2o_stub.h``) and its guided-search loops (``Frame::GetFeaturesInArea``,
 ``SPMatcher::SearchByProjection(Frame&, MapPoints)`` and ``(Cur, Last)``, the dust-track association
-block) verbatim against class skeletons (``ref_guided_driver.cc``), and (ii) OpenCV (``cv2.BFMatcher``, ``cv2.sortIdx``,
+block) and both ``SearchByBruteForce`` overloads verbatim against class skeletons
+(``ref_guided_driver.cc``, ``ref_bf_driver.cc``), and (ii) OpenCV (``cv2.BFMatcher``, ``cv2.sortIdx``,
 ``cv2.minMaxLoc``) for the third-party arithmetic the reference calls; the
 resulting vectors are committed under ``tests/golden/``.
 """

@@ -41,3 +41,8 @@ sed -n '18,20p' "$REF/orb_slam2/src/cv/sp_matcher.cpp" > "$OUT/gen/matcher_const
 sed -n '1439,1543p' "$REF/orb_slam2/src/cv/sp_matcher.cpp" > "$OUT/gen/matcher_last.inc"
 g++ -O2 -std=c++17 -ffp-contract=off -fPIC -shared -w -I"$OUT/gen" -I"$HERE" "$HERE/ref_guided_driver.cc" -o "$OUT/libspguided_ref.so"
 echo "built $OUT/libspguided_ref.so"
+# the reference's own SearchByBruteForce overloads, verbatim
+sed -n '1642,1674p' "$REF/orb_slam2/src/cv/sp_matcher.cpp" > "$OUT/gen/bf_kf_frame.inc"
+sed -n '334,376p' "$REF/orb_slam2/src/cv/sp_matcher_loop.cpp" > "$OUT/gen/bf_kf_kf.inc"
+g++ -O2 -std=c++17 -ffp-contract=off -fPIC -shared -w -I"$OUT/gen" -I"$HERE" "$HERE/ref_bf_driver.cc" -o "$OUT/libspbf_ref.so"
+echo "built $OUT/libspbf_ref.so"

@@ -53,6 +53,7 @@ class Mat {
   template <class T> T &at(int r, int c) { return *reinterpret_cast<T *>(data + r * step + c * sizeof(T)); }
   template <class T> const T &at(int r, int c) const { return *reinterpret_cast<const T *>(data + r * step + c * sizeof(T)); }
   Mat &setTo(const Scalar &s) { fill(s); return *this; }
+  bool empty_() const { return !data || rows == 0 || cols == 0; }
   Mat row(int r) const { Mat m = *this; m.rows = 1; m.data = data + r * step; return m; }  // header sharing the storage
   // sub-matrix headers and the small CV_32F algebra SearchByProjection(Cur, Last) uses on 3x3 / 3x1 blocks of mTcw
   Mat rowRange(int a, int b) const { Mat m = *this; m.rows = b - a; m.data = data + a * step; return m; }
@@ -69,6 +70,13 @@ class Mat {
     Mat m(rows, cols, type_);
     for (int r = 0; r < rows; r++) for (int c = 0; c < cols; c++) m.at<float>(r, c) = -at<float>(r, c);
     return m;
+  }
+  void push_back(const Mat &r) {  // append the rows of r (same width / type); an empty Mat adopts them
+    if (!data || rows == 0) { *this = r.clone(); return; }
+    Mat m(rows + r.rows, cols, type_);
+    for (int i = 0; i < rows; i++) memcpy(m.data + i * m.step, data + i * step, cols * elemSize());
+    for (int i = 0; i < r.rows; i++) memcpy(m.data + (rows + i) * m.step, r.data + i * r.step, cols * elemSize());
+    *this = m;
   }
   Mat clone() const {
     Mat m(rows, cols, type_);
@@ -124,6 +132,39 @@ inline double norm(const Mat &a, const Mat &b, int /*NORM_L2*/) {
   for (int i = 0; i < a.cols; i++) { const float t = pa[i] - pb[i]; s += t * t; }
   return (double)__builtin_sqrtf(s);
 }
+struct DMatch { int queryIdx, trainIdx, imgIdx; float distance; };
+template <class T> struct Ptr {
+  std::shared_ptr<T> p;
+  T *operator->() const { return p.get(); }
+};
+// cv::BFMatcher(NORM_L2, crossCheck = true): for every query row its first-index arg-min train row, kept only if that
+// train row's first-index arg-min query row is the same query (the semantics SURVEY.md 8c records; pinned against
+// cv2.BFMatcher in tests/test_oracle.py::test_matcher_vs_opencv).  Stand-in written for the verbatim compile of
+// SPMatcher::SearchByBruteForce -- what is checked there is the reference's row filtering and index mapping.
+class BFMatcher {
+ public:
+  static Ptr<BFMatcher> create(int /*normType*/, bool crossCheck) { Ptr<BFMatcher> r; r.p = std::make_shared<BFMatcher>(); r.p->cross_ = crossCheck; return r; }
+  void add(const Mat &train) { train_ = train; }
+  void train() {}
+  void match(const Mat &query, std::vector<DMatch> &matches) const {
+    matches.clear();
+    const int nq = query.empty_() ? 0 : query.rows, nt = train_.empty_() ? 0 : train_.rows;
+    std::vector<int> t2q(nt > 0 ? nt : 1, -1);
+    std::vector<float> tbest(nt > 0 ? nt : 1, 3.4e38f), qbest(nq > 0 ? nq : 1, 3.4e38f);
+    std::vector<int> q2t(nq > 0 ? nq : 1, -1);
+    for (int i = 0; i < nq; i++)
+      for (int j = 0; j < nt; j++) {
+        const float d = (float)norm(query.row(i), train_.row(j), NORM_L2);
+        if (d < qbest[i]) { qbest[i] = d; q2t[i] = j; }
+        if (d < tbest[j]) { tbest[j] = d; t2q[j] = i; }
+      }
+    for (int i = 0; i < nq; i++)
+      if (q2t[i] >= 0 && (!cross_ || t2q[q2t[i]] == i)) matches.push_back(DMatch{i, q2t[i], 0, qbest[i]});
+  }
+ private:
+  Mat train_;
+  bool cross_ = false;
+};
 }  // namespace cv
 
 namespace Eigen {

@@ -164,3 +164,43 @@ def search_by_projection_last(qdesc, Xw, occ, kp_un, kdesc, *, th, Tcw_cur, Tcw_
     nm = _guided().spref_search_by_projection_last(m, p(qdesc), p(Xw), p(has_mp), p(outlier), p(nobs), p(Tc), p(Tl), p(K), p(bounds), p(kdesc),
                                                    p(kp_un), n, p(occ), occ.shape[0], occ.shape[1], p(kp_taken), C.c_float(th), p(kp2mp))
     return kp2mp[:n], nm
+
+
+# ---- the reference's own SearchByBruteForce overloads (sp_matcher.cpp:1642-1674, sp_matcher_loop.cpp:334-376),
+# ---- oracle/_ref/libspbf_ref.so
+BF_LIB = os.path.join(_HERE, "_ref", "libspbf_ref.so")
+_bf_lib = None
+
+
+def bf_available() -> bool:
+    return os.path.exists(BF_LIB)
+
+
+def _bf():
+    global _bf_lib
+    if _bf_lib is None:
+        _bf_lib = C.CDLL(BF_LIB)
+        _bf_lib.spref_bruteforce_kf_frame.restype = None
+    return _bf_lib
+
+
+def bruteforce_kf_frame(desc1, has_mp1, bad1, desc2):
+    """SearchByBruteForce(KeyFrame*, Frame&, vpMatches12) -> matches12 [len(desc2)]: key-frame row or -1."""
+    d1, d2 = _f32(desc1, (-1, 256)), _f32(desc2, (-1, 256))
+    h1, b1 = np.ascontiguousarray(has_mp1, np.uint8), np.ascontiguousarray(bad1, np.uint8)
+    out = np.full(max(len(d2), 1), -1, np.int32)
+    vp = C.c_void_p
+    _bf().spref_bruteforce_kf_frame(vp(d1.ctypes.data), vp(h1.ctypes.data), vp(b1.ctypes.data), len(d1), vp(d2.ctypes.data), len(d2), vp(out.ctypes.data))
+    return out[:len(d2)]
+
+
+def bruteforce_kf_kf(desc1, has_mp1, bad1, desc2, has_mp2, bad2):
+    """SearchByBruteForce(KeyFrame*, KeyFrame*, vpMatches12) -> (matches12 [len(desc1)]: row of KF2 or -1, count)."""
+    d1, d2 = _f32(desc1, (-1, 256)), _f32(desc2, (-1, 256))
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    h1, b1, h2, b2 = u8(has_mp1), u8(bad1), u8(has_mp2), u8(bad2)
+    out = np.full(max(len(d1), 1), -1, np.int32)
+    vp = C.c_void_p
+    n = _bf().spref_bruteforce_kf_kf(vp(d1.ctypes.data), vp(h1.ctypes.data), vp(b1.ctypes.data), len(d1), vp(d2.ctypes.data), vp(h2.ctypes.data),
+                                     vp(b2.ctypes.data), len(d2), vp(out.ctypes.data))
+    return out[:len(d1)], n

@@ -267,3 +267,36 @@ def test_reference_post_pins_golden(name, golden):
         kps, occ, _ = RP.nms(pts[order], None, nf, W, H)
         assert np.array_equal(kps.astype(np.int16), g[f"f{t}_kp_xy"])
         assert np.array_equal(occ, g[f"f{t}_occ_grid"])
+
+
+@pytest.mark.parametrize("seed,n1,n2", [(1, 300, 320), (2, 801, 801), (3, 40, 7), (4, 5, 60)])
+def test_reference_bruteforce_pins_mirror_logic(seed, n1, n2):
+    """The reference's OWN SearchByBruteForce overloads (sp_matcher.cpp:1642-1674, sp_matcher_loop.cpp:334-376), compiled
+    verbatim into oracle/_ref around a BFMatcher stand-in: which rows enter the matcher and how matches map back.
+    (KeyFrame*, Frame&) keeps key-frame rows with a map point that is not bad and all frame rows; (KeyFrame*, KeyFrame*)
+    keeps rows with a map point on both sides -- bad ones included -- and writes vpMatches12[row of KF1] = map point of
+    the matched KF2 row.  Expected values = the index arithmetic of sp_orb_slam_b200.SPMatcher.SearchByBruteForce and of
+    cpp/sp_matcher.h on top of the oracle's mutual-NN."""
+    from oracle import ref_post as RP
+    if not RP.bf_available():
+        pytest.skip("oracle/_ref/libspbf_ref.so not built (run oracle/ref_build.sh where /root/reference exists)")
+    rng = np.random.RandomState(seed)
+    d1 = rng.randn(n1, 256).astype(np.float32); d1 /= np.linalg.norm(d1, axis=1, keepdims=True)
+    src = rng.randint(0, n1, n2)
+    d2 = (d1[src] + 0.05 * rng.randn(n2, 256)).astype(np.float32); d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
+    has1, bad1 = (rng.rand(n1) < 0.7).astype(np.uint8), (rng.rand(n1) < 0.15).astype(np.uint8)
+    has2, bad2 = (rng.rand(n2) < 0.75).astype(np.uint8), (rng.rand(n2) < 0.15).astype(np.uint8)
+    # (KeyFrame*, Frame&)
+    idx_t = np.flatnonzero((has1 == 1) & (bad1 == 0))
+    q2t, _, _ = O.match_mutual_nn(d2, d1[idx_t])
+    exp = np.where(q2t >= 0, idx_t[np.maximum(q2t, 0)] if len(idx_t) else -1, -1)
+    got = RP.bruteforce_kf_frame(d1, has1, bad1, d2)
+    assert np.array_equal(got, exp) and (n1 < 100 or (exp >= 0).sum() > 10)
+    # (KeyFrame*, KeyFrame*)
+    idx_t, idx_q = np.flatnonzero(has1 == 1), np.flatnonzero(has2 == 1)
+    q2t, _, _ = O.match_mutual_nn(d2[idx_q], d1[idx_t])
+    exp = -np.ones(n1, np.int64)
+    hit = np.flatnonzero(q2t >= 0)
+    exp[idx_t[q2t[hit]]] = idx_q[hit]
+    got, cnt = RP.bruteforce_kf_kf(d1, has1, bad1, d2, has2, bad2)
+    assert np.array_equal(got, exp) and cnt == len(hit)
