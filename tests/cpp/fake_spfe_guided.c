@@ -1,7 +1,7 @@
 /* TEST-ONLY stand-in for the libspfe entries that the guided-search templates of cpp/sp_matcher.h call, so that the
  * shim's host-side logic (hoisting the per-object tests of the reference's loops into flat arrays, applying the
- * assignments in map-point order) can run in the CPU test suite: spfe_search_guided is answered by the oracle
- * (oracle/sp_post.c).  Never linked into the product; the real entry is covered by the -m gpu tests. */
+ * assignments in map-point order; the row filtering / index mapping of SearchByBruteForce) can run in the CPU test suite:
+ * spfe_search_guided and spfe_match_mutual_nn are answered by the oracle (oracle/sp_post.c).  Never linked into the product; the real entry is covered by the -m gpu tests. */
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -28,9 +28,15 @@ int spfe_search_guided(spfe_ctx *ctx, const spfe_guided_search *g, int32_t *q2kp
   return SPFE_OK;
 }
 
+void orc_match_mutual(const float *q, int nq, const float *t, int nt, int d, int32_t *q2t, float *dist, float *second);
+
 int spfe_match_mutual_nn(spfe_ctx *ctx, const float *q, int32_t nq, const float *t, int32_t nt, int32_t *q2t, float *dist) {
-  (void)ctx; (void)q; (void)nq; (void)t; (void)nt; (void)q2t; (void)dist;
-  return SPFE_ERR_STATE;  /* not exercised by this test */
+  (void)ctx;
+  float *d = (float *)calloc(nq > 0 ? nq : 1, sizeof(float));
+  orc_match_mutual(q, nq, t, nt, 256, q2t, d, NULL);
+  if (dist) memcpy(dist, d, (size_t)nq * sizeof(float));
+  free(d);
+  return SPFE_OK;
 }
 float spfe_l2(const float *a, const float *b) { return orc_l2(a, b, 256); }
 const char *spfe_last_error(const spfe_ctx *ctx) { (void)ctx; return "fake backend"; }

@@ -21,6 +21,11 @@ struct MapPoint {
   int Observations() const { return nobs; }
   cv::Mat getDescTrack() const { return desc; }
 };
+struct KeyFrame {
+  cv::Mat mDescriptors;
+  std::vector<MapPoint *> mps;
+  std::vector<MapPoint *> GetMapPointMatches() { return mps; }
+};
 struct Frame {
   cv::Mat mDescriptors, occ_grid;
   int N = 0;
@@ -84,6 +89,24 @@ int main(int argc, char **argv) {
     for (int k = 0; k < n; k++) fprintf(o, "%ld ", F.mvpMapPoints[k] ? (long)(F.mvpMapPoints[k] - mps.data()) : -1L);
     fprintf(o, "\n");
     for (int i = 0; i < m; i++) fprintf(o, "%d", mps[i].dust_match ? 1 : 0);
+    fprintf(o, "\n");
+  }
+  {  // SearchByBruteForce: key frame = the map points' descriptors (rows without / with bad map points), frame = the keypoints
+    KeyFrame kf, kf2;
+    kf.mDescriptors.create(m, 256, CV_32FC1); memcpy(kf.mDescriptors.data, qdesc.data(), qdesc.size() * 4);
+    for (int i = 0; i < m; i++) kf.mps.push_back(in_view[i] ? &mps[i] : nullptr);   // in_view reused as "has a map point"
+    Frame F = make_frame(false);
+    std::vector<MapPoint *> m12;
+    matcher.SearchByBruteForce(&kf, F, m12);
+    for (int q = 0; q < n; q++) fprintf(o, "%ld ", m12[q] ? (long)(m12[q] - mps.data()) : -1L);
+    fprintf(o, "\n");
+    std::vector<MapPoint> store2(n);
+    kf2.mDescriptors = F.mDescriptors;
+    for (int k = 0; k < n; k++) kf2.mps.push_back(taken[k] ? nullptr : &store2[k]);         // taken reused as "no map point"
+    std::vector<MapPoint *> mkk;
+    const int cnt = matcher.SearchByBruteForce(&kf, &kf2, mkk);
+    fprintf(o, "%d\n", cnt);
+    for (int i = 0; i < m; i++) fprintf(o, "%ld ", mkk[i] ? (long)(mkk[i] - store2.data()) : -1L);
     fprintf(o, "\n");
   }
   fclose(o);

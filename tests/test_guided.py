@@ -189,10 +189,11 @@ def test_reference_dust_association_pins_oracle(seed, m):
 
 @pytest.mark.parametrize("seed,m,th,c2", [(1, 500, 3.0, 0.0), (2, 900, 1.0, 40.0)])
 def test_cpp_shim_guided_templates_match_reference_on_cpu(tmp_path, seed, m, th, c2):
-    """The drop-in templates of cpp/sp_matcher.h (SearchByProjection(Frame&, MapPoints), DustAssociate) on Frame / MapPoint
-    objects shaped like the reference's, run on the CPU with a test-only backend that answers spfe_search_guided with the
-    oracle (tests/cpp/fake_spfe_guided.c), against the REFERENCE's own functions compiled verbatim (oracle/_ref): the
-    same Frame::mvpMapPoints, match counts and dust_match flags.  Covers what the shim adds on the host: hoisting
+    """The drop-in templates of cpp/sp_matcher.h (SearchByProjection(Frame&, MapPoints), DustAssociate, both
+    SearchByBruteForce overloads) on Frame / KeyFrame / MapPoint objects shaped like the reference's, run on the CPU with a
+    test-only backend that answers spfe_search_guided / spfe_match_mutual_nn with the oracle
+    (tests/cpp/fake_spfe_guided.c), against the REFERENCE's own functions compiled verbatim (oracle/_ref): the same
+    Frame::mvpMapPoints / vpMatches12, match counts and dust_match flags.  Covers what the shim adds on the host: hoisting
     mbTrackInView / isBad() / Observations() / RadiusByViewingCos into flat arrays and applying the result in order."""
     import os
     import subprocess
@@ -233,6 +234,12 @@ def test_cpp_shim_guided_templates_match_reference_on_cpu(tmp_path, seed, m, th,
     assert int(L[2]) == nm_d and nm_d > m // 20
     assert np.array_equal(np.array(L[3].split(), np.int64), kp2mp_d)
     assert L[4] == "".join(map(str, dm))
+    # both SearchByBruteForce templates against the reference's own overloads (oracle/_ref/libspbf_ref.so)
+    if RP.bf_available():
+        got = RP.bruteforce_kf_frame(qdesc, in_view, bad, f["desc"])
+        assert np.array_equal(np.array(L[5].split(), np.int64), got) and (got >= 0).sum() > 20
+        got2, cnt = RP.bruteforce_kf_kf(qdesc, in_view, bad, f["desc"], 1 - taken, np.zeros(n, np.uint8))
+        assert int(L[6]) == cnt and np.array_equal(np.array(L[7].split(), np.int64), got2)
 
 
 def test_guided_struct_matches_header():
