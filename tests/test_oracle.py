@@ -300,3 +300,27 @@ def test_reference_bruteforce_pins_mirror_logic(seed, n1, n2):
     exp[idx_t[q2t[hit]]] = idx_q[hit]
     got, cnt = RP.bruteforce_kf_kf(d1, has1, bad1, d2, has2, bad2)
     assert np.array_equal(got, exp) and cnt == len(hit)
+
+
+@pytest.mark.parametrize("name", ["g120x160", "g480x752"])
+def test_reference_composed_extractor_reproduces_golden(name, weights, golden):
+    """SPExtractor::operator() re-assembled from the reference's OWN compiled pieces -- SPFrontend::forward (libspref), the
+    sort (:489-498, oracle / cv2-pinned), nms() and computeCovariance() (libsppost_ref) -- on the golden frames: keypoints,
+    occ_grid, responses and covariances of the committed fixtures come out bit for bit (the fixtures were minted with the
+    C restatements in place of the last two)."""
+    from oracle import ref_frontend as R
+    RP = _ref_post()
+    if not R.available():
+        pytest.skip("oracle/_ref not built")
+    g = golden(name)
+    nf = int(g["nfeatures"])
+    H, W = g["frames"].shape[1:]
+    for t in range(2):
+        r = R.forward(weights, g["frames"][t])
+        pts = r["pixels_in"].T.astype(np.float32) if r["pixels_in"].shape[0] == 2 else r["pixels_in"].astype(np.float32)
+        order = O.sort_desc(r["score"])
+        kps, occ, _ = RP.nms(pts[order], None, nf, W, H)
+        assert np.array_equal(kps.astype(np.int16), g[f"f{t}_kp_xy"]) and np.array_equal(occ, g[f"f{t}_occ_grid"])
+        _, heat_inv, _, _ = O.to_heat(r["heat_log"])
+        resp, cov2, _ = RP.covariance(heat_inv, kps)
+        assert np.array_equal(resp, g[f"f{t}_response"]) and np.array_equal(cov2, g[f"f{t}_cov2"])
