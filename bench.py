@@ -110,7 +110,7 @@ def cpu_reference_step(weights, frames, nf, use_ref, prev=None):
     return prev
 
 
-def cpu_baseline(H, W, nf, n_frames=6):
+def cpu_baseline(H, W, nf, n_frames=64):   # one bench step worth of frames: 10-20 s of host work
     import torch
     from oracle import ref_frontend as R, sp_oracle as O, weights as OW
     from sp_orb_slam_b200 import synth
