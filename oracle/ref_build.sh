@@ -46,3 +46,7 @@ sed -n '1642,1674p' "$REF/orb_slam2/src/cv/sp_matcher.cpp" > "$OUT/gen/bf_kf_fra
 sed -n '334,376p' "$REF/orb_slam2/src/cv/sp_matcher_loop.cpp" > "$OUT/gen/bf_kf_kf.inc"
 g++ -O2 -std=c++17 -ffp-contract=off -fPIC -shared -w -I"$OUT/gen" -I"$HERE" "$HERE/ref_bf_driver.cc" -o "$OUT/libspbf_ref.so"
 echo "built $OUT/libspbf_ref.so"
+# the reference's own BaseExtractor (scale-pyramid bookkeeping the drop-in class must reproduce), verbatim
+sed -n '7,95p' "$REF/orb_slam2/include/orb_slam/cv/base_extractor.h" > "$OUT/gen/base_extractor_decl.inc"
+g++ -O2 -std=c++17 -ffp-contract=off -w -I"$OUT/gen" -I"$HERE" "$HERE/ref_base_driver.cc" -o "$OUT/ref_base_probe"
+echo "built $OUT/ref_base_probe"

@@ -132,6 +132,8 @@ inline double norm(const Mat &a, const Mat &b, int /*NORM_L2*/) {
   for (int i = 0; i < a.cols; i++) { const float t = pa[i] - pb[i]; s += t * t; }
   return (double)__builtin_sqrtf(s);
 }
+typedef const Mat &InputArray;
+typedef Mat &OutputArray;
 struct DMatch { int queryIdx, trainIdx, imgIdx; float distance; };
 template <class T> struct Ptr {
   std::shared_ptr<T> p;
@@ -166,6 +168,8 @@ class BFMatcher {
   bool cross_ = false;
 };
 }  // namespace cv
+#include <cmath>
+inline int cvRound(double v) { return (int)std::lrint(v); }  // OpenCV: round to nearest even (cvtsd2si / lrint)
 
 namespace Eigen {
 struct Array2f {

@@ -36,14 +36,15 @@ BaseExtractor::BaseExtractor(int nfeatures_, float scale_factor, int nlevels_, i
   }
   mvImagePyramid.resize(nlevels);
   mnFeaturesPerLevel.assign(nlevels, 0);
-  const float inv = 1.0f / static_cast<float>(scaleFactor);
-  float per_level = nlevels > 1 ? nfeatures * (1 - inv) / (1 - static_cast<float>(std::pow(static_cast<double>(inv), static_cast<double>(nlevels))))
-                                : static_cast<float>(nfeatures);
+  // base_extractor.h:35-47, same arithmetic: factor = 1.0f / (double) scaleFactor narrowed to float, cvRound = round to
+  // nearest even (lrint).  With one level the quotient is 0 / 0 and never used, as upstream.
+  const float factor = static_cast<float>(1.0f / scaleFactor);
+  float per_level = nfeatures * (1 - factor) / (1 - static_cast<float>(std::pow(static_cast<double>(factor), static_cast<double>(nlevels))));
   int used = 0;
-  for (int l = 0; l + 1 < nlevels; l++) {
-    mnFeaturesPerLevel[l] = static_cast<int>(std::lround(per_level));
+  for (int l = 0; l < nlevels - 1; l++) {
+    mnFeaturesPerLevel[l] = static_cast<int>(std::lrint(per_level));
     used += mnFeaturesPerLevel[l];
-    per_level *= inv;
+    per_level *= factor;
   }
   mnFeaturesPerLevel[nlevels - 1] = nfeatures - used > 0 ? nfeatures - used : 0;
 }

@@ -96,3 +96,25 @@ def test_shim_compiles():
     from sp_orb_slam_b200 import build
     exe = build.build_shim()
     assert os.path.exists(exe)
+
+
+def test_base_extractor_matches_reference(tmp_path):
+    """The shim's stand-alone copy of BaseExtractor (scale-pyramid getters that Frame reads, frame.cpp:211-217) against the
+    REFERENCE's own class compiled verbatim (oracle/_ref/ref_base_probe, base_extractor.h:7-95): the SuperPoint
+    configuration (1 level, factor 1.0) and ORB-style pyramids print the same levels, factors, sigmas and per-level
+    feature budgets."""
+    import subprocess
+    from sp_orb_slam_b200 import build
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_base_probe")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/ref_base_probe not built (run oracle/ref_build.sh where /root/reference exists)")
+    build.build_lib()
+    exe = str(tmp_path / "base_probe_shim")
+    cpp = os.path.join(ROOT, "sp_orb_slam_b200", "cpp")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"), "-I", cpp,
+                           os.path.join(ROOT, "tests", "cpp", "base_probe_shim.cc"), os.path.join(cpp, "sp_shim.cc"),
+                           "-o", exe, "-L", build.LIB_DIR, "-lspfe", f"-Wl,-rpath,{build.LIB_DIR}"])
+    for cfg in (("800", "1.0", "1"), ("2000", "1.0", "1"), ("1000", "1.2", "8"), ("2000", "1.2", "8"), ("500", "1.5", "4"), ("1200", "2.0", "3"), ("7", "1.1", "12")):
+        a = subprocess.run([ref, *cfg], capture_output=True, text=True, check=True).stdout
+        b = subprocess.run([exe, *cfg], capture_output=True, text=True, check=True).stdout
+        assert a == b, (cfg, a, b)
