@@ -118,3 +118,34 @@ def test_base_extractor_matches_reference(tmp_path):
         a = subprocess.run([ref, *cfg], capture_output=True, text=True, check=True).stdout
         b = subprocess.run([exe, *cfg], capture_output=True, text=True, check=True).stdout
         assert a == b, (cfg, a, b)
+
+
+def test_abi_struct_layouts_match_ctypes(tmp_path):
+    """sizeof / offsetof of every struct in include/spfe.h as gcc lays them out, against the ctypes mirrors in
+    sp_orb_slam_b200/capi.py (field names, order, offsets, total size)."""
+    import subprocess
+    structs = {"spfe_config": capi.Config, "spfe_frame_out": capi.FrameOut, "spfe_guided_search": capi.GuidedSearch,
+               "spfe_dust_pose": capi.DustPose, "spfe_stage_time": capi.StageTime}
+    src = ['#include <stddef.h>', '#include <stdio.h>', '#include "spfe.h"', 'int main(void) {']
+    for cname, ct in structs.items():
+        src.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, *_ in ct._fields_:
+            src.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    src += ['  return 0;', '}']
+    (tmp_path / "probe.c").write_text("\n".join(src))
+    exe = str(tmp_path / "probe")
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(tmp_path / "probe.c"), "-o", exe])
+    got = dict(line.split() for line in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, ct in structs.items():
+        assert int(got[cname]) == C.sizeof(ct), cname
+        for fname, *_ in ct._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, (cname, fname)
+    # and no field of the C structs is missing from the mirrors
+    hdr = open(os.path.join(ROOT, "include", "spfe.h")).read()
+    for cname, ct in structs.items():
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), hdr, re.S).group(1)
+        n_decl = 0
+        for decl in re.sub(r"/\*.*?\*/", "", body, flags=re.S).split(";"):
+            if decl.strip():
+                n_decl += len(decl.split(","))
+        assert n_decl == len(ct._fields_), cname
