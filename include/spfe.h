@@ -60,6 +60,13 @@ enum {
                                kp_response (heat_inv at the keypoint), cov2, cov2_inv */
   SPFE_EMIT_HEAT_INV = 1u << 3, /* copy heat_inv_ (H x W f32 = 1 - heat_; a public member of SPExtractor that nothing outside
                                computeCovariance reads) to the host as well */
+  SPFE_LAZY_HEAT = 1u << 4, /* throughput mode: the heat maps are computed and stay on the device (what computeCovariance
+                               needs), spfe_fetch_heat copies heat_ / heat_inv_ of single frames on demand.  heat_ is
+                               read on the host only by PoseOptimizationHeat (orb_slam2/src/tracking/tracker.cpp:206-224,
+                               off the live path), so 1.44 MB per 752x480 frame need not cross PCIe */
+  SPFE_DESC_F16 = 1u << 5,  /* descriptors cross PCIe as IEEE fp16 (spfe_frame_out.desc_f16, desc == NULL): half the bytes
+                               of the dominant output; the C++ shim widens them to CV_32F (cosine to the fp32 rows
+                               >= 1 - 1e-6, the parity bar is 1 - 1e-3) */
   SPFE_MATCH_PREV = 1u << 2 /* a slot is one camera stream: also match every frame against the previous frame of
                                that slot (mutual NN, all descriptors as train set -- the BFMatcher call of
                                Tracking::trackReferenceKeyFrameANN, tracker.cpp:372-417); frame 0 of a batch is
@@ -104,6 +111,7 @@ typedef struct spfe_frame_out {
   int32_t n_prev;          /* SPFE_MATCH_PREV: keypoints of the previous frame of this stream (0 = none yet) */
   const int32_t *match_prev; /* [n] index into the previous frame's keypoints or -1; NULL without SPFE_MATCH_PREV */
   const float *match_dist; /* [n] L2 distance to the nearest previous descriptor */
+  const uint16_t *desc_f16;/* [n][256] IEEE binary16 bits, L2-normalised (SPFE_DESC_F16; desc is NULL then) */
 } spfe_frame_out;
 
 int spfe_create(const spfe_config *cfg, spfe_ctx **out);
@@ -123,6 +131,15 @@ int spfe_extract(spfe_ctx *ctx, const uint8_t *gray, size_t row_stride, spfe_fra
  * gives every slot one private stream instead.) */
 int spfe_submit(spfe_ctx *ctx, int32_t slot, const uint8_t *const *grays, int32_t batch, size_t row_stride);
 int spfe_wait(spfe_ctx *ctx, int32_t slot, spfe_frame_out *outs);
+/* Only the n[b] valid descriptor rows of every frame cross PCIe (not max_keypoints + 1): spfe_wait first waits for the
+ * counts and the small outputs, then copies exactly n[b] rows per frame.  spfe_last_d2h_bytes returns the bytes the
+ * last spfe_wait of `slot` moved device -> host in total (bench.py reports it). */
+int64_t spfe_last_d2h_bytes(const spfe_ctx *ctx, int32_t slot);
+/* heat_ / heat_inv_ (H x W f32 each; either pointer may be NULL) of frame `frame` of the last batch waited for on `slot`,
+ * copied on demand: needs SPFE_LAZY_HEAT, SPFE_EMIT_COV or SPFE_EMIT_HEAT* (the maps exist on the device) and is
+ * bit-identical to what SPFE_EMIT_HEAT / SPFE_EMIT_HEAT_INV deliver eagerly.  Valid until the slot is submitted again.
+ * Replaces the eager heat_ / heat_inv_ members of SPExtractor (sp_extractor.h:72-73) in throughput mode. */
+int spfe_fetch_heat(spfe_ctx *ctx, int32_t slot, int32_t frame, float *heat, float *heat_inv);
 /* Zero-staging variant of spfe_submit for a capture pipeline that already owns page-locked memory: `frames` is
  * [batch][H][W] u8, dense, and is DMA'd to the device straight from the caller's buffer (no host memcpy), so it must
  * stay valid and unmodified until spfe_wait returns for this slot.  Works with pageable memory too, only slower.

@@ -8,11 +8,11 @@ import os
 from . import build as _build
 
 DESC_DIM = 256
-EMIT_HEAT, EMIT_COV, MATCH_PREV, EMIT_HEAT_INV = 1, 2, 4, 8
+EMIT_HEAT, EMIT_COV, MATCH_PREV, EMIT_HEAT_INV, LAZY_HEAT, DESC_F16, EXACT = 1, 2, 4, 8, 16, 32, 64
 OK, ERR_INVALID, ERR_EMPTY, ERR_WEIGHTS, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
 
 EXPORTS = ["spfe_default_config", "spfe_create", "spfe_destroy", "spfe_last_error", "spfe_extract", "spfe_submit",
-           "spfe_wait", "spfe_submit_pinned", "spfe_host_alloc", "spfe_host_free", "spfe_submit_device", "spfe_slot_sync", "spfe_match_mutual_nn", "spfe_match_knn2", "spfe_search_guided", "spfe_dust_pose_optimize", "spfe_dust_pose_optimize_batch", "spfe_dust_linearize", "spfe_set_score_threshold", "spfe_reset_stream", "spfe_timer_start",
+           "spfe_wait", "spfe_last_d2h_bytes", "spfe_fetch_heat", "spfe_submit_pinned", "spfe_host_alloc", "spfe_host_free", "spfe_submit_device", "spfe_slot_sync", "spfe_match_mutual_nn", "spfe_match_knn2", "spfe_search_guided", "spfe_dust_pose_optimize", "spfe_dust_pose_optimize_batch", "spfe_dust_linearize", "spfe_set_score_threshold", "spfe_reset_stream", "spfe_timer_start",
            "spfe_timer_stop", "spfe_check_weights", "spfe_l2", "spfe_debug_read", "spfe_launch_count", "spfe_profile_device"]
 
 
@@ -29,7 +29,7 @@ class FrameOut(C.Structure):
     _fields_ = [("n", C.c_int32), ("kp_xy", _FP), ("kp_score", _FP), ("kp_response", _FP), ("desc", _FP),
                 ("occ_grid", C.POINTER(C.c_int16)), ("dense_dust", _FP), ("semi_dust", _FP), ("heat", _FP),
                 ("heat_inv", _FP), ("cov2", _FP), ("cov2_inv", _FP), ("n_prev", C.c_int32),
-                ("match_prev", C.POINTER(C.c_int32)), ("match_dist", _FP)]
+                ("match_prev", C.POINTER(C.c_int32)), ("match_dist", _FP), ("desc_f16", C.POINTER(C.c_uint16))]
 
 
 class GuidedSearch(C.Structure):
@@ -83,6 +83,9 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.spfe_extract.argtypes = [vp, vp, C.c_size_t, C.POINTER(FrameOut)]
     L.spfe_submit.argtypes = [vp, i32, C.POINTER(vp), i32, C.c_size_t]
     L.spfe_wait.argtypes = [vp, i32, C.POINTER(FrameOut)]
+    L.spfe_last_d2h_bytes.argtypes = [vp, i32]
+    L.spfe_last_d2h_bytes.restype = i64
+    L.spfe_fetch_heat.argtypes = [vp, i32, i32, vp, vp]
     L.spfe_submit_pinned.argtypes = [vp, i32, vp, i32]
     L.spfe_host_alloc.argtypes = [C.c_size_t]
     L.spfe_host_alloc.restype = vp

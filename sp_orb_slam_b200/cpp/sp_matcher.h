@@ -20,6 +20,7 @@ class SPMatcher {
   // Device context used for the brute-force search; set once after the
   // extractor exists (Tracking::Tracking creates both, tracker.cpp:131-144).
   static void SetBackend(spfe_ctx *ctx) { backend() = ctx; }
+  static spfe_ctx *Backend() { return backend(); }
 
   // cv::norm(a, b, NORM_L2) on two 1x256 CV_32F rows (sp_matcher.cpp:1636-1640).
   static float DescriptorDistance(const cv::Mat &a, const cv::Mat &b) { return spfe_l2(a.ptr<float>(), b.ptr<float>()); }

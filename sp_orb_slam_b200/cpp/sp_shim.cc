@@ -54,11 +54,18 @@ SPExtractor::SPExtractor(int nfeatures_) : BaseExtractor(nfeatures_, 1.0f, 1, 1,
   spfe_default_config(&cfg, camera::height, camera::width, nfeatures_);
   cfg.weights_path = common::model_path.c_str();
   if (spfe_create(&cfg, &ctx_) != SPFE_OK) throw std::runtime_error(std::string("SPExtractor: ") + spfe_last_error(nullptr));
-  SPMatcher::SetBackend(ctx_);
-  Optimizer::SetBackend(ctx_);
+  // The matcher and the optimiser share the FIRST extractor's device context (the reference has exactly one: the "ini"
+  // extractor aliases it, tracker.cpp:131,144); a second extractor (another camera) must not silently redirect them.
+  if (!SPMatcher::Backend()) SPMatcher::SetBackend(ctx_);
+  if (!Optimizer::DustBackend()) Optimizer::SetBackend(ctx_);
 }
 
-SPExtractor::~SPExtractor() { spfe_destroy(ctx_); }
+SPExtractor::~SPExtractor() {
+  // nobody may keep calling into a destroyed context
+  if (SPMatcher::Backend() == ctx_) SPMatcher::SetBackend(nullptr);
+  if (Optimizer::DustBackend() == ctx_) Optimizer::SetBackend(nullptr);
+  spfe_destroy(ctx_);
+}
 
 void SPExtractor::operator()(cv::InputArray image_, cv::InputArray /*mask*/, std::vector<cv::KeyPoint> &keypoints,
                              cv::OutputArray descriptors) {

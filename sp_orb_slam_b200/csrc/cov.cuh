@@ -67,7 +67,7 @@ struct CovArgs {
   float *response;        // [B][cap]
   float *cov2;            // [B][cap][2]
   float *cov2_inv;        // [B][cap][2]
-  int *overflow;          // [1] set if even the sequential queue overflowed (reported as an error)
+  int *overflow;          // [1] frame index + 1 if even the sequential queue overflowed (reported as an error; cleared per batch)
   int *n_replay;          // [B][2] statistics: keypoints / pixels replayed sequentially
   int H, W, cap, B, round;
   int epoch_tag;          // (508 - batches since the owner map was cleared) << 22
@@ -425,31 +425,33 @@ __global__ void __launch_bounds__(32) cov_replay_kernel(const CovArgs a) {
   const size_t px = static_cast<size_t>(a.H) * a.W;
   const float *heat = a.heat_inv + b * px;
   const int n_kp = a.count[b], W = a.W, H = a.H;
-  // ordered list of the keypoints to replay
+  // ordered list of the keypoints to replay, gathered in windows of at most 4096 (any key-point budget works)
+  int k_next = 0, n_total = 0, stat_p = 0;
+  bool vis_loaded = false;
+  const bool in_smem = a.vis_words <= COV_SEQ_BITMAP_WORDS;
+  uint32_t *vis = in_smem ? s_vis : g_vis;
+  if (lane == 0) {
+    a.n_replay[2 * b] = 0;
+    a.n_replay[2 * b + 1] = 0;
+  }
+  while (k_next < n_kp) {
   int n_dirty = 0;
-  for (int k0 = 0; k0 < n_kp; k0 += 32) {
-    const int k = k0 + lane;
+  for (; k_next < n_kp && n_dirty <= 4096 - 32; k_next += 32) {
+    const int k = k_next + lane;
     const bool d = k < n_kp && !a.done[static_cast<size_t>(b) * a.cap + k];
     const unsigned m = __ballot_sync(0xffffffffu, d);
-    if (d && n_dirty + __popc(m & ((1u << lane) - 1)) < 4096) s_dirty[n_dirty + __popc(m & ((1u << lane) - 1))] = static_cast<uint16_t>(k);
+    if (d) s_dirty[n_dirty + __popc(m & ((1u << lane) - 1))] = static_cast<uint16_t>(k);
     n_dirty += __popc(m);
   }
   __syncwarp();
-  if (lane == 0) {
-    a.n_replay[2 * b] = n_dirty;
-    a.n_replay[2 * b + 1] = 0;
+  if (n_dirty == 0) continue;
+  n_total += n_dirty;
+  if (!vis_loaded) {
+    if (in_smem)
+      for (int i = lane; i < a.vis_words; i += 32) s_vis[i] = g_vis[i];
+    vis_loaded = true;
+    __syncwarp();
   }
-  if (n_dirty == 0) return;
-  if (n_dirty > 4096) {  // cannot happen (cap <= 4096 keypoints are supported by the matcher as well)
-    if (lane == 0) atomicExch(a.overflow, 1);
-    return;
-  }
-  const bool in_smem = a.vis_words <= COV_SEQ_BITMAP_WORDS;
-  if (in_smem)
-    for (int i = lane; i < a.vis_words; i += 32) s_vis[i] = g_vis[i];
-  uint32_t *vis = in_smem ? s_vis : g_vis;
-  __syncwarp();
-  int stat_p = 0;
   for (int di = 0; di < n_dirty; di++) {
     const int k = s_dirty[di];
     const size_t ki = static_cast<size_t>(b) * a.cap + k;
@@ -488,7 +490,7 @@ __global__ void __launch_bounds__(32) cov_replay_kernel(const CovArgs a) {
     }
     tail = __shfl_sync(0xffffffffu, tail, 0);
     if (tail < 0) {
-      if (lane == 0) atomicExch(a.overflow, 1);
+      if (lane == 0) atomicMax(a.overflow, b + 1);  // which frame: reported by spfe_wait
       continue;
     }
     // moments (sp_extractor.cpp:316-333): sum of scores, then sum of (score / sum) * delta^2, both in pop order
@@ -529,7 +531,11 @@ __global__ void __launch_bounds__(32) cov_replay_kernel(const CovArgs a) {
     }
     stat_p += tail;
   }
-  if (lane == 0) a.n_replay[2 * b + 1] = stat_p;
+  }  // windows of the dirty list
+  if (lane == 0 && n_total > 0) {
+    a.n_replay[2 * b] = n_total;
+    a.n_replay[2 * b + 1] = stat_p;
+  }
 }
 
 }  // namespace spfe

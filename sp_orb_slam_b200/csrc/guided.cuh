@@ -23,7 +23,7 @@
 namespace spfe {
 
 constexpr int GUIDED_CAND = 64;    // candidate keypoints per map point (cells of a 2r+1 window, r <= ~24 px)
-constexpr int GUIDED_ROUNDS = 256;
+constexpr int GUIDED_ROUNDS = 256;  // <= 2038 (claim tags, guided_resolve_kernel)
 
 struct GuidedArgs {
   int mode, m, n, grid_rows, grid_cols;
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(1024) guided_resolve_kernel(const GuidedArgs a
   volatile uint8_t *decided = a.decided;
   bool left = true;
   for (int round = 0; round < GUIDED_ROUNDS && left; round++) {
-    const int tag = (2047 - round) << 20;
+    const int tag = (2038 - round) << 20;  // every tag stays below the cleared value 0x7F7F7F7F, so round 0 already claims
     for (int i = tid; i < a.m; i += nt) {
       if (decided[i]) continue;
       const int nc = a.ncand[i];

@@ -33,7 +33,10 @@ static constexpr int DUST_SMEM_MAX = 200 * 1024;  // dust_pose_kernel stages the
 
 namespace {
 
-thread_local std::string g_create_error;
+// Message of the last failure on the calling thread (like errno): the matcher / guided / dust entries run on the
+// tracking, local-mapping and loop-closing threads at once, so the message must not live in the shared context.
+thread_local std::string g_last_error;
+#define g_create_error g_last_error
 
 std::string fmt(const char *f, ...) {
   char buf[512];
@@ -117,6 +120,8 @@ struct Slot {
   float *h_kp_xy = nullptr, *h_kp_score = nullptr, *h_desc = nullptr, *h_dense = nullptr, *h_semi = nullptr,
         *h_heat = nullptr, *h_heat_inv = nullptr;
   int16_t *h_occ = nullptr;
+  uint16_t *h_desc16 = nullptr;  // DESC_F16: [Bm][cap][256] binary16 instead of h_desc
+  long long d2h_bytes = 0;       // what the last spfe_wait moved device -> host
   int *h_match = nullptr, *h_nprev = nullptr;
   float *h_mdist = nullptr;
   // covariance (device)
@@ -139,6 +144,9 @@ struct spfe_ctx {
   int rows_pad = 0, match_nb = 0, match_tiles = 0;  // tensor-core matcher geometry
   bool heat = false, cov = false, match_prev = false;  // heat: heat maps computed on the device (EMIT_HEAT or EMIT_COV)
   bool heat_host = false, heat_inv_host = false;       // EMIT_HEAT / EMIT_HEAT_INV: heat_ / heat_inv_ are also copied to the host
+  bool lazy_heat = false;   // LAZY_HEAT: heat_log + min / max stay on the device for spfe_fetch_heat
+  bool desc_f16 = false;    // DESC_F16: descriptors cross PCIe as fp16
+  float *fetch_heat = nullptr, *fetch_heat_inv = nullptr;  // [H*W] device staging of spfe_fetch_heat (guarded by match_mu)
   // conv1a + conv1b: 2 = one kernel, both layers on the tensor core (default); 1 = one kernel, conv1a on the CUDA cores
   // (SPFE_CONV1=ffma); 0 = two kernels (SPFE_CONV1=unfused or SPFE_FUSED_CONV1=0; materialises conv1a for inspection)
   bool pair = true;   // SPFE_PAIR=0: single-CTA MMAs for the 64 -> 64 layers as well
@@ -157,10 +165,10 @@ struct spfe_ctx {
   std::vector<Slot> slots;
   std::vector<void *> dev_allocs, host_allocs;
   std::atomic<long long> launches{0};
-  std::string error;
   std::mutex match_mu;
   cudaStream_t match_stream = nullptr;
   cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr, aux = nullptr;  // aux: covariance beside the matcher
+  cudaStream_t copy_late = nullptr;  // the n[b]-row descriptor copies spfe_wait issues once the counts are on the host
   bool slot_streams = false;
   MatchScratch match;  // for spfe_match_mutual_nn (host pointers)
   float *h_match_q = nullptr, *h_match_t = nullptr;
@@ -174,8 +182,8 @@ struct spfe_ctx {
   void *dust_stage = nullptr;
   size_t dust_stage_bytes = 0;
 
-  int fail(int code, const std::string &msg) {
-    error = msg;
+  int fail(int code, const std::string &msg) const {
+    g_last_error = msg;
     return code;
   }
 };
@@ -443,7 +451,7 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
   {
     dim3 grid((c->cap + 7) / 8, B);
     sample_desc_kernel<<<grid, 256, 0, st>>>(s.coarse, s.kp_xy, s.count, s.desc, hc, wc, c->cap,
-                                             c->match_prev ? s.x16 + static_cast<size_t>(c->rows_pad) * 256 : nullptr, c->rows_pad);
+                                             s.x16 ? s.x16 + static_cast<size_t>(c->rows_pad) * 256 : nullptr, c->rows_pad);
     c->launches++;
     CU_OK(c, cudaGetLastError());
     mark("sample_desc", 0, 3072.0 * c->cap * B);
@@ -458,7 +466,7 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     CU_OK(c, cudaStreamWaitEvent(c->aux, s.ev_fork, 0));
     st = c->aux;
   }
-  if (c->heat) {
+  if (c->cov || c->heat_host || c->heat_inv_host) {  // (LAZY_HEAT alone: heat_log + min / max stay put for spfe_fetch_heat)
     dim3 grid(64, B);
     heat_norm_kernel<<<grid, 256, 0, st>>>(s.heat_log, s.heat_mm, c->heat_host ? s.heat : nullptr, s.heat_inv, s.heat_mm_f, H * W);
     c->launches++;
@@ -473,6 +481,7 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     CU_OK(c, cudaMemsetAsync(s.cov_visited, 0, B * vis_words * sizeof(uint32_t), st));
     CU_OK(c, cudaMemsetAsync(s.cov_frame_flag, 0, B * sizeof(int), st));
     CU_OK(c, cudaMemsetAsync(s.cov_ctr, 0, COV_NCTR * sizeof(int), st));
+    CU_OK(c, cudaMemsetAsync(s.cov_overflow, 0, sizeof(int), st));  // per batch: one overflow must not fail every later batch
     CovArgs a;
     a.heat_inv = s.heat_inv; a.kp_xy = s.kp_xy; a.count = s.count; a.owner = s.cov_owner; a.visited = s.cov_visited;
     a.queue = s.cov_queue; a.qlen = s.cov_qlen; a.response = s.resp; a.cov2 = s.cov2; a.cov2_inv = s.cov2_inv;
@@ -561,7 +570,7 @@ void spfe_default_config(spfe_config *cfg, int32_t height, int32_t width, int32_
   cfg->weights_path = nullptr;
 }
 
-const char *spfe_last_error(const spfe_ctx *ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+const char *spfe_last_error(const spfe_ctx *) { return g_last_error.c_str(); }
 
 static int create_impl(spfe_ctx *c) {
   const spfe_config &cfg = c->cfg;
@@ -647,7 +656,12 @@ static int create_impl(spfe_ctx *c) {
       if (!(ax && ax[0] == '0')) CU_OK(c, cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
     }
   }
+  CU_OK(c, cudaStreamCreateWithFlags(&c->copy_late, cudaStreamNonBlocking));
   const size_t px = static_cast<size_t>(H) * W, cells = c->cells, cap = c->cap;
+  if (c->heat) {
+    if ((rc = dev_alloc(c, &c->fetch_heat, px))) return rc;
+    if ((rc = dev_alloc(c, &c->fetch_heat_inv, px))) return rc;
+  }
   for (Slot &s : c->slots) {
     if (c->slot_streams) {
       CU_OK(c, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -724,10 +738,13 @@ static int create_impl(spfe_ctx *c) {
     if ((rc = dev_alloc(c, &s.match.dist, Bm * cap))) return rc;
     if ((rc = dev_alloc(c, &s.match.dn, 2))) return rc;
     s.match.cap = static_cast<int>(cap);
-    if (c->match_prev) {
-      const size_t rp = c->rows_pad, nbk = c->match_nb;
+    if (c->match_prev || c->desc_f16) {
+      const size_t rp = c->rows_pad;
       if ((rc = dev_alloc(c, &s.x16, (Bm + 1) * rp * 256))) return rc;
       CU_OK(c, cudaMemset(s.x16, 0, (Bm + 1) * rp * 256 * sizeof(__half)));
+    }
+    if (c->match_prev) {
+      const size_t rp = c->rows_pad, nbk = c->match_nb;
       if ((rc = dev_alloc(c, &s.cand, 2 * Bm * rp * nbk * 2))) return rc;
       if ((rc = make_act_map(c, &s.tmQ, s.x16, 256, 8, static_cast<int>(rp / 8), Bm + 1, 16))) return rc;
       if ((rc = make_mat_map(c, &s.tmT, s.x16, 256, static_cast<int>((Bm + 1) * rp), 256))) return rc;
@@ -742,7 +759,8 @@ static int create_impl(spfe_ctx *c) {
     if ((rc = host_alloc(c, &s.h_count, Bm))) return rc;
     if ((rc = host_alloc(c, &s.h_kp_xy, Bm * cap * 2))) return rc;
     if ((rc = host_alloc(c, &s.h_kp_score, Bm * cap))) return rc;
-    if ((rc = host_alloc(c, &s.h_desc, Bm * cap * 256))) return rc;
+    if (c->desc_f16) { if ((rc = host_alloc(c, &s.h_desc16, Bm * cap * 256))) return rc; }
+    else if ((rc = host_alloc(c, &s.h_desc, Bm * cap * 256))) return rc;
     if ((rc = host_alloc(c, &s.h_dense, Bm * cells))) return rc;
     if ((rc = host_alloc(c, &s.h_semi, Bm * cells))) return rc;
     if ((rc = host_alloc(c, &s.h_occ, Bm * cells))) return rc;
@@ -799,7 +817,9 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
   c->cov = (cfg->flags & SPFE_EMIT_COV) != 0;
   c->heat_host = (cfg->flags & SPFE_EMIT_HEAT) != 0;
   c->heat_inv_host = (cfg->flags & SPFE_EMIT_HEAT_INV) != 0;
-  c->heat = c->cov || c->heat_host || c->heat_inv_host;
+  c->lazy_heat = (cfg->flags & SPFE_LAZY_HEAT) != 0;
+  c->desc_f16 = (cfg->flags & SPFE_DESC_F16) != 0;
+  c->heat = c->cov || c->heat_host || c->heat_inv_host || c->lazy_heat;
   c->match_prev = (cfg->flags & SPFE_MATCH_PREV) != 0;
   c->rows_pad = (c->cap + 255) / 256 * 256;
   c->match_nb = c->rows_pad / 256;
@@ -848,7 +868,6 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
     return SPFE_OK;
   }();
   if (rc != SPFE_OK) {
-    g_create_error = c->error;
     spfe_destroy(c);
     return rc;
   }
@@ -869,7 +888,7 @@ void spfe_destroy(spfe_ctx *c) {
   if (c->match_stream) cudaStreamDestroy(c->match_stream);
   if (c->guided_buf) cudaFree(c->guided_buf);
   if (c->dust_stage) cudaFreeHost(c->dust_stage);
-  for (cudaStream_t st : {c->compute, c->copy_in, c->copy_out, c->aux}) if (st) cudaStreamDestroy(st);
+  for (cudaStream_t st : {c->compute, c->copy_in, c->copy_out, c->aux, c->copy_late}) if (st) cudaStreamDestroy(st);
   for (void *p : c->dev_allocs) cudaFree(p);
   for (void *p : c->host_allocs) cudaFreeHost(p);
   delete c;
@@ -887,7 +906,13 @@ static int enqueue_d2h(spfe_ctx *c, Slot &s, int B) {
   CU_OK(c, cudaMemcpyAsync(s.h_count, s.count, B * sizeof(int), cudaMemcpyDeviceToHost, st));
   CU_OK(c, cudaMemcpyAsync(s.h_kp_xy, s.kp_xy, B * cap * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
   CU_OK(c, cudaMemcpyAsync(s.h_kp_score, s.kp_score, B * cap * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CU_OK(c, cudaMemcpyAsync(s.h_desc, s.desc, B * cap * 256 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  // (descriptors: spfe_wait copies exactly n[b] rows per frame once the counts are here)
+  long long bytes = B * (sizeof(int) + cap * 3 * sizeof(float) + cells * (sizeof(int16_t) + 2 * sizeof(float)));
+  if (c->heat_host) bytes += B * px * sizeof(float);
+  if (c->heat_inv_host) bytes += B * px * sizeof(float);
+  if (c->cov) bytes += B * cap * 5 * sizeof(float) + sizeof(int);
+  if (c->match_prev) bytes += B * cap * 8 + sizeof(int);
+  s.d2h_bytes = bytes;
   CU_OK(c, cudaMemcpyAsync(s.h_occ, s.occ, B * cells * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
   CU_OK(c, cudaMemcpyAsync(s.h_dense, s.dense_dust, B * cells * sizeof(float), cudaMemcpyDeviceToHost, st));
   CU_OK(c, cudaMemcpyAsync(s.h_semi, s.semi_dust, B * cells * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -982,16 +1007,33 @@ int spfe_wait(spfe_ctx *c, int32_t slot, spfe_frame_out *outs) {
   if (!s.pending || !s.on_host) return c->fail(SPFE_ERR_STATE, "spfe_wait: nothing submitted on this slot");
   CU_OK(c, cudaEventSynchronize(s.ev_out));
   s.pending = false;
-  if (c->cov && s.h_cov_overflow[0]) return c->fail(SPFE_ERR_STATE, "covariance flood queue overflow (more than 32768 queued pixels in one keypoint basin)");
-  if (!outs) return SPFE_OK;
   const size_t px = (size_t)c->H * c->W, cells = c->cells, cap = c->cap;
+  {  // the descriptors: exactly n[b] rows of every frame (fp32, or fp16 straight from the matcher's copy)
+    CU_OK(c, cudaSetDevice(c->cfg.device_id));
+    const size_t row = c->desc_f16 ? 256 * sizeof(uint16_t) : 256 * sizeof(float);
+    for (int b = 0; b < s.batch; b++) {
+      const size_t n = s.h_count[b] > 0 ? (size_t)s.h_count[b] : 0;
+      if (n == 0) continue;
+      if (c->desc_f16)
+        CU_OK(c, cudaMemcpyAsync(s.h_desc16 + b * cap * 256, s.x16 + (size_t)(b + 1) * c->rows_pad * 256, n * row, cudaMemcpyDeviceToHost, c->copy_late));
+      else
+        CU_OK(c, cudaMemcpyAsync(s.h_desc + b * cap * 256, s.desc + b * cap * 256, n * row, cudaMemcpyDeviceToHost, c->copy_late));
+      s.d2h_bytes += (long long)(n * row);
+    }
+    CU_OK(c, cudaStreamSynchronize(c->copy_late));
+  }
+  const int cov_bad = c->cov ? s.h_cov_overflow[0] : 0;
+  if (cov_bad && !outs)
+    return c->fail(SPFE_ERR_STATE, fmt("covariance flood queue overflow in frame %d of the batch (more than 32768 queued pixels in one keypoint basin)", cov_bad - 1));
+  if (!outs) return SPFE_OK;
   for (int b = 0; b < s.batch; b++) {
     spfe_frame_out &o = outs[b];
     memset(&o, 0, sizeof o);
     o.n = s.h_count[b];
     o.kp_xy = s.h_kp_xy + b * cap * 2;
     o.kp_score = s.h_kp_score + b * cap;
-    o.desc = s.h_desc + b * cap * 256;
+    if (c->desc_f16) o.desc_f16 = s.h_desc16 + b * cap * 256;
+    else o.desc = s.h_desc + b * cap * 256;
     o.occ_grid = s.h_occ + b * cells;
     o.dense_dust = s.h_dense + b * cells;
     o.semi_dust = s.h_semi + b * cells;
@@ -1008,6 +1050,37 @@ int spfe_wait(spfe_ctx *c, int32_t slot, spfe_frame_out *outs) {
       o.cov2_inv = s.h_cov2_inv + b * cap * 2;
     }
   }
+  if (cov_bad)  // the other frames of the batch are complete and valid
+    return c->fail(SPFE_ERR_STATE, fmt("covariance flood queue overflow in frame %d of the batch (more than 32768 queued pixels in one keypoint basin)", cov_bad - 1));
+  return SPFE_OK;
+}
+
+int64_t spfe_last_d2h_bytes(const spfe_ctx *c, int32_t slot) {
+  if (!c || slot < 0 || slot >= (int)c->slots.size()) return SPFE_ERR_INVALID;
+  return c->slots[slot].d2h_bytes;
+}
+
+int spfe_fetch_heat(spfe_ctx *c, int32_t slot, int32_t frame, float *heat, float *heat_inv) {
+  int rc = check_slot(c, slot);
+  if (rc) return rc;
+  Slot &s = c->slots[slot];
+  if (!c->heat) return c->fail(SPFE_ERR_STATE, "spfe_fetch_heat: the heat maps are not computed (set SPFE_LAZY_HEAT, SPFE_EMIT_COV or SPFE_EMIT_HEAT)");
+  if (s.pending) return c->fail(SPFE_ERR_STATE, "spfe_fetch_heat: slot still has an un-waited batch");
+  if (frame < 0 || frame >= s.batch) return c->fail(SPFE_ERR_STATE, fmt("spfe_fetch_heat: frame %d is not part of the slot's last batch (%d frames)", frame, s.batch));
+  if (!heat && !heat_inv) return SPFE_OK;
+  std::lock_guard<std::mutex> lock(c->match_mu);
+  CU_OK(c, cudaSetDevice(c->cfg.device_id));
+  cudaStream_t st = c->match_stream;
+  const size_t px = (size_t)c->H * c->W;
+  CU_OK(c, cudaStreamWaitEvent(st, s.ev_done, 0));
+  // the pipeline's own kernel on one frame: same arithmetic, same bits as the eager SPFE_EMIT_HEAT copy
+  heat_norm_kernel<<<dim3(64, 1), 256, 0, st>>>(s.heat_log + frame * px, s.heat_mm + 2 * frame, heat ? c->fetch_heat : nullptr,
+                                               c->fetch_heat_inv, nullptr, (int)px);
+  c->launches++;
+  CU_OK(c, cudaGetLastError());
+  if (heat) CU_OK(c, cudaMemcpyAsync(heat, c->fetch_heat, px * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (heat_inv) CU_OK(c, cudaMemcpyAsync(heat_inv, c->fetch_heat_inv, px * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU_OK(c, cudaStreamSynchronize(st));
   return SPFE_OK;
 }
 

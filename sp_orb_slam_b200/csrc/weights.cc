@@ -24,6 +24,20 @@ bool read_file(const std::string &path, std::vector<uint8_t> &buf, std::string &
 inline uint16_t rd16(const uint8_t *p) { return static_cast<uint16_t>(p[0] | (p[1] << 8)); }
 inline uint32_t rd32(const uint8_t *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | (static_cast<uint32_t>(p[3]) << 24); }
 
+// Element count of a tensor read from a file: every dimension in 1 .. 2^20 and the product below 2^28 (the largest
+// SuperPoint tensor has 589 824 elements), so that no later size computation can wrap.
+bool checked_numel(const std::vector<int> &dims, size_t &numel) {
+  if (dims.empty() || dims.size() > 4) return false;
+  uint64_t n = 1;
+  for (int d : dims) {
+    if (d <= 0 || d > (1 << 20)) return false;
+    n *= static_cast<uint64_t>(d);
+    if (n > (1u << 28)) return false;
+  }
+  numel = static_cast<size_t>(n);
+  return true;
+}
+
 // ---- .spw ------------------------------------------------------------------
 bool parse_spw(const std::vector<uint8_t> &buf, WeightMap &out, std::string &err) {
   const uint32_t n = rd32(&buf[4]);
@@ -38,8 +52,9 @@ bool parse_spw(const std::vector<uint8_t> &buf, WeightMap &out, std::string &err
     HostTensor t;
     for (uint32_t d = 0; d < ndim; d++) t.dims.push_back(static_cast<int>(rd32(&buf[off + 36 + 4 * d])));
     off += 52;
-    const size_t cnt = t.numel();
-    if (off + cnt * 4 > buf.size()) { err = "spw: truncated tensor data"; return false; }
+    size_t cnt = 0;
+    if (!checked_numel(t.dims, cnt)) { err = "spw: bad tensor dimensions"; return false; }
+    if (cnt > (buf.size() - off) / 4) { err = "spw: truncated tensor data"; return false; }
     t.data.resize(cnt);
     memcpy(t.data.data(), &buf[off], cnt * 4);
     off += cnt * 4;
@@ -63,6 +78,7 @@ struct JVal {
 struct JParser {
   const char *p, *end;
   bool ok = true;
+  int depth = 0;  // nesting of the value being parsed (a crafted file must not overflow the stack)
   void ws() { while (p < end && (*p == ' ' || *p == '\n' || *p == '\r' || *p == '\t')) p++; }
   std::string str() {
     std::string r;
@@ -77,11 +93,17 @@ struct JParser {
   }
   JVal val() {
     JVal v;
+    if (++depth > 64) ok = false;
+    if (ok) parse(v);
+    depth--;
+    return v;
+  }
+  void parse(JVal &v) {
     ws();
-    if (p >= end) { ok = false; return v; }
+    if (p >= end) { ok = false; return; }
     if (*p == '{') {
       v.kind = JVal::OBJ; p++; ws();
-      if (p < end && *p == '}') { p++; return v; }
+      if (p < end && *p == '}') { p++; return; }
       while (ok) {
         ws();
         if (p >= end || *p != '"') { ok = false; break; }
@@ -97,7 +119,7 @@ struct JParser {
       }
     } else if (*p == '[') {
       v.kind = JVal::ARR; p++; ws();
-      if (p < end && *p == ']') { p++; return v; }
+      if (p < end && *p == ']') { p++; return; }
       while (ok) {
         v.a.push_back(val());
         ws();
@@ -107,20 +129,19 @@ struct JParser {
       }
     } else if (*p == '"') {
       v.kind = JVal::STR; v.s = str();
-    } else if (!strncmp(p, "true", 4)) { v.kind = JVal::BOOL; v.s = "1"; p += 4; }
-    else if (!strncmp(p, "false", 5)) { v.kind = JVal::BOOL; v.s = "0"; p += 5; }
-    else if (!strncmp(p, "null", 4)) { p += 4; }
+    } else if (end - p >= 4 && !strncmp(p, "true", 4)) { v.kind = JVal::BOOL; v.s = "1"; p += 4; }
+    else if (end - p >= 5 && !strncmp(p, "false", 5)) { v.kind = JVal::BOOL; v.s = "0"; p += 5; }
+    else if (end - p >= 4 && !strncmp(p, "null", 4)) { p += 4; }
     else {
       v.kind = JVal::NUM;
       while (p < end && (strchr("+-.eE", *p) || (*p >= '0' && *p <= '9'))) v.s.push_back(*p++);
       if (v.s.empty()) ok = false;
     }
-    return v;
   }
 };
 
 // ---- legacy PyTorch-1.0 zip archive -------------------------------------------
-struct ZipEntry { uint32_t data_off, size; };
+struct ZipEntry { size_t data_off, size; };
 
 bool parse_zip(const std::vector<uint8_t> &buf, std::map<std::string, ZipEntry> &entries, std::string &err) {
   // End-of-central-directory record: signature 0x06054b50, scan backwards.
@@ -130,6 +151,7 @@ bool parse_zip(const std::vector<uint8_t> &buf, std::map<std::string, ZipEntry> 
     if (i == 0 || buf.size() - i > 66000) break;
   }
   if (eocd == std::string::npos) { err = "zip: end-of-central-directory not found"; return false; }
+  if (eocd + 22 > buf.size()) { err = "zip: truncated end-of-central-directory"; return false; }
   const uint16_t n = rd16(&buf[eocd + 10]);
   size_t cd = rd32(&buf[eocd + 16]);
   for (uint16_t i = 0; i < n; i++) {
@@ -137,14 +159,15 @@ bool parse_zip(const std::vector<uint8_t> &buf, std::map<std::string, ZipEntry> 
     const uint16_t method = rd16(&buf[cd + 10]);
     const uint32_t csize = rd32(&buf[cd + 20]), usize = rd32(&buf[cd + 24]);
     const uint16_t nlen = rd16(&buf[cd + 28]), xlen = rd16(&buf[cd + 30]), clen = rd16(&buf[cd + 32]);
-    const uint32_t lho = rd32(&buf[cd + 42]);
+    const size_t lho = rd32(&buf[cd + 42]);  // all offset arithmetic in size_t: 32-bit sums could wrap
+    if (cd + 46 + static_cast<size_t>(nlen) + xlen + clen > buf.size()) { err = "zip: central directory entry out of range"; return false; }
     std::string name(reinterpret_cast<const char *>(&buf[cd + 46]), nlen);
     if (method != 0 || csize != usize) { err = "zip: entry '" + name + "' is compressed (expected stored)"; return false; }
     if (lho + 30 > buf.size() || rd32(&buf[lho]) != 0x04034b50u) { err = "zip: bad local header"; return false; }
-    const uint32_t data_off = lho + 30 + rd16(&buf[lho + 26]) + rd16(&buf[lho + 28]);
-    if (static_cast<size_t>(data_off) + usize > buf.size()) { err = "zip: entry out of range"; return false; }
+    const size_t data_off = lho + 30 + rd16(&buf[lho + 26]) + rd16(&buf[lho + 28]);
+    if (data_off > buf.size() || usize > buf.size() - data_off) { err = "zip: entry out of range"; return false; }
     entries[name] = ZipEntry{data_off, usize};
-    cd += 46 + nlen + xlen + clen;
+    cd += 46 + static_cast<size_t>(nlen) + xlen + clen;
   }
   return true;
 }
@@ -164,15 +187,16 @@ bool parse_legacy_pt(const std::vector<uint8_t> &buf, WeightMap &out, std::strin
   const JVal *tensors = doc.get("tensors");
   const JVal *mm = doc.get("mainModule");
   const JVal *subs = mm ? mm->get("submodules") : nullptr;
-  if (!jp.ok || !tensors || !subs) { err = "legacy archive: malformed model.json"; return false; }
+  if (!jp.ok || !tensors || !subs || tensors->kind != JVal::ARR) { err = "legacy archive: malformed model.json"; return false; }
   for (const JVal &sub : subs->a) {
     const JVal *nm = sub.get("name"), *params = sub.get("parameters");
     if (!nm || !params) continue;
     for (const JVal &par : params->a) {
       const JVal *pid = par.get("tensorId"), *pn = par.get("name");
       if (!pid || !pn) continue;
-      const size_t id = static_cast<size_t>(atoi(pid->s.c_str()));
-      if (id >= tensors->a.size()) { err = "legacy archive: tensorId out of range"; return false; }
+      const long long id_ll = atoll(pid->s.c_str());
+      if (id_ll < 0 || static_cast<size_t>(id_ll) >= tensors->a.size()) { err = "legacy archive: tensorId out of range"; return false; }
+      const size_t id = static_cast<size_t>(id_ll);
       const JVal &t = tensors->a[id];
       const JVal *dims = t.get("dims"), *dt = t.get("dataType"), *data = t.get("data"), *off = t.get("offset");
       const JVal *key = data ? data->get("key") : nullptr;
@@ -180,10 +204,14 @@ bool parse_legacy_pt(const std::vector<uint8_t> &buf, WeightMap &out, std::strin
       HostTensor ht;
       for (const JVal &d : dims->a) ht.dims.push_back(atoi(d.s.c_str()));
       auto it = ent.find(root + "/" + key->s);
-      const size_t eoff = off ? static_cast<size_t>(atoll(off->s.c_str())) : 0;
-      if (it == ent.end() || (eoff + ht.numel()) * 4 > it->second.size) { err = "legacy archive: tensor data missing"; return false; }
-      ht.data.resize(ht.numel());
-      memcpy(ht.data.data(), &buf[it->second.data_off + eoff * 4], ht.numel() * 4);
+      const long long eoff_ll = off ? atoll(off->s.c_str()) : 0;
+      size_t cnt = 0;
+      if (!checked_numel(ht.dims, cnt)) { err = "legacy archive: bad tensor dimensions"; return false; }
+      if (it == ent.end() || eoff_ll < 0 || static_cast<unsigned long long>(eoff_ll) > it->second.size / 4 ||
+          cnt > it->second.size / 4 - static_cast<size_t>(eoff_ll)) { err = "legacy archive: tensor data missing"; return false; }
+      const size_t eoff = static_cast<size_t>(eoff_ll);
+      ht.data.resize(cnt);
+      memcpy(ht.data.data(), &buf[it->second.data_off + eoff * 4], cnt * 4);
       out[nm->s + "." + pn->s] = std::move(ht);
     }
   }

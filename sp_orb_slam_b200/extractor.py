@@ -39,7 +39,8 @@ class SPExtractor:
 
     def __init__(self, nfeatures: int, height: int, width: int, model_path: str, *, device_id: int = 0,
                  max_batch: int = 1, num_slots: int = 1, emit_heat: bool = True, emit_cov: bool = True,
-                 match_prev: bool = False, emit_heat_inv: bool | None = None):
+                 match_prev: bool = False, emit_heat_inv: bool | None = None, lazy_heat: bool = False,
+                 desc_f16: bool = False, exact: bool = False):
         self._lib = capi.load()
         self._ctx = C.c_void_p()
         cfg = capi.Config()
@@ -47,7 +48,11 @@ class SPExtractor:
         cfg.device_id, cfg.max_batch, cfg.num_slots = device_id, max_batch, num_slots
         emit_heat_inv = emit_heat if emit_heat_inv is None else emit_heat_inv
         cfg.flags = ((capi.EMIT_HEAT if emit_heat else 0) | (capi.EMIT_COV if emit_cov else 0)
-                     | (capi.MATCH_PREV if match_prev else 0) | (capi.EMIT_HEAT_INV if emit_heat_inv else 0))
+                     | (capi.MATCH_PREV if match_prev else 0) | (capi.EMIT_HEAT_INV if emit_heat_inv else 0)
+                     | (capi.LAZY_HEAT if lazy_heat else 0) | (capi.DESC_F16 if desc_f16 else 0)
+                     | (capi.EXACT if exact else 0))
+        self.exact = exact
+        self.lazy_heat, self.desc_f16 = lazy_heat, desc_f16
         self.emit_heat_inv = emit_heat_inv
         self.match_prev = match_prev
         self._path = str(model_path).encode()
@@ -97,8 +102,13 @@ class SPExtractor:
 
     def _unpack(self, o: capi.FrameOut) -> dict:
         n, hc, wc, H, W = o.n, self.hc, self.wc, self.height, self.width
+        if self.desc_f16:       # binary16 on the wire, widened here exactly like the C++ shim does
+            desc = (np.ctypeslib.as_array(o.desc_f16, shape=(n * 256,)).view(np.float16).reshape(n, 256).astype(np.float32)
+                    if n else np.zeros((0, 256), np.float32))
+        else:
+            desc = _as_np(o.desc, (n, 256), np.float32)
         d = dict(n=n, kp_xy=_as_np(o.kp_xy, (n, 2), np.float32), kp_score=_as_np(o.kp_score, (n,), np.float32),
-                 desc=_as_np(o.desc, (n, 256), np.float32), occ_grid=_as_np(o.occ_grid, (hc, wc), np.int16),
+                 desc=desc, occ_grid=_as_np(o.occ_grid, (hc, wc), np.int16),
                  dense_dust=_as_np(o.dense_dust, (hc, wc), np.float32), semi_dust=_as_np(o.semi_dust, (hc, wc), np.float32))
         if self.emit_heat:
             d["heat"] = _as_np(o.heat, (H, W), np.float32)
@@ -172,6 +182,18 @@ class SPExtractor:
         outs = (capi.FrameOut * n_frames)()
         self._check(self._lib.spfe_wait(self._ctx, slot, outs))
         return [self._unpack(o) for o in outs] if unpack else outs
+
+    def last_d2h_bytes(self, slot: int = 0) -> int:
+        """Bytes the last ``wait(slot)`` moved device -> host."""
+        return int(self._check(self._lib.spfe_last_d2h_bytes(self._ctx, slot)))
+
+    def fetch_heat(self, slot: int, frame: int, heat: bool = True, heat_inv: bool = False):
+        """``heat_`` / ``heat_inv_`` of one frame of the slot's last batch, copied on demand (spfe_fetch_heat)."""
+        h = np.empty((self.height, self.width), np.float32) if heat else None
+        hi = np.empty((self.height, self.width), np.float32) if heat_inv else None
+        self._check(self._lib.spfe_fetch_heat(self._ctx, slot, frame, None if h is None else h.ctypes.data,
+                                              None if hi is None else hi.ctypes.data))
+        return h, hi
 
     def extract_batch(self, frames, slot: int = 0):
         self.submit(slot, frames)
