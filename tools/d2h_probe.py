@@ -17,15 +17,16 @@ from sp_orb_slam_b200 import sharding  # noqa: E402
 
 
 def timed(fn, reps):
+    # the copies run on side streams: wall clock between two device-wide synchronisations (seconds of copying per call)
+    import time
     torch.cuda.synchronize()
     sharding.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     for _ in range(reps):
         fn()
-    e1.record()
     torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    ms = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device="cuda")
     if dist.is_initialized():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     return float(ms.item())
@@ -59,7 +60,7 @@ def main():
             d2h(); h2d()
         for name, fn in (("d2h", d2h), ("h2d", h2d), ("both", both)):
             fn()
-            reps = 8
+            reps = 24
             ms = timed(fn, reps)
             gb = chunks * n * reps * world / 1e9 * (2 if name == "both" else 1)
             out[f"{name}_{mb}MB_chunks_GBps_aggregate"] = round(gb / (ms * 1e-3), 1)
