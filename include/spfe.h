@@ -67,6 +67,11 @@ enum {
   SPFE_DESC_F16 = 1u << 5,  /* descriptors cross PCIe as IEEE fp16 (spfe_frame_out.desc_f16, desc == NULL): half the bytes
                                of the dominant output; the C++ shim widens them to CV_32F (cosine to the fp32 rows
                                >= 1 - 1e-6, the parity bar is 1 - 1e-3) */
+  SPFE_EXACT = 1u << 6,     /* "exact" mode: fp32-equivalent convolutions on the tensor core.  Activations and weights
+                               are carried as hi + lo fp16 pairs (22 significant bits) and every product is three MMAs
+                               (Ah*Wh + Ah*Wl + Al*Wh) into one fp32 accumulator; conv1a runs in fp32 on the CUDA cores.
+                               Logits agree with the fp32 reference to ~2e-4 (default mode: ~7e-2), which is what
+                               "identical keypoint sets after NMS" needs; costs ~3x the tensor work */
   SPFE_MATCH_PREV = 1u << 2 /* a slot is one camera stream: also match every frame against the previous frame of
                                that slot (mutual NN, all descriptors as train set -- the BFMatcher call of
                                Tracking::trackReferenceKeyFrameANN, tracker.cpp:372-417); frame 0 of a batch is

@@ -38,6 +38,7 @@ struct ConvArgs {
   int NB;                 // cout blocks of N channels each (work items per pixel tile)
   int n_items;            // B * tiles_y * tiles_x * NB
   int cin_off;            // first input channel inside the input tensor
+  int cin_blk_stride;     // 64-channel blocks between consecutive slabs (0 or 1 = dense; 2 = only the hi blocks of an XP tensor)
   int cout_stride;        // channels per pixel of the output tensor
   const float *bias;      // [NB*N]
   __half *out;            // RELU / RELU_POOL / L2NORM: NHWC fp16
@@ -56,8 +57,16 @@ struct ConvArgs {
   int m_tiles;            // 128-row tiles per slot that can hold valid rows
 };
 
-template <int TAPS_, int CB_, int N_, int EPI_, bool WRES_, int SA_, int SB_, int HALVES_ = 1, int EG_ = 1, bool PAIR_ = false>
+template <int TAPS_, int CB_, int N_, int EPI_, bool WRES_, int SA_, int SB_, int HALVES_ = 1, int EG_ = 1, bool PAIR_ = false, bool XP_ = false>
 struct ConvCfg {
+  // XP ("exact" mode, SPFE_EXACT): fp32-equivalent products out of fp16 tensor-core operands.  Activations and weights
+  // are held as hi + lo fp16 pairs (22 significant bits): an activation tensor has its channels interleaved in 64-blocks
+  // [hi_0 | lo_0 | hi_1 | lo_1 ...], the packed weights likewise [Wh_0 | Wl_0 | Wh_1 | Wl_1 ...] per tap, and a product is
+  // the three MMAs  Ah*Wh + Ah*Wl + Al*Wh  (Al*Wl, 2^-24 relative, is dropped) accumulated in the same fp32 TMEM
+  // accumulator.  CB counts SLABS (= 64-channel blocks of the XP tensor = 2 x real blocks): an even slab (hi) is
+  // multiplied with two weight sets (Wh, Wl), an odd one (lo) with Wh only.  RELU / RELU_POOL epilogues write hi and lo.
+  static constexpr bool XP = XP_;
+  static_assert(!XP_ || CB_ % 2 == 0, "XP: slabs come in (hi, lo) pairs");
   // PAIR: two CTAs of a cluster run every MMA together (cta_group::2, M = 256): each works on its own item (its own
   // slabs, accumulators and epilogue) but holds only half of the weights, so the shared-memory operand reads per SM and
   // MMA drop from A + B to A + B/2 -- the limiter of the N = 64 layers (tools/umma2_rate.cu).  The leader (rank 0)
@@ -113,6 +122,17 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   return *reinterpret_cast<uint32_t *>(&h);
 }
 
+// hi / lo split of two fp32 values: hi = fp16(v), lo = fp16(v - hi)  (XP activations)
+__device__ __forceinline__ void split_h2(float a, float b, uint32_t &hi, uint32_t &lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t *>(&h);
+  lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+// channel c of an XP tensor: hi at (c / 64) * 128 + c % 64, lo 64 further
+__device__ __forceinline__ int xp_off(int c) { return ((c >> 6) << 7) + (c & 63); }
+
 // Epilogue: bias + ReLU + 2x2 max-pool of one 8x16-pixel accumulator tile (lane = h*8 + w), fp16 NHWC store.
 // The pool partners are lane^1 (x) and lane^8 (y), both inside the warp.  The 2x2 maximum is a reduce-scatter: every
 // 32-channel chunk is first halved with the x partner (each lane keeps the 16 channels whose bit 3 equals its x parity
@@ -120,7 +140,7 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // four lanes of a 2x2 group ends up with the 8-channel slice it stores -- 24 shuffles per chunk instead of 64 (this
 // epilogue, not the MMAs, paced the pooled 64 -> 64 layers).  max is exact, so the result does not depend on the order.
 // All TMEM loads of the tile are issued before the first wait.
-template <int N>
+template <int N, bool XP = false>
 __device__ __forceinline__ void epilogue_relu_pool(uint32_t taddr, const float *bias, int lane, int hl, int wl, int x0,
                                                    int y0, int b, int nb, int H, int W, int cout_stride, __half *out) {
   static_assert(N == 64 || N == 128, "pooled layers have 64 or 128 output channels");
@@ -129,7 +149,7 @@ __device__ __forceinline__ void epilogue_relu_pool(uint32_t taddr, const float *
   const bool valid = (yo < Ho) && (xo < Wo);
   const bool px = lane & 1, py = (lane >> 3) & 1;
   const int q = (lane & 1) | (((lane >> 3) & 1) << 1);
-  __half *dst = out + ((static_cast<size_t>(b) * Ho + yo) * Wo + xo) * cout_stride + nb * N + q * 8;
+  __half *dst = out + ((static_cast<size_t>(b) * Ho + yo) * Wo + xo) * cout_stride + (XP ? 0 : nb * N + q * 8);
 #pragma unroll 1
   for (int c0 = 0; c0 < N; c0 += 64) {
     float v[64];
@@ -155,12 +175,23 @@ __device__ __forceinline__ void epilogue_relu_pool(uint32_t taddr, const float *
         w[j] = fmaxf(w[j] + bias[c0 + ch + q * 8 + j], 0.f);
       }
       if (valid) {
+        if constexpr (XP) {
+          uint4 o, l;
+          split_h2(w[0], w[1], o.x, l.x);
+          split_h2(w[2], w[3], o.y, l.y);
+          split_h2(w[4], w[5], o.z, l.z);
+          split_h2(w[6], w[7], o.w, l.w);
+          __half *d = dst + xp_off(nb * N + c0 + ch + q * 8);
+          *reinterpret_cast<uint4 *>(d) = o;
+          *reinterpret_cast<uint4 *>(d + 64) = l;
+        } else {
         uint4 o;
         o.x = pack_h2(w[0], w[1]);
         o.y = pack_h2(w[2], w[3]);
         o.z = pack_h2(w[4], w[5]);
         o.w = pack_h2(w[6], w[7]);
         *reinterpret_cast<uint4 *>(dst + c0 + ch) = o;
+        }
       }
     }
   }
@@ -172,7 +203,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int N = Cfg::N, CB = Cfg::CB, SA = Cfg::SA, SB = Cfg::SB;
   const int NB = p.NB;  // resident weights (WRES) require NB == 1 (checked on the host)
   constexpr int NDX = Cfg::NDX, NDY = Cfg::NDY, EPI = Cfg::EPI;
-  constexpr bool WRES = Cfg::WRES;
+  constexpr bool WRES = Cfg::WRES, XP = Cfg::XP;
+  // XP: weight sets per slab (hi slabs meet Wh and Wl, lo slabs Wh only) and the packed weight block of (slab, set)
+  auto n_wsets = [](int cb) { return (XP && !(cb & 1)) ? 2 : 1; };
+  auto w_block = [](int cb, int ws) { return XP ? ((cb & ~1) + ((cb & 1) ? 0 : ws)) : cb; };
+  const int cin_step = 64 * (p.cin_blk_stride > 1 ? p.cin_blk_stride : 1);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -272,11 +307,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(a_empty(s), ((it / SA) & 1) ^ 1);
           if constexpr (Cfg::PAIR) {  // both ranks' slabs complete on the leader's barrier (the leader issues the MMAs)
             if (rank == 0) mbar_expect_tx(a_full(s), 2 * Cfg::SLAB_BYTES);
-            tma_load_4d_pair(smem_u32(sA + s * Cfg::SLAB_BYTES), &tmA, mapa_shared(a_full(s), 0), p.cin_off + cb * 64,
+            tma_load_4d_pair(smem_u32(sA + s * Cfg::SLAB_BYTES), &tmA, mapa_shared(a_full(s), 0), p.cin_off + cb * cin_step,
                              x0 - (NDX == 3 ? 1 : 0), y0 - (NDY == 3 ? 1 : 0), b);
           } else {
             mbar_expect_tx(a_full(s), Cfg::SLAB_BYTES);
-            tma_load_4d(smem_u32(sA + s * Cfg::SLAB_BYTES), &tmA, a_full(s), p.cin_off + cb * 64,
+            tma_load_4d(smem_u32(sA + s * Cfg::SLAB_BYTES), &tmA, a_full(s), p.cin_off + cb * cin_step,
                         x0 - (NDX == 3 ? 1 : 0), y0 - (NDY == 3 ? 1 : 0), b);
           }
         }
@@ -296,11 +331,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int item = item_of(q);
           const int nb = item % NB;  // (a pair's two items share nb: NB divides 2 or is 1, see the host-side check)
           for (int cb = 0; cb < CB; cb++)
+           for (int ws = 0; ws < n_wsets(cb); ws++)
             for (int dx = 0; dx < NDX; dx++)
               for (int dy = 0; dy < NDY; dy++, jt++) {
                 const int s = jt % SB;
                 mbar_wait(b_empty(s), ((jt / SB) & 1) ^ 1);
-                const int wb = (dy * NDX + dx) * CB + cb;
+                const int wb = (dy * NDX + dx) * CB + w_block(cb, ws);
                 if constexpr (Cfg::PAIR) {  // each rank streams its N/2 rows of the block; both halves complete on the leader's barrier
                   if (rank == 0) mbar_expect_tx(b_full(s), 2 * Cfg::BBLK_BYTES);
                   tma_load_2d_pair(smem_u32(sB + s * Cfg::BBLK_BYTES), &tmW, mapa_shared(b_full(s), 0), 0,
@@ -350,18 +386,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int cb = 0; cb < CB; cb++) {
             const uint64_t a0 = umma_desc_sw128(sA_u + st[cb] * Cfg::SLAB_BYTES, Cfg::SBO);
 #pragma unroll
+           for (int ws = 0; ws < ((XP && !(cb & 1)) ? 2 : 1); ws++)
+#pragma unroll
             for (int dx = 0; dx < NDX; dx++)
 #pragma unroll
               for (int dy = 0; dy < NDY; dy++) {
-                const uint64_t b0 = umma_desc_sw128(sB_u + ((dy * NDX + dx) * CB + cb) * Cfg::BBLK_BYTES, 1024);
+                const uint64_t b0 = umma_desc_sw128(sB_u + ((dy * NDX + dx) * CB + w_block(cb, ws)) * Cfg::BBLK_BYTES, 1024);
 #pragma unroll
                 for (int h = 0; h < HALVES; h++)
 #pragma unroll
                   for (int k = 0; k < 4; k++) {
                     if constexpr (Cfg::PAIR)
-                      umma_f16_pair(d_tmem + h * Cfg::ACC_STRIDE, a0 + a_off(dy, dx, h, k), b0 + 2 * k, idesc, (cb | dx | dy | k) ? 1u : 0u);
+                      umma_f16_pair(d_tmem + h * Cfg::ACC_STRIDE, a0 + a_off(dy, dx, h, k), b0 + 2 * k, idesc, (cb | ws | dx | dy | k) ? 1u : 0u);
                     else
-                      umma_f16(d_tmem + h * Cfg::ACC_STRIDE, a0 + a_off(dy, dx, h, k), b0 + 2 * k, idesc, (cb | dx | dy | k) ? 1u : 0u);
+                      umma_f16(d_tmem + h * Cfg::ACC_STRIDE, a0 + a_off(dy, dx, h, k), b0 + 2 * k, idesc, (cb | ws | dx | dy | k) ? 1u : 0u);
                   }
               }
             // the slab is free as soon as its own MMAs retire (keeps the TMA ring busy); in a pair both ranks are told
@@ -381,6 +419,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t s = it % SA;
           mbar_wait(a_full(s), (it / SA) & 1);
           const uint64_t a0 = umma_desc_sw128(sA_u + s * Cfg::SLAB_BYTES, Cfg::SBO);
+          const int nws = n_wsets(cb);
+#pragma unroll 1
+         for (int ws = 0; ws < nws; ws++) {
 #pragma unroll
           for (int dx = 0; dx < NDX; dx++) {
 #pragma unroll
@@ -402,13 +443,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                       if constexpr (Cfg::PAIR)
-                        umma_f16_pair(d_tmem + h * Cfg::ACC_STRIDE, a0 + a_off(dy, dx, h, k), b0 + 2 * k, idesc, (cb | dx | dy | k) ? 1u : 0u);
+                        umma_f16_pair(d_tmem + h * Cfg::ACC_STRIDE, a0 + a_off(dy, dx, h, k), b0 + 2 * k, idesc, (cb | ws | dx | dy | k) ? 1u : 0u);
                       else
-                        umma_f16(d_tmem + h * Cfg::ACC_STRIDE, a0 + a_off(dy, dx, h, k), b0 + 2 * k, idesc, (cb | dx | dy | k) ? 1u : 0u);
+                        umma_f16(d_tmem + h * Cfg::ACC_STRIDE, a0 + a_off(dy, dx, h, k), b0 + 2 * k, idesc, (cb | ws | dx | dy | k) ? 1u : 0u);
                     }
                   if constexpr (Cfg::PAIR) umma_commit_pair(b_empty(sb[d])); else umma_commit(b_empty(sb[d]));
                 }
-                if (dx == NDX - 1 && g + GDY >= NDY) {
+                if (dx == NDX - 1 && g + GDY >= NDY && ws == nws - 1) {
                   if constexpr (Cfg::PAIR) umma_commit_pair(a_empty(s)); else umma_commit(a_empty(s));
                   if (cb == CB - 1) { if constexpr (Cfg::PAIR) umma_commit_pair(t_full(acc)); else umma_commit(t_full(acc)); }
                 }
@@ -417,6 +458,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               jt += GDY;
             }
           }
+         }  // weight sets
         }
       }
     }
@@ -444,7 +486,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       if constexpr (EPI == EPI_RELU) {
         const bool valid = (y < p.H) && (x < p.W);
-        __half *dst = p.out + ((static_cast<size_t>(b) * p.H + y) * p.W + x) * p.cout_stride + nb * N;
+        __half *dst = p.out + ((static_cast<size_t>(b) * p.H + y) * p.W + x) * p.cout_stride + (XP ? 0 : nb * N);
 #pragma unroll 1
         for (int c0 = 0; c0 < N; c0 += 32) {
           float v[32];
@@ -456,17 +498,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int g = 0; g < 4; g += 2) {
               uint4 o[2];
               uint32_t *ow = reinterpret_cast<uint32_t *>(o);
+              if constexpr (XP) {  // hi and lo halves of the same 16 channels, 64 channels apart
+                uint4 l[2];
+                uint32_t *lw = reinterpret_cast<uint32_t *>(l);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                  const int c = g * 8 + j * 2;
+                  split_h2(fmaxf(v[c] + bias[c0 + c], 0.f), fmaxf(v[c + 1] + bias[c0 + c + 1], 0.f), ow[j], lw[j]);
+                }
+                __half *d = dst + xp_off(nb * N + c0 + g * 8);
+                st_global_v8(d, o[0], o[1]);
+                st_global_v8(d + 64, l[0], l[1]);
+              } else {
 #pragma unroll
               for (int j = 0; j < 8; j++) {
                 const int c = g * 8 + j * 2;
                 ow[j] = pack_h2(fmaxf(v[c] + bias[c0 + c], 0.f), fmaxf(v[c + 1] + bias[c0 + c + 1], 0.f));
               }
               st_global_v8(dst + c0 + g * 8, o[0], o[1]);
+              }
             }
           }
         }
       } else if constexpr (EPI == EPI_RELU_POOL) {
-        epilogue_relu_pool<N>(taddr, bias, lane, hl, wl, x0, y0, b, nb, p.H, p.W, p.cout_stride, p.out);
+        epilogue_relu_pool<N, XP>(taddr, bias, lane, hl, wl, x0, y0, b, nb, p.H, p.W, p.cout_stride, p.out);
       } else if constexpr (EPI == EPI_TOP2) {
         // One thread = one descriptor row of the A slot: best two dot products (first index on ties) among this
         // item's 256 columns of the B slot.  The exact fp32 re-rank happens in match_rerank_kernel.

@@ -20,7 +20,9 @@ namespace spfe {
 // (broadcast reads), and a warp stores 4 pixels x 128 B = 512 contiguous bytes
 // per instruction.  72 FFMA per 9 LDS + 1 STG.128.
 // ---------------------------------------------------------------------------
+// XP (exact mode): the fp32 result is stored as a hi + lo fp16 pair, 128 channels per pixel ([hi 64 | lo 64]).
 constexpr int C1A_TW = 64, C1A_TH = 16;
+template <bool XP>
 __global__ void __launch_bounds__(256) conv1a_kernel(const uint8_t *__restrict__ in, __half *__restrict__ out,
                                                      const float *__restrict__ wgt /*[9][64]*/,
                                                      const float *__restrict__ bias /*[64]*/, int B, int H, int W) {
@@ -62,12 +64,23 @@ __global__ void __launch_bounds__(256) conv1a_kernel(const uint8_t *__restrict__
       for (int c = 0; c < 4; c++) ffma2(acc[c], w[t][c], x2);
     }
     if (x < W && y < H) {
+      if constexpr (XP) {
+        uint4 o, l;
+        split_h2(fmaxf(acc[0].x, 0.f), fmaxf(acc[0].y, 0.f), o.x, l.x);
+        split_h2(fmaxf(acc[1].x, 0.f), fmaxf(acc[1].y, 0.f), o.y, l.y);
+        split_h2(fmaxf(acc[2].x, 0.f), fmaxf(acc[2].y, 0.f), o.z, l.z);
+        split_h2(fmaxf(acc[3].x, 0.f), fmaxf(acc[3].y, 0.f), o.w, l.w);
+        __half *d = out + ((static_cast<size_t>(b) * H + y) * W + x) * 128 + g * 8;
+        *reinterpret_cast<uint4 *>(d) = o;
+        *reinterpret_cast<uint4 *>(d + 64) = l;
+      } else {
       uint4 o;
       o.x = pack_h2(fmaxf(acc[0].x, 0.f), fmaxf(acc[0].y, 0.f));
       o.y = pack_h2(fmaxf(acc[1].x, 0.f), fmaxf(acc[1].y, 0.f));
       o.z = pack_h2(fmaxf(acc[2].x, 0.f), fmaxf(acc[2].y, 0.f));
       o.w = pack_h2(fmaxf(acc[3].x, 0.f), fmaxf(acc[3].y, 0.f));
       *reinterpret_cast<uint4 *>(out + ((static_cast<size_t>(b) * H + y) * W + x) * 64 + g * 8) = o;
+      }
     }
   }
 }

@@ -69,6 +69,16 @@ using CfgPb = ConvCfg<1, 4, 80, EPI_DETECT, true, 4, 1, 1, 2>;  // convPb + dete
 using CfgDb = ConvCfg<1, 4, 256, EPI_L2NORM, true, 4, 1, 1, 2>; // convDb + L2 norm
 using CfgMatch = ConvCfg<1, 4, 256, EPI_TOP2, false, 4, 4, 1, 2>;  // descriptor matching: Q.T^T + top-2 per 256-column block
 
+// "exact" mode (SPFE_EXACT): hi/lo-split operands, three MMAs per product (ConvCfg::XP); CB counts slabs = 2 x real
+// 64-channel blocks.  Weights are streamed as CTA pairs for every 3x3 layer, resident for the 1x1 detector head.
+using CfgX64 = ConvCfg<9, 2, 64, EPI_RELU, false, 3, 9, 2, 1, true, true>;          // conv2a
+using CfgX64P = ConvCfg<9, 2, 64, EPI_RELU_POOL, false, 3, 9, 2, 1, true, true>;    // conv1b, conv2b
+using CfgX3a = ConvCfg<9, 2, 128, EPI_RELU, false, 2, 9, 2, 1, true, true>;         // conv3a
+using CfgX128 = ConvCfg<9, 4, 128, EPI_RELU, false, 2, 9, 2, 1, true, true>;        // conv4a, conv4b
+using CfgX128P = ConvCfg<9, 4, 128, EPI_RELU_POOL, false, 2, 9, 2, 1, true, true>;  // conv3b
+using CfgXHeads = ConvCfg<9, 4, 256, EPI_RELU, false, 2, 8, 1, 1, true, true>;      // convPa || convDa
+using CfgXPb = ConvCfg<1, 8, 80, EPI_DETECT, true, 8, 1, 1, 2, false, true>;        // convPb + detector head (Wh | Wl resident)
+
 enum { L1B = 0, L2A, L2B, L3A, L3B, L4A, L4B, LHEADS, LPB, LDB, NLAYERS };
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -104,6 +114,7 @@ struct Slot {
   int16_t *occ = nullptr;
   unsigned long long *scratch = nullptr;
   CUtensorMap tmA[NLAYERS];
+  CUtensorMap tmXA[NLAYERS];  // exact mode: maps over the hi/lo-interleaved activation tensors
   CUtensorMap tmA3aX;  // conv3a as a CTA pair works on tile pairs (slab of 24 pixels per row instead of 16)
   MatchScratch match;
   // SPFE_MATCH_PREV: descriptor "slots": slot 0 = last frame of the previous batch (carry), slot z+1 = frame z
@@ -144,6 +155,7 @@ struct spfe_ctx {
   int rows_pad = 0, match_nb = 0, match_tiles = 0;  // tensor-core matcher geometry
   bool heat = false, cov = false, match_prev = false;  // heat: heat maps computed on the device (EMIT_HEAT or EMIT_COV)
   bool heat_host = false, heat_inv_host = false;       // EMIT_HEAT / EMIT_HEAT_INV: heat_ / heat_inv_ are also copied to the host
+  bool exact = false;       // EXACT: hi/lo-split operands, 3 MMAs per product, conv1a in fp32 (unfused)
   bool lazy_heat = false;   // LAZY_HEAT: heat_log + min / max stay on the device for spfe_fetch_heat
   bool desc_f16 = false;    // DESC_F16: descriptors cross PCIe as fp16
   float *fetch_heat = nullptr, *fetch_heat_inv = nullptr;  // [H*W] device staging of spfe_fetch_heat (guarded by match_mu)
@@ -162,6 +174,7 @@ struct spfe_ctx {
   EncodeTiledFn encode = nullptr;
   float *w1a = nullptr, *b1a = nullptr;  // conv1a fp32 [9][64], [64]
   Layer layers[NLAYERS];
+  Layer xlayers[NLAYERS];  // exact mode: [tap][Wh_0 | Wl_0 | Wh_1 | Wl_1 ...][cout][64]
   std::vector<Slot> slots;
   std::vector<void *> dev_allocs, host_allocs;
   std::atomic<long long> launches{0};
@@ -242,10 +255,10 @@ int make_mat_map(spfe_ctx *c, CUtensorMap *tm, const void *ptr, int cols, int ro
 // Pack OIHW fp32 conv weights of one or two layers (concatenated along cout)
 // into [tap][cblock][cout_total][64] fp16; couts beyond the real ones are zero.
 int upload_layer(spfe_ctx *c, Layer &L, const std::vector<const HostTensor *> &ws, const std::vector<const HostTensor *> &bs,
-                 int n_tile, int cout_total) {
+                 int n_tile, int cout_total, bool xp = false) {
   const int ci = ws[0]->dims[1], k = ws[0]->dims[2];
   L.taps = k * k;
-  L.cb = ci / 64;
+  L.cb = ci / 64 * (xp ? 2 : 1);  // exact mode: every 64-channel block is a (hi, lo) pair of weight blocks
   L.cout_total = cout_total;
   L.n_tile = n_tile;
   std::vector<__half> packed(static_cast<size_t>(L.taps) * L.cb * cout_total * 64, __float2half(0.f));
@@ -261,6 +274,13 @@ int upload_layer(spfe_ctx *c, Layer &L, const std::vector<const HostTensor *> &w
       for (int ch = 0; ch < ci; ch++)
         for (int t = 0; t < L.taps; t++) {
           const float v = w.data[(static_cast<size_t>(o) * ci + ch) * L.taps + t];
+          if (xp) {
+            const size_t wb = static_cast<size_t>(t) * L.cb + 2 * (ch / 64);
+            const __half hi = __float2half_rn(v);
+            packed[(wb * cout_total + o0 + o) * 64 + (ch % 64)] = hi;
+            packed[((wb + 1) * cout_total + o0 + o) * 64 + (ch % 64)] = __float2half_rn(v - __half2float(hi));
+            continue;
+          }
           const size_t wb = static_cast<size_t>(t) * L.cb + ch / 64;
           packed[(wb * cout_total + o0 + o) * 64 + (ch % 64)] = __float2half_rn(v);
         }
@@ -345,6 +365,62 @@ struct StageTimer {
 
 int run_match(spfe_ctx *c, cudaStream_t st, const MatchArgs &a, int Z, int rows);
 
+// The convolution stack in "exact" mode (SPFE_EXACT): conv1a in fp32 on the CUDA cores, stored as hi + lo fp16; every
+// other layer as three MMAs per product on hi/lo-split operands (ConvCfg::XP).  Same stage names / algorithmic FLOPs as
+// the default path, so the bench's roofline block reads the same way.
+int run_convs_exact(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
+  const int H = c->H, W = c->W, hc = c->hc, wc = c->wc;
+  cudaStream_t st = s.stream;
+  auto mark = [&](const char *n, double f = 0, double b = 0) { if (tm) tm->mark(n, f, b); };
+  int rc;
+  {
+    dim3 grid((W + C1A_TW - 1) / C1A_TW, (H + C1A_TH - 1) / C1A_TH, B);
+    conv1a_kernel<true><<<grid, 256, 0, st>>>(s.d_gray, s.a1a, c->w1a, c->b1a, B, H, W);
+    c->launches++;
+    CU_OK(c, cudaGetLastError());
+    mark("conv1a", 2.0 * 9 * 64 * H * W * B, (1.0 + 256.0) * H * W * B);
+  }
+  auto args = [&](int h, int w, int nb, int cout_stride, __half *out) {
+    ConvArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = B; a.H = h; a.W = w; a.NB = nb; a.cout_stride = cout_stride; a.out = out;
+    return a;
+  };
+  auto flop = [&](int l, int h, int w) { return c->layers[l].flop_per_px * h * w * B; };
+  if ((rc = launch_conv<CfgX64P>(c, st, s.tmXA[L1B], c->xlayers[L1B], args(H, W, 1, 128, s.a1b)))) return rc;
+  mark("conv1b", flop(L1B, H, W), (256.0 + 64.0) * H * W * B);
+  if ((rc = launch_conv<CfgX64>(c, st, s.tmXA[L2A], c->xlayers[L2A], args(H / 2, W / 2, 1, 128, s.a2a)))) return rc;
+  mark("conv2a", flop(L2A, H / 2, W / 2), 512.0 * (H / 2) * (W / 2) * B);
+  if ((rc = launch_conv<CfgX64P>(c, st, s.tmXA[L2B], c->xlayers[L2B], args(H / 2, W / 2, 1, 128, s.a2b)))) return rc;
+  mark("conv2b", flop(L2B, H / 2, W / 2), 320.0 * (H / 2) * (W / 2) * B);
+  if ((rc = launch_conv<CfgX3a>(c, st, s.tmXA[L3A], c->xlayers[L3A], args(H / 4, W / 4, 1, 256, s.a3a)))) return rc;
+  mark("conv3a", flop(L3A, H / 4, W / 4), 768.0 * (H / 4) * (W / 4) * B);
+  if ((rc = launch_conv<CfgX128P>(c, st, s.tmXA[L3B], c->xlayers[L3B], args(H / 4, W / 4, 1, 256, s.a3b)))) return rc;
+  mark("conv3b", flop(L3B, H / 4, W / 4), 640.0 * (H / 4) * (W / 4) * B);
+  if ((rc = launch_conv<CfgX128>(c, st, s.tmXA[L4A], c->xlayers[L4A], args(hc, wc, 1, 256, s.a4a)))) return rc;
+  mark("conv4a", flop(L4A, hc, wc), 1024.0 * hc * wc * B);
+  if ((rc = launch_conv<CfgX128>(c, st, s.tmXA[L4B], c->xlayers[L4B], args(hc, wc, 1, 256, s.a4b)))) return rc;
+  mark("conv4b", flop(L4B, hc, wc), 1024.0 * hc * wc * B);
+  if ((rc = launch_conv<CfgXHeads>(c, st, s.tmXA[LHEADS], c->xlayers[LHEADS], args(hc, wc, 2, 1024, s.heads)))) return rc;
+  mark("convPa|Da", flop(LHEADS, hc, wc), (512.0 + 2048.0) * hc * wc * B);
+  {
+    ConvArgs a = args(hc, wc, 1, 0, nullptr);
+    a.score = s.score; a.argmax = s.argmax; a.semi_dust = s.semi_dust; a.dense_dust = s.dense_dust;
+    a.heat_log = c->heat ? s.heat_log : nullptr;
+    a.heat_minmax = c->heat ? s.heat_mm : nullptr;
+    if ((rc = launch_conv<CfgXPb>(c, st, s.tmXA[LPB], c->xlayers[LPB], a))) return rc;
+    mark("convPb+det", flop(LPB, hc, wc), (1024.0 + 13.0 + (c->heat ? 256.0 : 0.0)) * hc * wc * B);
+  }
+  {  // descriptor head: the parity bar is 1e-3 cosine, so convDb stays a single product on the hi halves of convDa
+    ConvArgs a = args(hc, wc, 1, 256, s.coarse);
+    a.cin_off = 512;         // convDa's (hi, lo) blocks follow convPa's four pairs
+    a.cin_blk_stride = 2;    // hi blocks only
+    if ((rc = launch_conv<CfgDb>(c, st, s.tmXA[LDB], c->layers[LDB], a))) return rc;
+    mark("convDb+norm", flop(LDB, hc, wc), (512.0 + 512.0) * hc * wc * B);
+  }
+  return SPFE_OK;
+}
+
 // Enqueue the whole per-batch launch plan on the slot's stream.
 int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
   const int H = c->H, W = c->W, hc = c->hc, wc = c->wc;
@@ -356,6 +432,9 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     c->launches++;
   }
   int rc;
+  if (c->exact) {
+    if ((rc = run_convs_exact(c, s, B, tm))) return rc;
+  } else {
   if (c->fused_conv1) {  // conv1a + conv1b + pool in one kernel: u8 image -> fp16 [H/2][W/2][64]
     Conv1abArgs a;
     a.img = s.d_gray; a.w1a = c->w1a; a.b1a = c->b1a; a.w1m = c->w1m; a.b1b = c->layers[L1B].bias; a.out = s.a1b;
@@ -378,7 +457,7 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     mark("conv1a+1b", 2.0 * 9 * 64 * H * W * B + c->layers[L1B].flop_per_px * H * W * B, (1.0 + 32.0) * H * W * B);
   } else {  // unfused path (debugging aid: materialises the conv1a activation)
     dim3 grid((W + C1A_TW - 1) / C1A_TW, (H + C1A_TH - 1) / C1A_TH, B);
-    conv1a_kernel<<<grid, 256, 0, st>>>(s.d_gray, s.a1a, c->w1a, c->b1a, B, H, W);
+    conv1a_kernel<false><<<grid, 256, 0, st>>>(s.d_gray, s.a1a, c->w1a, c->b1a, B, H, W);
     c->launches++;
     CU_OK(c, cudaGetLastError());
     mark("conv1a", 2.0 * 9 * 64 * H * W * B, (1.0 + 128.0) * H * W * B);
@@ -437,6 +516,7 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     if ((rc = launch_conv<CfgDb>(c, st, s.tmA[LDB], c->layers[LDB], a))) return rc;
     mark("convDb+norm", stage_flop(LDB, hc, wc), (512.0 + 512.0) * hc * wc * B);
   }
+  }  // default (fp16) convolutions
   {
     NmsArgs n;
     n.score = s.score; n.argmax = s.argmax; n.hc = hc; n.wc = wc; n.thresh = c->cfg.score_thresh;
@@ -642,6 +722,25 @@ static int create_impl(spfe_ctx *c) {
   if ((rc = up(LHEADS, {"convPa", "convDa"}, 256, 512))) return rc;
   if ((rc = up(LPB, {"convPb"}, 80, 80))) return rc;
   if ((rc = up(LDB, {"convDb"}, 256, 256))) return rc;
+  if (c->exact) {
+    auto upx = [&](int l, std::vector<const char *> names, int n_tile, int cout_total) {
+      std::vector<const HostTensor *> ws, bs;
+      for (const char *n : names) {
+        ws.push_back(&wm[std::string(n) + ".weight"]);
+        bs.push_back(&wm[std::string(n) + ".bias"]);
+      }
+      return upload_layer(c, c->xlayers[l], ws, bs, n_tile, cout_total, true);
+    };
+    if ((rc = upx(L1B, {"conv1b"}, 64, 64))) return rc;
+    if ((rc = upx(L2A, {"conv2a"}, 64, 64))) return rc;
+    if ((rc = upx(L2B, {"conv2b"}, 64, 64))) return rc;
+    if ((rc = upx(L3A, {"conv3a"}, 128, 128))) return rc;
+    if ((rc = upx(L3B, {"conv3b"}, 128, 128))) return rc;
+    if ((rc = upx(L4A, {"conv4a"}, 128, 128))) return rc;
+    if ((rc = upx(L4B, {"conv4b"}, 128, 128))) return rc;
+    if ((rc = upx(LHEADS, {"convPa", "convDa"}, 256, 512))) return rc;
+    if ((rc = upx(LPB, {"convPb"}, 80, 80))) return rc;
+  }
 
   // ---- per-slot buffers
   c->slots.resize(cfg.num_slots);
@@ -674,16 +773,17 @@ static int create_impl(spfe_ctx *c) {
     CU_OK(c, cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
     CU_OK(c, cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
     CU_OK(c, cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
+    const size_t xm = c->exact ? 2 : 1;  // exact mode: every activation is a (hi, lo) pair
     if ((rc = dev_alloc(c, &s.d_gray, Bm * px))) return rc;
-    if (!c->fused_conv1 && (rc = dev_alloc(c, &s.a1a, Bm * px * 64))) return rc;
-    if ((rc = dev_alloc(c, &s.a1b, Bm * px / 4 * 64))) return rc;
-    if ((rc = dev_alloc(c, &s.a2a, Bm * px / 4 * 64))) return rc;
-    if ((rc = dev_alloc(c, &s.a2b, Bm * px / 16 * 64))) return rc;
-    if ((rc = dev_alloc(c, &s.a3a, Bm * px / 16 * 128))) return rc;
-    if ((rc = dev_alloc(c, &s.a3b, Bm * cells * 128))) return rc;
-    if ((rc = dev_alloc(c, &s.a4a, Bm * cells * 128))) return rc;
-    if ((rc = dev_alloc(c, &s.a4b, Bm * cells * 128))) return rc;
-    if ((rc = dev_alloc(c, &s.heads, Bm * cells * 512))) return rc;
+    if (!c->fused_conv1 && (rc = dev_alloc(c, &s.a1a, Bm * px * 64 * xm))) return rc;
+    if ((rc = dev_alloc(c, &s.a1b, Bm * px / 4 * 64 * xm))) return rc;
+    if ((rc = dev_alloc(c, &s.a2a, Bm * px / 4 * 64 * xm))) return rc;
+    if ((rc = dev_alloc(c, &s.a2b, Bm * px / 16 * 64 * xm))) return rc;
+    if ((rc = dev_alloc(c, &s.a3a, Bm * px / 16 * 128 * xm))) return rc;
+    if ((rc = dev_alloc(c, &s.a3b, Bm * cells * 128 * xm))) return rc;
+    if ((rc = dev_alloc(c, &s.a4a, Bm * cells * 128 * xm))) return rc;
+    if ((rc = dev_alloc(c, &s.a4b, Bm * cells * 128 * xm))) return rc;
+    if ((rc = dev_alloc(c, &s.heads, Bm * cells * 512 * xm))) return rc;
     if ((rc = dev_alloc(c, &s.coarse, Bm * cells * 256))) return rc;
     if ((rc = dev_alloc(c, &s.score, Bm * cells))) return rc;
     if ((rc = dev_alloc(c, &s.argmax, Bm * cells))) return rc;
@@ -764,6 +864,19 @@ static int create_impl(spfe_ctx *c) {
     if ((rc = host_alloc(c, &s.h_dense, Bm * cells))) return rc;
     if ((rc = host_alloc(c, &s.h_semi, Bm * cells))) return rc;
     if ((rc = host_alloc(c, &s.h_occ, Bm * cells))) return rc;
+    if (c->exact) {  // maps over the hi/lo-interleaved tensors (twice the channels)
+      if ((rc = make_act_map(c, &s.tmXA[L1B], s.a1a, 128, W, H, Bm, 18, CfgX64P::PW))) return rc;
+      if ((rc = make_act_map(c, &s.tmXA[L2A], s.a1b, 128, W / 2, H / 2, Bm, 18, CfgX64::PW))) return rc;
+      if ((rc = make_act_map(c, &s.tmXA[L2B], s.a2a, 128, W / 2, H / 2, Bm, 18, CfgX64P::PW))) return rc;
+      if ((rc = make_act_map(c, &s.tmXA[L3A], s.a2b, 128, W / 4, H / 4, Bm, 18, CfgX3a::PW))) return rc;
+      if ((rc = make_act_map(c, &s.tmXA[L3B], s.a3a, 256, W / 4, H / 4, Bm, 18, CfgX128P::PW))) return rc;
+      if ((rc = make_act_map(c, &s.tmXA[L4A], s.a3b, 256, wc, hc, Bm, 18, CfgX128::PW))) return rc;
+      if ((rc = make_act_map(c, &s.tmXA[L4B], s.a4a, 256, wc, hc, Bm, 18, CfgX128::PW))) return rc;
+      if ((rc = make_act_map(c, &s.tmXA[LHEADS], s.a4b, 256, wc, hc, Bm, 18, CfgXHeads::PW))) return rc;
+      if ((rc = make_act_map(c, &s.tmXA[LPB], s.heads, 1024, wc, hc, Bm, 16))) return rc;
+      if ((rc = make_act_map(c, &s.tmXA[LDB], s.heads, 1024, wc, hc, Bm, 16))) return rc;
+      continue;
+    }
     // TMA maps of every layer's input tensor
     // 3x3 layers: one slab of 18 rows x PW pixels per item (PW = 24 for tile pairs, 16 for single tiles)
     if (!c->fused_conv1 && (rc = make_act_map(c, &s.tmA[L1B], s.a1a, 64, W, H, Bm, 18, CfgC64P::PW))) return rc;
@@ -817,6 +930,7 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
   c->cov = (cfg->flags & SPFE_EMIT_COV) != 0;
   c->heat_host = (cfg->flags & SPFE_EMIT_HEAT) != 0;
   c->heat_inv_host = (cfg->flags & SPFE_EMIT_HEAT_INV) != 0;
+  c->exact = (cfg->flags & SPFE_EXACT) != 0;
   c->lazy_heat = (cfg->flags & SPFE_LAZY_HEAT) != 0;
   c->desc_f16 = (cfg->flags & SPFE_DESC_F16) != 0;
   c->heat = c->cov || c->heat_host || c->heat_inv_host || c->lazy_heat;
@@ -828,6 +942,7 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
     const char *e = getenv("SPFE_FUSED_CONV1"), *m = getenv("SPFE_CONV1");
     if (m && !strcmp(m, "ffma")) c->conv1_mode = 1;
     if ((m && !strcmp(m, "unfused")) || (e && e[0] == '0')) c->conv1_mode = 0;
+    if (c->exact) c->conv1_mode = 0;  // exact mode: conv1a in fp32 on the CUDA cores, materialised as hi + lo
     c->fused_conv1 = c->conv1_mode != 0;
     const char *pd = getenv("SPFE_PDL");
     c->pdl = pd && pd[0] == '1';
@@ -1514,12 +1629,13 @@ int64_t spfe_debug_read(spfe_ctx *c, int32_t slot, const char *name, void *dst, 
   if (!name || !dst) return c->fail(SPFE_ERR_INVALID, "spfe_debug_read: NULL argument");
   Slot &s = c->slots[slot];
   const size_t B = s.batch > 0 ? s.batch : 1, px = (size_t)c->H * c->W, cells = c->cells, cap = c->cap;
+  const size_t xm = c->exact ? 2 : 1;  // exact mode: [hi 64 | lo 64] per 64-channel block
   struct Ent { const char *n; const void *p; size_t bytes; } tab[] = {
-      {"conv1a", c->fused_conv1 ? nullptr : s.a1a, B * px * 64 * 2},        {"conv1b", s.a1b, B * px / 4 * 64 * 2},
-      {"conv2a", s.a2a, B * px / 4 * 64 * 2},    {"conv2b", s.a2b, B * px / 16 * 64 * 2},
-      {"conv3a", s.a3a, B * px / 16 * 128 * 2},  {"conv3b", s.a3b, B * cells * 128 * 2},
-      {"conv4a", s.a4a, B * cells * 128 * 2},    {"conv4b", s.a4b, B * cells * 128 * 2},
-      {"heads", s.heads, B * cells * 512 * 2},   {"coarse", s.coarse, B * cells * 256 * 2},
+      {"conv1a", c->fused_conv1 ? nullptr : s.a1a, B * px * 64 * 2 * xm},        {"conv1b", s.a1b, B * px / 4 * 64 * 2 * xm},
+      {"conv2a", s.a2a, B * px / 4 * 64 * 2 * xm},    {"conv2b", s.a2b, B * px / 16 * 64 * 2 * xm},
+      {"conv3a", s.a3a, B * px / 16 * 128 * 2 * xm},  {"conv3b", s.a3b, B * cells * 128 * 2 * xm},
+      {"conv4a", s.a4a, B * cells * 128 * 2 * xm},    {"conv4b", s.a4b, B * cells * 128 * 2 * xm},
+      {"heads", s.heads, B * cells * 512 * 2 * xm},   {"coarse", s.coarse, B * cells * 256 * 2},
       {"score", s.score, B * cells * 4},         {"argmax", s.argmax, B * cells},
       {"semi_dust", s.semi_dust, B * cells * 4}, {"dense_dust", s.dense_dust, B * cells * 4},
       {"heat_log", s.heat_log, B * px * 4},      {"heat", s.heat, B * px * 4},

@@ -347,10 +347,19 @@ class SPExtractor:
               "cov_qlen": (lambda s: (s.cap,), np.int32), "cov_done": (lambda s: (s.cap,), np.int32),
               "cov_counters": (lambda s: (4,), np.int32), "cov_replayed": (lambda s: (2,), np.int32)}
 
+    _XP_LAYERS = ("conv1a", "conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b", "heads")
+
     def debug_read(self, slot: int, name: str, batch: int) -> np.ndarray:
         shape_fn, dt = self._DEBUG[name]
-        arr = np.empty((batch,) + tuple(shape_fn(self)), dt)
+        shape = tuple(shape_fn(self))
+        xp = self.exact and name in self._XP_LAYERS   # exact mode: [hi 64 | lo 64] per 64-channel block -> hi + lo as fp32
+        if xp:
+            shape = shape[:-1] + (2 * shape[-1],)
+        arr = np.empty((batch,) + shape, dt)
         self._check(self._lib.spfe_debug_read(self._ctx, slot, name.encode(), arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+        if xp:
+            pairs = arr.reshape(arr.shape[:-1] + (shape[-1] // 128, 2, 64)).astype(np.float32)
+            return (pairs[..., 0, :] + pairs[..., 1, :]).reshape(arr.shape[:-1] + (shape[-1] // 2,))
         return arr
 
     def launch_count(self) -> int:

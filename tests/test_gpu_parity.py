@@ -3,14 +3,16 @@ the committed golden vectors.  Integer / index work is checked bit-exactly;
 floating-point work within the tolerances stated here (north star: identical
 keypoint sets after NMS, descriptors within 1e-3 cosine).
 
-The network runs in fp16 operands / fp32 accumulation while the reference is
-fp32, and two fp32 implementations of the reference already differ by ~3e-5 in
-the logits (tests/test_oracle.py::test_reference_frontend_pins_oracle), so
-"identical keypoint sets" is stated the way SURVEY.md §7 prescribes:
+This file tests the DEFAULT mode: fp16 operands / fp32 accumulation, against the fp32 reference.  (The "exact" mode,
+tests/test_gpu_exact.py, reaches IDENTICAL key-point sets on every fixture and fresh frame.)  Measured on a B200 over
+34 frames of five geometries (tools/parity_margins.py, profiles/r02_parity_margins.txt): score error at most 4.3 % of
+the score (4.0e-3 absolute, at scores ~0.3), 0 - 10 differing key points per frame of 250 - 801, and every one of them
+sits at an oracle decision whose own log-ratio margin is below 0.011 (tests/parity_util.py: threshold, arg-max, greedy
+order between suppression neighbours, the nf + 1 cut).  The gates:
   (a) given the SAME score / arg-max maps, threshold + NMS + cap + border + raster order + occ_grid are bit-exact;
-  (b) every oracle keypoint whose decision margins exceed EPS is present, and nothing outside the
-      EPS-fragile set differs;
-  (c) the score map itself is within SCORE_ATOL of the oracle.
+  (b) every difference of the key-point sets is explained by an oracle margin below EPS_MARGIN, at most
+      MAX_DIFF_PER_FRAME of them (no Jaccard-style allowance);
+  (c) the score map is within SCORE_RTOL * score + SCORE_ATOL of the oracle: 6.2e-4 at the 0.007 threshold.
 """
 import os
 import subprocess
@@ -20,12 +22,16 @@ import pytest
 
 from conftest import GOLDEN_CASES, ROOT, WEIGHTS
 from oracle import sp_oracle as O
+from parity_util import explain_differences
 from sp_orb_slam_b200 import SPExtractor, SPMatcher, SpfeError, synth
 
 pytestmark = pytest.mark.gpu
 
-SCORE_ATOL = 6e-3        # abs tolerance on the softmax score map (fp16 network vs fp32 oracle)
-SCORE_RTOL = 2e-2
+SCORE_RTOL = 6e-2        # score error relative to the score (measured <= 4.3e-2; the error is ~ s (1 - s) d logit)
+SCORE_ATOL = 2e-4        # floor for tiny scores (threshold: 7e-3)
+EPS_MARGIN = 0.02        # log-ratio margin that must explain every key-point difference (measured <= 0.011)
+ARGMAX_EPS = 0.05        # log-ratio of the best two positions below which the arg-max of a cell may flip (measured <= 0.02)
+MAX_DIFF_PER_FRAME = 12  # differing key points per frame, 752x480 at the 801 cap (measured <= 10)
 COS_TOL = 1e-3           # north star: descriptors within 1e-3 cosine
 LAYER_RTOL = 6e-3        # per-layer activations, relative to the layer's max |activation|
 
@@ -52,15 +58,6 @@ def oracle_nms_on(score, argmax, nf, H, W):
     order = O.sort_desc(sc)
     sel, occ = O.nms(pts[order], nf, W, H)
     return pts[order][sel], sc[order][sel], occ
-
-
-def fragile_pixels(fwd, got_score, eps):
-    """Candidate pixels of cells whose keep/drop decision is within eps of a tie in the oracle."""
-    sm = fwd["score_map"]
-    near_thr = np.abs(sm - O.SCORE_THRESH) < eps
-    top2 = np.sort(fwd["nodust"], axis=0)[-2:]
-    near_arg = (top2[1] - top2[0]) < eps
-    return near_thr | near_arg
 
 
 @pytest.mark.parametrize("H,W", [(64, 96), (120, 136)])
@@ -105,15 +102,17 @@ def test_extract_vs_golden(name, golden, weights, ex_cache):
         # (c) score map within tolerance of the golden (reference-compiled) score map
         np.testing.assert_allclose(score, g[f"f{t}_score_map"], atol=SCORE_ATOL, rtol=SCORE_RTOL)
         agree = argmax == g[f"f{t}_argmax"]
-        assert np.all(agree | (g[f"f{t}_argmax_margin"] < 2 * SCORE_ATOL))        # arg-max flips only at near-ties
-        cand = g[f"f{t}_score_map"] >= O.SCORE_THRESH + SCORE_ATOL
-        assert np.all(agree[cand] | (g[f"f{t}_argmax_margin"][cand] < 2 * SCORE_ATOL))
-        # (b) keypoint sets: large overlap, descriptors of common keypoints within 1e-3 cosine
+        gs = g[f"f{t}_score_map"].astype(np.float64)
+        arg_margin = np.log(gs / np.maximum(gs - g[f"f{t}_argmax_margin"], 1e-30))
+        assert np.all(agree | (arg_margin < ARGMAX_EPS) | (gs < 0.5 * O.SCORE_THRESH))   # arg-max flips only at near-ties
+        # (b) keypoint sets: every difference explained by an oracle near-tie; descriptors of common keypoints within 1e-3 cosine
         gold = {(int(x), int(y)): i for i, (x, y) in enumerate(g[f"f{t}_kp_xy"])}
         mine = {(int(x), int(y)): i for i, (x, y) in enumerate(o["kp_xy"])}
         common = set(gold) & set(mine)
-        jacc = len(common) / max(1, len(set(gold) | set(mine)))
-        assert jacc >= (0.95 if nf >= 800 else 0.85), f"keypoint-set Jaccard {jacc:.4f}"
+        fwd = dict(score_map=g[f"f{t}_score_map"], argmax=g[f"f{t}_argmax"], argmax_margin=g[f"f{t}_argmax_margin"])
+        diffs = explain_differences(fwd, g[f"f{t}_kp_xy"], o["kp_xy"], nf)
+        assert len(diffs) <= MAX_DIFF_PER_FRAME, diffs
+        assert all(e < EPS_MARGIN for _, _, e in diffs), diffs
         gd = g[f"f{t}_desc"].astype(np.float32)
         cos = np.array([np.dot(o["desc"][mine[k]], gd[gold[k]]) / np.linalg.norm(gd[gold[k]]) for k in common])
         assert cos.min() > 1 - COS_TOL
@@ -123,33 +122,20 @@ def test_extract_vs_golden(name, golden, weights, ex_cache):
         np.testing.assert_allclose(o["heat"] + o["heat_inv"], 1.0, atol=1e-5)
 
 
-def test_margin_robust_keypoints_identical(weights, ex_cache):
-    """Frames on which the oracle's own decisions have margin: every robust oracle keypoint must be found,
-    and every difference must trace back to an EPS-fragile cell (threshold / arg-max near-tie) or its NMS neighbourhood."""
-    H, W, nf = 240, 320, 800
-    ex = ex_cache(H, W, nf, max_batch=4)
-    frames = synth.make_stream(H, W, 4, seed=31)
-    outs = ex.extract_batch(list(frames))
-    eps = 2 * SCORE_ATOL
-    total = miss = 0
-    for t, o in enumerate(outs):
-        ref = O.extract(weights, frames[t], nf, keep_forward=True)
-        frag = fragile_pixels(ref["forward"], None, eps)
-        # a difference is explained if a fragile cell lies within 1 cell (NMS reach) of it ...
-        fr = np.pad(frag, 2)
-        near = np.zeros_like(frag)
-        for dy in range(5):
-            for dx in range(5):
-                near |= fr[dy:dy + frag.shape[0], dx:dx + frag.shape[1]]
-        gs = {(int(x), int(y)) for x, y in o["kp_xy"]}
-        rs = {(int(x), int(y)) for x, y in ref["kp_xy"]}
-        # ... or the score ORDER of two NMS-competing candidates is within eps (greedy order fragility)
-        for (x, y) in gs ^ rs:
-            total += 1
-            if not near[y // 8, x // 8]:
-                miss += 1
-        assert len(gs & rs) >= 0.95 * len(rs)
-    assert miss <= max(2, total // 2), f"{miss} of {total} keypoint differences not explained by an eps-fragile cell"
+def test_every_keypoint_difference_is_an_oracle_near_tie(weights, ex_cache):
+    """Fresh frames (sparse and at the cap): every key point the default mode adds or misses sits at an oracle decision
+    (threshold, arg-max, greedy order, cap cut) whose own margin is below EPS_MARGIN; all others are identical."""
+    for (H, W, nf, shapes, seed) in [(240, 320, 800, 260, 31), (480, 752, 800, 900, 33)]:
+        ex = ex_cache(H, W, nf, max_batch=4)
+        frames = synth.make_stream(H, W, 4, seed=seed, n_shapes=shapes)
+        outs = ex.extract_batch(list(frames))
+        score = ex.debug_read(0, "score", 4)
+        for t, o in enumerate(outs):
+            ref = O.extract(weights, frames[t], nf, keep_forward=True)
+            np.testing.assert_allclose(score[t], ref["forward"]["score_map"], atol=SCORE_ATOL, rtol=SCORE_RTOL)
+            diffs = explain_differences(ref["forward"], ref["kp_xy"], o["kp_xy"], nf)
+            assert len(diffs) <= MAX_DIFF_PER_FRAME, diffs
+            assert all(e < EPS_MARGIN for _, _, e in diffs), diffs
 
 
 @pytest.mark.parametrize("mode", ["mma", "ffma"])
@@ -211,7 +197,9 @@ def test_1080p_2000_keypoints_vs_live_oracle(weights, ex_cache):
     gold = {(int(x), int(y)): i for i, (x, y) in enumerate(ref["kp_xy"])}
     mine = {(int(x), int(y)): i for i, (x, y) in enumerate(o["kp_xy"])}
     common = set(gold) & set(mine)
-    assert len(common) / len(set(gold) | set(mine)) >= 0.93          # the cap makes the set sensitive to score order near the cut
+    diffs = explain_differences(ref["forward"], ref["kp_xy"], o["kp_xy"], nf)
+    assert len(diffs) <= 3 * MAX_DIFF_PER_FRAME, diffs               # 2001 key points, 5.7x the cells of 752x480
+    assert all(e < EPS_MARGIN for _, _, e in diffs), diffs
     cos = np.array([np.dot(o["desc"][mine[k]], ref["desc"][gold[k]]) for k in common])
     assert cos.min() > 1 - COS_TOL
     resp, cov2, cov2_inv = O.covariance(o["heat_inv"], o["kp_xy"])
