@@ -162,7 +162,11 @@ int spfe_slot_sync(spfe_ctx *ctx, int32_t slot);
 /* Mutual nearest neighbour under L2 over 256-d float rows (host pointers):
  * q2t[i] = first-index arg-min train row of query i if that row's first-index
  * arg-min query is i, else -1; dist[i] = L2 distance to the arg-min (may be NULL).
- * Thread-safe (per-call scratch), as SearchByBruteForce runs on two threads. */
+ * Unit-norm rows (SuperPoint descriptors) take the tensor-core path: an fp16 distance GEMM (tcgen05) nominates three
+ * columns per 256-column block, every nominee within the fp16 error bound of the row's best -- and the whole block
+ * where three near-ties could hide a fourth -- is re-ranked with the exact fp32 distance, so the result is the exact
+ * fp32 one (match.cuh has the argument).  Rows that are not unit vectors take an exact fp32 CUDA-core kernel.
+ * Thread-safe (serialised on the context), as SearchByBruteForce runs on two threads. */
 int spfe_match_mutual_nn(spfe_ctx *ctx, const float *q, int32_t nq, const float *t, int32_t nt,
                          int32_t *q2t, float *dist);
 /* Exact 2 nearest neighbours under L2 of every query row among the train rows (host pointers): idx[i][0..1] = best /
@@ -171,6 +175,24 @@ int spfe_match_mutual_nn(spfe_ctx *ctx, const float *q, int32_t nq, const float 
  * SPMatcher::SearchForTriByFlann / SearchByFlann (orb_slam2/src/cv/sp_matcher.cpp:183-200, :262-270) -- exact where the
  * reference's KD-tree search is approximate; the ratio test (0.7, :203-206) stays with the caller.  Thread-safe. */
 int spfe_match_knn2(spfe_ctx *ctx, const float *q, int32_t nq, const float *t, int32_t nt, int32_t *idx, float *dist);
+
+/* Device-resident descriptor sets.  The host-pointer entries above upload both descriptor matrices on every call; a
+ * SLAM front-end matches the same rows many times (a key frame's map-point descriptors against every following frame,
+ * the frame's own descriptors against several key frames), so a set keeps them in HBM (fp32 rows for the exact
+ * re-rank and the guided searches + an fp16 copy for the tensor-core nomination):
+ *   spfe_desc_set_upload      host rows -> set (e.g. KeyFrame::mDescriptors rows of the valid map points, once per key frame)
+ *   spfe_desc_set_from_frame  rows[0..n) (NULL: all key points) of frame `frame` of the last batch waited for on `slot`,
+ *                             gathered device -> device: the descriptors never cross PCIe for matching
+ *   spfe_match_mutual_nn_sets / spfe_match_knn2_sets   the two matchers on sets (results as in the host-pointer forms)
+ * Capacity <= 4096 rows (the matcher's limit).  All set entries are thread-safe like spfe_match_mutual_nn. */
+typedef struct spfe_desc_set spfe_desc_set;
+int spfe_desc_set_create(spfe_ctx *ctx, int32_t capacity, spfe_desc_set **out);
+void spfe_desc_set_destroy(spfe_ctx *ctx, spfe_desc_set *set);
+int32_t spfe_desc_set_size(const spfe_desc_set *set);
+int spfe_desc_set_upload(spfe_ctx *ctx, spfe_desc_set *set, const float *rows, int32_t n);
+int spfe_desc_set_from_frame(spfe_ctx *ctx, spfe_desc_set *set, int32_t slot, int32_t frame, const int32_t *rows, int32_t n);
+int spfe_match_mutual_nn_sets(spfe_ctx *ctx, const spfe_desc_set *q, const spfe_desc_set *t, int32_t *q2t, float *dist);
+int spfe_match_knn2_sets(spfe_ctx *ctx, const spfe_desc_set *q, const spfe_desc_set *t, int32_t *idx, float *dist);
 
 /* Guided (cell-grid) searches -- the greedy candidate loops of
  *   SPMatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, th_dist)   orb_slam2/src/cv/sp_matcher.cpp:344-432

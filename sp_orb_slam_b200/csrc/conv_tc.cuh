@@ -30,7 +30,7 @@
 
 namespace spfe {
 
-enum { EPI_RELU = 0, EPI_RELU_POOL = 1, EPI_L2NORM = 2, EPI_DETECT = 3, EPI_TOP2 = 4 };
+enum { EPI_RELU = 0, EPI_RELU_POOL = 1, EPI_L2NORM = 2, EPI_DETECT = 3, EPI_TOP2 = 4, EPI_TOP3 = 5 };
 
 struct ConvArgs {
   int B, H, W;            // conv spatial size (input == output, before pooling)
@@ -55,6 +55,9 @@ struct ConvArgs {
   float2 *m_cand;         // [2][Z][rows_pad][NB][2] (score, index-as-float-bits) top-2 per row and column block
   int m_rows_pad;         // rows per slot in the fp16 descriptor tensor (multiple of 256)
   int m_tiles;            // 128-row tiles per slot that can hold valid rows
+  // descriptor-SET mode (spfe_match_*: one direction per launch): tmA = the A set's rows, tmW = the B set's rows, both
+  // tensors hold a single slot; row counts are host-known
+  int m_set, m_na, m_nb, m_dir;
 };
 
 template <int TAPS_, int CB_, int N_, int EPI_, bool WRES_, int SA_, int SB_, int HALVES_ = 1, int EG_ = 1, bool PAIR_ = false, bool XP_ = false>
@@ -72,12 +75,13 @@ struct ConvCfg {
   // MMA drop from A + B to A + B/2 -- the limiter of the N = 64 layers (tools/umma2_rate.cu).  The leader (rank 0)
   // issues the MMAs for both; items 2q and 2q+1 go to ranks 0 and 1 of pair q mod (grid / 2).
   static constexpr bool PAIR = PAIR_;
-  static_assert(!PAIR_ || (N_ % 32 == 0 && EPI_ != EPI_TOP2), "pairs: convolution layers with N a multiple of 32");
+  static_assert(!PAIR_ || (N_ % 32 == 0 && EPI_ != EPI_TOP2 && EPI_ != EPI_TOP3), "pairs: convolution layers with N a multiple of 32");
   // EG = epilogue warp groups (4 warps each).  With 2, group g drains accumulator set g, so the epilogues of two
   // consecutive items run side by side: for the layers whose epilogue (softmax / log / norm), not the MMAs, paces the CTA.
   static constexpr int EG = EG_, THREADS = 128 + 128 * EG_;
   static_assert(EG_ == 1 || EG_ == 2, "one or two epilogue groups");
-  static constexpr bool MATCH = (EPI_ == EPI_TOP2);
+  static constexpr bool MATCH = (EPI_ == EPI_TOP2 || EPI_ == EPI_TOP3);
+  static constexpr int TOPK = EPI_ == EPI_TOP3 ? 3 : 2;  // candidates nominated per row and 256-column block
   static constexpr int TAPS = TAPS_, CB = CB_, N = N_, EPI = EPI_, SA = SA_, SB = SB_, HALVES = HALVES_;
   static constexpr bool WRES = WRES_;
   static constexpr int NDX = TAPS == 9 ? 3 : 1;
@@ -285,7 +289,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       x0 = 0;
       y0 = (t % p.m_tiles) * 16;
       t /= p.m_tiles;
-      b = (t >> 1) + 1 - (t & 1);  // pair z = t >> 1, direction = t & 1
+      b = p.m_set ? 0 : (t >> 1) + 1 - (t & 1);  // pair z = t >> 1, direction = t & 1
       return;
     }
     x0 = (t % p.tiles_x) * Cfg::TILE_W;
@@ -346,7 +350,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_expect_tx(b_full(s), Cfg::BBLK_BYTES);
                 if constexpr (Cfg::MATCH) {
                   const int t = item / NB / p.m_tiles;  // B operand = descriptor rows of the other slot of the pair
-                  const int bslot = (t >> 1) + (t & 1);
+                  const int bslot = p.m_set ? 0 : (t >> 1) + (t & 1);
                   tma_load_2d(smem_u32(sB + s * Cfg::BBLK_BYTES), &tmW, b_full(s), cb * 64, bslot * p.m_rows_pad + nb * N);
                 } else {
                   tma_load_2d(smem_u32(sB + s * Cfg::BBLK_BYTES), &tmW, b_full(s), 0, (wb * NB + nb) * N);
@@ -522,17 +526,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       } else if constexpr (EPI == EPI_RELU_POOL) {
         epilogue_relu_pool<N, XP>(taddr, bias, lane, hl, wl, x0, y0, b, nb, p.H, p.W, p.cout_stride, p.out);
-      } else if constexpr (EPI == EPI_TOP2) {
-        // One thread = one descriptor row of the A slot: best two dot products (first index on ties) among this
-        // item's 256 columns of the B slot.  The exact fp32 re-rank happens in match_rerank_kernel.
+      } else if constexpr (Cfg::MATCH) {
+        // One thread = one descriptor row of the A slot: best TOPK dot products (first index on ties) among this
+        // item's 256 columns of the B slot.  The exact fp32 re-rank happens in match.cuh.
+        constexpr int TOPK = Cfg::TOPK;
         const int t = item / NB / p.m_tiles;
-        const int z = t >> 1, dir = t & 1;
-        const int n_a = p.m_count[b], n_b = p.m_count[z + dir];
+        const int z = p.m_set ? 0 : t >> 1, dir = p.m_set ? p.m_dir : t & 1;
+        const int n_a = p.m_set ? p.m_na : p.m_count[b], n_b = p.m_set ? p.m_nb : p.m_count[z + dir];
         const int row = y0 * 8 + wq * 32 + lane;
         // Sortable 32-bit keys: ordered score bits with the low byte replaced by (255 - column) -- a larger key is a
         // larger score, ties go to the lower column.  Dropping 8 mantissa bits (2^-15 relative) is harmless: the keys
-        // only nominate candidates.  Four independent (best, second) chains keep the dependency depth short.
-        unsigned m1[4] = {0u, 0u, 0u, 0u}, m2[4] = {0u, 0u, 0u, 0u};
+        // only nominate candidates.  Four independent (best, second[, third]) chains keep the dependency depth short.
+        unsigned m1[4] = {0u, 0u, 0u, 0u}, m2[4] = {0u, 0u, 0u, 0u}, m3[4] = {0u, 0u, 0u, 0u};
 #pragma unroll 1
         for (int c0 = 0; c0 < N; c0 += 32) {
           float v[32];
@@ -546,20 +551,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             key = (nb * N + cl < n_b) ? key : 0u;
             const unsigned lo = min(m1[j & 3], key);
             m1[j & 3] = max(m1[j & 3], key);
-            m2[j & 3] = max(m2[j & 3], lo);
+            if constexpr (TOPK == 3) {
+              const unsigned lo2 = min(m2[j & 3], lo);
+              m2[j & 3] = max(m2[j & 3], lo);
+              m3[j & 3] = max(m3[j & 3], lo2);
+            } else {
+              m2[j & 3] = max(m2[j & 3], lo);
+            }
           }
         }
-        unsigned b1 = 0u, b2 = 0u;
+        unsigned b1 = 0u, b2 = 0u, b3 = 0u;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {  // merge the four chains
-          const unsigned lo = min(b1, m1[k]);
-          b1 = max(b1, m1[k]);
-          b2 = max(max(b2, lo), m2[k]);
+        for (int k = 0; k < 4; k++) {  // merge the four chains (each sorted m1 >= m2 >= m3)
+          const unsigned in[3] = {m1[k], m2[k], m3[k]};
+#pragma unroll
+          for (int e = 0; e < TOPK; e++) {
+            unsigned x = in[e];
+            unsigned lo = min(b1, x); b1 = max(b1, x); x = lo;
+            lo = min(b2, x); b2 = max(b2, x); x = lo;
+            b3 = max(b3, x);
+          }
         }
         if (row < n_a) {
-          float2 *dst = p.m_cand + (((static_cast<size_t>(dir) * p.B + z) * p.m_rows_pad + row) * NB + nb) * 2;
-          dst[0] = make_float2(b1 ? f32_from_ordered(b1 & 0xFFFFFF00u) : -INFINITY, __int_as_float(b1 ? nb * N + 255 - static_cast<int>(b1 & 0xFFu) : -1));
-          dst[1] = make_float2(b2 ? f32_from_ordered(b2 & 0xFFFFFF00u) : -INFINITY, __int_as_float(b2 ? nb * N + 255 - static_cast<int>(b2 & 0xFFu) : -1));
+          float2 *dst = p.m_cand + (((static_cast<size_t>(dir) * p.B + z) * p.m_rows_pad + row) * NB + nb) * TOPK;
+          const unsigned bk[3] = {b1, b2, b3};
+#pragma unroll
+          for (int e = 0; e < TOPK; e++)
+            dst[e] = make_float2(bk[e] ? f32_from_ordered(bk[e] & 0xFFFFFF00u) : -INFINITY,
+                                 __int_as_float(bk[e] ? nb * N + 255 - static_cast<int>(bk[e] & 0xFFu) : -1));
         }
       } else if constexpr (EPI == EPI_L2NORM) {
         // convDb + channel-wise L2 normalisation (sp_extractor.cpp:100-103); N == all 256 channels.

@@ -10,6 +10,7 @@
 // (float_bits(d2) << 32 | index) -- smaller distance wins, ties go to the lower
 // index, which is BFMatcher's first-index rule.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -199,7 +200,73 @@ __global__ void knn2_final_kernel(const unsigned long long *first, const unsigne
 // exact fp32 squared distance (ties -> lower index, BFMatcher's rule).
 // One warp per row; grid (ceil(cap / 8), Z pairs, 2 directions).
 // ---------------------------------------------------------------------------
+// Why the result is provably the exact one.  Descriptors are unit vectors; rounding both operands to fp16 changes a
+// dot product by at most 2 * 2^-11 * sum |q_k t_k| <= 2^-10 (Cauchy-Schwarz), the fp32 tensor-core accumulation and the
+// 8 dropped key bits add < 5e-5: |observed - exact| <= beta = 1.03e-3.  Let s_R be the R-th largest observed score of a
+// row over all columns (R = 1: nearest neighbour, R = 2: two nearest).  A column of the true top R has an observed
+// score >= s_R - 2 beta, and the top R observed columns are among the K >= R nominees of their 256-column blocks, so
+// s_R is known from the nominees.  A true top-R column can be missing from the nominees only if its block holds K
+// other columns at or above it, i.e. the block's K-th nominee is >= s_R - 2 beta: such a block is re-scanned
+// completely in fp32 (rare: three near-ties inside one block); everywhere else the nominees within MATCH_MARGIN
+// (>= 2 beta) of s_R contain the answer.  All survivors are ranked by the exact fp32 squared distance, ties to the
+// lower index (BFMatcher's first-index rule).
 constexpr float MATCH_MARGIN = 4e-3f;
+
+// exact fp32 squared distance of two 256-d rows held 8 dimensions per lane (all lanes return the sum)
+__device__ __forceinline__ float warp_dist2(const float4 &m0, const float4 &m1, const float *other, int lane) {
+  const float4 o0 = *reinterpret_cast<const float4 *>(other + lane * 8), o1 = *reinterpret_cast<const float4 *>(other + lane * 8 + 4);
+  float d, acc = 0.f;
+  d = m0.x - o0.x; acc = fmaf(d, d, acc);
+  d = m0.y - o0.y; acc = fmaf(d, d, acc);
+  d = m0.z - o0.z; acc = fmaf(d, d, acc);
+  d = m0.w - o0.w; acc = fmaf(d, d, acc);
+  d = m1.x - o1.x; acc = fmaf(d, d, acc);
+  d = m1.y - o1.y; acc = fmaf(d, d, acc);
+  d = m1.z - o1.z; acc = fmaf(d, d, acc);
+  d = m1.w - o1.w; acc = fmaf(d, d, acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
+// One warp re-ranks one row: `c` = its [NB][K] nominees (observed score, column), `other` = the fp32 rows of the other
+// set (n_other of them).  best[0 .. R) receive the R smallest keys (bits(d^2) << 32 | column), ~0 where none exists.
+template <int K, int R>
+__device__ __forceinline__ void rerank_row(const float *me, const float *other, int n_other, const float2 *c, int NB, int lane,
+                                           unsigned long long (&best)[R]) {
+  static_assert(K >= R && R >= 1 && R <= 2, "nominees per block must cover the ranks asked for");
+  float s1 = -INFINITY, s2 = -INFINITY;  // best / second-best observed score among the nominees
+  for (int k = 0; k < NB * K; k++) {
+    const float x = c[k].x;
+    if (x > s1) { s2 = s1; s1 = x; }
+    else if (x > s2) s2 = x;
+  }
+#pragma unroll
+  for (int r = 0; r < R; r++) best[r] = ~0ull;
+  if (s1 == -INFINITY) return;
+  const float thr = (R == 1 ? s1 : (s2 == -INFINITY ? s1 : s2)) - MATCH_MARGIN;
+  const float4 m0 = *reinterpret_cast<const float4 *>(me + lane * 8), m1 = *reinterpret_cast<const float4 *>(me + lane * 8 + 4);
+  auto consider = [&](int idx) {
+    const float d2 = warp_dist2(m0, m1, other + static_cast<size_t>(idx) * 256, lane);
+    unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(d2)) << 32) | static_cast<unsigned>(idx);
+#pragma unroll
+    for (int r = 0; r < R; r++)
+      if (key < best[r]) { const unsigned long long t = best[r]; best[r] = key; key = t; }
+  };
+  for (int nb = 0; nb < NB; nb++) {
+    const float2 *cb = c + nb * K;
+    if (cb[K - 1].x >= thr && __float_as_int(cb[K - 1].y) >= 0) {  // K near-ties in one block: a (K+1)-th may hide behind them
+      const int j1 = min(n_other, nb * 256 + 256);
+      for (int j = nb * 256; j < j1; j++) consider(j);
+      continue;
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const int idx = __float_as_int(cb[k].y);
+      if (idx >= 0 && cb[k].x >= thr) consider(idx);  // warp-uniform
+    }
+  }
+}
 
 struct RerankArgs {
   const float *desc_all;   // [slots][cap][256] fp32 descriptors, slot 0 = carry, slot z+1 = frame z
@@ -209,40 +276,79 @@ struct RerankArgs {
   int cap, rows_pad, NB, Z;
 };
 
+// in-pipeline stream matching (SPFE_MATCH_PREV): one warp per row; grid (ceil(cap / 8), Z pairs, 2 directions)
 __global__ void __launch_bounds__(256) match_rerank_kernel(const RerankArgs a) {
   const int z = blockIdx.y, dir = blockIdx.z;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int self_slot = z + 1 - dir, other_slot = z + dir;
   if (row >= a.count_all[self_slot]) return;
   const float2 *c = a.cand + ((static_cast<size_t>(dir) * a.Z + z) * a.rows_pad + row) * a.NB * 2;
-  float best_s = -INFINITY;
-  for (int k = 0; k < a.NB * 2; k++) best_s = fmaxf(best_s, c[k].x);
-  unsigned long long best = ~0ull;
-  if (best_s > -INFINITY) {
-    const float *me = a.desc_all + (static_cast<size_t>(self_slot) * a.cap + row) * 256 + lane * 8;
-    const float4 m0 = *reinterpret_cast<const float4 *>(me), m1 = *reinterpret_cast<const float4 *>(me + 4);
-    for (int k = 0; k < a.NB * 2; k++) {
-      const float2 ck = c[k];
-      const int idx = __float_as_int(ck.y);
-      if (idx < 0 || ck.x < best_s - MATCH_MARGIN) continue;  // warp-uniform
-      const float *ot = a.desc_all + (static_cast<size_t>(other_slot) * a.cap + idx) * 256 + lane * 8;
-      const float4 o0 = *reinterpret_cast<const float4 *>(ot), o1 = *reinterpret_cast<const float4 *>(ot + 4);
-      float d, acc = 0.f;
-      d = m0.x - o0.x; acc = fmaf(d, d, acc);
-      d = m0.y - o0.y; acc = fmaf(d, d, acc);
-      d = m0.z - o0.z; acc = fmaf(d, d, acc);
-      d = m0.w - o0.w; acc = fmaf(d, d, acc);
-      d = m1.x - o1.x; acc = fmaf(d, d, acc);
-      d = m1.y - o1.y; acc = fmaf(d, d, acc);
-      d = m1.z - o1.z; acc = fmaf(d, d, acc);
-      d = m1.w - o1.w; acc = fmaf(d, d, acc);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(acc)) << 32) | static_cast<unsigned>(idx);
-      best = key < best ? key : best;
-    }
+  unsigned long long best[1];
+  rerank_row<2, 1>(a.desc_all + (static_cast<size_t>(self_slot) * a.cap + row) * 256, a.desc_all + static_cast<size_t>(other_slot) * a.cap * 256,
+                   a.count_all[other_slot], c, a.NB, lane, best);
+  if (lane == 0) (dir == 0 ? a.rowbest : a.colbest)[static_cast<size_t>(z) * a.cap + row] = best[0];
+}
+
+// descriptor-set matching (spfe_match_mutual_nn / spfe_match_knn2 and their *_sets forms): one direction per launch,
+// three nominees per block, exact best (R = 1) or best two (R = 2) of every row of set A among the rows of set B
+struct SetRerankArgs {
+  const float *a_rows, *b_rows;  // fp32 [n][256]
+  int n_a, n_b, rows_pad, NB, dir;
+  const float2 *cand;            // [2][1][rows_pad][NB][3]
+  unsigned long long *out1, *out2;  // [n_a] best key (and second best for R = 2)
+};
+template <int R>
+__global__ void __launch_bounds__(256) match_rerank_set_kernel(const SetRerankArgs a) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= a.n_a) return;
+  const float2 *c = a.cand + (static_cast<size_t>(a.dir) * a.rows_pad + row) * a.NB * 3;
+  unsigned long long best[R];
+  rerank_row<3, R>(a.a_rows + static_cast<size_t>(row) * 256, a.b_rows, a.n_b, c, a.NB, lane, best);
+  if (lane == 0) {
+    a.out1[row] = best[0];
+    if (R == 2) a.out2[row] = best[R - 1];
   }
-  if (lane == 0) (dir == 0 ? a.rowbest : a.colbest)[static_cast<size_t>(z) * a.cap + row] = best;
+}
+
+// mutual nearest neighbour from the two directions' exact keys
+__global__ void match_cross_kernel(const unsigned long long *rowbest, const unsigned long long *colbest, int nq, int *q2t, float *dist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const unsigned long long rb = rowbest[i];
+  int out = -1;
+  float d = 0.f;
+  if (rb != ~0ull) {
+    const int j = static_cast<int>(rb & 0xFFFFFFFFu);
+    d = sqrtf(__uint_as_float(static_cast<unsigned>(rb >> 32)));
+    if (static_cast<int>(colbest[j] & 0xFFFFFFFFu) == i) out = j;
+  }
+  q2t[i] = out;
+  dist[i] = d;
+}
+
+// fp32 rows -> the fp16 copy the tensor-core nomination reads (+ a flag if a row is not a unit vector: the score bound
+// above needs |x| = 1, such sets take the CUDA-core exact path); optional gather (rows == nullptr: identity)
+__global__ void __launch_bounds__(256) desc_prepare_kernel(const float *__restrict__ src, const int *__restrict__ rows, int n,
+                                                           float *__restrict__ dst32, __half *__restrict__ dst16, int *nonunit) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const float *s = src + static_cast<size_t>(rows ? rows[i] : i) * 256 + lane * 8;
+  const float4 v0 = *reinterpret_cast<const float4 *>(s), v1 = *reinterpret_cast<const float4 *>(s + 4);
+  if (dst32 != nullptr && dst32 + static_cast<size_t>(i) * 256 + lane * 8 != s) {
+    *reinterpret_cast<float4 *>(dst32 + static_cast<size_t>(i) * 256 + lane * 8) = v0;
+    *reinterpret_cast<float4 *>(dst32 + static_cast<size_t>(i) * 256 + lane * 8 + 4) = v1;
+  }
+  uint4 o;
+  __half2 h;
+  h = __floats2half2_rn(v0.x, v0.y); o.x = *reinterpret_cast<uint32_t *>(&h);
+  h = __floats2half2_rn(v0.z, v0.w); o.y = *reinterpret_cast<uint32_t *>(&h);
+  h = __floats2half2_rn(v1.x, v1.y); o.z = *reinterpret_cast<uint32_t *>(&h);
+  h = __floats2half2_rn(v1.z, v1.w); o.w = *reinterpret_cast<uint32_t *>(&h);
+  *reinterpret_cast<uint4 *>(dst16 + static_cast<size_t>(i) * 256 + lane * 8) = o;
+  float ss = v0.x * v0.x + v0.y * v0.y + v0.z * v0.z + v0.w * v0.w + v1.x * v1.x + v1.y * v1.y + v1.z * v1.z + v1.w * v1.w;
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, k);
+  if (lane == 0 && !(fabsf(ss - 1.0f) <= 1e-3f)) atomicExch(nonunit, 1);
 }
 
 }  // namespace spfe

@@ -68,6 +68,7 @@ using CfgHeadsX = ConvCfg<9, 2, 256, EPI_RELU, false, 2, 8, 1, 1, true>;
 using CfgPb = ConvCfg<1, 4, 80, EPI_DETECT, true, 4, 1, 1, 2>;  // convPb + detector head   (epilogue-bound: two epilogue groups)
 using CfgDb = ConvCfg<1, 4, 256, EPI_L2NORM, true, 4, 1, 1, 2>; // convDb + L2 norm
 using CfgMatch = ConvCfg<1, 4, 256, EPI_TOP2, false, 4, 4, 1, 2>;  // descriptor matching: Q.T^T + top-2 per 256-column block
+using CfgMatch3 = ConvCfg<1, 4, 256, EPI_TOP3, false, 4, 4, 1, 2>; // descriptor-set matching (spfe_match_*): top-3 per block
 
 // "exact" mode (SPFE_EXACT): hi/lo-split operands, three MMAs per product (ConvCfg::XP); CB counts slabs = 2 x real
 // 64-channel blocks.  Weights are streamed as CTA pairs for every 3x3 layer, resident for the 1x1 detector head.
@@ -148,6 +149,17 @@ struct Slot {
 
 }  // namespace
 
+// Device-resident descriptor rows: fp32 (exact re-rank, guided searches) + the fp16 copy the tensor-core nomination
+// reads, with their TMA views.  Guarded by the context's match_mu like every matcher entry.
+struct spfe_desc_set {
+  spfe_ctx *ctx = nullptr;
+  int cap = 0, rows_pad = 0, n = 0;
+  bool unit = true;       // every row is a unit vector (what the tensor-core score bound needs)
+  float *d32 = nullptr;   // [rows_pad][256]
+  __half *d16 = nullptr;  // [rows_pad][256]
+  CUtensorMap tmA, tmB;   // d16 as the A operand (128-row tiles) / the B operand (256-row blocks)
+};
+
 struct spfe_ctx {
   spfe_config cfg;
   std::string weights_path;
@@ -183,8 +195,14 @@ struct spfe_ctx {
   cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr, aux = nullptr;  // aux: covariance beside the matcher
   cudaStream_t copy_late = nullptr;  // the n[b]-row descriptor copies spfe_wait issues once the counts are on the host
   bool slot_streams = false;
-  MatchScratch match;  // for spfe_match_mutual_nn (host pointers)
-  float *h_match_q = nullptr, *h_match_t = nullptr;
+  MatchScratch match;  // for spfe_match_* (descriptor sets)
+  spfe_desc_set *tmp_q = nullptr, *tmp_t = nullptr;  // the host-pointer entries upload into these
+  float2 *set_cand[2] = {nullptr, nullptr};            // [match_cap rows][match_cap / 256][3] nominees per direction
+  unsigned long long *set_second = nullptr;            // [match_cap] second-best keys (k-NN 2)
+  int *set_flag = nullptr, *h_set_flag = nullptr;      // "a row is not a unit vector" (device / pinned host)
+  int *set_rows = nullptr, *h_set_rows = nullptr;      // gather lists of spfe_desc_set_from_frame
+  Layer match_layer;                                   // dummy layer record for launch_conv<CfgMatch3>
+  float *h_match_q = nullptr;
   int *h_match_idx = nullptr;
   float *h_match_dist = nullptr;
   int match_cap = 0;
@@ -317,7 +335,7 @@ int launch_conv(spfe_ctx *c, cudaStream_t st, const CUtensorMap &tmA, const Laye
   a.tiles_x = (a.W + Cfg::TILE_W - 1) / Cfg::TILE_W;
   a.tiles_y = (a.H + 15) / 16;
   a.n_items = a.B * a.tiles_x * a.tiles_y * a.NB;
-  if (Cfg::MATCH) a.n_items = a.B * 2 * a.m_tiles * a.NB;
+  if (Cfg::MATCH) a.n_items = (a.m_set ? 1 : a.B * 2) * a.m_tiles * a.NB;
   int grid = a.n_items < c->num_sms ? a.n_items : c->num_sms;
   if (Cfg::PAIR) {  // clusters of two CTAs; every pair works on two items at a time
     const int pair_items = (a.n_items / a.NB + 1) / 2 * a.NB;
@@ -364,6 +382,8 @@ struct StageTimer {
 };
 
 int run_match(spfe_ctx *c, cudaStream_t st, const MatchArgs &a, int Z, int rows);
+int set_alloc(spfe_ctx *c, int capacity, spfe_desc_set **out);
+void set_free(spfe_desc_set *s);
 
 // The convolution stack in "exact" mode (SPFE_EXACT): conv1a in fp32 on the CUDA cores, stored as hi + lo fp16; every
 // other layer as three MMAs per product on hi/lo-split operands (ConvCfg::XP).  Same stage names / algorithmic FLOPs as
@@ -892,18 +912,25 @@ static int create_impl(spfe_ctx *c) {
     if ((rc = make_act_map(c, &s.tmA[LDB], s.heads, 512, wc, hc, Bm, 16))) return rc;
   }
   // ---- host-pointer matcher scratch
-  c->match_cap = static_cast<int>(cap) > 4096 ? static_cast<int>(cap) : 4096;
+  c->match_cap = ((static_cast<int>(cap) > 4096 ? static_cast<int>(cap) : 4096) + 255) / 256 * 256;
   CU_OK(c, cudaStreamCreateWithFlags(&c->match_stream, cudaStreamNonBlocking));
   if ((rc = dev_alloc(c, &c->match.rowbest, c->match_cap))) return rc;
   if ((rc = dev_alloc(c, &c->match.colbest, c->match_cap))) return rc;
   if ((rc = dev_alloc(c, &c->match.q2t, c->match_cap))) return rc;
   if ((rc = dev_alloc(c, &c->match.dist, c->match_cap))) return rc;
-  if ((rc = dev_alloc(c, &c->match.dq, static_cast<size_t>(c->match_cap) * 256))) return rc;
-  if ((rc = dev_alloc(c, &c->match.dt, static_cast<size_t>(c->match_cap) * 256))) return rc;
+  for (int d = 0; d < 2; d++)
+    if ((rc = dev_alloc(c, &c->set_cand[d], static_cast<size_t>(c->match_cap) * (c->match_cap / 256) * 3))) return rc;
+  if ((rc = dev_alloc(c, &c->set_second, c->match_cap))) return rc;
+  if ((rc = dev_alloc(c, &c->set_flag, 2))) return rc;
+  if ((rc = host_alloc(c, &c->h_set_flag, 2))) return rc;
+  if ((rc = dev_alloc(c, &c->set_rows, c->match_cap))) return rc;
+  if ((rc = host_alloc(c, &c->h_set_rows, c->match_cap))) return rc;
+  c->match_layer.taps = 1; c->match_layer.cb = 4; c->match_layer.n_tile = 256; c->match_layer.cout_total = 256;
+  if ((rc = set_alloc(c, c->match_cap, &c->tmp_q))) return rc;
+  if ((rc = set_alloc(c, c->match_cap, &c->tmp_t))) return rc;
   if ((rc = dev_alloc(c, &c->match.dn, 2))) return rc;
   c->match.cap = c->match_cap;
-  if ((rc = host_alloc(c, &c->h_match_q, static_cast<size_t>(c->match_cap) * 256))) return rc;
-  if ((rc = host_alloc(c, &c->h_match_t, static_cast<size_t>(c->match_cap) * 256))) return rc;
+  if ((rc = host_alloc(c, &c->h_match_q, static_cast<size_t>(c->match_cap) * 4))) return rc;  // k-NN results: [nq][2] idx + [nq][2] dist
   if ((rc = host_alloc(c, &c->h_match_idx, c->match_cap + 2))) return rc;
   if ((rc = host_alloc(c, &c->h_match_dist, c->match_cap))) return rc;
 #ifdef SPFE_C1M_TRACE
@@ -1000,6 +1027,8 @@ void spfe_destroy(spfe_ctx *c) {
     if (s.ev0) cudaEventDestroy(s.ev0);
     if (s.ev1) cudaEventDestroy(s.ev1);
   }
+  set_free(c->tmp_q);
+  set_free(c->tmp_t);
   if (c->match_stream) cudaStreamDestroy(c->match_stream);
   if (c->guided_buf) cudaFree(c->guided_buf);
   if (c->dust_stage) cudaFreeHost(c->dust_stage);
@@ -1248,6 +1277,251 @@ int run_match(spfe_ctx *c, cudaStream_t st, const MatchArgs &a, int Z, int rows)
 }  // namespace
 extern "C" {
 
+// ---- descriptor sets ------------------------------------------------------------------------------------------------
+}  // extern "C"
+namespace {
+int set_alloc(spfe_ctx *c, int capacity, spfe_desc_set **out) {
+  spfe_desc_set *s = new spfe_desc_set();
+  s->ctx = c;
+  s->cap = capacity;
+  s->rows_pad = (capacity + 255) / 256 * 256;
+  const size_t elems = static_cast<size_t>(s->rows_pad) * 256;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&s->d32), elems * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&s->d16), elems * sizeof(__half));
+  if (e == cudaSuccess) e = cudaMemset(s->d16, 0, elems * sizeof(__half));
+  if (e == cudaSuccess) e = cudaMemset(s->d32, 0, elems * sizeof(float));
+  int rc = e == cudaSuccess ? SPFE_OK : c->fail(SPFE_ERR_CUDA, fmt("descriptor set of %d rows: %s", capacity, cudaGetErrorString(e)));
+  if (!rc) rc = make_act_map(c, &s->tmA, s->d16, 256, 8, s->rows_pad / 8, 1, 16);
+  if (!rc) rc = make_mat_map(c, &s->tmB, s->d16, 256, s->rows_pad, 256);
+  if (rc) {
+    if (s->d32) cudaFree(s->d32);
+    if (s->d16) cudaFree(s->d16);
+    delete s;
+    return rc;
+  }
+  *out = s;
+  return SPFE_OK;
+}
+void set_free(spfe_desc_set *s) {
+  if (!s) return;
+  cudaFree(s->d32);
+  cudaFree(s->d16);
+  delete s;
+}
+// (match_mu held) fp32 rows already in s->d32 or at `src` on the device -> d32 + fp16 copy + unit flag
+int set_prepare(spfe_ctx *c, spfe_desc_set *s, const float *d_src, const int *d_rows, int n, bool check_unit) {
+  cudaStream_t st = c->match_stream;
+  s->n = n;
+  s->unit = true;
+  if (n == 0) return SPFE_OK;
+  if (check_unit) CU_OK(c, cudaMemsetAsync(c->set_flag, 0, sizeof(int), st));
+  desc_prepare_kernel<<<(n + 7) / 8, 256, 0, st>>>(d_src, d_rows, n, s->d32, s->d16, c->set_flag);
+  c->launches++;
+  CU_OK(c, cudaGetLastError());
+  if (check_unit) {
+    CU_OK(c, cudaMemcpyAsync(c->h_set_flag, c->set_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_OK(c, cudaStreamSynchronize(st));
+    s->unit = c->h_set_flag[0] == 0;
+  }
+  return SPFE_OK;
+}
+int set_upload_locked(spfe_ctx *c, spfe_desc_set *s, const float *rows, int n) {
+  if (n > 0) CU_OK(c, cudaMemcpyAsync(s->d32, rows, static_cast<size_t>(n) * 256 * sizeof(float), cudaMemcpyHostToDevice, c->match_stream));
+  return set_prepare(c, s, s->d32, nullptr, n, true);
+}
+// (match_mu held) one direction of the tensor-core nomination: top-3 columns of B per 256-column block for every row of A
+int set_nominate(spfe_ctx *c, const spfe_desc_set *A, const spfe_desc_set *B, float2 *cand) {
+  ConvArgs a;
+  memset(&a, 0, sizeof a);
+  a.B = 1; a.H = A->rows_pad / 8; a.W = 8; a.NB = (B->n + 255) / 256;
+  a.m_cand = cand; a.m_rows_pad = c->match_cap; a.m_tiles = (A->n + 127) / 128;
+  a.m_set = 1; a.m_na = A->n; a.m_nb = B->n; a.m_dir = 0;
+  return launch_conv<CfgMatch3>(c, c->match_stream, A->tmA, c->match_layer, a, &B->tmB);
+}
+int set_rerank(spfe_ctx *c, const spfe_desc_set *A, const spfe_desc_set *B, const float2 *cand, int R, unsigned long long *out1, unsigned long long *out2) {
+  SetRerankArgs r;
+  r.a_rows = A->d32; r.b_rows = B->d32; r.n_a = A->n; r.n_b = B->n; r.rows_pad = c->match_cap; r.NB = (B->n + 255) / 256; r.dir = 0;
+  r.cand = cand; r.out1 = out1; r.out2 = out2;
+  if (R == 1) match_rerank_set_kernel<1><<<(A->n + 7) / 8, 256, 0, c->match_stream>>>(r);
+  else match_rerank_set_kernel<2><<<(A->n + 7) / 8, 256, 0, c->match_stream>>>(r);
+  c->launches++;
+  CU_OK(c, cudaGetLastError());
+  return SPFE_OK;
+}
+// exact CUDA-core path for sets whose rows are not unit vectors (the tensor-core score bound does not hold for them)
+int set_match_general(spfe_ctx *c, const spfe_desc_set *Q, const spfe_desc_set *T, bool knn2) {
+  cudaStream_t st = c->match_stream;
+  MatchScratch &m = c->match;
+  c->h_match_idx[c->match_cap] = Q->n;
+  c->h_match_idx[c->match_cap + 1] = T->n;
+  CU_OK(c, cudaMemcpyAsync(m.dn, c->h_match_idx + c->match_cap, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
+  MatchArgs a;
+  memset(&a, 0, sizeof a);
+  a.q = Q->d32; a.nq = m.dn; a.t0 = T->d32; a.nt0 = m.dn + 1;
+  a.rowbest = m.rowbest; a.colbest = m.colbest; a.q2t = m.q2t; a.dist = m.dist; a.cap = c->match_cap;
+  const int rows = Q->n > T->n ? Q->n : T->n;
+  if (!knn2) return run_match(c, st, a, 1, rows);
+  dim3 grid((rows + 63) / 64, (rows + 63) / 64, 1);
+  match_init_kernel<<<(a.cap + 255) / 256, 256, 0, st>>>(a.rowbest, a.colbest, a.cap);
+  match_dist_kernel<<<grid, 256, 0, st>>>(a);                        // pass 1: nearest row of every query
+  match_init_kernel<<<(a.cap + 255) / 256, 256, 0, st>>>(c->set_second, c->set_second, a.cap);
+  MatchArgs b = a;
+  b.excl = m.rowbest;
+  b.rowbest = c->set_second;                                         // pass 2: nearest among the others -> second best
+  match_dist_kernel<<<grid, 256, 0, st>>>(b);
+  c->launches += 4;
+  CU_OK(c, cudaGetLastError());
+  return SPFE_OK;
+}
+int check_set(spfe_ctx *c, const spfe_desc_set *s, const char *fn) {
+  if (!s || s->ctx != c) return c->fail(SPFE_ERR_INVALID, fmt("%s: descriptor set is NULL or belongs to another context", fn));
+  return SPFE_OK;
+}
+int match_sets_locked(spfe_ctx *c, const spfe_desc_set *Q, const spfe_desc_set *T, int32_t *q2t, float *dist) {
+  const int nq = Q->n, nt = T->n;
+  if (nq == 0) return SPFE_OK;
+  if (nt == 0) {
+    for (int i = 0; i < nq; i++) { q2t[i] = -1; if (dist) dist[i] = 0.f; }
+    return SPFE_OK;
+  }
+  cudaStream_t st = c->match_stream;
+  MatchScratch &m = c->match;
+  int rc;
+  if (Q->unit && T->unit) {  // tensor-core nomination in both directions, exact fp32 re-rank, cross-check
+    if ((rc = set_nominate(c, Q, T, c->set_cand[0]))) return rc;
+    if ((rc = set_nominate(c, T, Q, c->set_cand[1]))) return rc;
+    if ((rc = set_rerank(c, Q, T, c->set_cand[0], 1, m.rowbest, nullptr))) return rc;
+    if ((rc = set_rerank(c, T, Q, c->set_cand[1], 1, m.colbest, nullptr))) return rc;
+    match_cross_kernel<<<(nq + 255) / 256, 256, 0, st>>>(m.rowbest, m.colbest, nq, m.q2t, m.dist);
+    c->launches++;
+    CU_OK(c, cudaGetLastError());
+  } else if ((rc = set_match_general(c, Q, T, false))) {
+    return rc;
+  }
+  CU_OK(c, cudaMemcpyAsync(c->h_match_idx, m.q2t, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU_OK(c, cudaMemcpyAsync(c->h_match_dist, m.dist, nq * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU_OK(c, cudaStreamSynchronize(st));
+  memcpy(q2t, c->h_match_idx, nq * sizeof(int));
+  if (dist) memcpy(dist, c->h_match_dist, nq * sizeof(float));
+  return SPFE_OK;
+}
+int knn2_sets_locked(spfe_ctx *c, const spfe_desc_set *Q, const spfe_desc_set *T, int32_t *idx, float *dist) {
+  const int nq = Q->n, nt = T->n;
+  if (nq == 0) return SPFE_OK;
+  if (nt == 0) {
+    for (int i = 0; i < 2 * nq; i++) { idx[i] = -1; dist[i] = 0.f; }
+    return SPFE_OK;
+  }
+  cudaStream_t st = c->match_stream;
+  MatchScratch &m = c->match;
+  int rc;
+  if (Q->unit && T->unit) {  // ONE nomination pass gives both neighbours (top-3 per block, exact re-rank of the best two)
+    if ((rc = set_nominate(c, Q, T, c->set_cand[0]))) return rc;
+    if ((rc = set_rerank(c, Q, T, c->set_cand[0], 2, m.rowbest, c->set_second))) return rc;
+  } else if ((rc = set_match_general(c, Q, T, true))) {
+    return rc;
+  }
+  // results as [nq][2] indices followed by [nq][2] distances in the (idle) second nominee buffer
+  knn2_final_kernel<<<(nq + 255) / 256, 256, 0, st>>>(m.rowbest, c->set_second, nq, reinterpret_cast<int *>(c->set_cand[1]),
+                                                      reinterpret_cast<float *>(c->set_cand[1]) + 2 * (size_t)nq);
+  c->launches++;
+  CU_OK(c, cudaGetLastError());
+  CU_OK(c, cudaMemcpyAsync(c->h_match_q, c->set_cand[1], (size_t)nq * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU_OK(c, cudaStreamSynchronize(st));
+  memcpy(idx, c->h_match_q, (size_t)nq * 2 * sizeof(int));
+  memcpy(dist, reinterpret_cast<float *>(c->h_match_q) + 2 * (size_t)nq, (size_t)nq * 2 * sizeof(float));
+  return SPFE_OK;
+}
+}  // namespace
+extern "C" {
+
+int spfe_desc_set_create(spfe_ctx *c, int32_t capacity, spfe_desc_set **out) {
+  if (out) *out = nullptr;
+  if (!c) return SPFE_ERR_INVALID;
+  if (!out || capacity < 1 || capacity > c->match_cap) return c->fail(SPFE_ERR_INVALID, fmt("spfe_desc_set_create: capacity must be 1 .. %d rows", c->match_cap));
+  std::lock_guard<std::mutex> lock(c->match_mu);
+  CU_OK(c, cudaSetDevice(c->cfg.device_id));
+  return set_alloc(c, capacity, out);
+}
+
+void spfe_desc_set_destroy(spfe_ctx *c, spfe_desc_set *s) {
+  if (!c || !s || s->ctx != c) return;
+  std::lock_guard<std::mutex> lock(c->match_mu);
+  cudaSetDevice(c->cfg.device_id);
+  cudaStreamSynchronize(c->match_stream);
+  set_free(s);
+}
+
+int32_t spfe_desc_set_size(const spfe_desc_set *s) { return s ? s->n : SPFE_ERR_INVALID; }
+
+int spfe_desc_set_upload(spfe_ctx *c, spfe_desc_set *s, const float *rows, int32_t n) {
+  if (!c) return SPFE_ERR_INVALID;
+  int rc = check_set(c, s, "spfe_desc_set_upload");
+  if (rc) return rc;
+  if (n < 0 || n > s->cap || (n > 0 && !rows)) return c->fail(SPFE_ERR_INVALID, fmt("spfe_desc_set_upload: bad rows / n (capacity %d)", s->cap));
+  std::lock_guard<std::mutex> lock(c->match_mu);
+  CU_OK(c, cudaSetDevice(c->cfg.device_id));
+  return set_upload_locked(c, s, rows, n);
+}
+
+int spfe_desc_set_from_frame(spfe_ctx *c, spfe_desc_set *s, int32_t slot, int32_t frame, const int32_t *rows, int32_t n) {
+  if (!c) return SPFE_ERR_INVALID;
+  int rc = check_set(c, s, "spfe_desc_set_from_frame");
+  if (rc) return rc;
+  if ((rc = check_slot(c, slot))) return rc;
+  Slot &sl = c->slots[slot];
+  if (sl.pending) return c->fail(SPFE_ERR_STATE, "spfe_desc_set_from_frame: slot still has an un-waited batch");
+  if (frame < 0 || frame >= sl.batch) return c->fail(SPFE_ERR_STATE, fmt("spfe_desc_set_from_frame: frame %d is not part of the slot's last batch (%d frames)", frame, sl.batch));
+  std::lock_guard<std::mutex> lock(c->match_mu);
+  CU_OK(c, cudaSetDevice(c->cfg.device_id));
+  cudaStream_t st = c->match_stream;
+  CU_OK(c, cudaStreamWaitEvent(st, sl.ev_done, 0));
+  int n_frame = 0;
+  if (sl.on_host) n_frame = sl.h_count[frame];
+  else {
+    CU_OK(c, cudaMemcpyAsync(c->h_set_flag + 1, sl.count + frame, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_OK(c, cudaStreamSynchronize(st));
+    n_frame = c->h_set_flag[1];
+  }
+  const float *src = sl.desc + static_cast<size_t>(frame) * c->cap * 256;
+  if (!rows) {  // all key points of the frame
+    if (n_frame > s->cap) return c->fail(SPFE_ERR_INVALID, fmt("spfe_desc_set_from_frame: the frame has %d key points, the set holds %d", n_frame, s->cap));
+    return set_prepare(c, s, src, nullptr, n_frame, false);  // the extractor's rows are normalised in fp32
+  }
+  if (n < 0 || n > s->cap) return c->fail(SPFE_ERR_INVALID, "spfe_desc_set_from_frame: bad n");
+  for (int i = 0; i < n; i++)
+    if (rows[i] < 0 || rows[i] >= n_frame) return c->fail(SPFE_ERR_INVALID, fmt("spfe_desc_set_from_frame: row %d out of range (%d key points)", rows[i], n_frame));
+  if (n > 0) {
+    memcpy(c->h_set_rows, rows, n * sizeof(int));
+    CU_OK(c, cudaMemcpyAsync(c->set_rows, c->h_set_rows, n * sizeof(int), cudaMemcpyHostToDevice, st));
+  }
+  rc = set_prepare(c, s, src, c->set_rows, n, false);
+  if (!rc && n > 0) CU_OK(c, cudaStreamSynchronize(st));  // h_set_rows may be reused by the next call
+  return rc;
+}
+
+int spfe_match_mutual_nn_sets(spfe_ctx *c, const spfe_desc_set *q, const spfe_desc_set *t, int32_t *q2t, float *dist) {
+  if (!c) return SPFE_ERR_INVALID;
+  int rc = check_set(c, q, "spfe_match_mutual_nn_sets");
+  if (!rc) rc = check_set(c, t, "spfe_match_mutual_nn_sets");
+  if (rc) return rc;
+  if (q->n > 0 && !q2t) return c->fail(SPFE_ERR_INVALID, "spfe_match_mutual_nn_sets: q2t is NULL");
+  std::lock_guard<std::mutex> lock(c->match_mu);
+  CU_OK(c, cudaSetDevice(c->cfg.device_id));
+  return match_sets_locked(c, q, t, q2t, dist);
+}
+
+int spfe_match_knn2_sets(spfe_ctx *c, const spfe_desc_set *q, const spfe_desc_set *t, int32_t *idx, float *dist) {
+  if (!c) return SPFE_ERR_INVALID;
+  int rc = check_set(c, q, "spfe_match_knn2_sets");
+  if (!rc) rc = check_set(c, t, "spfe_match_knn2_sets");
+  if (rc) return rc;
+  if (q->n > 0 && (!idx || !dist)) return c->fail(SPFE_ERR_INVALID, "spfe_match_knn2_sets: NULL output");
+  std::lock_guard<std::mutex> lock(c->match_mu);
+  CU_OK(c, cudaSetDevice(c->cfg.device_id));
+  return knn2_sets_locked(c, q, t, idx, dist);
+}
+
 int spfe_match_mutual_nn(spfe_ctx *c, const float *q, int32_t nq, const float *t, int32_t nt, int32_t *q2t, float *dist) {
   if (!c) return SPFE_ERR_INVALID;
   if (nq < 0 || nt < 0 || (nq > 0 && !q) || (nt > 0 && !t) || (nq > 0 && !q2t)) return c->fail(SPFE_ERR_INVALID, "spfe_match_mutual_nn: bad arguments");
@@ -1259,27 +1533,10 @@ int spfe_match_mutual_nn(spfe_ctx *c, const float *q, int32_t nq, const float *t
   }
   std::lock_guard<std::mutex> lock(c->match_mu);
   CU_OK(c, cudaSetDevice(c->cfg.device_id));
-  cudaStream_t st = c->match_stream;
-  MatchScratch &m = c->match;
-  memcpy(c->h_match_q, q, (size_t)nq * 256 * sizeof(float));
-  memcpy(c->h_match_t, t, (size_t)nt * 256 * sizeof(float));
-  c->h_match_idx[c->match_cap] = nq;
-  c->h_match_idx[c->match_cap + 1] = nt;
-  CU_OK(c, cudaMemcpyAsync(m.dq, c->h_match_q, (size_t)nq * 256 * sizeof(float), cudaMemcpyHostToDevice, st));
-  CU_OK(c, cudaMemcpyAsync(m.dt, c->h_match_t, (size_t)nt * 256 * sizeof(float), cudaMemcpyHostToDevice, st));
-  CU_OK(c, cudaMemcpyAsync(m.dn, c->h_match_idx + c->match_cap, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
-  MatchArgs a;
-  memset(&a, 0, sizeof a);
-  a.q = m.dq; a.nq = m.dn; a.t0 = m.dt; a.nt0 = m.dn + 1;
-  a.rowbest = m.rowbest; a.colbest = m.colbest; a.q2t = m.q2t; a.dist = m.dist; a.cap = c->match_cap;
-  int rc = run_match(c, st, a, 1, nq > nt ? nq : nt);
-  if (rc) return rc;
-  CU_OK(c, cudaMemcpyAsync(c->h_match_idx, m.q2t, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
-  CU_OK(c, cudaMemcpyAsync(c->h_match_dist, m.dist, nq * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CU_OK(c, cudaStreamSynchronize(st));
-  memcpy(q2t, c->h_match_idx, nq * sizeof(int));
-  if (dist) memcpy(dist, c->h_match_dist, nq * sizeof(float));
-  return SPFE_OK;
+  int rc;
+  if ((rc = set_upload_locked(c, c->tmp_q, q, nq))) return rc;
+  if ((rc = set_upload_locked(c, c->tmp_t, t, nt))) return rc;
+  return match_sets_locked(c, c->tmp_q, c->tmp_t, q2t, dist);
 }
 
 int spfe_match_knn2(spfe_ctx *c, const float *q, int32_t nq, const float *t, int32_t nt, int32_t *idx, float *dist) {
@@ -1293,39 +1550,10 @@ int spfe_match_knn2(spfe_ctx *c, const float *q, int32_t nq, const float *t, int
   }
   std::lock_guard<std::mutex> lock(c->match_mu);
   CU_OK(c, cudaSetDevice(c->cfg.device_id));
-  cudaStream_t st = c->match_stream;
-  MatchScratch &m = c->match;
-  memcpy(c->h_match_q, q, (size_t)nq * 256 * sizeof(float));
-  memcpy(c->h_match_t, t, (size_t)nt * 256 * sizeof(float));
-  c->h_match_idx[c->match_cap] = nq;
-  c->h_match_idx[c->match_cap + 1] = nt;
-  CU_OK(c, cudaMemcpyAsync(m.dq, c->h_match_q, (size_t)nq * 256 * sizeof(float), cudaMemcpyHostToDevice, st));
-  CU_OK(c, cudaMemcpyAsync(m.dt, c->h_match_t, (size_t)nt * 256 * sizeof(float), cudaMemcpyHostToDevice, st));
-  CU_OK(c, cudaMemcpyAsync(m.dn, c->h_match_idx + c->match_cap, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
-  MatchArgs a;
-  memset(&a, 0, sizeof a);
-  a.q = m.dq; a.nq = m.dn; a.t0 = m.dt; a.nt0 = m.dn + 1;
-  a.rowbest = m.rowbest; a.colbest = m.colbest; a.q2t = m.q2t; a.dist = m.dist; a.cap = c->match_cap;
-  const int rows = nq > nt ? nq : nt;
-  dim3 grid((rows + 63) / 64, (rows + 63) / 64, 1);
-  match_init_kernel<<<(a.cap + 255) / 256, 256, 0, st>>>(a.rowbest, a.colbest, a.cap);
-  match_dist_kernel<<<grid, 256, 0, st>>>(a);                        // pass 1: nearest row of every query (and of every train row)
-  match_init_kernel<<<(a.cap + 255) / 256, 256, 0, st>>>(m.colbest, m.colbest, a.cap);
-  MatchArgs b = a;
-  b.excl = m.rowbest;
-  b.rowbest = m.colbest;                                             // pass 2: nearest among the others -> second best
-  match_dist_kernel<<<grid, 256, 0, st>>>(b);
-  // q2t / dist scratch hold >= 2 * cap entries only if cap >= 2 * nq: use the staging descriptors' space instead
-  int *d_idx = reinterpret_cast<int *>(m.dq);
-  float *d_dist = reinterpret_cast<float *>(m.dq) + 2 * (size_t)nq;
-  knn2_final_kernel<<<(nq + 255) / 256, 256, 0, st>>>(m.rowbest, m.colbest, nq, d_idx, d_dist);
-  c->launches += 5;
-  CU_OK(c, cudaGetLastError());
-  CU_OK(c, cudaMemcpyAsync(c->h_match_q, d_idx, (size_t)nq * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-  CU_OK(c, cudaStreamSynchronize(st));
-  memcpy(idx, c->h_match_q, (size_t)nq * 2 * sizeof(int));
-  memcpy(dist, reinterpret_cast<float *>(c->h_match_q) + 2 * (size_t)nq, (size_t)nq * 2 * sizeof(float));
-  return SPFE_OK;
+  int rc;
+  if ((rc = set_upload_locked(c, c->tmp_q, q, nq))) return rc;
+  if ((rc = set_upload_locked(c, c->tmp_t, t, nt))) return rc;
+  return knn2_sets_locked(c, c->tmp_q, c->tmp_t, idx, dist);
 }
 
 int spfe_search_guided(spfe_ctx *c, const spfe_guided_search *g, int32_t *q2kp, float *qdist, uint8_t *kp_taken_out) {

@@ -241,6 +241,22 @@ class SPExtractor:
                                               idx.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p)))
         return idx[:len(q)], dist[:len(q)]
 
+    # -- device-resident descriptor sets (spfe_desc_set_*)
+    def desc_set(self, capacity: int) -> "DescSet":
+        return DescSet(self, capacity)
+
+    def match_sets(self, q: "DescSet", t: "DescSet"):
+        n = q.size()
+        q2t, dist = np.empty(max(n, 1), np.int32), np.empty(max(n, 1), np.float32)
+        self._check(self._lib.spfe_match_mutual_nn_sets(self._ctx, q._h, t._h, q2t.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p)))
+        return q2t[:n], dist[:n]
+
+    def knn2_sets(self, q: "DescSet", t: "DescSet"):
+        n = q.size()
+        idx, dist = np.empty((max(n, 1), 2), np.int32), np.empty((max(n, 1), 2), np.float32)
+        self._check(self._lib.spfe_match_knn2_sets(self._ctx, q._h, t._h, idx.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p)))
+        return idx[:n], dist[:n]
+
     def search_guided(self, qdesc, qxy, qradius, occ, kp_un, kdesc, *, mode: int, best_init: float, th_le: float, th_lt: float,
                       c2_adaptive: float = 0.0, qvalid=None, qblocks=None, kp_taken=None, min_x: float = 0.0, min_y: float = 0.0):
         """spfe_search_guided on plain arrays -> (q2kp int32[m], qdist f32[m], kp_taken_after u8[n])."""
@@ -369,6 +385,35 @@ class SPExtractor:
         st = (capi.StageTime * 32)()
         n = self._check(self._lib.spfe_profile_device(self._ctx, slot, C.c_void_p(d_ptr), batch, st, 32))
         return [dict(name=st[i].name.decode(), ms=st[i].ms, flop=st[i].flop, bytes=st[i].bytes) for i in range(n)]
+
+
+class DescSet:
+    """Device-resident descriptor rows (``spfe_desc_set``): upload once, match many times."""
+
+    def __init__(self, ex: SPExtractor, capacity: int):
+        self._ex, self._h = ex, C.c_void_p()
+        ex._check(ex._lib.spfe_desc_set_create(ex._ctx, capacity, C.byref(self._h)))
+
+    def upload(self, rows: np.ndarray) -> "DescSet":
+        rows = np.ascontiguousarray(rows, np.float32).reshape(-1, 256)
+        self._ex._check(self._ex._lib.spfe_desc_set_upload(self._ex._ctx, self._h, rows.ctypes.data_as(C.c_void_p), len(rows)))
+        return self
+
+    def from_frame(self, slot: int, frame: int, rows=None) -> "DescSet":
+        if rows is None:
+            self._ex._check(self._ex._lib.spfe_desc_set_from_frame(self._ex._ctx, self._h, slot, frame, None, 0))
+        else:
+            rows = np.ascontiguousarray(rows, np.int32)
+            self._ex._check(self._ex._lib.spfe_desc_set_from_frame(self._ex._ctx, self._h, slot, frame, rows.ctypes.data_as(C.c_void_p), len(rows)))
+        return self
+
+    def size(self) -> int:
+        return int(self._ex._lib.spfe_desc_set_size(self._h))
+
+    def close(self):
+        if self._h and self._ex._ctx.value:
+            self._ex._lib.spfe_desc_set_destroy(self._ex._ctx, self._h)
+        self._h = C.c_void_p()
 
 
 class SPMatcher:
