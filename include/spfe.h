@@ -229,6 +229,12 @@ typedef struct spfe_guided_search {
   float best_init, th_le, th_lt, c2_adaptive;
 } spfe_guided_search;
 int spfe_search_guided(spfe_ctx *ctx, const spfe_guided_search *g, int32_t *q2kp, float *qdist, uint8_t *kp_taken_out);
+/* The same search with the descriptors already on the device: qset replaces g->qdesc (m rows: the local map's
+ * getDescTrack() rows, uploaded when the local map changes), kset replaces g->kdesc (n rows: the current frame's
+ * descriptors, spfe_desc_set_from_frame).  Either may be NULL (then the host pointer of g is used).  Only the small
+ * per-call arrays (projections, radii, flags, occ_grid: ~20 KB) cross PCIe, in one block each way. */
+int spfe_search_guided_sets(spfe_ctx *ctx, const spfe_guided_search *g, const spfe_desc_set *qset, const spfe_desc_set *kset,
+                            int32_t *q2kp, float *qdist, uint8_t *kp_taken_out);
 
 /* Dust-map pose optimisation -- the inner loop of
  *   Optimizer::PoseOptimizationDust(Frame*, const vector<MapPoint*>&, vector<bool>&)   orb_slam2/src/mapping/optimizer_dust.cpp:170-293

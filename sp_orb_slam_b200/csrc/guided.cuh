@@ -9,13 +9,15 @@
 // that already carry an observed map point, take the nearest descriptor (first one on ties), accept it under a
 // distance rule, and make it unavailable to the map points that follow.
 //
-//   guided_cand_kernel     one warp per map point: candidate keypoints in the reference's order (ix outer, iy inner,
-//                          ordered ballot compaction) and their 256-d L2 distances (lanes own 8 dimensions each).
-//   guided_resolve_kernel  the order-dependent part, exact: the greedy loop is the fixpoint of "a map point decides once
-//                          it is the lowest-indexed undecided map point on every still-available candidate of its"
-//                          (claims by atomicMin with a per-round tag, as in cov.cuh); map points deciding in the same
-//                          round have disjoint available candidates.  One CTA; chains deeper than GUIDED_ROUNDS are
-//                          finished sequentially by one thread.
+// ONE launch (guided_kernel), two phases:
+//   candidates   one warp per map point: candidate keypoints in the reference's order (ix outer, iy inner, ordered
+//                ballot compaction) and their 256-d L2 distances (lanes own 8 dimensions each).
+//   resolve      the order-dependent part, exact, run by the LAST CTA to finish the first phase (atomic ticket): the
+//                greedy loop is the fixpoint of "a map point decides once it is the lowest-indexed undecided map point
+//                on every still-available candidate of its" (claims by atomicMin with a per-round tag, as in cov.cuh);
+//                map points deciding in the same round have disjoint available candidates.  Chains deeper than
+//                GUIDED_ROUNDS are finished sequentially by one thread.  The results are then written straight into
+//                the caller's page-locked result block (mapped host memory): no device -> host copy is enqueued.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -31,7 +33,8 @@ struct GuidedArgs {
   const uint8_t *qvalid, *qblocks;  // may be null
   const float *kdesc, *kp_un;
   const int16_t *occ;
-  uint8_t *taken;   // [n] in / out
+  const uint8_t *taken_in;  // [n] keypoints that already carry an observed map point
+  uint8_t *taken;   // [n] out: taken_in plus the keypoints claimed by this search (initialised by guided_cand_kernel)
   int *kpmin;       // [n] scratch, 0x7F7F7F7F
   int *cand;        // [m][GUIDED_CAND]
   float *cdist;     // [m][GUIDED_CAND]
@@ -40,12 +43,15 @@ struct GuidedArgs {
   int *q2kp;        // [m]
   float *qdist;     // [m]
   int *overflow;    // [1] a map point had more than GUIDED_CAND candidates
+  int *ticket;      // [1] CTAs that finished the candidate phase (0 at launch)
+  int *h_q2kp;      // mapped host memory: results of the call (the last CTA copies them out)
+  float *h_qdist;
+  uint8_t *h_taken;
+  int *h_overflow;
   float min_x, min_y, best_init, th_le, th_lt, c2;
 };
 
-__global__ void __launch_bounds__(256) guided_cand_kernel(const GuidedArgs a) {
-  const int lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (i >= a.m) return;
+__device__ __forceinline__ void guided_candidates(const GuidedArgs &a, int i, int lane) {
   if (lane == 0) {
     a.q2kp[i] = -1;
     a.qdist[i] = 0.0f;
@@ -145,7 +151,7 @@ __device__ __forceinline__ void guided_decide(const GuidedArgs &a, int i, volati
   if (a.qblocks == nullptr || a.qblocks[i]) taken[bi] = 1;
 }
 
-__global__ void __launch_bounds__(1024) guided_resolve_kernel(const GuidedArgs a) {
+__device__ __forceinline__ void guided_resolve(const GuidedArgs &a) {
   const int tid = threadIdx.x, nt = blockDim.x;
   volatile uint8_t *taken = a.taken;
   volatile int *kpmin = a.kpmin;
@@ -179,6 +185,30 @@ __global__ void __launch_bounds__(1024) guided_resolve_kernel(const GuidedArgs a
   if (left && tid == 0)  // conflict chains deeper than GUIDED_ROUNDS: the plain sequential loop for the rest
     for (int i = 0; i < a.m; i++)
       if (!decided[i]) guided_decide(a, i, taken);
+}
+
+constexpr int GUIDED_THREADS = 1024;  // 32 map points per CTA in the candidate phase; the resolve phase uses all of them
+
+__global__ void __launch_bounds__(GUIDED_THREADS) guided_kernel(const GuidedArgs a) {
+  __shared__ int s_last;
+  for (int k = blockIdx.x * GUIDED_THREADS + threadIdx.x; k < a.n; k += gridDim.x * GUIDED_THREADS) a.taken[k] = a.taken_in[k];
+  const int lane = threadIdx.x & 31, i = blockIdx.x * (GUIDED_THREADS / 32) + (threadIdx.x >> 5);
+  if (i < a.m) guided_candidates(a, i, lane);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(a.ticket, 1) == static_cast<int>(gridDim.x) - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();  // every other CTA's candidates / taken copy are visible now
+  guided_resolve(a);
+  __syncthreads();
+  for (int k = threadIdx.x; k < a.m; k += GUIDED_THREADS) {
+    a.h_q2kp[k] = a.q2kp[k];
+    a.h_qdist[k] = a.qdist[k];
+  }
+  for (int k = threadIdx.x; k < a.n; k += GUIDED_THREADS) a.h_taken[k] = a.taken[k];
+  if (threadIdx.x == 0) *a.h_overflow = *a.overflow;
+  __threadfence_system();
 }
 
 }  // namespace spfe

@@ -209,6 +209,8 @@ struct spfe_ctx {
   // spfe_search_guided scratch (device, grown on demand; guarded by match_mu)
   void *guided_buf = nullptr;
   size_t guided_bytes = 0;
+  void *guided_stage = nullptr;  // page-locked staging of the per-call arrays and results of spfe_search_guided*
+  size_t guided_stage_bytes = 0;
   // spfe_dust_pose_* page-locked staging block (grown on demand; guarded by match_mu)
   void *dust_stage = nullptr;
   size_t dust_stage_bytes = 0;
@@ -1032,6 +1034,7 @@ void spfe_destroy(spfe_ctx *c) {
   if (c->match_stream) cudaStreamDestroy(c->match_stream);
   if (c->guided_buf) cudaFree(c->guided_buf);
   if (c->dust_stage) cudaFreeHost(c->dust_stage);
+  if (c->guided_stage) cudaFreeHost(c->guided_stage);
   for (cudaStream_t st : {c->compute, c->copy_in, c->copy_out, c->aux, c->copy_late}) if (st) cudaStreamDestroy(st);
   for (void *p : c->dev_allocs) cudaFree(p);
   for (void *p : c->host_allocs) cudaFreeHost(p);
@@ -1556,16 +1559,22 @@ int spfe_match_knn2(spfe_ctx *c, const float *q, int32_t nq, const float *t, int
   return knn2_sets_locked(c, c->tmp_q, c->tmp_t, idx, dist);
 }
 
-int spfe_search_guided(spfe_ctx *c, const spfe_guided_search *g, int32_t *q2kp, float *qdist, uint8_t *kp_taken_out) {
-  if (!c) return SPFE_ERR_INVALID;
-  if (!g || g->struct_size != (int32_t)sizeof(spfe_guided_search)) return c->fail(SPFE_ERR_INVALID, "spfe_search_guided: bad struct pointer / struct_size");
+}  // extern "C"
+namespace {
+// Guided search on descriptors that are on the device already (sets) or still on the host (uploaded here).  All the
+// small per-call arrays travel in ONE page-locked block (one H2D), the results come back in one D2H.
+int guided_run(spfe_ctx *c, const spfe_guided_search *g, const spfe_desc_set *qset, const spfe_desc_set *kset, int32_t *q2kp,
+               float *qdist, uint8_t *kp_taken_out, const char *fn) {
+  if (!g || g->struct_size != (int32_t)sizeof(spfe_guided_search)) return c->fail(SPFE_ERR_INVALID, fmt("%s: bad struct pointer / struct_size", fn));
   const int m = g->m, n = g->n, cells = g->grid_rows * g->grid_cols;
   if (m < 0 || n < 0 || m >= (1 << 20) || g->grid_rows <= 0 || g->grid_cols <= 0 || (g->mode != SPFE_GUIDED_AREA && g->mode != SPFE_GUIDED_DUST_CELLS))
-    return c->fail(SPFE_ERR_INVALID, "spfe_search_guided: bad m / n / grid / mode");
-  if (m > 0 && (!g->qdesc || !g->qxy || !q2kp || !qdist || !g->occ_grid || (g->mode == SPFE_GUIDED_AREA && !g->qradius)))
-    return c->fail(SPFE_ERR_INVALID, "spfe_search_guided: NULL query / output / occ_grid pointer");
-  if (n > 0 && (!g->kdesc || (!g->kp_un && (g->mode == SPFE_GUIDED_AREA || g->c2_adaptive > 0.0f))))
-    return c->fail(SPFE_ERR_INVALID, "spfe_search_guided: NULL keypoint pointer");
+    return c->fail(SPFE_ERR_INVALID, fmt("%s: bad m / n / grid / mode", fn));
+  if (qset && qset->n != m) return c->fail(SPFE_ERR_INVALID, fmt("%s: the query set holds %d rows, m = %d", fn, qset->n, m));
+  if (kset && kset->n != n) return c->fail(SPFE_ERR_INVALID, fmt("%s: the key-point set holds %d rows, n = %d", fn, kset->n, n));
+  if (m > 0 && ((!qset && !g->qdesc) || !g->qxy || !q2kp || !qdist || !g->occ_grid || (g->mode == SPFE_GUIDED_AREA && !g->qradius)))
+    return c->fail(SPFE_ERR_INVALID, fmt("%s: NULL query / output / occ_grid pointer", fn));
+  if (n > 0 && ((!kset && !g->kdesc) || (!g->kp_un && (g->mode == SPFE_GUIDED_AREA || g->c2_adaptive > 0.0f))))
+    return c->fail(SPFE_ERR_INVALID, fmt("%s: NULL keypoint pointer", fn));
   if (m == 0) {
     if (kp_taken_out && n > 0) { if (g->kp_taken) memcpy(kp_taken_out, g->kp_taken, n); else memset(kp_taken_out, 0, n); }
     return SPFE_OK;
@@ -1573,15 +1582,20 @@ int spfe_search_guided(spfe_ctx *c, const spfe_guided_search *g, int32_t *q2kp, 
   std::lock_guard<std::mutex> lock(c->match_mu);
   CU_OK(c, cudaSetDevice(c->cfg.device_id));
   cudaStream_t st = c->match_stream;
-  // one device block, carved into 256-byte aligned pieces
+  // one device block, carved into 256-byte aligned pieces: [staged inputs][results][descriptor uploads + scratch]
   size_t off = 0;
   auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
   const size_t nn = n > 0 ? n : 1;
-  const size_t o_qdesc = carve((size_t)m * 1024), o_qxy = carve((size_t)m * 8), o_qr = carve((size_t)m * 4), o_qvalid = carve(m),
-               o_qblocks = carve(m), o_kdesc = carve(nn * 1024), o_kpun = carve(nn * 8), o_occ = carve((size_t)cells * 2),
-               o_taken = carve(nn), o_kpmin = carve(nn * 4), o_cand = carve((size_t)m * GUIDED_CAND * 4),
-               o_cdist = carve((size_t)m * GUIDED_CAND * 4), o_ncand = carve((size_t)m * 4), o_dec = carve(m),
-               o_q2kp = carve((size_t)m * 4), o_qdist = carve((size_t)m * 4), o_over = carve(4);
+  const size_t o_qxy = carve((size_t)m * 8), o_qr = carve((size_t)m * 4), o_qvalid = carve(m), o_qblocks = carve(m),
+               o_kpun = carve(nn * 8), o_occ = carve((size_t)cells * 2), o_taken_in = carve(nn), o_kpmin = carve(nn * 4),
+               o_ctl = carve(8);  // [overflow flag, ticket of the candidate phase], both 0 at launch
+  const size_t in_bytes = off;
+  // results: device copies the kernel works on, mirrored at the same offsets of the page-locked block, where the
+  // kernel's last CTA writes them directly (mapped host memory)
+  const size_t o_q2kp = carve((size_t)m * 4), o_qdist = carve((size_t)m * 4), o_taken = carve(nn), o_over = carve(4);
+  const size_t out_end = off;
+  const size_t o_qdesc = carve(qset ? 0 : (size_t)m * 1024), o_kdesc = carve(kset ? 0 : nn * 1024),
+               o_cand = carve((size_t)m * GUIDED_CAND * 4), o_cdist = carve((size_t)m * GUIDED_CAND * 4), o_ncand = carve((size_t)m * 4), o_dec = carve(m);
   if (off > c->guided_bytes) {
     if (c->guided_buf) cudaFree(c->guided_buf);
     c->guided_buf = nullptr;
@@ -1589,44 +1603,66 @@ int spfe_search_guided(spfe_ctx *c, const spfe_guided_search *g, int32_t *q2kp, 
     CU_OK(c, cudaMalloc(&c->guided_buf, off + off / 2));
     c->guided_bytes = off + off / 2;
   }
-  uint8_t *base = static_cast<uint8_t *>(c->guided_buf);
-  auto up = [&](size_t o, const void *src, size_t bytes) { return src ? cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess; };
-  CU_OK(c, up(o_qdesc, g->qdesc, (size_t)m * 1024));
-  CU_OK(c, up(o_qxy, g->qxy, (size_t)m * 8));
-  CU_OK(c, up(o_qr, g->qradius, (size_t)m * 4));
-  CU_OK(c, up(o_qvalid, g->qvalid, m));
-  CU_OK(c, up(o_qblocks, g->qblocks, m));
-  CU_OK(c, up(o_kdesc, g->kdesc, (size_t)n * 1024));
-  CU_OK(c, up(o_kpun, g->kp_un, (size_t)n * 8));
-  CU_OK(c, up(o_occ, g->occ_grid, (size_t)cells * 2));
-  if (g->kp_taken) CU_OK(c, up(o_taken, g->kp_taken, n));
-  else CU_OK(c, cudaMemsetAsync(base + o_taken, 0, nn, st));
-  CU_OK(c, cudaMemsetAsync(base + o_kpmin, 0x7F, nn * 4, st));
-  CU_OK(c, cudaMemsetAsync(base + o_over, 0, 4, st));
+  if (out_end > c->guided_stage_bytes) {
+    if (c->guided_stage) cudaFreeHost(c->guided_stage);
+    c->guided_stage = nullptr;
+    c->guided_stage_bytes = 0;
+    CU_OK(c, cudaMallocHost(&c->guided_stage, out_end + out_end / 2));
+    c->guided_stage_bytes = out_end + out_end / 2;
+  }
+  uint8_t *base = static_cast<uint8_t *>(c->guided_buf), *hb = static_cast<uint8_t *>(c->guided_stage);
+  memcpy(hb + o_qxy, g->qxy, (size_t)m * 8);
+  if (g->qradius) memcpy(hb + o_qr, g->qradius, (size_t)m * 4);
+  if (g->qvalid) memcpy(hb + o_qvalid, g->qvalid, m);
+  if (g->qblocks) memcpy(hb + o_qblocks, g->qblocks, m);
+  if (g->kp_un && n > 0) memcpy(hb + o_kpun, g->kp_un, (size_t)n * 8);
+  memcpy(hb + o_occ, g->occ_grid, (size_t)cells * 2);
+  if (g->kp_taken && n > 0) memcpy(hb + o_taken_in, g->kp_taken, n); else memset(hb + o_taken_in, 0, nn);
+  memset(hb + o_kpmin, 0x7F, nn * 4);
+  memset(hb + o_ctl, 0, 8);
+  CU_OK(c, cudaMemcpyAsync(base, hb, in_bytes, cudaMemcpyHostToDevice, st));
+  if (!qset) CU_OK(c, cudaMemcpyAsync(base + o_qdesc, g->qdesc, (size_t)m * 1024, cudaMemcpyHostToDevice, st));
+  if (!kset && n > 0) CU_OK(c, cudaMemcpyAsync(base + o_kdesc, g->kdesc, (size_t)n * 1024, cudaMemcpyHostToDevice, st));
   GuidedArgs a;
   a.mode = g->mode; a.m = m; a.n = n; a.grid_rows = g->grid_rows; a.grid_cols = g->grid_cols;
-  a.qdesc = reinterpret_cast<float *>(base + o_qdesc); a.qxy = reinterpret_cast<float *>(base + o_qxy);
+  a.qdesc = qset ? qset->d32 : reinterpret_cast<float *>(base + o_qdesc); a.qxy = reinterpret_cast<float *>(base + o_qxy);
   a.qr = reinterpret_cast<float *>(base + o_qr);
   a.qvalid = g->qvalid ? base + o_qvalid : nullptr; a.qblocks = g->qblocks ? base + o_qblocks : nullptr;
-  a.kdesc = reinterpret_cast<float *>(base + o_kdesc); a.kp_un = reinterpret_cast<float *>(base + o_kpun);
-  a.occ = reinterpret_cast<int16_t *>(base + o_occ); a.taken = base + o_taken; a.kpmin = reinterpret_cast<int *>(base + o_kpmin);
+  a.kdesc = kset ? kset->d32 : reinterpret_cast<float *>(base + o_kdesc); a.kp_un = reinterpret_cast<float *>(base + o_kpun);
+  a.occ = reinterpret_cast<int16_t *>(base + o_occ); a.taken_in = base + o_taken_in; a.taken = base + o_taken;
+  a.kpmin = reinterpret_cast<int *>(base + o_kpmin);
   a.cand = reinterpret_cast<int *>(base + o_cand); a.cdist = reinterpret_cast<float *>(base + o_cdist);
   a.ncand = reinterpret_cast<int *>(base + o_ncand); a.decided = base + o_dec;
   a.q2kp = reinterpret_cast<int *>(base + o_q2kp); a.qdist = reinterpret_cast<float *>(base + o_qdist);
-  a.overflow = reinterpret_cast<int *>(base + o_over);
+  a.overflow = reinterpret_cast<int *>(base + o_ctl); a.ticket = reinterpret_cast<int *>(base + o_ctl) + 1;
+  a.h_q2kp = reinterpret_cast<int *>(hb + o_q2kp); a.h_qdist = reinterpret_cast<float *>(hb + o_qdist);
+  a.h_taken = hb + o_taken; a.h_overflow = reinterpret_cast<int *>(hb + o_over);
   a.min_x = g->min_x; a.min_y = g->min_y; a.best_init = g->best_init; a.th_le = g->th_le; a.th_lt = g->th_lt; a.c2 = g->c2_adaptive;
-  guided_cand_kernel<<<(m + 7) / 8, 256, 0, st>>>(a);
-  guided_resolve_kernel<<<1, 1024, 0, st>>>(a);
-  c->launches += 2;
+  guided_kernel<<<(m + GUIDED_THREADS / 32 - 1) / (GUIDED_THREADS / 32), GUIDED_THREADS, 0, st>>>(a);
+  c->launches += 1;
   CU_OK(c, cudaGetLastError());
+  CU_OK(c, cudaStreamSynchronize(st));  // the kernel's last CTA wrote the results into the page-locked block
+  memcpy(q2kp, hb + o_q2kp, (size_t)m * 4);
+  memcpy(qdist, hb + o_qdist, (size_t)m * 4);
+  if (kp_taken_out && n > 0) memcpy(kp_taken_out, hb + o_taken, n);
   int over = 0;
-  CU_OK(c, cudaMemcpyAsync(q2kp, base + o_q2kp, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-  CU_OK(c, cudaMemcpyAsync(qdist, base + o_qdist, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-  if (kp_taken_out && n > 0) CU_OK(c, cudaMemcpyAsync(kp_taken_out, base + o_taken, n, cudaMemcpyDeviceToHost, st));
-  CU_OK(c, cudaMemcpyAsync(&over, base + o_over, 4, cudaMemcpyDeviceToHost, st));
-  CU_OK(c, cudaStreamSynchronize(st));
-  if (over) return c->fail(SPFE_ERR_INVALID, fmt("spfe_search_guided: a query has more than %d candidate keypoints (radius too large)", GUIDED_CAND));
+  memcpy(&over, hb + o_over, 4);
+  if (over) return c->fail(SPFE_ERR_INVALID, fmt("%s: a query has more than %d candidate keypoints (radius too large)", fn, GUIDED_CAND));
   return SPFE_OK;
+}
+}  // namespace
+extern "C" {
+
+int spfe_search_guided(spfe_ctx *c, const spfe_guided_search *g, int32_t *q2kp, float *qdist, uint8_t *kp_taken_out) {
+  if (!c) return SPFE_ERR_INVALID;
+  return guided_run(c, g, nullptr, nullptr, q2kp, qdist, kp_taken_out, "spfe_search_guided");
+}
+
+int spfe_search_guided_sets(spfe_ctx *c, const spfe_guided_search *g, const spfe_desc_set *qset, const spfe_desc_set *kset,
+                            int32_t *q2kp, float *qdist, uint8_t *kp_taken_out) {
+  if (!c) return SPFE_ERR_INVALID;
+  if ((qset && qset->ctx != c) || (kset && kset->ctx != c)) return c->fail(SPFE_ERR_INVALID, "spfe_search_guided_sets: a descriptor set belongs to another context");
+  return guided_run(c, g, qset, kset, q2kp, qdist, kp_taken_out, "spfe_search_guided_sets");
 }
 
 // spfe_dust_pose_optimize[_batch] (mode 1) / spfe_dust_linearize (mode 0): `count` problems = one launch of

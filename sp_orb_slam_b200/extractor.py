@@ -259,11 +259,14 @@ class SPExtractor:
 
     def search_guided(self, qdesc, qxy, qradius, occ, kp_un, kdesc, *, mode: int, best_init: float, th_le: float, th_lt: float,
                       c2_adaptive: float = 0.0, qvalid=None, qblocks=None, kp_taken=None, min_x: float = 0.0, min_y: float = 0.0):
-        """spfe_search_guided on plain arrays -> (q2kp int32[m], qdist f32[m], kp_taken_after u8[n])."""
-        qdesc = np.ascontiguousarray(qdesc, np.float32).reshape(-1, 256)
-        m = len(qdesc)
-        kdesc = np.ascontiguousarray(kdesc, np.float32).reshape(-1, 256)
-        n = len(kdesc)
+        """spfe_search_guided on plain arrays -> (q2kp int32[m], qdist f32[m], kp_taken_after u8[n]).  ``qdesc`` / ``kdesc``
+        may be ``DescSet`` objects (spfe_search_guided_sets: the descriptors are on the device already)."""
+        qset = qdesc if isinstance(qdesc, DescSet) else None
+        kset = kdesc if isinstance(kdesc, DescSet) else None
+        qdesc = None if qset else np.ascontiguousarray(qdesc, np.float32).reshape(-1, 256)
+        m = qset.size() if qset else len(qdesc)
+        kdesc = None if kset else np.ascontiguousarray(kdesc, np.float32).reshape(-1, 256)
+        n = kset.size() if kset else len(kdesc)
         qxy = np.ascontiguousarray(qxy, np.float32).reshape(m, 2)
         qr = np.ascontiguousarray(np.broadcast_to(np.asarray(qradius, np.float32), (m,)))
         occ = np.ascontiguousarray(occ, np.int16)
@@ -280,8 +283,13 @@ class SPExtractor:
         q2kp = np.empty(max(m, 1), np.int32)
         qdist = np.empty(max(m, 1), np.float32)
         taken = np.zeros(max(n, 1), np.uint8)
-        self._check(self._lib.spfe_search_guided(self._ctx, C.byref(g), q2kp.ctypes.data_as(C.c_void_p),
-                                                 qdist.ctypes.data_as(C.c_void_p), taken.ctypes.data_as(C.c_void_p)))
+        if qset or kset:
+            self._check(self._lib.spfe_search_guided_sets(self._ctx, C.byref(g), qset._h if qset else None, kset._h if kset else None,
+                                                          q2kp.ctypes.data_as(C.c_void_p), qdist.ctypes.data_as(C.c_void_p),
+                                                          taken.ctypes.data_as(C.c_void_p)))
+        else:
+            self._check(self._lib.spfe_search_guided(self._ctx, C.byref(g), q2kp.ctypes.data_as(C.c_void_p),
+                                                     qdist.ctypes.data_as(C.c_void_p), taken.ctypes.data_as(C.c_void_p)))
         return q2kp[:m], qdist[:m], taken[:n]
 
     def _dust_struct(self, Xw, dust, fx, fy, cx, cy, huber, chi2_inlier, iterations, slot, frame):

@@ -7,7 +7,7 @@ import pytest
 
 from conftest import WEIGHTS
 from oracle import sp_oracle as O
-from sp_orb_slam_b200 import SPExtractor, SPMatcher, capi, synth
+from sp_orb_slam_b200 import SpfeError, SPExtractor, SPMatcher, capi, synth
 
 
 def random_frame(rng, hc=30, wc=40, fill=0.45):
@@ -303,6 +303,33 @@ def test_search_by_projection_matches_oracle(gpu_frame, seed, m, jitter):
                                        best_init=O.FLT_MAX, th_le=0.7, th_lt=-np.inf, qvalid=valid, qblocks=observed, kp_taken=frame["taken"])
     assert np.array_equal(taken, taken_ref)
     np.testing.assert_allclose(qd[ref >= 0], rd[ref >= 0], rtol=2e-6)
+
+
+@pytest.mark.gpu
+def test_guided_search_on_device_resident_sets(gpu_frame):
+    """spfe_search_guided_sets: the frame's descriptors gathered device -> device from the extractor's slot, the map
+    points' descriptors uploaded once -- identical assignments to the host-pointer entry and to the oracle."""
+    ex, fr = gpu_frame
+    rng = np.random.RandomState(5)
+    m = 900
+    qdesc, qxy, valid, observed = _scenario(rng, fr, m, 3.0)
+    taken = (rng.rand(fr["n"]) < 0.1).astype(np.uint8)
+    kset = ex.desc_set(1024).from_frame(0, 0)                  # gpu_frame extracted one frame on slot 0
+    qset = ex.desc_set(1024).upload(qdesc)
+    kw = dict(mode=capi.GUIDED_AREA, best_init=256.0, th_le=0.7, th_lt=0.7, qvalid=valid, qblocks=observed, kp_taken=taken)
+    a = ex.search_guided(qdesc, qxy, 4.0, fr["occ_grid"], fr["kp_xy"], fr["desc"], **kw)
+    b = ex.search_guided(qset, qxy, 4.0, fr["occ_grid"], fr["kp_xy"], kset, **kw)
+    c = ex.search_guided(qdesc, qxy, 4.0, fr["occ_grid"], fr["kp_xy"], kset, **kw)
+    ref = O.search_guided(qdesc, qxy, 4.0, fr["occ_grid"], fr["kp_xy"], fr["desc"], mode=0, best_init=256.0, th_le=0.7, th_lt=0.7,
+                          qvalid=valid, qblocks=observed, kp_taken=taken)
+    for got in (a, b, c):
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[2], ref[2])
+        np.testing.assert_allclose(got[1][ref[0] >= 0], ref[1][ref[0] >= 0], rtol=2e-6)
+    assert (ref[0] >= 0).sum() > 300
+    with pytest.raises((SpfeError, ValueError)):               # a set of the wrong size is an error, not a silent mismatch
+        ex.search_guided(qset, qxy[:10], 4.0, fr["occ_grid"], fr["kp_xy"], kset, **{**kw, "qvalid": valid[:10], "qblocks": observed[:10]})
+    kset.close()
+    qset.close()
 
 
 @pytest.mark.gpu

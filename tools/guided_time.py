@@ -26,10 +26,20 @@ for m, r in [(300, 4.0), (1000, 7.0), (4000, 15.0)]:
     for _ in range(20):
         ex.search_guided(qdesc, qxy, r, fr["occ_grid"], fr["kp_xy"], fr["desc"], **kw)
     t_gpu = (time.perf_counter() - t0) / 20
+    kset = ex.desc_set(1024).from_frame(0, 0)       # the frame's descriptors where the extractor left them
+    qset = ex.desc_set(4096).upload(qdesc)          # the local map's descriptors, uploaded once
+    for _ in range(3):
+        got_s = ex.search_guided(qset, qxy, r, fr["occ_grid"], fr["kp_xy"], kset, **kw)[0]
+    t0 = time.perf_counter()
+    for _ in range(50):
+        ex.search_guided(qset, qxy, r, fr["occ_grid"], fr["kp_xy"], kset, **kw)
+    t_set = (time.perf_counter() - t0) / 50
+    kset.close(); qset.close()
     t0 = time.perf_counter()
     for _ in range(5):
         ref = O.search_guided(qdesc, qxy, r, fr["occ_grid"], fr["kp_xy"], fr["desc"], mode=0, best_init=256.0, th_le=0.7, th_lt=0.7)[0]
     t_cpu = (time.perf_counter() - t0) / 5
-    print(f"m={m:5d} n={fr['n']} r={r:4.1f}: device call {t_gpu * 1e3:7.3f} ms (incl. H2D of {(m + fr['n']) * 1024 / 1e6:.1f} MB), "
-          f"CPU oracle loop {t_cpu * 1e3:7.3f} ms, identical {np.array_equal(got, ref)}, matches {(ref >= 0).sum()}", flush=True)
+    print(f"m={m:5d} n={fr['n']} r={r:4.1f}: host-pointer call {t_gpu * 1e3:7.3f} ms (incl. H2D of {(m + fr['n']) * 1024 / 1e6:.1f} MB), "
+          f"device-resident sets {t_set * 1e3:7.3f} ms, CPU oracle loop {t_cpu * 1e3:7.3f} ms, identical {np.array_equal(got, ref) and np.array_equal(got_s, ref)}, "
+          f"matches {(ref >= 0).sum()}", flush=True)
 ex.close()
