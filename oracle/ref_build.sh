@@ -50,3 +50,8 @@ echo "built $OUT/libspbf_ref.so"
 sed -n '7,95p' "$REF/orb_slam2/include/orb_slam/cv/base_extractor.h" > "$OUT/gen/base_extractor_decl.inc"
 g++ -O2 -std=c++17 -ffp-contract=off -w -I"$OUT/gen" -I"$HERE" "$HERE/ref_base_driver.cc" -o "$OUT/ref_base_probe"
 echo "built $OUT/ref_base_probe"
+# the reference's own SearchForTriByFlann + CheckDistEpipolarLine, verbatim (FLANN itself replaced by an exact k-NN stand-in)
+sed -n '183,262p' "$REF/orb_slam2/src/cv/sp_matcher.cpp" > "$OUT/gen/flann_tri.inc"
+sed -n '441,469p' "$REF/orb_slam2/src/cv/sp_matcher.cpp" > "$OUT/gen/epi_check.inc"
+g++ -O2 -std=c++17 -ffp-contract=off -fPIC -shared -w -I"$OUT/gen" -I"$HERE" "$HERE/ref_flann_driver.cc" -o "$OUT/libspflann_ref.so"
+echo "built $OUT/libspflann_ref.so"

@@ -167,6 +167,37 @@ class BFMatcher {
   Mat train_;
   bool cross_ = false;
 };
+// cv::FlannBasedMatcher stand-in for the verbatim compile of SPMatcher::SearchForTriByFlann: knnMatch returns the EXACT k
+// nearest train rows (first index on ties), i.e. what the KD-tree search returns whenever it finds the true neighbours.
+// What this pins is the reference's control flow after the search (ratio test, map-point / epipole / epipolar filters,
+// the order in which pairs are claimed); exact-vs-approximate is counted separately against cv2.FlannBasedMatcher.
+class FlannBasedMatcher {
+ public:
+  void add(const Mat &train) { train_ = train; }
+  void train() {}
+  void knnMatch(const Mat &query, std::vector<std::vector<DMatch>> &matches, int k) const {
+    matches.clear();
+    const int nq = query.empty_() ? 0 : query.rows, nt = train_.empty_() ? 0 : train_.rows;
+    for (int i = 0; i < nq; i++) {
+      std::vector<DMatch> row;
+      for (int r = 0; r < k && r < nt; r++) {
+        int best = -1;
+        float bd = 3.4e38f;
+        for (int j = 0; j < nt; j++) {
+          bool used = false;
+          for (const DMatch &m : row) used |= m.trainIdx == j;
+          if (used) continue;
+          const float d = (float)norm(query.row(i), train_.row(j), NORM_L2);
+          if (d < bd) { bd = d; best = j; }
+        }
+        row.push_back(DMatch{i, best, 0, bd});
+      }
+      matches.push_back(row);
+    }
+  }
+ private:
+  Mat train_;
+};
 }  // namespace cv
 #include <cmath>
 inline int cvRound(double v) { return (int)std::lrint(v); }  // OpenCV: round to nearest even (cvtsd2si / lrint)

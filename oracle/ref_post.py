@@ -204,3 +204,33 @@ def bruteforce_kf_kf(desc1, has_mp1, bad1, desc2, has_mp2, bad2):
     n = _bf().spref_bruteforce_kf_kf(vp(d1.ctypes.data), vp(h1.ctypes.data), vp(b1.ctypes.data), len(d1), vp(d2.ctypes.data), vp(h2.ctypes.data),
                                      vp(b2.ctypes.data), len(d2), vp(out.ctypes.data))
     return out[:len(d1)], n
+
+
+FLANN_LIB = os.path.join(_HERE, "_ref", "libspflann_ref.so")
+_flann_lib = None
+
+
+def flann_available() -> bool:
+    return os.path.exists(FLANN_LIB)
+
+
+def search_tri_flann(desc1, has_mp1, kp1, cov2inv1, desc2, has_mp2, kp2, cov2inv2, F12, Cw1, R2w, t2w, intr2):
+    """The reference's own SPMatcher::SearchForTriByFlann (sp_matcher.cpp:183-262, with CheckDistEpipolarLine :441-469)
+    compiled verbatim, cv::FlannBasedMatcher replaced by an exact k-NN stand-in.  -> (pairs int64 [k, 2] = (row of KF1, row
+    of KF2), nmatches)."""
+    global _flann_lib
+    if _flann_lib is None:
+        _flann_lib = C.CDLL(FLANN_LIB)
+    d1, d2 = _f32(desc1, (-1, 256)), _f32(desc2, (-1, 256))
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    h1, h2, k1, k2, c1, c2 = u8(has_mp1), u8(has_mp2), f32(kp1), f32(kp2), f32(cov2inv1), f32(cov2inv2)
+    F, cw, R, t, intr = f32(F12), f32(Cw1), f32(R2w), f32(t2w), f32(intr2)
+    pairs = np.zeros((max(len(d1), 1), 2), np.int64)
+    npairs = C.c_int(0)
+    vp = C.c_void_p
+    n = _flann_lib.spref_search_tri_flann(vp(d1.ctypes.data), vp(h1.ctypes.data), vp(k1.ctypes.data), vp(c1.ctypes.data), len(d1),
+                                          vp(d2.ctypes.data), vp(h2.ctypes.data), vp(k2.ctypes.data), vp(c2.ctypes.data), len(d2),
+                                          vp(F.ctypes.data), vp(cw.ctypes.data), vp(R.ctypes.data), vp(t.ctypes.data), vp(intr.ctypes.data),
+                                          vp(pairs.ctypes.data), C.byref(npairs))
+    return pairs[:npairs.value].copy(), n

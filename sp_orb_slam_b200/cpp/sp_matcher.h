@@ -6,6 +6,7 @@
 #pragma once
 #include <cstring>
 #include <stdexcept>
+#include <utility>
 #include <vector>
 
 #include "mini_cv.h"
@@ -71,6 +72,111 @@ class SPMatcher {
     for (size_t q = 0; q < q2t.size(); q++)
       if (q2t[q] >= 0) vpMatches12[rows1[q2t[q]]] = mps2[rows2[q]];
     return n;
+  }
+
+  // Exact 2-NN of every query row among the train rows + the reference's ratio test (0.7): knn[q] = {best, second} train
+  // rows, good[q] = d_best < ratio * d_second.  Replaces `flann->knnMatch(query, matches, 2)` on the key frame's KD-tree
+  // (KeyFrame::buildIndexes, keyframe.cpp:487-511) -- exact where FLANN is approximate, so the matches FLANN finds with
+  // the true neighbours are reproduced and the ones it misses are found.
+  static void KnnRatio(const cv::Mat &query, const cv::Mat &train, float ratio, std::vector<int32_t> &idx, std::vector<float> &dist,
+                       std::vector<uint8_t> &good) {
+    const int nq = query.rows;
+    idx.assign(2 * static_cast<size_t>(nq), -1);
+    dist.assign(2 * static_cast<size_t>(nq), 0.f);
+    good.assign(nq, 0);
+    if (nq == 0 || train.rows == 0) return;
+    if (!backend()) throw std::runtime_error("SPMatcher: no backend set (call SPMatcher::SetBackend)");
+    cv::Mat q = Contiguous(query), t = Contiguous(train);
+    if (spfe_match_knn2(backend(), q.ptr<float>(), nq, t.ptr<float>(), t.rows, idx.data(), dist.data()) != SPFE_OK)
+      throw std::runtime_error(spfe_last_error(backend()));
+    for (int i = 0; i < nq; i++) good[i] = idx[2 * i] >= 0 && idx[2 * i + 1] >= 0 && dist[2 * i] < ratio * dist[2 * i + 1];
+  }
+
+  // sp_matcher.cpp:441-469, same arithmetic: squared distance of kp2 to the epipolar line of kp1 against
+  // 3.84 / min(cov2_inv) of the key point's covariance (computeCovariance's output).
+  template <class KeyFrameT>
+  static bool CheckDistEpipolarLine(const cv::KeyPoint &kp1, const cv::KeyPoint &kp2, const cv::Mat &F12, const KeyFrameT *pKF2, const int idx) {
+    const float a = kp1.pt.x * F12.at<float>(0, 0) + kp1.pt.y * F12.at<float>(1, 0) + F12.at<float>(2, 0);
+    const float b = kp1.pt.x * F12.at<float>(0, 1) + kp1.pt.y * F12.at<float>(1, 1) + F12.at<float>(2, 1);
+    const float c = kp1.pt.x * F12.at<float>(0, 2) + kp1.pt.y * F12.at<float>(1, 2) + F12.at<float>(2, 2);
+    const auto sigma = pKF2->cov2_inv_[idx];
+    const float sx = sigma.x(), sy = sigma.y();
+    const float factor = 1.0f / (sx < sy ? sx : sy);
+    const float num = a * kp2.pt.x + b * kp2.pt.y + c;
+    const float den = a * a + b * b;
+    if (den == 0) return false;
+    const float dsqr = num * num / den;
+    return dsqr < 3.84 * factor;
+  }
+
+  // SearchForTriByFlann(KeyFrame *pKF1, KeyFrame *pKF2, cv::Mat F12, vector<pair<size_t, size_t>> &), sp_matcher.cpp:183-262
+  // (LocalMapping::CreateNewMapPoints, local_mapper.cpp:620-631): the unmatched descriptors of pKF2 against pKF1's, ratio
+  // test, then the reference's own filters in its own order (map point on either side, already matched, epipole
+  // distance, epipolar line).  `ex`, `ey` = the epipole of pKF1's centre in pKF2 (the caller's R2w * Cw + t2w projection,
+  // :186-192) so that this header needs no matrix algebra.
+  template <class KeyFrameT>
+  int SearchForTriByFlann(KeyFrameT *pKF1, KeyFrameT *pKF2, const cv::Mat &F12, const float ex, const float ey,
+                          std::vector<std::pair<size_t, size_t>> &vMatchedPairs) {
+    int nmatches = 0;
+    std::vector<bool> vbMatched2(pKF2->N, false);
+    std::vector<int> vMatches12(pKF1->N, -1);
+    std::vector<int32_t> idx;
+    std::vector<float> dist;
+    std::vector<uint8_t> good;
+    KnnRatio(pKF2->mDescReamin, pKF1->mDescReamin, 0.7f, idx, dist, good);
+    for (size_t i = 0; i < good.size(); i++) {
+      if (!good[i]) continue;
+      const size_t idx1 = pKF1->mIndicesRemain[idx[2 * i]];
+      if (pKF1->GetMapPoint(idx1)) continue;
+      const size_t idx2 = pKF2->mIndicesRemain[i];
+      if (vbMatched2[idx2] || pKF2->GetMapPoint(idx2)) continue;
+      const cv::KeyPoint &kp1 = pKF1->mvKeysUn[idx1];
+      const cv::KeyPoint &kp2 = pKF2->mvKeysUn[idx2];
+      const float distex = ex - kp2.pt.x, distey = ey - kp2.pt.y;
+      if (distex * distex + distey * distey < 100 * pKF2->mvScaleFactors[kp2.octave]) continue;
+      if (CheckDistEpipolarLine(kp1, kp2, F12, pKF2, static_cast<int>(idx2))) {
+        vMatches12[idx1] = static_cast<int>(idx2);
+        vbMatched2[idx2] = true;
+        nmatches++;
+      }
+    }
+    vMatchedPairs.clear();
+    vMatchedPairs.reserve(nmatches);
+    for (size_t i = 0, iend = vMatches12.size(); i < iend; i++)
+      if (vMatches12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, static_cast<size_t>(vMatches12[i])));
+    return nmatches;
+  }
+
+  // The reference's own signature: the epipole of pKF1's camera centre in pKF2 as at sp_matcher.cpp:186-192
+  // (C2 = R2w * Cw + t2w: CV_32F product with OpenCV's double accumulator, then the float sum).
+  template <class KeyFrameT>
+  int SearchForTriByFlann(KeyFrameT *pKF1, KeyFrameT *pKF2, cv::Mat F12, std::vector<std::pair<size_t, size_t>> &vMatchedPairs) {
+    const cv::Mat Cw = pKF1->GetCameraCenter(), R2w = pKF2->GetRotation(), t2w = pKF2->GetTranslation();
+    float C2[3];
+    for (int i = 0; i < 3; i++) {
+      double s = 0;
+      for (int k = 0; k < 3; k++) s += static_cast<double>(R2w.template at<float>(i, k)) * Cw.template at<float>(k, 0);
+      C2[i] = static_cast<float>(s) + t2w.template at<float>(i, 0);
+    }
+    const float invz = 1.0f / C2[2];
+    const float ex = pKF2->fx * C2[0] * invz + pKF2->cx;
+    const float ey = pKF2->fy * C2[1] * invz + pKF2->cy;
+    return SearchForTriByFlann(pKF1, pKF2, F12, ex, ey, vMatchedPairs);
+  }
+
+  // SearchByFlann(KeyFrame *kf_db, KeyFrame *kf_qry, vector<pair<size_t, size_t>> &), sp_matcher.cpp:264-279: upstream the body
+  // stops after the ratio test (nothing is pushed, no return value).  Here the survivors are delivered as
+  // (row of kf_db, row of kf_qry) in query order and counted.
+  template <class KeyFrameT>
+  int SearchByFlann(KeyFrameT *kf_db_ptr, KeyFrameT *kf_qry_ptr, std::vector<std::pair<size_t, size_t>> &vMatchesPairs) {
+    std::vector<int32_t> idx;
+    std::vector<float> dist;
+    std::vector<uint8_t> good;
+    KnnRatio(kf_qry_ptr->mDescReamin, kf_db_ptr->mDescReamin, 0.7f, idx, dist, good);
+    vMatchesPairs.clear();
+    for (size_t i = 0; i < good.size(); i++)
+      if (good[i]) vMatchesPairs.push_back(std::make_pair(static_cast<size_t>(kf_db_ptr->mIndicesRemain[idx[2 * i]]), static_cast<size_t>(kf_qry_ptr->mIndicesRemain[i])));
+    return static_cast<int>(vMatchesPairs.size());
   }
 
   // sp_matcher.cpp:434-439

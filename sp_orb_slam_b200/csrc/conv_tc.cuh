@@ -52,7 +52,8 @@ struct ConvArgs {
   // EPI_TOP2 (descriptor matching as a GEMM, see match.cuh): "frame slot" s holds descriptor rows of one frame;
   // item = (pair z, direction, 128-row tile, 256-column block): A = slot z+1-dir, B = slot z+dir
   const int *m_count;     // [slots] valid rows per slot
-  float2 *m_cand;         // [2][Z][rows_pad][NB][2] (score, index-as-float-bits) top-2 per row and column block
+  float2 *m_cand;         // [2][Z][rows_pad][NB][4][TOPK] (score, index-as-float-bits): best TOPK per row, 256-column block
+                          // and column residue mod 4 (a "virtual block" of 64 columns)
   int m_rows_pad;         // rows per slot in the fp16 descriptor tensor (multiple of 256)
   int m_tiles;            // 128-row tiles per slot that can hold valid rows
   // descriptor-SET mode (spfe_match_*: one direction per launch): tmA = the A set's rows, tmW = the B set's rows, both
@@ -560,25 +561,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        unsigned b1 = 0u, b2 = 0u, b3 = 0u;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {  // merge the four chains (each sorted m1 >= m2 >= m3)
-          const unsigned in[3] = {m1[k], m2[k], m3[k]};
-#pragma unroll
-          for (int e = 0; e < TOPK; e++) {
-            unsigned x = in[e];
-            unsigned lo = min(b1, x); b1 = max(b1, x); x = lo;
-            lo = min(b2, x); b2 = max(b2, x); x = lo;
-            b3 = max(b3, x);
-          }
-        }
+        // The four chains are NOT merged: chain k holds the best TOPK of the 64 columns == k (mod 4), a "virtual block".
+        // Near-ties then rarely share a block (the exact re-scan of match.cuh triggers 16x less often than with one list
+        // per 256 columns) and a re-scan touches 64 columns instead of 256.
         if (row < n_a) {
-          float2 *dst = p.m_cand + (((static_cast<size_t>(dir) * p.B + z) * p.m_rows_pad + row) * NB + nb) * TOPK;
-          const unsigned bk[3] = {b1, b2, b3};
+          float2 *dst = p.m_cand + (((static_cast<size_t>(dir) * p.B + z) * p.m_rows_pad + row) * NB + nb) * 4 * TOPK;
 #pragma unroll
-          for (int e = 0; e < TOPK; e++)
-            dst[e] = make_float2(bk[e] ? f32_from_ordered(bk[e] & 0xFFFFFF00u) : -INFINITY,
-                                 __int_as_float(bk[e] ? nb * N + 255 - static_cast<int>(bk[e] & 0xFFu) : -1));
+          for (int k = 0; k < 4; k++) {
+            const unsigned bk[3] = {m1[k], m2[k], m3[k]};
+#pragma unroll
+            for (int e = 0; e < TOPK; e++)
+              dst[k * TOPK + e] = make_float2(bk[e] ? f32_from_ordered(bk[e] & 0xFFFFFF00u) : -INFINITY,
+                                              __int_as_float(bk[e] ? nb * N + 255 - static_cast<int>(bk[e] & 0xFFu) : -1));
+          }
         }
       } else if constexpr (EPI == EPI_L2NORM) {
         // convDb + channel-wise L2 normalisation (sp_extractor.cpp:100-103); N == all 256 channels.

@@ -192,11 +192,53 @@ __global__ void __launch_bounds__(1024) nms_kernel(const NmsArgs p) {
   __syncthreads();
   const int K = s_cnt;
   if (K > p.cap) {
+    // the cap-th largest key by radix selection (8 passes over the K keys, one byte each): O(K) instead of the O(K^2)
+    // rank-by-counting that cost 0.1 ms per 1920x1080 frame (K ~ 5300 survivors against a budget of 2001)
+    __shared__ int s_hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_want;
+    if (tid == 0) { s_prefix = 0ull; s_want = p.cap; }
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      if (tid < 256) s_hist[tid] = 0;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      const unsigned long long hi_mask = shift == 56 ? 0ull : (~0ull << (shift + 8));
+      for (int e = tid; e < K; e += nt) {
+        const unsigned long long key = list[e];
+        if ((key & hi_mask) == prefix) atomicAdd(&s_hist[static_cast<int>((key >> shift) & 255ull)], 1);
+      }
+      __syncthreads();
+      if (tid < 32) {  // digit d of the threshold: the largest d with  #(keys with a digit >= d)  >= want
+        int cnt[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { cnt[j] = s_hist[255 - (tid * 8 + j)]; sum += cnt[j]; }  // lane 0 owns digits 255..248
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (tid >= o) incl += v;
+        }
+        const int want = s_want;
+        int above = incl - sum;  // keys with a larger digit than this lane's eight
+        const bool mine = above < want && incl >= want;
+        if (mine) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            if (above + cnt[j] >= want) {
+              s_prefix = prefix | (static_cast<unsigned long long>(255 - (tid * 8 + j)) << shift);
+              s_want = want - above;
+              break;
+            }
+            above += cnt[j];
+          }
+        }
+      }
+      __syncthreads();
+    }
+    const unsigned long long cut = s_prefix;  // == the cap-th largest key (keys are unique: the cell index is part of them)
     for (int e = tid; e < K; e += nt) {
       const unsigned long long key = list[e];
-      int rank = 0;
-      for (int f = 0; f < K; f++) rank += (list[f] > key);
-      if (rank >= p.cap) s_st[0xFFFFFFFFu - static_cast<unsigned>(key & 0xFFFFFFFFu)] = ST_SUPP;
+      if (key < cut) s_st[0xFFFFFFFFu - static_cast<unsigned>(key & 0xFFFFFFFFu)] = ST_SUPP;
     }
   }
   __syncthreads();

@@ -207,10 +207,12 @@ __global__ void knn2_final_kernel(const unsigned long long *first, const unsigne
 // score >= s_R - 2 beta, and the top R observed columns are among the K >= R nominees of their 256-column blocks, so
 // s_R is known from the nominees.  A true top-R column can be missing from the nominees only if its block holds K
 // other columns at or above it, i.e. the block's K-th nominee is >= s_R - 2 beta: such a block is re-scanned
-// completely in fp32 (rare: three near-ties inside one block); everywhere else the nominees within MATCH_MARGIN
-// (>= 2 beta) of s_R contain the answer.  All survivors are ranked by the exact fp32 squared distance, ties to the
+// completely in fp32; everywhere else the nominees within MATCH_MARGIN (>= 2 beta) of s_R contain the answer.  "Block"
+// is a VIRTUAL block: the 64 columns of a 256-column GEMM tile with the same residue mod 4 (the epilogue's four
+// independent chains, kept apart), so that K near-ties must share a residue class to force a 64-column re-scan.  All survivors are ranked by the exact fp32 squared distance, ties to the
 // lower index (BFMatcher's first-index rule).
 constexpr float MATCH_MARGIN = 4e-3f;
+constexpr float MATCH_RESCAN = 2.1e-3f;  // >= 2 beta
 
 // exact fp32 squared distance of two 256-d rows held 8 dimensions per lane (all lanes return the sum)
 __device__ __forceinline__ float warp_dist2(const float4 &m0, const float4 &m1, const float *other, int lane) {
@@ -229,14 +231,15 @@ __device__ __forceinline__ float warp_dist2(const float4 &m0, const float4 &m1, 
   return acc;
 }
 
-// One warp re-ranks one row: `c` = its [NB][K] nominees (observed score, column), `other` = the fp32 rows of the other
-// set (n_other of them).  best[0 .. R) receive the R smallest keys (bits(d^2) << 32 | column), ~0 where none exists.
+// One warp re-ranks one row: `c` = its [NV][K] nominees (observed score, column) of the NV = 4 * NB virtual blocks (the
+// 64 columns of a 256-column block with the same residue mod 4), `other` = the fp32 rows of the other set (n_other of
+// them).  best[0 .. R) receive the R smallest keys (bits(d^2) << 32 | column), ~0 where none exists.
 template <int K, int R>
 __device__ __forceinline__ void rerank_row(const float *me, const float *other, int n_other, const float2 *c, int NB, int lane,
                                            unsigned long long (&best)[R]) {
   static_assert(K >= R && R >= 1 && R <= 2, "nominees per block must cover the ranks asked for");
   float s1 = -INFINITY, s2 = -INFINITY;  // best / second-best observed score among the nominees
-  for (int k = 0; k < NB * K; k++) {
+  for (int k = 0; k < NB * 4 * K; k++) {
     const float x = c[k].x;
     if (x > s1) { s2 = s1; s1 = x; }
     else if (x > s2) s2 = x;
@@ -244,7 +247,9 @@ __device__ __forceinline__ void rerank_row(const float *me, const float *other, 
 #pragma unroll
   for (int r = 0; r < R; r++) best[r] = ~0ull;
   if (s1 == -INFINITY) return;
-  const float thr = (R == 1 ? s1 : (s2 == -INFINITY ? s1 : s2)) - MATCH_MARGIN;
+  const float s_r = R == 1 ? s1 : (s2 == -INFINITY ? s1 : s2);
+  const float thr = s_r - MATCH_MARGIN;        // nominees re-ranked exactly (generous: costs one row read each)
+  const float thr_scan = s_r - MATCH_RESCAN;   // blocks re-scanned (tight: 2 beta is what the proof needs)
   const float4 m0 = *reinterpret_cast<const float4 *>(me + lane * 8), m1 = *reinterpret_cast<const float4 *>(me + lane * 8 + 4);
   auto consider = [&](int idx) {
     const float d2 = warp_dist2(m0, m1, other + static_cast<size_t>(idx) * 256, lane);
@@ -253,11 +258,11 @@ __device__ __forceinline__ void rerank_row(const float *me, const float *other, 
     for (int r = 0; r < R; r++)
       if (key < best[r]) { const unsigned long long t = best[r]; best[r] = key; key = t; }
   };
-  for (int nb = 0; nb < NB; nb++) {
-    const float2 *cb = c + nb * K;
-    if (cb[K - 1].x >= thr && __float_as_int(cb[K - 1].y) >= 0) {  // K near-ties in one block: a (K+1)-th may hide behind them
-      const int j1 = min(n_other, nb * 256 + 256);
-      for (int j = nb * 256; j < j1; j++) consider(j);
+  for (int v = 0; v < NB * 4; v++) {
+    const float2 *cb = c + v * K;
+    if (cb[K - 1].x >= thr_scan && __float_as_int(cb[K - 1].y) >= 0) {  // K near-ties in one virtual block: a (K+1)-th may hide behind them
+      const int j1 = min(n_other, (v >> 2) * 256 + 256);
+      for (int j = (v >> 2) * 256 + (v & 3); j < j1; j += 4) consider(j);
       continue;
     }
 #pragma unroll
@@ -282,7 +287,7 @@ __global__ void __launch_bounds__(256) match_rerank_kernel(const RerankArgs a) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int self_slot = z + 1 - dir, other_slot = z + dir;
   if (row >= a.count_all[self_slot]) return;
-  const float2 *c = a.cand + ((static_cast<size_t>(dir) * a.Z + z) * a.rows_pad + row) * a.NB * 2;
+  const float2 *c = a.cand + ((static_cast<size_t>(dir) * a.Z + z) * a.rows_pad + row) * a.NB * 4 * 2;
   unsigned long long best[1];
   rerank_row<2, 1>(a.desc_all + (static_cast<size_t>(self_slot) * a.cap + row) * 256, a.desc_all + static_cast<size_t>(other_slot) * a.cap * 256,
                    a.count_all[other_slot], c, a.NB, lane, best);
@@ -301,7 +306,7 @@ template <int R>
 __global__ void __launch_bounds__(256) match_rerank_set_kernel(const SetRerankArgs a) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= a.n_a) return;
-  const float2 *c = a.cand + (static_cast<size_t>(a.dir) * a.rows_pad + row) * a.NB * 3;
+  const float2 *c = a.cand + (static_cast<size_t>(a.dir) * a.rows_pad + row) * a.NB * 4 * 3;
   unsigned long long best[R];
   rerank_row<3, R>(a.a_rows + static_cast<size_t>(row) * 256, a.b_rows, a.n_b, c, a.NB, lane, best);
   if (lane == 0) {

@@ -867,7 +867,7 @@ static int create_impl(spfe_ctx *c) {
     }
     if (c->match_prev) {
       const size_t rp = c->rows_pad, nbk = c->match_nb;
-      if ((rc = dev_alloc(c, &s.cand, 2 * Bm * rp * nbk * 2))) return rc;
+      if ((rc = dev_alloc(c, &s.cand, 2 * Bm * rp * nbk * 4 * 2))) return rc;  // [dir][frame][row][block][residue][top-2]
       if ((rc = make_act_map(c, &s.tmQ, s.x16, 256, 8, static_cast<int>(rp / 8), Bm + 1, 16))) return rc;
       if ((rc = make_mat_map(c, &s.tmT, s.x16, 256, static_cast<int>((Bm + 1) * rp), 256))) return rc;
       s.match_layer.taps = 1; s.match_layer.cb = 4; s.match_layer.n_tile = 256; s.match_layer.cout_total = 256;
@@ -921,7 +921,7 @@ static int create_impl(spfe_ctx *c) {
   if ((rc = dev_alloc(c, &c->match.q2t, c->match_cap))) return rc;
   if ((rc = dev_alloc(c, &c->match.dist, c->match_cap))) return rc;
   for (int d = 0; d < 2; d++)
-    if ((rc = dev_alloc(c, &c->set_cand[d], static_cast<size_t>(c->match_cap) * (c->match_cap / 256) * 3))) return rc;
+    if ((rc = dev_alloc(c, &c->set_cand[d], static_cast<size_t>(c->match_cap) * (c->match_cap / 256) * 4 * 3))) return rc;
   if ((rc = dev_alloc(c, &c->set_second, c->match_cap))) return rc;
   if ((rc = dev_alloc(c, &c->set_flag, 2))) return rc;
   if ((rc = host_alloc(c, &c->h_set_flag, 2))) return rc;

@@ -40,3 +40,10 @@ int spfe_match_mutual_nn(spfe_ctx *ctx, const float *q, int32_t nq, const float 
 }
 float spfe_l2(const float *a, const float *b) { return orc_l2(a, b, 256); }
 const char *spfe_last_error(const spfe_ctx *ctx) { (void)ctx; return "fake backend"; }
+
+void orc_knn2(const float *q, int nq, const float *t, int nt, int d, int32_t *idx, float *dist);
+int spfe_match_knn2(spfe_ctx *ctx, const float *q, int32_t nq, const float *t, int32_t nt, int32_t *idx, float *dist) {
+  (void)ctx;
+  orc_knn2(q, nq, t, nt, 256, idx, dist);
+  return SPFE_OK;
+}

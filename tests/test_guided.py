@@ -405,3 +405,98 @@ def test_knn2_matches_oracle(gpu_frame):
     good, idx, dist = SPMatcher(ex).KnnMatchRatio(q, t, 0.7)
     ridx, rdist = O.knn2(q, t)
     assert np.array_equal(good, np.where(rdist[:, 0] < np.float32(0.7) * rdist[:, 1], ridx[:, 0], -1)) and (good >= 0).sum() > 100
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# SearchForTriByFlann / SearchByFlann over the exact 2-NN
+# ---------------------------------------------------------------------------------------------------------------------
+def _tri_scene(rng, n1, n2, epipole_inside):
+    """Two key frames looking at the same scene: KF2's key points are KF1's shifted along horizontal epipolar lines (plus
+    vertical noise so that the epipolar test rejects some), descriptors are noisy copies; a share of the rows of both
+    already carries map points."""
+    d1 = rng.randn(n1, 256).astype(np.float32)
+    d1 /= np.linalg.norm(d1, axis=1, keepdims=True)
+    src = rng.permutation(n1)[:n2] if n2 <= n1 else rng.randint(0, n1, n2)
+    d2 = d1[src] + 0.05 * rng.randn(n2, 256).astype(np.float32)
+    amb = rng.rand(n2) < 0.2                                       # ambiguous rows: fail the ratio test
+    d2[amb] = rng.randn(int(amb.sum()), 256).astype(np.float32)
+    d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
+    kp1 = np.stack([rng.uniform(8, 744, n1), rng.uniform(8, 472, n1)], 1).astype(np.float32)
+    kp2 = (kp1[src] + np.stack([rng.uniform(-30, -5, n2), rng.normal(0, 1.5, n2)], 1)).astype(np.float32)
+    cov1 = rng.uniform(0.05, 1.0, (n1, 2)).astype(np.float32)
+    cov2 = rng.uniform(0.05, 1.0, (n2, 2)).astype(np.float32)
+    has1, has2 = (rng.rand(n1) < 0.3).astype(np.uint8), (rng.rand(n2) < 0.3).astype(np.uint8)
+    F12 = np.array([[0, 0, 0], [0, 0, -1], [0, 1, 0]], np.float32)     # x1^T F12 = (0, 1, -y1): horizontal epipolar lines
+    Cw = np.array([0.05, -0.02, 1.0] if epipole_inside else [-1.0, 0.0, 0.8], np.float32)
+    R = np.eye(3, dtype=np.float32)
+    t = np.zeros(3, np.float32)
+    intr = np.array([458.0, 457.0, 367.0, 248.0], np.float32)
+    return dict(d1=d1, d2=d2, kp1=kp1, kp2=kp2, cov1=cov1, cov2=cov2, has1=has1, has2=has2, F12=F12, Cw=Cw, R=R, t=t, intr=intr)
+
+
+@pytest.mark.parametrize("seed,n1,n2,inside", [(0, 700, 650, False), (1, 400, 520, True)])
+def test_cpp_shim_search_for_tri_by_flann_matches_reference_on_cpu(tmp_path, seed, n1, n2, inside):
+    """SPMatcher::SearchForTriByFlann of cpp/sp_matcher.h (exact 2-NN through spfe_match_knn2, here answered by the oracle)
+    against the REFERENCE's own function compiled verbatim around an exact k-NN stand-in for FLANN: identical pairs and
+    count -- ratio test, map-point / already-matched / epipole / epipolar-line filters, claim order."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    from oracle import ref_post as RP
+    if not RP.flann_available():
+        pytest.skip("oracle/_ref/libspflann_ref.so not built (needs /root/reference)")
+    inc = ["-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "sp_orb_slam_b200", "cpp")]
+    objs = []
+    for src in ("tests/cpp/fake_spfe_guided.c", "oracle/sp_post.c"):
+        o = str(tmp_path / (os.path.basename(src) + ".o"))
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", *inc, "-c", os.path.join(ROOT, src), "-o", o])
+        objs.append(o)
+    exe = str(tmp_path / "flann_cpu")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", *inc, os.path.join(ROOT, "tests/cpp/flann_shim_cpu.cc"), *objs, "-o", exe, "-lm"])
+    s = _tri_scene(np.random.RandomState(40 + seed), n1, n2, inside)
+    with open(tmp_path / "scene.bin", "wb") as fh:
+        np.array([n1, n2], np.int32).tofile(fh)
+        for a in (s["F12"], s["Cw"], s["R"], s["t"], s["intr"], s["d1"], s["kp1"], s["cov1"], s["has1"], s["d2"], s["kp2"], s["cov2"], s["has2"]):
+            np.ascontiguousarray(a).tofile(fh)
+    subprocess.check_call([exe, str(tmp_path / "scene.bin"), str(tmp_path / "out.txt")])
+    L = open(tmp_path / "out.txt").read().split("\n")
+    pairs, n = RP.search_tri_flann(s["d1"], s["has1"], s["kp1"], s["cov1"], s["d2"], s["has2"], s["kp2"], s["cov2"], s["F12"], s["Cw"],
+                                   s["R"], s["t"], s["intr"])
+    got = np.array(L[1].split(), np.int64).reshape(-1, 2)
+    assert int(L[0]) == n and n > 40
+    assert np.array_equal(got, pairs)
+    assert not s["has1"][got[:, 0]].any() and not s["has2"][got[:, 1]].any()
+    # SearchByFlann (unfinished upstream): the ratio-test survivors, a superset of the triangulation pairs' rows
+    allp = np.array(L[3].split(), np.int64).reshape(-1, 2)
+    assert int(L[2]) == len(allp) >= n
+    assert set(map(tuple, got)) <= set(map(tuple, allp))
+
+
+def test_exact_knn_vs_opencv_flann_on_golden_descriptors(golden):
+    """Parity story of rank 3: the reference searches a KD-tree (cv::FlannBasedMatcher, KDTreeIndexParams(ntree),
+    SearchParams(nchecks)), which is approximate; the drop-in searches exactly.  On the golden descriptors: every
+    ratio-test match FLANN returns with the true two neighbours is returned identically, and the exact search finds
+    the ones the KD-tree misses.  (cv2's FLANN is randomised: the counts are bounded, not pinned.)"""
+    cv2 = pytest.importorskip("cv2")
+    if not hasattr(cv2, "FlannBasedMatcher"):
+        pytest.skip("cv2 without FLANN")
+    g = golden("g480x752")
+    q, t = g["f1_desc"].astype(np.float32), g["f0_desc"].astype(np.float32)
+    idx, dist = O.knn2(q, t)
+    exact = {i: int(idx[i, 0]) for i in range(len(q)) if dist[i, 0] < np.float32(0.7) * dist[i, 1]}
+    fl = cv2.FlannBasedMatcher(dict(algorithm=1, trees=4), dict(checks=32))
+    fl.add([t])
+    fl.train()
+    approx, same_nn = {}, 0
+    for m in fl.knnMatch(q, k=2):
+        if len(m) == 2 and m[0].distance < 0.7 * m[1].distance:
+            approx[m[0].queryIdx] = m[0].trainIdx
+        if len(m) == 2 and (m[0].trainIdx, m[1].trainIdx) == (idx[m[0].queryIdx, 0], idx[m[0].queryIdx, 1]):
+            same_nn += 1
+    agree = sum(1 for k, v in approx.items() if exact.get(k) == v)
+    assert len(exact) > 300
+    assert agree >= 0.9 * len(approx)                      # where the KD-tree found the true neighbours the match is the same
+    only_flann = [k for k in approx if k not in exact]     # these exist only because FLANN missed the true 2nd neighbour
+    for k in only_flann:
+        assert not (approx[k] == idx[k, 0] and dist[k, 0] < np.float32(0.7) * dist[k, 1])
+    assert same_nn >= 0.5 * len(q)
