@@ -238,11 +238,19 @@ template <int K, int R>
 __device__ __forceinline__ void rerank_row(const float *me, const float *other, int n_other, const float2 *c, int NB, int lane,
                                            unsigned long long (&best)[R]) {
   static_assert(K >= R && R >= 1 && R <= 2, "nominees per block must cover the ranks asked for");
-  float s1 = -INFINITY, s2 = -INFINITY;  // best / second-best observed score among the nominees
-  for (int k = 0; k < NB * 4 * K; k++) {
-    const float x = c[k].x;
+  const int total = NB * 4 * K;
+  // best / second-best observed score among the nominees: lanes scan disjoint entries, then a butterfly merge
+  float s1 = -INFINITY, s2 = -INFINITY;
+  for (int e = lane; e < total; e += 32) {
+    const float x = c[e].x;
     if (x > s1) { s2 = s1; s1 = x; }
     else if (x > s2) s2 = x;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float t1 = __shfl_xor_sync(0xffffffffu, s1, o), t2 = __shfl_xor_sync(0xffffffffu, s2, o);
+    s2 = fmaxf(fminf(s1, t1), fmaxf(s2, t2));
+    s1 = fmaxf(s1, t1);
   }
 #pragma unroll
   for (int r = 0; r < R; r++) best[r] = ~0ull;
@@ -251,24 +259,61 @@ __device__ __forceinline__ void rerank_row(const float *me, const float *other, 
   const float thr = s_r - MATCH_MARGIN;        // nominees re-ranked exactly (generous: costs one row read each)
   const float thr_scan = s_r - MATCH_RESCAN;   // blocks re-scanned (tight: 2 beta is what the proof needs)
   const float4 m0 = *reinterpret_cast<const float4 *>(me + lane * 8), m1 = *reinterpret_cast<const float4 *>(me + lane * 8 + 4);
-  auto consider = [&](int idx) {
-    const float d2 = warp_dist2(m0, m1, other + static_cast<size_t>(idx) * 256, lane);
+  auto insert = [&](float d2, int idx) {
     unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(d2)) << 32) | static_cast<unsigned>(idx);
 #pragma unroll
     for (int r = 0; r < R; r++)
       if (key < best[r]) { const unsigned long long t = best[r]; best[r] = key; key = t; }
   };
-  for (int v = 0; v < NB * 4; v++) {
-    const float2 *cb = c + v * K;
-    if (cb[K - 1].x >= thr_scan && __float_as_int(cb[K - 1].y) >= 0) {  // K near-ties in one virtual block: a (K+1)-th may hide behind them
-      const int j1 = min(n_other, (v >> 2) * 256 + 256);
-      for (int j = (v >> 2) * 256 + (v & 3); j < j1; j += 4) consider(j);
-      continue;
+  constexpr int CH = (32 / K) * K;  // entries per step: whole virtual blocks only
+  for (int base = 0; base < total; base += CH) {
+    const int e = base + lane;
+    const bool live = lane < CH && e < total;
+    const float2 ce = live ? c[e] : make_float2(-INFINITY, __int_as_float(-1));
+    const int idx = __float_as_int(ce.y);
+    // K near-ties in one virtual block (its K-th nominee is within 2 beta of s_R): a (K+1)-th may hide behind them
+    const unsigned scan = __ballot_sync(0xffffffffu, live && (lane % K) == K - 1 && idx >= 0 && ce.x >= thr_scan);
+    const bool block_scanned = (scan >> ((lane / K) * K + K - 1)) & 1u;
+    unsigned nom = __ballot_sync(0xffffffffu, live && idx >= 0 && ce.x >= thr && !block_scanned);
+    while (nom) {  // warp-uniform
+      const int l = __ffs(nom) - 1;
+      nom &= nom - 1;
+      const int j = __shfl_sync(0xffffffffu, idx, l);
+      insert(warp_dist2(m0, m1, other + static_cast<size_t>(j) * 256, lane), j);
     }
+    unsigned sc = scan;
+    while (sc) {
+      const int l = __ffs(sc) - 1;
+      sc &= sc - 1;
+      const int v = (base + l) / K;  // virtual block: 256-column block v >> 2, residue v & 3
+      const int j1 = min(n_other, (v >> 2) * 256 + 256);
+      // four columns per step: their row loads and shuffle reductions overlap (the loop is latency-bound otherwise)
+      for (int j = (v >> 2) * 256 + (v & 3); j < j1; j += 16) {
+        float acc[4];
 #pragma unroll
-    for (int k = 0; k < K; k++) {
-      const int idx = __float_as_int(cb[k].y);
-      if (idx >= 0 && cb[k].x >= thr) consider(idx);  // warp-uniform
+        for (int u = 0; u < 4; u++) {
+          const int ju = min(j + 4 * u, j1 - 1);  // clamped duplicates are skipped below
+          const float *o = other + static_cast<size_t>(ju) * 256 + lane * 8;
+          const float4 o0 = *reinterpret_cast<const float4 *>(o), o1 = *reinterpret_cast<const float4 *>(o + 4);
+          float d, a = 0.f;
+          d = m0.x - o0.x; a = fmaf(d, d, a);
+          d = m0.y - o0.y; a = fmaf(d, d, a);
+          d = m0.z - o0.z; a = fmaf(d, d, a);
+          d = m0.w - o0.w; a = fmaf(d, d, a);
+          d = m1.x - o1.x; a = fmaf(d, d, a);
+          d = m1.y - o1.y; a = fmaf(d, d, a);
+          d = m1.z - o1.z; a = fmaf(d, d, a);
+          d = m1.w - o1.w; a = fmaf(d, d, a);
+          acc[u] = a;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int u = 0; u < 4; u++) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (j + 4 * u < j1) insert(acc[u], j + 4 * u);
+      }
     }
   }
 }

@@ -134,6 +134,13 @@ struct Slot {
   int16_t *h_occ = nullptr;
   uint16_t *h_desc16 = nullptr;  // DESC_F16: [Bm][cap][256] binary16 instead of h_desc
   long long d2h_bytes = 0;       // what the last spfe_wait moved device -> host
+  // spfe_extract's single-frame launch plan as a CUDA graph (slot 0): H2D, every kernel, all D2H copies in one launch
+  cudaGraphExec_t graph = nullptr;
+  cudaEvent_t ev_graph = nullptr, ev_heat = nullptr;
+  bool capturing = false, graph_inflight = false, eager_desc = false;
+  long long graph_launches = 0, graph_d2h = 0;
+  float graph_thresh = 0.f;
+  int extract_calls = 0;
   int *h_match = nullptr, *h_nprev = nullptr;
   float *h_mdist = nullptr;
   // covariance (device)
@@ -179,6 +186,7 @@ struct spfe_ctx {
   bool pair_conv1 = true;    // SPFE_PAIR_CONV1=0: the fused conv1a+1b kernel single-CTA
   int nms_smem = 0, nms_list_smem = 0;  // dynamic shared memory of nms_kernel / whether its key list fits in it
   int cov_force = 0;  // SPFE_COV_FORCE (test hook): push floods down the big / sequential fallback paths
+  bool use_graph = true;  // SPFE_GRAPH=0: spfe_extract enqueues its launch plan call by call instead of replaying a CUDA graph
   bool pdl = false;  // SPFE_PDL=1: programmatic dependent launch of the tensor-core kernels (measured: no gain, the board is power-capped)
   int conv1_mode = 2;
   bool fused_conv1 = true;
@@ -574,10 +582,13 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     c->launches++;
     CU_OK(c, cudaGetLastError());
     mark("heat_norm", 0, (c->heat_host ? 12.0 : 8.0) * H * W * B);
+    if (!tm && (c->heat_host || c->heat_inv_host)) CU_OK(c, cudaEventRecord(s.ev_heat, st));  // the heat maps may leave while the floods run
   }
   if (c->cov) {  // computeCovariance on the device (cov.cuh): parallel floods, then sequential replay of the conflicted few
     const size_t px = static_cast<size_t>(H) * W;
-    if (s.cov_epoch % 509 == 0)  // claims carry a falling batch tag (cov_tag): the 4-byte-per-pixel map needs no clearing in between
+    if (s.capturing)  // a replayed graph cannot count epochs: it clears its own frames and claims with the largest tag
+      CU_OK(c, cudaMemsetAsync(s.cov_owner, 0x7F, static_cast<size_t>(B) * px * sizeof(int), st));
+    else if (s.cov_epoch % 509 == 0)  // claims carry a falling batch tag (cov_tag): the 4-byte-per-pixel map needs no clearing in between
       CU_OK(c, cudaMemsetAsync(s.cov_owner, 0x7F, static_cast<size_t>(c->cfg.max_batch) * px * sizeof(int), st));
     const size_t vis_words = (px + 31) / 32;
     CU_OK(c, cudaMemsetAsync(s.cov_visited, 0, B * vis_words * sizeof(uint32_t), st));
@@ -589,8 +600,8 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     a.queue = s.cov_queue; a.qlen = s.cov_qlen; a.response = s.resp; a.cov2 = s.cov2; a.cov2_inv = s.cov2_inv;
     a.overflow = s.cov_overflow; a.H = H; a.W = W; a.cap = c->cap; a.B = B; a.round = 0;
     a.force = c->cov_force;
-    a.epoch_tag = (508 - static_cast<int>(s.cov_epoch % 509)) << 22;  // every tag stays below the cleared value 0x7F7F7F7F
-    s.cov_epoch++;
+    a.epoch_tag = (508 - static_cast<int>(s.capturing ? 0 : s.cov_epoch % 509)) << 22;  // every tag stays below the cleared value 0x7F7F7F7F
+    if (!s.capturing) s.cov_epoch++;
     a.done = s.cov_done; a.isbig = s.cov_isbig; a.ctr = s.cov_ctr; a.big = s.cov_big; a.pend = s.cov_pend;
     a.frame_flag = s.cov_frame_flag; a.n_replay = s.cov_n_replay; a.vis_words = static_cast<int>(vis_words);
     mark("cov_memset", 0, 5.0 * px * B);
@@ -795,6 +806,8 @@ static int create_impl(spfe_ctx *c) {
     CU_OK(c, cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
     CU_OK(c, cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
     CU_OK(c, cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
+    CU_OK(c, cudaEventCreateWithFlags(&s.ev_graph, cudaEventDisableTiming));
+    CU_OK(c, cudaEventCreateWithFlags(&s.ev_heat, cudaEventDisableTiming));
     const size_t xm = c->exact ? 2 : 1;  // exact mode: every activation is a (hi, lo) pair
     if ((rc = dev_alloc(c, &s.d_gray, Bm * px))) return rc;
     if (!c->fused_conv1 && (rc = dev_alloc(c, &s.a1a, Bm * px * 64 * xm))) return rc;
@@ -983,6 +996,8 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
     c->pair_stream = c->pair && !(p3 && p3[0] == '0');
     const char *p1 = getenv("SPFE_PAIR_CONV1");
     c->pair_conv1 = c->pair && !(p1 && p1[0] == '0');
+    const char *gr = getenv("SPFE_GRAPH");
+    c->use_graph = !(gr && gr[0] == '0') && !c->slot_streams;
     const char *cf = getenv("SPFE_COV_FORCE");
     c->cov_force = cf ? atoi(cf) : 0;
   }
@@ -1025,7 +1040,8 @@ void spfe_destroy(spfe_ctx *c) {
   cudaDeviceSynchronize();
   for (Slot &s : c->slots) {
     if (s.stream && c->slot_streams) cudaStreamDestroy(s.stream);
-    for (cudaEvent_t e : {s.ev_in, s.ev_done, s.ev_out, s.ev_fork, s.ev_join}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {s.ev_in, s.ev_done, s.ev_out, s.ev_fork, s.ev_join, s.ev_graph, s.ev_heat}) if (e) cudaEventDestroy(e);
+    if (s.graph) cudaGraphExecDestroy(s.graph);
     if (s.ev0) cudaEventDestroy(s.ev0);
     if (s.ev1) cudaEventDestroy(s.ev1);
   }
@@ -1047,6 +1063,17 @@ static int check_slot(spfe_ctx *c, int32_t slot) {
   return SPFE_OK;
 }
 
+// heat_ / heat_inv_: the largest outputs; they are final after heat_norm, long before the batch's last kernel
+static int enqueue_d2h_heat(spfe_ctx *c, Slot &s, int B) {
+  const size_t px = (size_t)c->H * c->W;
+  cudaStream_t st = s.out_stream;
+  if (!(c->heat_host || c->heat_inv_host)) return SPFE_OK;
+  if (s.out_stream != s.stream) CU_OK(c, cudaStreamWaitEvent(st, s.ev_heat, 0));
+  if (c->heat_host) CU_OK(c, cudaMemcpyAsync(s.h_heat, s.heat, B * px * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (c->heat_inv_host) CU_OK(c, cudaMemcpyAsync(s.h_heat_inv, s.heat_inv, B * px * sizeof(float), cudaMemcpyDeviceToHost, st));
+  return SPFE_OK;
+}
+
 static int enqueue_d2h(spfe_ctx *c, Slot &s, int B) {
   const size_t px = (size_t)c->H * c->W, cells = c->cells, cap = c->cap;
   cudaStream_t st = s.out_stream;
@@ -1059,12 +1086,15 @@ static int enqueue_d2h(spfe_ctx *c, Slot &s, int B) {
   if (c->heat_inv_host) bytes += B * px * sizeof(float);
   if (c->cov) bytes += B * cap * 5 * sizeof(float) + sizeof(int);
   if (c->match_prev) bytes += B * cap * 8 + sizeof(int);
+  if (s.eager_desc) bytes += B * cap * 256 * (c->desc_f16 ? 2 : 4);
   s.d2h_bytes = bytes;
   CU_OK(c, cudaMemcpyAsync(s.h_occ, s.occ, B * cells * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
   CU_OK(c, cudaMemcpyAsync(s.h_dense, s.dense_dust, B * cells * sizeof(float), cudaMemcpyDeviceToHost, st));
   CU_OK(c, cudaMemcpyAsync(s.h_semi, s.semi_dust, B * cells * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (c->heat_host) CU_OK(c, cudaMemcpyAsync(s.h_heat, s.heat, B * px * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (c->heat_inv_host) CU_OK(c, cudaMemcpyAsync(s.h_heat_inv, s.heat_inv, B * px * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (s.eager_desc) {  // single-frame graph: all cap rows inside the graph instead of the n-row copy of spfe_wait
+    if (c->desc_f16) CU_OK(c, cudaMemcpyAsync(s.h_desc16, s.x16 + (size_t)c->rows_pad * 256, B * cap * 256 * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+    else CU_OK(c, cudaMemcpyAsync(s.h_desc, s.desc, B * cap * 256 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
   if (c->cov) {
     CU_OK(c, cudaMemcpyAsync(s.h_resp, s.resp, B * cap * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU_OK(c, cudaMemcpyAsync(s.h_cov2, s.cov2, B * cap * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -1106,12 +1136,46 @@ static int submit_host(spfe_ctx *c, Slot &s, const uint8_t *src, int batch) {
   }
   if ((rc = run_pipeline(c, s, batch, nullptr))) return rc;
   CU_OK(c, cudaEventRecord(s.ev_done, s.stream));
+  if ((rc = enqueue_d2h_heat(c, s, batch))) return rc;
   if (s.out_stream != s.stream) CU_OK(c, cudaStreamWaitEvent(s.out_stream, s.ev_done, 0));
   if ((rc = enqueue_d2h(c, s, batch))) return rc;
   CU_OK(c, cudaEventRecord(s.ev_out, s.out_stream));
   s.pending = true;
   s.on_host = true;
   return SPFE_OK;
+}
+
+// spfe_extract's launch plan (slot 0, one frame, page-locked staging buffer -> every output) captured once into a CUDA
+// graph: ~27 kernel launches, ~15 copies and the event chain between the three queues become ONE launch per frame.
+static int capture_extract_graph(spfe_ctx *c, Slot &s) {
+  cudaGraph_t g = nullptr;
+  s.capturing = true;
+  s.eager_desc = true;
+  const long long l0 = c->launches.load();
+  cudaError_t e = cudaStreamBeginCapture(s.in_stream, cudaStreamCaptureModeThreadLocal);
+  int rc = e == cudaSuccess ? submit_host(c, s, s.h_gray, 1) : c->fail(SPFE_ERR_CUDA, fmt("cudaStreamBeginCapture: %s", cudaGetErrorString(e)));
+  if (e == cudaSuccess) {
+    if (!rc && s.out_stream != s.in_stream) {  // join the copy-out queue (and through it the compute queue) back into the origin
+      cudaEventRecord(s.ev_out, s.out_stream);
+      cudaStreamWaitEvent(s.in_stream, s.ev_out, 0);
+    }
+    const cudaError_t e2 = cudaStreamEndCapture(s.in_stream, &g);
+    if (!rc && e2 != cudaSuccess) rc = c->fail(SPFE_ERR_CUDA, fmt("cudaStreamEndCapture: %s", cudaGetErrorString(e2)));
+  }
+  s.capturing = false;
+  s.eager_desc = false;  // only the graph copies all cap rows; batched submits keep the n-row copy of spfe_wait
+  s.pending = false;
+  s.graph_d2h = s.d2h_bytes;
+  s.graph_launches = c->launches.load() - l0;
+  c->launches -= s.graph_launches;  // nothing ran yet
+  if (!rc) {
+    const cudaError_t e3 = cudaGraphInstantiate(&s.graph, g, 0);
+    if (e3 != cudaSuccess) rc = c->fail(SPFE_ERR_CUDA, fmt("cudaGraphInstantiate: %s", cudaGetErrorString(e3)));
+  }
+  if (g) cudaGraphDestroy(g);
+  if (rc) { s.graph = nullptr; cudaGetLastError(); }
+  s.graph_thresh = c->cfg.score_thresh;
+  return rc;
 }
 
 int spfe_submit(spfe_ctx *c, int32_t slot, const uint8_t *const *grays, int32_t batch, size_t row_stride) {
@@ -1152,10 +1216,11 @@ int spfe_wait(spfe_ctx *c, int32_t slot, spfe_frame_out *outs) {
   if (rc) return rc;
   Slot &s = c->slots[slot];
   if (!s.pending || !s.on_host) return c->fail(SPFE_ERR_STATE, "spfe_wait: nothing submitted on this slot");
-  CU_OK(c, cudaEventSynchronize(s.ev_out));
+  CU_OK(c, cudaEventSynchronize(s.graph_inflight ? s.ev_graph : s.ev_out));
   s.pending = false;
   const size_t px = (size_t)c->H * c->W, cells = c->cells, cap = c->cap;
-  {  // the descriptors: exactly n[b] rows of every frame (fp32, or fp16 straight from the matcher's copy)
+  if (s.graph_inflight) s.graph_inflight = false;  // (the graph copied the descriptors itself)
+  else {  // the descriptors: exactly n[b] rows of every frame (fp32, or fp16 straight from the matcher's copy)
     CU_OK(c, cudaSetDevice(c->cfg.device_id));
     const size_t row = c->desc_f16 ? 256 * sizeof(uint16_t) : 256 * sizeof(float);
     for (int b = 0; b < s.batch; b++) {
@@ -1235,6 +1300,30 @@ int spfe_extract(spfe_ctx *c, const uint8_t *gray, size_t row_stride, spfe_frame
   if (!c) return SPFE_ERR_INVALID;
   if (!gray) return c->fail(SPFE_ERR_EMPTY, "input image is empty");
   if (!out) return c->fail(SPFE_ERR_INVALID, "spfe_extract: out is NULL");
+  Slot &s = c->slots[0];
+  if (c->use_graph && !s.pending && row_stride >= (size_t)c->W) {
+    // first call: plain enqueue (also settles every per-kernel attribute); second call: capture; from then on: replay
+    if (s.graph && s.graph_thresh != c->cfg.score_thresh) { cudaGraphExecDestroy(s.graph); s.graph = nullptr; s.extract_calls = 1; }
+    if (!s.graph && s.extract_calls == 1) {
+      CU_OK(c, cudaSetDevice(c->cfg.device_id));
+      CU_OK(c, cudaDeviceSynchronize());  // nothing of this context in flight while the streams are in capture mode
+      if (capture_extract_graph(c, s) != SPFE_OK) c->use_graph = false;  // keep working call by call
+    }
+    if (s.graph) {
+      CU_OK(c, cudaSetDevice(c->cfg.device_id));
+      const uint8_t *one[1] = {gray};
+      stage_frames(c, s, one, 1, row_stride);
+      CU_OK(c, cudaGraphLaunch(s.graph, s.in_stream));
+      CU_OK(c, cudaEventRecord(s.ev_graph, s.in_stream));
+      CU_OK(c, cudaEventRecord(s.ev_done, s.in_stream));  // what spfe_fetch_heat / the dust-pose entries order themselves after
+      c->launches += s.graph_launches;
+      s.d2h_bytes = s.graph_d2h;
+      s.batch = 1;
+      s.pending = s.on_host = s.graph_inflight = true;
+      return spfe_wait(c, 0, out);
+    }
+  }
+  s.extract_calls++;
   const uint8_t *one[1] = {gray};
   int rc = spfe_submit(c, 0, one, 1, row_stride);
   if (rc) return rc;

@@ -89,3 +89,39 @@ def test_error_messages_are_per_thread():
     assert "slot out of range" in seen["bad"]
     assert (ex._lib.spfe_last_error(ex._ctx) or b"") != seen["bad"].encode()      # this thread saw no failure of that call
     ex.close()
+
+
+def test_extract_graph_replay_equals_call_by_call(frames, monkeypatch):
+    """spfe_extract replays its single-frame launch plan as a CUDA graph from the third call on: every output must be
+    bit-identical to the call-by-call enqueue (SPFE_GRAPH=0), also after a threshold change (re-capture) and when
+    batched submits on the same slot are mixed in."""
+    monkeypatch.setenv("SPFE_GRAPH", "0")
+    plain = SPExtractor(NF, H, W, WEIGHTS, max_batch=2)
+    ref = [plain.extract(f) for f in frames]
+    plain.set_score_threshold(0.02)
+    ref_hi = plain.extract(frames[0])
+    plain.close()
+    monkeypatch.setenv("SPFE_GRAPH", "1")
+    ex = SPExtractor(NF, H, W, WEIGHTS, max_batch=2)
+    keys = ["kp_xy", "kp_score", "desc", "occ_grid", "dense_dust", "semi_dust", "heat", "heat_inv", "cov2", "cov2_inv", "kp_response"]
+    l0 = ex.launch_count()
+    got = [ex.extract(f) for f in frames]                 # call 1 plain, call 2 captures + replays, 3.. replay
+    per_call = (ex.launch_count() - l0) / len(frames)
+    assert 20 <= per_call <= 40
+    for a, b in zip(ref, got):
+        assert a["n"] == b["n"]
+        for k in keys:
+            assert np.array_equal(a[k], b[k]), k
+    batch = ex.extract_batch([frames[1], frames[2]])       # a batched submit on the same slot in between
+    for a, b in zip(ref[1:3], batch):
+        for k in keys:
+            assert np.array_equal(a[k], b[k]), k
+    again = ex.extract(frames[3])
+    for k in keys:
+        assert np.array_equal(again[k], ref[3][k]), k
+    ex.set_score_threshold(0.02)                           # baked into the graph: must be re-captured
+    hi = ex.extract(frames[0])
+    assert hi["n"] == ref_hi["n"] < ref[0]["n"]
+    for k in keys:
+        assert np.array_equal(hi[k], ref_hi[k]), k
+    ex.close()
