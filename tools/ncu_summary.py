@@ -21,13 +21,17 @@ TO_BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
 def main(rep, md_out, json_out, title, frames):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):      # the raw page exported on the GPU box (reports above 64 MiB do not travel back)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     kcol = hdr.index("Kernel Name")
     out = [f"# {title}", "",
-           f"Workload: `python tools/bringup.py profile 480 752 {frames}` = {frames} frames of 752x480 per launch. ncu replays each kernel "
-           "~40x cold-cache and serialised: compare shares and ratios, not absolute times.", ""]
+           f"Workload: `python tools/r02_kernels.py` (default plan: {frames} frames of 752x480 per launch; exact-mode plan: 16 frames; matcher "
+           "2001 x 1777 rows; guided search m = 1000). ncu replays each kernel ~40x cold-cache and serialised: compare shares and ratios, "
+           "not absolute times.", ""]
     traffic = {"frames_per_launch": frames}
     for r in rows[2:]:
         name = r[kcol]
@@ -43,6 +47,8 @@ def main(rep, md_out, json_out, title, frames):
         key = re.sub(r"^void ", "", name)
         key = key[:key.rindex("(")] if "(" in key else key      # drop the parameter list, keep template arguments
         traffic.setdefault(key, by)
+        if "sm__throughput.avg.pct_of_peak_sustained_elapsed" in hdr:
+            out.insert(len(out) - 1, f"| sm__throughput.avg.pct_of_peak_sustained_elapsed | {r[hdr.index('sm__throughput.avg.pct_of_peak_sustained_elapsed')]} | % |")
     open(md_out, "w").write("\n".join(out))
     json.dump(traffic, open(json_out, "w"), indent=1)
     print(json.dumps(traffic, indent=1))
