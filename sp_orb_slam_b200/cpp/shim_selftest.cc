@@ -1,8 +1,11 @@
 // Exercises the drop-in classes the way the reference's callers do
 // (Frame::ExtractORB, frame.cpp:296-314; trackReferenceKeyFrameANN, tracker.cpp:372-417).
 // usage: shim_selftest <weights> <H> <W> <raw u8 frame A> <raw u8 frame B> <out prefix>
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 
@@ -103,6 +106,27 @@ int main(int argc, char **argv) {
   f = fopen((pre + "_kps_a.txt").c_str(), "w");
   for (size_t i = 0; i < ka.size(); i++) fprintf(f, "%.1f %.1f %.9g %.9g %.9g\n", ka[i].pt.x, ka[i].pt.y, ka[i].response, cov[i].x(), cov[i].y());
   fclose(f);
+  {  // throughput mode of the shim: same key points, fp16-rounded descriptors, heat maps fetched on demand and bit-identical
+    setenv("SPFE_SHIM_LAZY_HEAT", "1", 1);
+    setenv("SPFE_SHIM_DESC_F16", "1", 1);
+    SPExtractor lazy(800);
+    unsetenv("SPFE_SHIM_LAZY_HEAT");
+    unsetenv("SPFE_SHIM_DESC_F16");
+    std::vector<cv::KeyPoint> kl;
+    cv::Mat dl;
+    lazy(b, cv::Mat(), kl, dl);
+    bool same = kl.size() == kb.size() && lazy.heat_.empty();
+    double worst = 0;
+    for (size_t i = 0; same && i < kl.size(); i++) {
+      same = kl[i].pt.x == kb[i].pt.x && kl[i].pt.y == kb[i].pt.y && kl[i].response == kb[i].response;
+      for (int k = 0; k < 256; k++) worst = std::max(worst, (double)std::fabs(dl.at<float>((int)i, k) - db.at<float>((int)i, k)));
+    }
+    cv::Mat h = lazy.getHeatMap(), hi = lazy.getHeatInv();
+    same = same && !h.empty() && memcmp(h.data, sp->heat_.data, (size_t)camera::height * camera::width * 4) == 0 &&
+           memcmp(hi.data, sp->heat_inv_.data, (size_t)camera::height * camera::width * 4) == 0;
+    printf("throughput mode (lazy heat, fp16 descriptors): %s, max |d desc| %.2e\n", same ? "identical" : "DIFFERENT", worst);
+    if (!same || worst > 5e-4) return 3;
+  }
   bool threw = false;
   try { std::vector<cv::KeyPoint> k; cv::Mat d; (*ex)(cv::Mat(), cv::Mat(), k, d); } catch (const std::runtime_error &e) { threw = std::string(e.what()) == "input image is empty"; }
   printf("empty image throws runtime_error(\"input image is empty\"): %s\n", threw ? "yes" : "NO");

@@ -55,7 +55,12 @@ class SPExtractor : public BaseExtractor {
                   cv::OutputArray descriptors) override;
 
   cv::Mat getMask() { return mask_; }
-  cv::Mat getHeatMap() { return heat_; }
+  // Throughput mode (environment SPFE_SHIM_LAZY_HEAT=1 when the extractor is constructed): heat_ / heat_inv_ are not
+  // copied on every call -- they stay on the device, where computeCovariance consumed them -- and these two getters
+  // fetch them for the last frame on demand (spfe_fetch_heat, bit-identical to the eager copy).  The reference reads the
+  // member directly at frame.cpp:304; in this mode that line becomes `getHeatMap()`.
+  cv::Mat getHeatMap();
+  cv::Mat getHeatInv();
   const std::vector<Eigen::Vector2f> getCov() { return cov2_; }
   const std::vector<Eigen::Vector2f> getCov2Inv() { return cov2_inv_; }
 
@@ -70,6 +75,7 @@ class SPExtractor : public BaseExtractor {
   std::vector<Eigen::Vector2f> cov2_, cov2_inv_;
   int num_feature_;
   spfe_ctx *ctx_ = nullptr;
+  bool lazy_heat_ = false, desc_f16_ = false;  // SPFE_SHIM_LAZY_HEAT / SPFE_SHIM_DESC_F16 at construction
 };
 
 }  // namespace orbslam

@@ -1,5 +1,7 @@
 // Implementation of the drop-in classes declared in sp_extractor.h / sp_matcher.h.
 #include <cmath>
+#include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -8,6 +10,27 @@
 #include "optimizer_dust.h"
 
 namespace orbslam {
+
+namespace {
+// IEEE binary16 -> binary32 (subnormals and infinities included)
+inline float half_to_float(uint16_t h) {
+  const uint32_t sign = static_cast<uint32_t>(h & 0x8000u) << 16, exp = (h >> 10) & 0x1Fu, man = h & 0x3FFu;
+  uint32_t bits;
+  if (exp == 0) {
+    if (man == 0) bits = sign;
+    else {
+      int e = -1;
+      uint32_t m = man;
+      do { e++; m <<= 1; } while (!(m & 0x400u));
+      bits = sign | static_cast<uint32_t>(127 - 15 - e) << 23 | (m & 0x3FFu) << 13;
+    }
+  } else if (exp == 31) bits = sign | 0x7F800000u | man << 13;
+  else bits = sign | (exp + 127 - 15) << 23 | man << 13;
+  float f;
+  memcpy(&f, &bits, 4);
+  return f;
+}
+}  // namespace
 
 #ifndef SPFE_WITH_ORBSLAM_CONFIG
 namespace camera { int width = 752, height = 480; }
@@ -53,6 +76,12 @@ SPExtractor::SPExtractor(int nfeatures_) : BaseExtractor(nfeatures_, 1.0f, 1, 1,
   spfe_config cfg;
   spfe_default_config(&cfg, camera::height, camera::width, nfeatures_);
   cfg.weights_path = common::model_path.c_str();
+  // Opt-in throughput mode: the two largest outputs shrink.  Defaults = the reference's behaviour.
+  const char *lz = getenv("SPFE_SHIM_LAZY_HEAT"), *h16 = getenv("SPFE_SHIM_DESC_F16");
+  lazy_heat_ = lz && lz[0] == '1';
+  desc_f16_ = h16 && h16[0] == '1';
+  if (lazy_heat_) cfg.flags = (cfg.flags & ~(SPFE_EMIT_HEAT | SPFE_EMIT_HEAT_INV)) | SPFE_LAZY_HEAT;
+  if (desc_f16_) cfg.flags |= SPFE_DESC_F16;
   if (spfe_create(&cfg, &ctx_) != SPFE_OK) throw std::runtime_error(std::string("SPExtractor: ") + spfe_last_error(nullptr));
   // The matcher and the optimiser share the FIRST extractor's device context (the reference has exactly one: the "ini"
   // extractor aliases it, tracker.cpp:131,144); a second extractor (another camera) must not silently redirect them.
@@ -82,8 +111,13 @@ void SPExtractor::operator()(cv::InputArray image_, cv::InputArray /*mask*/, std
   semi_dust_ = wrap(hc, wc, CV_32FC1, o.semi_dust);
   dense_dust_ = wrap(hc, wc, CV_32FC1, o.dense_dust);
   occ_grid_ = wrap(hc, wc, CV_16SC1, o.occ_grid);
-  heat_ = wrap(image.rows, image.cols, CV_32FC1, o.heat);
-  heat_inv_ = wrap(image.rows, image.cols, CV_32FC1, o.heat_inv);
+  if (lazy_heat_) {
+    heat_ = cv::Mat();  // fetched by getHeatMap() / getHeatInv() if somebody asks
+    heat_inv_ = cv::Mat();
+  } else {
+    heat_ = wrap(image.rows, image.cols, CV_32FC1, o.heat);
+    heat_inv_ = wrap(image.rows, image.cols, CV_32FC1, o.heat_inv);
+  }
   keypoints.clear();
   keypoints.reserve(o.n);
   cov2_.clear();
@@ -96,7 +130,27 @@ void SPExtractor::operator()(cv::InputArray image_, cv::InputArray /*mask*/, std
     cov2_inv_.emplace_back(o.cov2_inv[2 * i], o.cov2_inv[2 * i + 1]);
   }
   descriptors.create(o.n, SPFE_DESC_DIM, CV_32FC1);  // sp_extractor.cpp:512-513
-  if (o.n > 0) memcpy(descriptors.getMat().data, o.desc, static_cast<size_t>(o.n) * SPFE_DESC_DIM * sizeof(float));
+  if (o.n > 0 && !desc_f16_) memcpy(descriptors.getMat().data, o.desc, static_cast<size_t>(o.n) * SPFE_DESC_DIM * sizeof(float));
+  if (o.n > 0 && desc_f16_) {  // binary16 on the wire, widened here (exact: every fp16 value is an fp32 value)
+    float *dst = reinterpret_cast<float *>(descriptors.getMat().data);
+    for (size_t i = 0; i < static_cast<size_t>(o.n) * SPFE_DESC_DIM; i++) dst[i] = half_to_float(o.desc_f16[i]);
+  }
+}
+
+cv::Mat SPExtractor::getHeatMap() {
+  if (lazy_heat_ && heat_.empty()) {
+    heat_.create(camera::height, camera::width, CV_32FC1);
+    if (spfe_fetch_heat(ctx_, 0, 0, reinterpret_cast<float *>(heat_.data), nullptr) != SPFE_OK) throw std::runtime_error(spfe_last_error(ctx_));
+  }
+  return heat_;
+}
+
+cv::Mat SPExtractor::getHeatInv() {
+  if (lazy_heat_ && heat_inv_.empty()) {
+    heat_inv_.create(camera::height, camera::width, CV_32FC1);
+    if (spfe_fetch_heat(ctx_, 0, 0, nullptr, reinterpret_cast<float *>(heat_inv_.data)) != SPFE_OK) throw std::runtime_error(spfe_last_error(ctx_));
+  }
+  return heat_inv_;
 }
 
 }  // namespace orbslam

@@ -509,6 +509,7 @@ def test_cpp_shim_selftest(tmp_path, ex_cache):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert 'throws runtime_error("input image is empty"): yes' in r.stdout
+    assert "throughput mode (lazy heat, fp16 descriptors): identical" in r.stdout
     ex = ex_cache(H, W, 800, max_batch=4)
     a, b = ex.extract(frames[0]), ex.extract(frames[1])
     kps = np.loadtxt(pre + "_kps_a.txt").reshape(-1, 5)
