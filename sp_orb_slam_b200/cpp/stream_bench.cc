@@ -1,7 +1,9 @@
 // Native throughput harness over the C ABI (no Python in the loop): one camera stream, `slots` batches in flight,
 // frames wait in page-locked memory (spfe_host_alloc), results land in the context's pinned buffers.
-// usage: stream_bench <weights> <H> <W> <batch> <slots> <steps>
+// usage: stream_bench <weights> <H> <W> <batch> <slots> <steps> [full]
 // Prints one JSON line: frames/s end to end (H2D + extract + covariance + match to the previous frame + D2H).
+// Default = the throughput output set of bench.py (n fp16 descriptor rows per frame, heat maps stay on the device);
+// "full" = every output of SPExtractor::operator() copied eagerly (fp32 descriptors, H x W heat_).
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -27,14 +29,16 @@ static void make_frame(uint8_t *img, int H, int W, int t) {
 }
 
 int main(int argc, char **argv) {
-  if (argc < 7) { fprintf(stderr, "usage: stream_bench <weights> <H> <W> <batch> <slots> <steps>\n"); return 2; }
+  if (argc < 7) { fprintf(stderr, "usage: stream_bench <weights> <H> <W> <batch> <slots> <steps> [full]\n"); return 2; }
+  const bool full = argc > 7 && !strcmp(argv[7], "full");
   const int H = atoi(argv[2]), W = atoi(argv[3]), B = atoi(argv[4]), S = atoi(argv[5]), steps = atoi(argv[6]);
   spfe_config cfg;
   spfe_default_config(&cfg, H, W, 800);
   cfg.weights_path = argv[1];
   cfg.max_batch = B;
   cfg.num_slots = S;
-  cfg.flags = SPFE_EMIT_HEAT | SPFE_EMIT_COV | SPFE_MATCH_PREV;  // everything Frame::ExtractORB reads
+  cfg.flags = full ? (SPFE_EMIT_HEAT | SPFE_EMIT_COV | SPFE_MATCH_PREV)  // everything Frame::ExtractORB reads, eagerly
+                   : (SPFE_EMIT_COV | SPFE_MATCH_PREV | SPFE_LAZY_HEAT | SPFE_DESC_F16);
   spfe_ctx *ctx = nullptr;
   if (spfe_create(&cfg, &ctx) != SPFE_OK) { fprintf(stderr, "spfe_create: %s\n", spfe_last_error(nullptr)); return 1; }
   const size_t px = static_cast<size_t>(H) * W;
@@ -43,12 +47,13 @@ int main(int argc, char **argv) {
   if (!frames) { fprintf(stderr, "spfe_host_alloc failed\n"); return 1; }
   for (int i = 0; i < pool * B; i++) make_frame(frames + i * px, H, W, i);
   std::vector<spfe_frame_out> outs(B);
-  long long kps = 0, matches = 0;
+  long long kps = 0, matches = 0, d2h = 0;
   auto run = [&](int n, bool count) -> int {
     for (int i = 0; i < n + S; i++) {
       const int s = i % S;
       if (i >= S) {
         if (spfe_wait(ctx, s, outs.data()) != SPFE_OK) { fprintf(stderr, "spfe_wait: %s\n", spfe_last_error(ctx)); return 1; }
+        if (count) d2h += spfe_last_d2h_bytes(ctx, s);
         if (count)
           for (int b = 0; b < B; b++) {
             kps += outs[b].n;
@@ -67,9 +72,9 @@ int main(int argc, char **argv) {
   if (run(steps, true)) return 1;
   const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   printf("{\"frames_per_s\": %.1f, \"frames\": %d, \"ms_per_step\": %.3f, \"keypoints_per_frame\": %.1f, \"matches_per_frame\": %.1f, "
-         "\"launches\": %lld}\n",
+         "\"launches\": %lld, \"d2h_bytes_per_frame\": %.0f, \"outputs\": \"%s\"}\n",
          steps * B / sec, steps * B, sec / steps * 1e3, double(kps) / (steps * B), double(matches) / (steps * B),
-         static_cast<long long>(spfe_launch_count(ctx)));
+         static_cast<long long>(spfe_launch_count(ctx)), double(d2h) / (steps * B), full ? "full" : "throughput");
   spfe_host_free(frames);
   spfe_destroy(ctx);
   return 0;
