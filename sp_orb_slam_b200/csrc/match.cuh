@@ -20,7 +20,6 @@ struct MatchScratch {
   unsigned long long *rowbest = nullptr, *colbest = nullptr;  // [cap]
   int *q2t = nullptr;                                          // [cap]
   float *dist = nullptr;                                       // [cap]
-  float *dq = nullptr, *dt = nullptr;                          // [cap][256] staging for host-pointer calls
   int *dn = nullptr;                                           // [2] nq, nt
   int cap = 0;
 };
