@@ -97,3 +97,20 @@ def test_exact_identical_on_fresh_frames(weights, ex_cache):
             assert np.array_equal(o["occ_grid"], ref["occ_grid"])
             total += o["n"]
     assert total > 1500
+
+
+def test_exact_1080p_2000_keypoints_identical(weights, ex_cache):
+    """BASELINE configs[4] geometry: 1920x1080, 2000-key-point budget, cap reached -- the exact mode's key-point set,
+    raster order and occ_grid equal the oracle's; covariance responses follow."""
+    H, W, nf = 1080, 1920, 2000
+    ex = ex_cache(H, W, nf, max_batch=1, emit_cov=True, emit_heat=True)
+    frame = synth.make_frame(H, W, seed=17, n_shapes=3600)
+    o = ex.extract_batch([frame])[0]
+    ref = O.extract(weights, frame, nf)
+    assert o["n"] == ref["n"] == nf + 1
+    assert np.array_equal(o["kp_xy"], ref["kp_xy"]) and np.array_equal(o["occ_grid"], ref["occ_grid"])
+    np.testing.assert_allclose(o["kp_score"], ref["score"], atol=EXACT_SCORE_ATOL, rtol=EXACT_SCORE_RTOL)
+    cos = np.einsum("ij,ij->i", o["desc"], ref["desc"])
+    assert cos.min() > 1 - COS_TOL
+    np.testing.assert_allclose(o["heat"], ref["heat"], atol=2e-4)                     # measured 6e-5 .. 8e-5 (default mode: 2e-2)
+    assert np.isclose(o["kp_response"], ref["kp_response"], atol=2e-4).mean() > 0.999
