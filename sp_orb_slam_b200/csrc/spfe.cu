@@ -1929,6 +1929,7 @@ int spfe_reset_stream(spfe_ctx *c, int32_t slot) {
   if (rc) return rc;
   CU_OK(c, cudaSetDevice(c->cfg.device_id));
   CU_OK(c, cudaMemsetAsync(c->slots[slot].count_all, 0, sizeof(int), c->slots[slot].stream));
+  CU_OK(c, cudaStreamSynchronize(c->slots[slot].stream));  // the next frame may arrive as a graph launch on another queue
   return SPFE_OK;
 }
 
