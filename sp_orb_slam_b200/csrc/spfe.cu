@@ -136,7 +136,7 @@ struct Slot {
   long long d2h_bytes = 0;       // what the last spfe_wait moved device -> host
   // spfe_extract's single-frame launch plan as a CUDA graph (slot 0): H2D, every kernel, all D2H copies in one launch
   cudaGraphExec_t graph = nullptr;
-  cudaEvent_t ev_graph = nullptr, ev_heat = nullptr;
+  cudaEvent_t ev_graph = nullptr, ev_heat = nullptr, ev_nms = nullptr;
   bool capturing = false, graph_inflight = false, eager_desc = false;
   long long graph_launches = 0, graph_d2h = 0;
   float graph_thresh = 0.f;
@@ -547,28 +547,10 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     mark("convDb+norm", stage_flop(LDB, hc, wc), (512.0 + 512.0) * hc * wc * B);
   }
   }  // default (fp16) convolutions
-  {
-    NmsArgs n;
-    n.score = s.score; n.argmax = s.argmax; n.hc = hc; n.wc = wc; n.thresh = c->cfg.score_thresh;
-    n.radius = c->cfg.nms_radius; n.border = c->cfg.border; n.cap = c->cap;
-    n.count = s.count; n.kp_xy = s.kp_xy; n.kp_score = s.kp_score; n.occ = s.occ; n.scratch = s.scratch;
-    n.list_smem = c->nms_list_smem;
-    nms_kernel<<<B, 1024, c->nms_smem, st>>>(n);
-    c->launches++;
-    CU_OK(c, cudaGetLastError());
-    mark("nms", 0, 7.0 * c->cells * B);
-  }
-  {
-    dim3 grid((c->cap + 7) / 8, B);
-    sample_desc_kernel<<<grid, 256, 0, st>>>(s.coarse, s.kp_xy, s.count, s.desc, hc, wc, c->cap,
-                                             s.x16 ? s.x16 + static_cast<size_t>(c->rows_pad) * 256 : nullptr, c->rows_pad);
-    c->launches++;
-    CU_OK(c, cudaGetLastError());
-    mark("sample_desc", 0, 3072.0 * c->cap * B);
-  }
-  // computeCovariance (with to_heat) and the match to the previous frame both depend only on what is on the stream so
-  // far: outside profiling runs the former goes to the auxiliary queue so that its latency-bound kernels overlap the
-  // matcher's; the two queues join again at the end of the plan
+  // computeCovariance (with to_heat) runs beside the rest of the tail: outside profiling runs it goes to the auxiliary
+  // queue.  to_heat depends only on the detector head, so it starts at once (next to the NMS, which occupies 64 SMs);
+  // the floods wait for the NMS (they need the key points) and overlap the descriptor sampling and the matcher; the two
+  // queues join again at the end of the plan.
   const bool fork = tm == nullptr && c->cov && c->match_prev && c->aux != nullptr && !c->slot_streams;
   cudaStream_t st_main = st;
   if (fork) {
@@ -584,6 +566,31 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     mark("heat_norm", 0, (c->heat_host ? 12.0 : 8.0) * H * W * B);
     if (!tm && (c->heat_host || c->heat_inv_host)) CU_OK(c, cudaEventRecord(s.ev_heat, st));  // the heat maps may leave while the floods run
   }
+  st = st_main;
+  {
+    NmsArgs n;
+    n.score = s.score; n.argmax = s.argmax; n.hc = hc; n.wc = wc; n.thresh = c->cfg.score_thresh;
+    n.radius = c->cfg.nms_radius; n.border = c->cfg.border; n.cap = c->cap;
+    n.count = s.count; n.kp_xy = s.kp_xy; n.kp_score = s.kp_score; n.occ = s.occ; n.scratch = s.scratch;
+    n.list_smem = c->nms_list_smem;
+    nms_kernel<<<B, 1024, c->nms_smem, st>>>(n);
+    c->launches++;
+    CU_OK(c, cudaGetLastError());
+    mark("nms", 0, 7.0 * c->cells * B);
+  }
+  if (fork) {
+    CU_OK(c, cudaEventRecord(s.ev_nms, st_main));
+    CU_OK(c, cudaStreamWaitEvent(c->aux, s.ev_nms, 0));
+  }
+  {
+    dim3 grid((c->cap + 7) / 8, B);
+    sample_desc_kernel<<<grid, 256, 0, st>>>(s.coarse, s.kp_xy, s.count, s.desc, hc, wc, c->cap,
+                                             s.x16 ? s.x16 + static_cast<size_t>(c->rows_pad) * 256 : nullptr, c->rows_pad);
+    c->launches++;
+    CU_OK(c, cudaGetLastError());
+    mark("sample_desc", 0, 3072.0 * c->cap * B);
+  }
+  if (fork) st = c->aux;
   if (c->cov) {  // computeCovariance on the device (cov.cuh): parallel floods, then sequential replay of the conflicted few
     const size_t px = static_cast<size_t>(H) * W;
     if (s.capturing)  // a replayed graph cannot count epochs: it clears its own frames and claims with the largest tag
@@ -808,6 +815,7 @@ static int create_impl(spfe_ctx *c) {
     CU_OK(c, cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
     CU_OK(c, cudaEventCreateWithFlags(&s.ev_graph, cudaEventDisableTiming));
     CU_OK(c, cudaEventCreateWithFlags(&s.ev_heat, cudaEventDisableTiming));
+    CU_OK(c, cudaEventCreateWithFlags(&s.ev_nms, cudaEventDisableTiming));
     const size_t xm = c->exact ? 2 : 1;  // exact mode: every activation is a (hi, lo) pair
     if ((rc = dev_alloc(c, &s.d_gray, Bm * px))) return rc;
     if (!c->fused_conv1 && (rc = dev_alloc(c, &s.a1a, Bm * px * 64 * xm))) return rc;
@@ -1040,7 +1048,7 @@ void spfe_destroy(spfe_ctx *c) {
   cudaDeviceSynchronize();
   for (Slot &s : c->slots) {
     if (s.stream && c->slot_streams) cudaStreamDestroy(s.stream);
-    for (cudaEvent_t e : {s.ev_in, s.ev_done, s.ev_out, s.ev_fork, s.ev_join, s.ev_graph, s.ev_heat}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {s.ev_in, s.ev_done, s.ev_out, s.ev_fork, s.ev_join, s.ev_graph, s.ev_heat, s.ev_nms}) if (e) cudaEventDestroy(e);
     if (s.graph) cudaGraphExecDestroy(s.graph);
     if (s.ev0) cudaEventDestroy(s.ev0);
     if (s.ev1) cudaEventDestroy(s.ev1);
