@@ -2,7 +2,7 @@
 // (oracle/sp_post.c::orc_search_guided, pinned to the reference's own SearchByProjection) on the same inputs -- without
 // the Python wrapper in the timed region.  Measurement tool, not product code.
 //   g++ -O2 -std=c++17 -I include tools/guided_native.cc -L sp_orb_slam_b200/lib -lspfe -L oracle/_build -lsporacle \
-//       -Wl,-rpath,\$ORIGIN -Wl,-rpath,\$ORIGIN/../../oracle/_build -o sp_orb_slam_b200/lib/guided_native
+//       -Wl,-rpath,\$ORIGIN/../../sp_orb_slam_b200/lib -Wl,-rpath,\$ORIGIN/../../oracle/_build -o tools/_build/guided_native
 #include <chrono>
 #include <cmath>
 #include <cstdio>
