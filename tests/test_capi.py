@@ -149,3 +149,23 @@ def test_abi_struct_layouts_match_ctypes(tmp_path):
             if decl.strip():
                 n_decl += len(decl.split(","))
         assert n_decl == len(ct._fields_), cname
+
+
+def test_round2_entries_reject_null_arguments(lib):
+    """The entries added in round 2 validate their arguments before touching CUDA (no GPU needed): NULL context / set."""
+    ctx_null = C.c_void_p()
+    assert lib.spfe_desc_set_size(None) == capi.ERR_INVALID
+    assert lib.spfe_last_d2h_bytes(None, 0) == capi.ERR_INVALID
+    assert lib.spfe_fetch_heat(None, 0, 0, None, None) == capi.ERR_INVALID
+    out = C.c_void_p()
+    assert lib.spfe_desc_set_create(None, 16, C.byref(out)) == capi.ERR_INVALID and not out.value
+    assert lib.spfe_desc_set_upload(None, None, None, 0) == capi.ERR_INVALID
+    assert lib.spfe_desc_set_from_frame(None, None, 0, 0, None, 0) == capi.ERR_INVALID
+    assert lib.spfe_match_mutual_nn_sets(None, None, None, None, None) == capi.ERR_INVALID
+    assert lib.spfe_match_knn2_sets(None, None, None, None, None) == capi.ERR_INVALID
+    assert lib.spfe_search_guided_sets(None, None, None, None, None, None, None) == capi.ERR_INVALID
+    lib.spfe_desc_set_destroy(None, None)                      # a no-op, not a crash
+    assert capi.LAZY_HEAT == 16 and capi.DESC_F16 == 32 and capi.EXACT == 64
+    hdr = open(os.path.join(ROOT, "include", "spfe.h")).read()
+    for name, val in (("SPFE_LAZY_HEAT", 4), ("SPFE_DESC_F16", 5), ("SPFE_EXACT", 6)):
+        assert re.search(rf"{name}\s*=\s*1u\s*<<\s*{val}\b", hdr), name
