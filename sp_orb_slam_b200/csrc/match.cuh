@@ -272,7 +272,7 @@ __device__ __forceinline__ void rerank_row(const float *me, const float *other, 
     const int idx = __float_as_int(ce.y);
     // K near-ties in one virtual block (its K-th nominee is within 2 beta of s_R): a (K+1)-th may hide behind them
     const unsigned scan = __ballot_sync(0xffffffffu, live && (lane % K) == K - 1 && idx >= 0 && ce.x >= thr_scan);
-    const bool block_scanned = (scan >> ((lane / K) * K + K - 1)) & 1u;
+    const bool block_scanned = lane < CH && ((scan >> ((lane / K) * K + K - 1)) & 1u);  // (lanes >= CH are not live)
     unsigned nom = __ballot_sync(0xffffffffu, live && idx >= 0 && ce.x >= thr && !block_scanned);
     while (nom) {  // warp-uniform
       const int l = __ffs(nom) - 1;
