@@ -130,21 +130,36 @@ __global__ void __launch_bounds__(1024) nms_kernel(const NmsArgs p) {
   const int W = p.wc * 8, H = p.hc * 8;
 
   if (tid == 0) { s_cnt = 0; s_cnt2 = 0; }
-  for (int c = tid; c < cells; c += nt) {
-    const float sc = score[c];
-    const bool cand = sc >= p.thresh;
-    s_sc[c] = sc;
-    s_pos[c] = amax[c];
-    s_st[c] = cand ? ST_UNDEC : ST_NONE;
-    occ[c] = -1;
+  __syncthreads();
+  // The undecided candidates live in a compact list (two halves of the frame's scratch, ping-pong): a round touches only
+  // the cells that are still open -- a quarter of the cells in round 0 on dense frames, a handful after three rounds --
+  // instead of striding over every cell (1920x1080: 32 400 cells per round and frame on one SM).
+  int *ul_cur = reinterpret_cast<int *>(p.scratch + static_cast<size_t>(b) * cells), *ul_nxt = ul_cur + cells;
+  const unsigned lane_lt0 = (1u << (tid & 31)) - 1u;
+  for (int c0 = 0; c0 < cells; c0 += nt) {
+    const int c = c0 + tid;
+    bool cand = false;
+    if (c < cells) {
+      const float sc = score[c];
+      cand = sc >= p.thresh;
+      s_sc[c] = sc;
+      s_pos[c] = amax[c];
+      s_st[c] = cand ? ST_UNDEC : ST_NONE;
+      occ[c] = -1;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, cand);
+    int base = 0;
+    if ((tid & 31) == 0 && m) base = atomicAdd(&s_cnt, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (cand) ul_cur[base + __popc(m & lane_lt0)] = c;
   }
   __syncthreads();
 
-  // ---- fixpoint of the greedy suppression
-  for (int round = 0; round < cells + 2; round++) {
-    int undecided = 0;
-    for (int c = tid; c < cells; c += nt) {
-      if (s_st[c] != ST_UNDEC) continue;
+  // ---- fixpoint of the greedy suppression (Jacobi: a round reads only the previous round's states)
+  int U = s_cnt;
+  for (int round = 0; round < cells + 2 && U > 0; round++) {
+    for (int e = tid; e < U; e += nt) {
+      const int c = ul_cur[e];
       const int cy = c / p.wc, cx = c - cy * p.wc;
       const int px = cx * 8 + (s_pos[c] & 7), py = cy * 8 + (s_pos[c] >> 3);
       const float sc = s_sc[c];
@@ -168,13 +183,32 @@ __global__ void __launch_bounds__(1024) nms_kernel(const NmsArgs p) {
         }
       }
       s_new[c] = any_kept ? ST_SUPP : (all_supp ? ST_KEPT : ST_UNDEC);
-      if (!any_kept && !all_supp) undecided = 1;
+    }
+    if (tid == 0) s_cnt2 = 0;
+    __syncthreads();
+    for (int e0 = 0; e0 < U; e0 += nt) {  // apply, and keep the still-undecided cells for the next round
+      const int e = e0 + tid;
+      bool open = false;
+      int c = 0;
+      if (e < U) {
+        c = ul_cur[e];
+        const uint8_t st = s_new[c];
+        s_st[c] = st;
+        open = st == ST_UNDEC;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, open);
+      int base = 0;
+      if ((tid & 31) == 0 && m) base = atomicAdd(&s_cnt2, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (open) ul_nxt[base + __popc(m & lane_lt0)] = c;
     }
     __syncthreads();
-    for (int c = tid; c < cells; c += nt)
-      if (s_st[c] == ST_UNDEC) s_st[c] = s_new[c];
-    if (!__syncthreads_or(undecided)) break;
+    U = s_cnt2;
+    int *t = ul_cur; ul_cur = ul_nxt; ul_nxt = t;
+    __syncthreads();  // everybody has read s_cnt2 before the next round clears it
   }
+  if (tid == 0) { s_cnt = 0; s_cnt2 = 0; }
+  __syncthreads();
 
   // ---- cap: keep the `cap` best survivors (score desc, ties by cell index asc)
   // (list appends are warp-aggregated: one shared-memory atomic per warp instead of one per survivor)
