@@ -305,6 +305,11 @@ int spfe_timer_stop(spfe_ctx *ctx, int32_t slot, float *ms);
 int64_t spfe_check_weights(const char *path, char *err, size_t errcap);
 /* Number of kernels this library has launched on the context so far. */
 int64_t spfe_launch_count(const spfe_ctx *ctx);
+/* CUDA events around the dominant kernel (the fused conv1a + conv1b) of every batch submitted from now on, the last 64
+ * kept: spfe_dom_time returns their average launch duration -- the kernel timed INSIDE a long run (bench.py quotes it
+ * against the sustained peak), where spfe_profile_device times it in an isolated 4-ms pass.  Default mode only. */
+int spfe_dom_timing(spfe_ctx *ctx, int32_t enable);
+int spfe_dom_time(spfe_ctx *ctx, float *avg_ms, int32_t *count);
 /* Runs one device-resident batch with CUDA events around every stage; writes
  * up to `cap` (name, ms) pairs.  Returns the number of stages. */
 typedef struct spfe_stage_time { char name[24]; float ms; double flop; double bytes; } spfe_stage_time;

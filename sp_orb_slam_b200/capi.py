@@ -13,7 +13,7 @@ OK, ERR_INVALID, ERR_EMPTY, ERR_WEIGHTS, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE = 0,
 
 EXPORTS = ["spfe_default_config", "spfe_create", "spfe_destroy", "spfe_last_error", "spfe_extract", "spfe_submit",
            "spfe_wait", "spfe_last_d2h_bytes", "spfe_fetch_heat", "spfe_submit_pinned", "spfe_host_alloc", "spfe_host_free", "spfe_submit_device", "spfe_slot_sync", "spfe_match_mutual_nn", "spfe_match_knn2", "spfe_desc_set_create", "spfe_desc_set_destroy", "spfe_desc_set_size", "spfe_desc_set_upload", "spfe_desc_set_from_frame", "spfe_match_mutual_nn_sets", "spfe_match_knn2_sets", "spfe_search_guided", "spfe_search_guided_sets", "spfe_dust_pose_optimize", "spfe_dust_pose_optimize_batch", "spfe_dust_linearize", "spfe_set_score_threshold", "spfe_reset_stream", "spfe_timer_start",
-           "spfe_timer_stop", "spfe_check_weights", "spfe_l2", "spfe_debug_read", "spfe_launch_count", "spfe_profile_device"]
+           "spfe_timer_stop", "spfe_check_weights", "spfe_l2", "spfe_debug_read", "spfe_launch_count", "spfe_dom_timing", "spfe_dom_time", "spfe_profile_device"]
 
 
 class Config(C.Structure):
@@ -120,6 +120,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.spfe_debug_read.restype = i64
     L.spfe_launch_count.argtypes = [vp]
     L.spfe_launch_count.restype = i64
+    L.spfe_dom_timing.argtypes = [vp, i32]
+    L.spfe_dom_time.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32)]
     L.spfe_profile_device.argtypes = [vp, i32, vp, i32, C.POINTER(StageTime), i32]
     _lib = L
     return L

@@ -186,6 +186,11 @@ struct spfe_ctx {
   bool pair_conv1 = true;    // SPFE_PAIR_CONV1=0: the fused conv1a+1b kernel single-CTA
   int nms_smem = 0, nms_list_smem = 0;  // dynamic shared memory of nms_kernel / whether its key list fits in it
   int cov_force = 0;  // SPFE_COV_FORCE (test hook): push floods down the big / sequential fallback paths
+  // spfe_dom_timing: CUDA events around the dominant kernel (conv1a+1b) of every batch, the last 64 kept -- its launch
+  // duration INSIDE a long run, which is what bench.py's roofline block quotes against the sustained peak
+  bool dom_timing = false;
+  std::vector<cudaEvent_t> dom_ev;
+  long long dom_n = 0;
   bool use_graph = true;  // SPFE_GRAPH=0: spfe_extract enqueues its launch plan call by call instead of replaying a CUDA graph
   bool pdl = false;  // SPFE_PDL=1: programmatic dependent launch of the tensor-core kernels (measured: no gain, the board is power-capped)
   int conv1_mode = 2;
@@ -462,6 +467,8 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     c->launches++;
   }
   int rc;
+  const bool dom = c->dom_timing && !tm && !s.capturing && !c->exact && c->fused_conv1 && !c->dom_ev.empty();
+  if (dom) CU_OK(c, cudaEventRecord(c->dom_ev[2 * (c->dom_n % 64)], st));
   if (c->exact) {
     if ((rc = run_convs_exact(c, s, B, tm))) return rc;
   } else {
@@ -485,6 +492,10 @@ int run_pipeline(spfe_ctx *c, Slot &s, int B, StageTimer *tm) {
     c->launches++;
     CU_OK(c, cudaGetLastError());
     mark("conv1a+1b", 2.0 * 9 * 64 * H * W * B + c->layers[L1B].flop_per_px * H * W * B, (1.0 + 32.0) * H * W * B);
+    if (dom) {
+      CU_OK(c, cudaEventRecord(c->dom_ev[2 * (c->dom_n % 64) + 1], st));
+      c->dom_n++;
+    }
   } else {  // unfused path (debugging aid: materialises the conv1a activation)
     dim3 grid((W + C1A_TW - 1) / C1A_TW, (H + C1A_TH - 1) / C1A_TH, B);
     conv1a_kernel<false><<<grid, 256, 0, st>>>(s.d_gray, s.a1a, c->w1a, c->b1a, B, H, W);
@@ -1055,6 +1066,7 @@ void spfe_destroy(spfe_ctx *c) {
   }
   set_free(c->tmp_q);
   set_free(c->tmp_t);
+  for (cudaEvent_t e : c->dom_ev) cudaEventDestroy(e);
   if (c->match_stream) cudaStreamDestroy(c->match_stream);
   if (c->guided_buf) cudaFree(c->guided_buf);
   if (c->dust_stage) cudaFreeHost(c->dust_stage);
@@ -2021,6 +2033,35 @@ int64_t spfe_debug_read(spfe_ctx *c, int32_t slot, const char *name, void *dst, 
 }
 
 int64_t spfe_launch_count(const spfe_ctx *c) { return c ? (int64_t)c->launches.load() : 0; }
+
+int spfe_dom_timing(spfe_ctx *c, int32_t enable) {
+  if (!c) return SPFE_ERR_INVALID;
+  CU_OK(c, cudaSetDevice(c->cfg.device_id));
+  if (enable && c->dom_ev.empty()) {
+    c->dom_ev.resize(128);
+    for (cudaEvent_t &e : c->dom_ev) CU_OK(c, cudaEventCreate(&e));
+  }
+  c->dom_timing = enable != 0;
+  c->dom_n = 0;
+  return SPFE_OK;
+}
+
+int spfe_dom_time(spfe_ctx *c, float *avg_ms, int32_t *count) {
+  if (!c) return SPFE_ERR_INVALID;
+  if (!avg_ms || !count) return c->fail(SPFE_ERR_INVALID, "spfe_dom_time: NULL output");
+  CU_OK(c, cudaSetDevice(c->cfg.device_id));
+  const int n = static_cast<int>(c->dom_n < 64 ? c->dom_n : 64);
+  double sum = 0;
+  for (int i = 0; i < n; i++) {
+    float ms = 0.f;
+    CU_OK(c, cudaEventSynchronize(c->dom_ev[2 * i + 1]));
+    CU_OK(c, cudaEventElapsedTime(&ms, c->dom_ev[2 * i], c->dom_ev[2 * i + 1]));
+    sum += ms;
+  }
+  *avg_ms = n ? static_cast<float>(sum / n) : 0.f;
+  *count = n;
+  return SPFE_OK;
+}
 
 int spfe_profile_device(spfe_ctx *c, int32_t slot, const void *d_gray, int32_t batch, spfe_stage_time *stages, int32_t cap) {
   int rc = check_slot(c, slot);

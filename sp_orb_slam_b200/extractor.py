@@ -389,6 +389,15 @@ class SPExtractor:
     def launch_count(self) -> int:
         return int(self._lib.spfe_launch_count(self._ctx))
 
+    def dom_timing(self, enable: bool) -> None:
+        self._check(self._lib.spfe_dom_timing(self._ctx, 1 if enable else 0))
+
+    def dom_time(self):
+        """-> (average launch duration in ms of the dominant kernel over the last <= 64 batches, how many)."""
+        ms, n = C.c_float(), C.c_int32()
+        self._check(self._lib.spfe_dom_time(self._ctx, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
     def profile_device(self, slot: int, d_ptr: int, batch: int):
         st = (capi.StageTime * 32)()
         n = self._check(self._lib.spfe_profile_device(self._ctx, slot, C.c_void_p(d_ptr), batch, st, 32))
