@@ -114,3 +114,24 @@ def test_exact_1080p_2000_keypoints_identical(weights, ex_cache):
     assert cos.min() > 1 - COS_TOL
     np.testing.assert_allclose(o["heat"], ref["heat"], atol=2e-4)                     # measured 6e-5 .. 8e-5 (default mode: 2e-2)
     assert np.isclose(o["kp_response"], ref["kp_response"], atol=2e-4).mean() > 0.999
+
+
+def test_exact_mode_through_every_entry(weights):
+    """Exact mode is a property of the context: the blocking call (CUDA-graph replay from the third call on), the batched
+    pipeline with the throughput output set and the in-pipeline matcher all give the exact-mode results."""
+    H, W, nf = 240, 320, 800
+    frames = synth.make_stream(H, W, 4, seed=31, n_shapes=260)
+    ex = SPExtractor(nf, H, W, WEIGHTS, max_batch=4, exact=True, match_prev=True, lazy_heat=True, desc_f16=True, emit_heat=False,
+                     emit_heat_inv=False, emit_cov=True)
+    batch = ex.extract_batch(list(frames))
+    ex.reset_stream(0)
+    single = [ex.extract(f) for f in frames]
+    for t, (a, b) in enumerate(zip(batch, single)):
+        ref = O.extract(weights, frames[t], nf)
+        assert np.array_equal(a["kp_xy"], ref["kp_xy"]) and np.array_equal(b["kp_xy"], ref["kp_xy"])
+        for k in ["kp_score", "desc", "occ_grid", "dense_dust", "cov2", "kp_response", "match_prev"]:
+            assert np.array_equal(a[k], b[k]), k
+        heat, _ = ex.fetch_heat(0, 0) if t == 3 else (None, None)
+        if heat is not None:
+            np.testing.assert_allclose(heat, ref["heat"], atol=2e-4)
+    ex.close()
