@@ -48,6 +48,7 @@ struct GuidedArgs {
   float *h_qdist;
   uint8_t *h_taken;
   int *h_overflow;
+  int smem_state;   // 1: the launch carries n * 5 + 16 bytes of dynamic shared memory for the resolve phase's taken / claim arrays
   float min_x, min_y, best_init, th_le, th_lt, c2;
 };
 
@@ -152,9 +153,21 @@ __device__ __forceinline__ void guided_decide(const GuidedArgs &a, int i, volati
 }
 
 __device__ __forceinline__ void guided_resolve(const GuidedArgs &a) {
+  extern __shared__ __align__(16) uint8_t guided_smem[];
   const int tid = threadIdx.x, nt = blockDim.x;
-  volatile uint8_t *taken = a.taken;
-  volatile int *kpmin = a.kpmin;
+  // The two arrays every round hammers -- which key points are taken, who claims which -- live in shared memory when
+  // they fit (n * 5 bytes): a round then costs shared-memory latencies instead of L2 round trips (the kernel is a chain
+  // of dependent rounds on one SM: 33 -> ~15 us at 1000 map points).
+  uint8_t *g_taken = a.taken;
+  int *g_kpmin = a.kpmin;
+  if (a.smem_state) {
+    g_taken = guided_smem;
+    g_kpmin = reinterpret_cast<int *>(guided_smem + ((a.n + 15) & ~15));
+    for (int k = tid; k < a.n; k += nt) { g_taken[k] = a.taken[k]; g_kpmin[k] = 0x7F7F7F7F; }
+    __syncthreads();
+  }
+  volatile uint8_t *taken = g_taken;
+  volatile int *kpmin = g_kpmin;
   volatile uint8_t *decided = a.decided;
   bool left = true;
   for (int round = 0; round < GUIDED_ROUNDS && left; round++) {
@@ -164,7 +177,7 @@ __device__ __forceinline__ void guided_resolve(const GuidedArgs &a) {
       const int nc = a.ncand[i];
       for (int c = 0; c < nc; c++) {
         const int kp = a.cand[static_cast<size_t>(i) * GUIDED_CAND + c];
-        if (!taken[kp]) atomicMin(a.kpmin + kp, tag | i);
+        if (!taken[kp]) atomicMin(g_kpmin + kp, tag | i);
       }
     }
     __syncthreads();
@@ -185,6 +198,10 @@ __device__ __forceinline__ void guided_resolve(const GuidedArgs &a) {
   if (left && tid == 0)  // conflict chains deeper than GUIDED_ROUNDS: the plain sequential loop for the rest
     for (int i = 0; i < a.m; i++)
       if (!decided[i]) guided_decide(a, i, taken);
+  if (a.smem_state) {
+    __syncthreads();
+    for (int k = tid; k < a.n; k += nt) a.taken[k] = g_taken[k];
+  }
 }
 
 constexpr int GUIDED_THREADS = 1024;  // 32 map points per CTA in the candidate phase; the resolve phase uses all of them

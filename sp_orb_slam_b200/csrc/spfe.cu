@@ -29,6 +29,7 @@
 
 using namespace spfe;
 
+static constexpr int GUIDED_SMEM_MAX = 160 * 1024;  // guided_kernel: taken / claim arrays of the resolve phase (n * 5 bytes)
 static constexpr int DUST_SMEM_MAX = 200 * 1024;  // dust_pose_kernel stages the dust map in shared memory up to this size
 
 namespace {
@@ -1036,6 +1037,7 @@ int spfe_create(const spfe_config *cfg, spfe_ctx **out) {
       nms_smem_max = c->nms_smem;
     }
     CU_OK(c, cudaFuncSetAttribute(dust_pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DUST_SMEM_MAX));
+    CU_OK(c, cudaFuncSetAttribute(guided_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GUIDED_SMEM_MAX));
     CU_OK(c, cudaFuncSetAttribute(conv1ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1ab::SMEM));
     CU_OK(c, cudaFuncSetAttribute(conv1ab_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c1m::SMEM));
     CU_OK(c, cudaFuncSetAttribute(conv1ab_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c1m::SMEM));
@@ -1747,7 +1749,9 @@ int guided_run(spfe_ctx *c, const spfe_guided_search *g, const spfe_desc_set *qs
   a.h_q2kp = reinterpret_cast<int *>(hb + o_q2kp); a.h_qdist = reinterpret_cast<float *>(hb + o_qdist);
   a.h_taken = hb + o_taken; a.h_overflow = reinterpret_cast<int *>(hb + o_over);
   a.min_x = g->min_x; a.min_y = g->min_y; a.best_init = g->best_init; a.th_le = g->th_le; a.th_lt = g->th_lt; a.c2 = g->c2_adaptive;
-  guided_kernel<<<(m + GUIDED_THREADS / 32 - 1) / (GUIDED_THREADS / 32), GUIDED_THREADS, 0, st>>>(a);
+  const size_t g_smem = ((static_cast<size_t>(n) + 15) & ~size_t(15)) + static_cast<size_t>(n) * 4 + 16;
+  a.smem_state = g_smem <= static_cast<size_t>(GUIDED_SMEM_MAX);
+  guided_kernel<<<(m + GUIDED_THREADS / 32 - 1) / (GUIDED_THREADS / 32), GUIDED_THREADS, a.smem_state ? g_smem : 0, st>>>(a);
   c->launches += 1;
   CU_OK(c, cudaGetLastError());
   CU_OK(c, cudaStreamSynchronize(st));  // the kernel's last CTA wrote the results into the page-locked block
