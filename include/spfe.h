@@ -303,6 +303,9 @@ int spfe_timer_stop(spfe_ctx *ctx, int32_t slot, float *ms);
 /* Parses a weight file with the library's own readers (no GPU needed).  Returns the number of
  * parameters (1300865 for SuperPoint) or a negative error; message in err[0..errcap). */
 int64_t spfe_check_weights(const char *path, char *err, size_t errcap);
+/* Parallel rounds the resolve phase of the last spfe_search_guided* call on this context ran (1 = no two queries
+ * competed for a key point; tests). */
+int32_t spfe_guided_last_rounds(const spfe_ctx *ctx);
 /* Number of kernels this library has launched on the context so far. */
 int64_t spfe_launch_count(const spfe_ctx *ctx);
 /* CUDA events around the dominant kernel (the fused conv1a + conv1b) of every batch submitted from now on, the last 64

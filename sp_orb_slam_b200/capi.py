@@ -12,7 +12,7 @@ EMIT_HEAT, EMIT_COV, MATCH_PREV, EMIT_HEAT_INV, LAZY_HEAT, DESC_F16, EXACT = 1, 
 OK, ERR_INVALID, ERR_EMPTY, ERR_WEIGHTS, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
 
 EXPORTS = ["spfe_default_config", "spfe_create", "spfe_destroy", "spfe_last_error", "spfe_extract", "spfe_submit",
-           "spfe_wait", "spfe_last_d2h_bytes", "spfe_fetch_heat", "spfe_submit_pinned", "spfe_host_alloc", "spfe_host_free", "spfe_submit_device", "spfe_slot_sync", "spfe_match_mutual_nn", "spfe_match_knn2", "spfe_desc_set_create", "spfe_desc_set_destroy", "spfe_desc_set_size", "spfe_desc_set_upload", "spfe_desc_set_from_frame", "spfe_match_mutual_nn_sets", "spfe_match_knn2_sets", "spfe_search_guided", "spfe_search_guided_sets", "spfe_dust_pose_optimize", "spfe_dust_pose_optimize_batch", "spfe_dust_linearize", "spfe_set_score_threshold", "spfe_reset_stream", "spfe_timer_start",
+           "spfe_wait", "spfe_last_d2h_bytes", "spfe_fetch_heat", "spfe_submit_pinned", "spfe_host_alloc", "spfe_host_free", "spfe_submit_device", "spfe_slot_sync", "spfe_match_mutual_nn", "spfe_match_knn2", "spfe_desc_set_create", "spfe_desc_set_destroy", "spfe_desc_set_size", "spfe_desc_set_upload", "spfe_desc_set_from_frame", "spfe_match_mutual_nn_sets", "spfe_match_knn2_sets", "spfe_search_guided", "spfe_search_guided_sets", "spfe_guided_last_rounds", "spfe_dust_pose_optimize", "spfe_dust_pose_optimize_batch", "spfe_dust_linearize", "spfe_set_score_threshold", "spfe_reset_stream", "spfe_timer_start",
            "spfe_timer_stop", "spfe_check_weights", "spfe_l2", "spfe_debug_read", "spfe_launch_count", "spfe_dom_timing", "spfe_dom_time", "spfe_profile_device"]
 
 
@@ -105,6 +105,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.spfe_match_knn2_sets.argtypes = [vp, vp, vp, vp, vp]
     L.spfe_search_guided.argtypes = [vp, C.POINTER(GuidedSearch), vp, vp, vp]
     L.spfe_search_guided_sets.argtypes = [vp, C.POINTER(GuidedSearch), vp, vp, vp, vp, vp]
+    L.spfe_guided_last_rounds.argtypes = [vp]
     L.spfe_dust_pose_optimize.argtypes = [vp, C.POINTER(DustPose), vp, vp, vp, C.POINTER(i32), C.POINTER(i32), vp]
     L.spfe_dust_pose_optimize_batch.argtypes = [vp, C.POINTER(DustPose), i32, vp, vp, vp, vp, vp]
     L.spfe_dust_linearize.argtypes = [vp, C.POINTER(DustPose), vp, vp, vp, vp, vp, vp]

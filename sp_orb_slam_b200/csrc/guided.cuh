@@ -47,7 +47,7 @@ struct GuidedArgs {
   int *h_q2kp;      // mapped host memory: results of the call (the last CTA copies them out)
   float *h_qdist;
   uint8_t *h_taken;
-  int *h_overflow;
+  int *h_overflow;  // [2] overflow flag, parallel rounds the resolve phase ran
   int smem_state;   // 1: the launch carries n * 5 + 16 bytes of dynamic shared memory for the resolve phase's taken / claim arrays
   float min_x, min_y, best_init, th_le, th_lt, c2;
 };
@@ -170,7 +170,8 @@ __device__ __forceinline__ void guided_resolve(const GuidedArgs &a) {
   volatile int *kpmin = g_kpmin;
   volatile uint8_t *decided = a.decided;
   bool left = true;
-  for (int round = 0; round < GUIDED_ROUNDS && left; round++) {
+  int rounds = 0;
+  for (int round = 0; round < GUIDED_ROUNDS && left; round++, rounds++) {
     const int tag = (2038 - round) << 20;  // every tag stays below the cleared value 0x7F7F7F7F, so round 0 already claims
     for (int i = tid; i < a.m; i += nt) {
       if (decided[i]) continue;
@@ -202,6 +203,7 @@ __device__ __forceinline__ void guided_resolve(const GuidedArgs &a) {
     __syncthreads();
     for (int k = tid; k < a.n; k += nt) a.taken[k] = g_taken[k];
   }
+  if (tid == 0) a.h_overflow[1] = rounds;
 }
 
 constexpr int GUIDED_THREADS = 1024;  // 32 map points per CTA in the candidate phase; the resolve phase uses all of them

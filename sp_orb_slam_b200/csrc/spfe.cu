@@ -223,6 +223,7 @@ struct spfe_ctx {
   // spfe_search_guided scratch (device, grown on demand; guarded by match_mu)
   void *guided_buf = nullptr;
   size_t guided_bytes = 0;
+  int guided_rounds = 0;         // parallel rounds of the last guided search's resolve phase (spfe_guided_last_rounds)
   void *guided_stage = nullptr;  // page-locked staging of the per-call arrays and results of spfe_search_guided*
   size_t guided_stage_bytes = 0;
   // spfe_dust_pose_* page-locked staging block (grown on demand; guarded by match_mu)
@@ -1703,7 +1704,7 @@ int guided_run(spfe_ctx *c, const spfe_guided_search *g, const spfe_desc_set *qs
   const size_t in_bytes = off;
   // results: device copies the kernel works on, mirrored at the same offsets of the page-locked block, where the
   // kernel's last CTA writes them directly (mapped host memory)
-  const size_t o_q2kp = carve((size_t)m * 4), o_qdist = carve((size_t)m * 4), o_taken = carve(nn), o_over = carve(4);
+  const size_t o_q2kp = carve((size_t)m * 4), o_qdist = carve((size_t)m * 4), o_taken = carve(nn), o_over = carve(8);
   const size_t out_end = off;
   const size_t o_qdesc = carve(qset ? 0 : (size_t)m * 1024), o_kdesc = carve(kset ? 0 : nn * 1024),
                o_cand = carve((size_t)m * GUIDED_CAND * 4), o_cdist = carve((size_t)m * GUIDED_CAND * 4), o_ncand = carve((size_t)m * 4), o_dec = carve(m);
@@ -1760,6 +1761,7 @@ int guided_run(spfe_ctx *c, const spfe_guided_search *g, const spfe_desc_set *qs
   if (kp_taken_out && n > 0) memcpy(kp_taken_out, hb + o_taken, n);
   int over = 0;
   memcpy(&over, hb + o_over, 4);
+  memcpy(&c->guided_rounds, hb + o_over + 4, 4);
   if (over) return c->fail(SPFE_ERR_INVALID, fmt("%s: a query has more than %d candidate keypoints (radius too large)", fn, GUIDED_CAND));
   return SPFE_OK;
 }
@@ -1770,6 +1772,8 @@ int spfe_search_guided(spfe_ctx *c, const spfe_guided_search *g, int32_t *q2kp, 
   if (!c) return SPFE_ERR_INVALID;
   return guided_run(c, g, nullptr, nullptr, q2kp, qdist, kp_taken_out, "spfe_search_guided");
 }
+
+int32_t spfe_guided_last_rounds(const spfe_ctx *c) { return c ? c->guided_rounds : SPFE_ERR_INVALID; }
 
 int spfe_search_guided_sets(spfe_ctx *c, const spfe_guided_search *g, const spfe_desc_set *qset, const spfe_desc_set *kset,
                             int32_t *q2kp, float *qdist, uint8_t *kp_taken_out) {

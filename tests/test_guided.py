@@ -333,6 +333,26 @@ def test_guided_search_on_device_resident_sets(gpu_frame):
 
 
 @pytest.mark.gpu
+def test_conflict_free_search_resolves_in_one_round(gpu_frame):
+    """Claim tags start below the cleared value: when no two map points compete for a key point, every one
+    of them decides in the first parallel round; a pile-up on one key point takes as many rounds as it has claimants."""
+    ex, fr = gpu_frame
+    rng = np.random.RandomState(3)
+    src = rng.permutation(fr["n"])[:200]                      # distinct key points, tiny radius: one candidate each
+    qdesc = fr["desc"][src]
+    qxy = fr["kp_xy"][src].astype(np.float32)
+    kw = dict(mode=capi.GUIDED_AREA, best_init=256.0, th_le=0.7, th_lt=0.7)
+    q2kp, _, _ = ex.search_guided(qdesc, qxy, 1.5, fr["occ_grid"], fr["kp_xy"], fr["desc"], **kw)
+    assert np.array_equal(q2kp, src)
+    assert ex._lib.spfe_guided_last_rounds(ex._ctx) == 1
+    k0 = int(src[0])                                          # five map points on one key point: a chain of five decisions
+    q2kp, _, _ = ex.search_guided(np.repeat(fr["desc"][k0:k0 + 1], 5, 0), np.repeat(fr["kp_xy"][k0:k0 + 1], 5, 0).astype(np.float32),
+                                  1.5, fr["occ_grid"], fr["kp_xy"], fr["desc"], **kw)
+    assert q2kp.tolist() == [k0, -1, -1, -1, -1]
+    assert 2 <= ex._lib.spfe_guided_last_rounds(ex._ctx) <= 5
+
+
+@pytest.mark.gpu
 def test_dust_association_matches_oracle(gpu_frame):
     ex, fr = gpu_frame
     rng = np.random.RandomState(7)
