@@ -184,7 +184,8 @@ int spfe_match_knn2(spfe_ctx *ctx, const float *q, int32_t nq, const float *t, i
  *   spfe_desc_set_from_frame  rows[0..n) (NULL: all key points) of frame `frame` of the last batch waited for on `slot`,
  *                             gathered device -> device: the descriptors never cross PCIe for matching
  *   spfe_match_mutual_nn_sets / spfe_match_knn2_sets   the two matchers on sets (results as in the host-pointer forms)
- * Capacity <= 4096 rows (the matcher's limit).  All set entries are thread-safe like spfe_match_mutual_nn. */
+ * Capacity <= 4096 rows (the matcher's limit).  All set entries are thread-safe like spfe_match_mutual_nn.  Sets belong
+ * to their context: spfe_destroy frees the ones still alive (their handles are dead afterwards). */
 typedef struct spfe_desc_set spfe_desc_set;
 int spfe_desc_set_create(spfe_ctx *ctx, int32_t capacity, spfe_desc_set **out);
 void spfe_desc_set_destroy(spfe_ctx *ctx, spfe_desc_set *set);

@@ -211,6 +211,7 @@ struct spfe_ctx {
   bool slot_streams = false;
   MatchScratch match;  // for spfe_match_* (descriptor sets)
   spfe_desc_set *tmp_q = nullptr, *tmp_t = nullptr;  // the host-pointer entries upload into these
+  std::vector<spfe_desc_set *> sets;                 // every live descriptor set (leftovers are freed with the context)
   float2 *set_cand[2] = {nullptr, nullptr};            // [match_cap rows][match_cap / 256][3] nominees per direction
   unsigned long long *set_second = nullptr;            // [match_cap] second-best keys (k-NN 2)
   int *set_flag = nullptr, *h_set_flag = nullptr;      // "a row is not a unit vector" (device / pinned host)
@@ -1067,8 +1068,7 @@ void spfe_destroy(spfe_ctx *c) {
     if (s.ev0) cudaEventDestroy(s.ev0);
     if (s.ev1) cudaEventDestroy(s.ev1);
   }
-  set_free(c->tmp_q);
-  set_free(c->tmp_t);
+  while (!c->sets.empty()) set_free(c->sets.back());  // tmp_q / tmp_t and any set the caller did not destroy
   for (cudaEvent_t e : c->dom_ev) cudaEventDestroy(e);
   if (c->match_stream) cudaStreamDestroy(c->match_stream);
   if (c->guided_buf) cudaFree(c->guided_buf);
@@ -1414,11 +1414,15 @@ int set_alloc(spfe_ctx *c, int capacity, spfe_desc_set **out) {
     delete s;
     return rc;
   }
+  c->sets.push_back(s);
   *out = s;
   return SPFE_OK;
 }
 void set_free(spfe_desc_set *s) {
   if (!s) return;
+  std::vector<spfe_desc_set *> &v = s->ctx->sets;
+  for (size_t i = 0; i < v.size(); i++)
+    if (v[i] == s) { v.erase(v.begin() + i); break; }
   cudaFree(s->d32);
   cudaFree(s->d16);
   delete s;
@@ -1560,8 +1564,11 @@ int spfe_desc_set_create(spfe_ctx *c, int32_t capacity, spfe_desc_set **out) {
 }
 
 void spfe_desc_set_destroy(spfe_ctx *c, spfe_desc_set *s) {
-  if (!c || !s || s->ctx != c) return;
+  if (!c || !s) return;
   std::lock_guard<std::mutex> lock(c->match_mu);
+  bool mine = false;
+  for (spfe_desc_set *p : c->sets) mine |= p == s;
+  if (!mine || s == c->tmp_q || s == c->tmp_t) return;  // not a live set of this context
   cudaSetDevice(c->cfg.device_id);
   cudaStreamSynchronize(c->match_stream);
   set_free(s);

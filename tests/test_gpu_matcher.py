@@ -131,3 +131,16 @@ def test_stream_match_prev_is_exact_on_near_ties():
         assert np.array_equal(outs[t]["match_prev"], ref)
         assert outs[t]["n"] > 100
     e.close()
+
+
+def test_sets_left_alive_are_freed_with_the_context():
+    e = SPExtractor(800, 64, 64, WEIGHTS, emit_heat=False, emit_cov=False)
+    rng = np.random.RandomState(1)
+    a = e.desc_set(300).upload(unit(rng.randn(300, 256)))
+    b = e.desc_set(300).upload(unit(rng.randn(200, 256)))
+    q2t, _ = e.match_sets(a, b)
+    assert len(q2t) == 300
+    b.close()
+    b.close()                                               # double destroy: ignored
+    e.close()                                               # `a` is still alive: freed by spfe_destroy
+    a.close()                                               # dead handle, dead context: a no-op in the mirror
