@@ -144,3 +144,43 @@ def test_sets_left_alive_are_freed_with_the_context():
     b.close()                                               # double destroy: ignored
     e.close()                                               # `a` is still alive: freed by spfe_destroy
     a.close()                                               # dead handle, dead context: a no-op in the mirror
+
+
+def test_matcher_entries_from_three_threads_while_extracting():
+    """SearchByBruteForce runs on the tracking and the loop-closing thread, the FLANN replacement on the mapping thread,
+    while the tracking thread keeps extracting (graph replays): concurrent calls give the single-threaded answers."""
+    import threading
+    H, W = 240, 320
+    e = SPExtractor(800, H, W, WEIGHTS, emit_heat=False, emit_cov=True)
+    frames = synth.make_stream(H, W, 4, seed=23, n_shapes=240)
+    outs = [e.extract(f) for f in frames]                  # the third call on replays the captured graph
+    cur = e.desc_set(1024).from_frame(0, 0)                 # slot 0 holds frames[3] now
+    assert cur.size() == outs[3]["n"]
+    q2t_set, _ = e.match_sets(cur, e.desc_set(1024).upload(outs[2]["desc"]))
+    ref32, _, _ = O.match_mutual_nn(outs[3]["desc"], outs[2]["desc"])
+    assert np.array_equal(q2t_set, ref32)
+    want_m, _, _ = O.match_mutual_nn(outs[1]["desc"], outs[0]["desc"])
+    want_k, _ = O.knn2(outs[2]["desc"], outs[1]["desc"])
+    errors = []
+
+    def worker(kind):
+        try:
+            for _ in range(25):
+                if kind == "knn":
+                    idx, _ = e.knn2(outs[2]["desc"], outs[1]["desc"])
+                    assert np.array_equal(idx, want_k)
+                else:
+                    q2t, _ = e.match(outs[1]["desc"], outs[0]["desc"])
+                    assert np.array_equal(q2t, want_m)
+        except Exception as ex:                             # noqa: BLE001
+            errors.append(repr(ex))
+    threads = [threading.Thread(target=worker, args=(k,)) for k in ("mutual", "mutual", "knn")]
+    for t in threads:
+        t.start()
+    for i in range(40):                                     # the tracking thread
+        o = e.extract(frames[i % 4])
+        assert np.array_equal(o["kp_xy"], outs[i % 4]["kp_xy"]) and np.array_equal(o["cov2"], outs[i % 4]["cov2"])
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    e.close()
